@@ -1,0 +1,385 @@
+#!/usr/bin/env python3
+"""bench.py -- time-samples/s of the FRF -> GPR-selection -> FIR hot path on N B200s (one JSON line).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 ... bench.py --gpus N ...
+
+A "step" is one pass of the hot path over one batch of synthetic input (BASELINE.json configs[1],
+scaled weakly over ranks as configs[4] does): per rank one 10^7-sample multisine training record and
+one 10^7-sample square-wave validation record (dt = 2 ms, FP64), N_d = 100:
+  FRF of the training record (100 bins)  ->  cross-power (all-reduce of per-bin num/den over ranks)
+  150-bin FRF of the validation record   ->  grid-search targets (validation-RMSE metric)
+  Matern-5/2 grid search, 900 candidates x 2 targets (candidates sharded over ranks, argmin gather)
+  final fit x2, GP mean on the 1000-point uniform grid, Hermitian IDFT -> 1024 taps
+  FIR validation of the taps over the validation record (all-reduce of the fused error sums)
+value = training samples processed by all ranks / step time (device-resident inputs, CUDA events,
+max over ranks).  e2e = same metric with HOST (pinned) buffers: H2D of both records and D2H of the
+result inside the timed region.  See DESIGN.md section "Measurement" for the roofline arithmetic.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+PKG = ROOT / "gauss-process_b200"
+for p in (str(ROOT), str(PKG)):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+METRIC = "time-samples/s (FRF+GPR-selection+FIR pipeline)"
+UNIT = "samples/s"
+KERNEL = "matern52"
+NOISE = 1e-6
+N_TAPS = 1024
+VAL_ND = 150
+FRF_BYTES_PER_SAMPLE = 24        # t, u, y FP64 read once
+FIR_BYTES_PER_SAMPLE = 16        # u, y FP64 read once, y_pred not materialised
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=10_000_000, help="samples per record (per rank)")
+    ap.add_argument("--nd", type=int, default=100)
+    ap.add_argument("--cpu-sample", type=int, default=400_000, help="samples of the bounded CPU-baseline pass")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(a, world):
+    return {
+        "workload": f"cfg2 full pipeline per rank: {a.n}-sample multisine train record + {a.n}-sample square-wave "
+                    f"validation record, N_d={a.nd}, validation FRF {VAL_ND} bins, Matern-5/2 grid 900 candidates x 2 "
+                    f"targets (val-RMSE), 1000-pt GP mean, Hermitian IDFT -> {N_TAPS} taps, FIR validation",
+        "n_samples_per_record": a.n, "n_d": a.nd, "records_per_rank": 2, "ranks": world,
+        "gp_candidates_per_step": 1800, "fir_taps": N_TAPS, "noise_variance": NOISE,
+        "l2_policy": "inputs larger than L2 (2 records x 240 MB per rank vs 126 MB L2)",
+        "parallelism": f"records x{world} (weak), candidates round-robin over ranks",
+    }
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic inputs (outside every timed region)
+def make_records(n, nd, seed, dev=None):
+    """(train, val) host records.  The multisine is summed on the GPU when one is present (10^9 sines
+    at n = 10^7 take ~15 s in NumPy); the plant is scipy.signal.lfilter on the host either way."""
+    from b200id import synth
+    if dev is None or n < 1_000_000:
+        return synth.make_record(n, nd, "multisine", seed=seed), synth.make_record(n, nd, "square", seed=seed + 1)
+    import torch
+    rng = np.random.default_rng(seed)
+    f, w = synth.log_grid(nd)
+    amp = torch.from_numpy(rng.uniform(0.0, 20.0 / nd, size=nd)).to(dev)
+    ph = torch.from_numpy(rng.uniform(0.0, 2.0 * np.pi, size=nd)).to(dev)
+    w_d = torch.from_numpy(w).to(dev)
+    t = np.arange(n, dtype=np.float64) * synth.DT
+    u = np.empty(n)
+    chunk = 1 << 20
+    for s in range(0, n, chunk):
+        e = min(n, s + chunk)
+        tc = torch.from_numpy(t[s:e]).to(dev)
+        u[s:e] = (torch.sin(tc[:, None] * w_d[None, :] + ph[None, :]) @ amp).cpu().numpy()
+    y = synth.apply_plant(u, seed=seed + 7)
+    tv, uv = synth.square_wave(n, seed=seed + 1)
+    yv = synth.apply_plant(uv, seed=seed + 8)
+    return (t, u, y), (tv, uv, yv)
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); smax.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for nm, v in zip(names, r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_pipeline_pass(n_s, nd, threads):
+    """One pass of the SAME pipeline through the NumPy oracle (the reference's algorithm) on a bounded
+    sample of n_s samples per record.  Returns seconds per stage."""
+    from b200id import synth
+    from oracle import frf as ofrf, gp as ogp, fir as ofir
+    (t, u, y), (tv, uv, yv) = make_records(n_s, nd, seed=0)
+    st = {}
+    t0 = time.perf_counter()
+    w, G = ofrf.estimate_frf([(t, u, y)], nd, threads=threads)
+    st["frf_train"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    wv, Gv = ofrf.estimate_frf([(tv, uv, yv)], VAL_ND, threads=threads)
+    st["frf_val"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    X, xm, xs = ogp.standardize(np.log10(w))
+    Xv = (np.log10(wv) - xm) / xs
+    fits = []
+    with np.errstate(all="ignore"):
+        for target, tv_ in ((G.real, Gv.real), (G.imag, Gv.imag)):
+            z, m, s = ogp.standardize(target)
+            best, _, _, _ = ogp.grid_search(KERNEL, X, z, NOISE, 5000, Xv=Xv, yv=tv_, y_mean=m, y_scale=s)
+            alpha, Kinv, _ = ogp.fit(KERNEL, best, X, z, NOISE)
+            fits.append((best, alpha, Kinv, m, s))
+    st["gp"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
+
+    def predict(w_new):
+        Xn = (np.log10(w_new) - xm) / xs
+        parts = [ogp.predict(KERNEL, b, X, a, K, Xn) * s + m for (b, a, K, m, s) in fits]
+        return parts[0] + 1j * parts[1]
+
+    taps, *_ = ofir.paper_fir(w, G, predict=predict)
+    metrics, _ = ofir.fir_validate(uv, yv, taps)
+    st["fir"] = time.perf_counter() - t0
+    return st, metrics
+
+
+def run_reference_arm(a, rank, world):
+    """--impl reference: the reference's CPU algorithm (oracle port; the reference itself is pure Python and
+    /root/reference does not exist on the GPU box) on the host cores, bounded sample per step."""
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    n_s = min(a.n, a.cpu_sample)
+    times = []
+    for i in range(a.warmup + a.steps):
+        t0 = time.perf_counter()
+        st, _ = cpu_pipeline_pass(n_s, a.nd, threads)
+        dt = sum(st.values())
+        if i >= a.warmup:
+            times.append(dt)
+    sec = float(np.mean(times))
+    value = n_s / sec
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": workload_config(a, 1),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{n_s} samples per record of the same workload (same bins, same 1800 GP candidates, "
+                                   f"same {N_TAPS}-tap FIR); per-bin FRF loop on a {threads}-thread pool"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    a = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if a.impl == "reference":
+        run_reference_arm(a, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from b200id import _lib, dist as bdist, pipeline as P
+    from b200id.runtime import require_cuda, to_device, empty
+    import ctypes as C
+
+    rank, world, local = bdist.init_from_env()
+    dev = require_cuda()
+    sm, major, minor = _lib.device_info()
+    peaks = {}
+    pk = ROOT / "MEASURED_PEAKS.json"
+    if pk.exists():
+        peaks = json.loads(pk.read_text())
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+
+    # ---- inputs: generated once, kept on the host (pinned) for e2e and on the device for `value`
+    train_h, val_h = make_records(a.n, a.nd, seed=100 * rank, dev=dev)
+    pinned = [[torch.from_numpy(x).pin_memory() for x in rec] for rec in (train_h, val_h)]
+    spans = [float(rec[0][-1] - rec[0][0]) for rec in (train_h, val_h)]
+    skip = min(10, N_TAPS // 10)
+    y0 = float(val_h[2][skip])
+    dev_recs = [[x.to(dev) for x in rec] for rec in pinned]
+    cands = P.CandidateSet.build(KERNEL, P.grid_candidates(KERNEL), dev, rank=rank, world_size=world)
+
+    def step_resident():
+        tr = [(dev_recs[0][0], dev_recs[0][1], dev_recs[0][2], spans[0])]
+        va = (dev_recs[1][0], dev_recs[1][1], dev_recs[1][2], spans[1], y0)
+        return P.identify_device(tr, va, a.nd, KERNEL, NOISE, cands, n_taps=N_TAPS)
+
+    def step_e2e():
+        d = [[x.to(dev, non_blocking=True) for x in rec] for rec in pinned]
+        tr = [(d[0][0], d[0][1], d[0][2], spans[0])]
+        va = (d[1][0], d[1][1], d[1][2], spans[1], y0)
+        res = P.identify_device(tr, va, a.nd, KERNEL, NOISE, cands, n_taps=N_TAPS)
+        taps = res.taps.cpu()           # D2H of the step's result (taps + the metrics already read back)
+        return res, taps
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup, with_events=False):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        _lib.launch_count = 0
+        if with_events:
+            _lib.event_log = {}
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = None
+        for _ in range(steps):
+            out = fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        log, _lib.event_log = _lib.event_log, None
+        launches = _lib.launch_count
+        if world > 1:
+            tt = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms = float(tt.item())
+        return ms / steps, out, log, launches
+
+    # ---- device-resident timing (value) with clocks sampled during the timed region
+    clocks = ClockSampler(torch.cuda.current_device())
+    if rank == 0:
+        clocks.start()
+    ms_step, res, _, launches = timed(step_resident, a.steps, a.warmup)
+    clk = clocks.stop() if rank == 0 else {}
+    # ---- per-stage kernel times from a second, event-instrumented run (same work, same stream)
+    ms_inst, _, log, _ = timed(step_resident, a.steps, 1, with_events=True)
+    stage_ms = {k: sum(s.elapsed_time(e) for s, e in v) / a.steps for k, v in (log or {}).items()}
+    # ---- e2e timing: host pinned buffers in, result out
+    ms_e2e, (res_e, taps_e), _, _ = timed(step_e2e, a.steps, a.warmup)
+    h2d = sum(x.numel() * 8 for rec in pinned for x in rec)
+    d2h = N_TAPS * 8 + 2 * 2 * 8 + 4 * 8 + 2 * 16     # taps + scaler stats + FIR sums + argmin pairs
+
+    total_samples = a.n * world
+    value = total_samples / (ms_step * 1e-3)
+    e2e_value = total_samples / (ms_e2e * 1e-3)
+
+    # ---- FP64 peak probe (roofline denominator for the FP64-bound kernels; not in MEASURED_PEAKS.json)
+    fp64 = {}
+    if rank == 0:
+        sink = empty(1, dev)
+        for mode, name in ((0, "dfma"), (1, "dmma")):
+            flops = C.c_double(0.0)
+            from b200id.runtime import ptr, stream_ptr
+            iters = 4000
+            _lib.call("b200id_fp64_peak_probe", C.c_int(mode), C.c_int(iters), ptr(sink), C.byref(flops), stream_ptr())
+            torch.cuda.synchronize()
+            best = 0.0
+            for _ in range(3):
+                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s.record()
+                _lib.call("b200id_fp64_peak_probe", C.c_int(mode), C.c_int(iters), ptr(sink), C.byref(flops), stream_ptr())
+                e.record()
+                torch.cuda.synchronize()
+                best = max(best, flops.value / (s.elapsed_time(e) * 1e-3) / 1e12)
+            fp64[name + "_tflops"] = best
+
+    if rank != 0:
+        return
+
+    # ---- roofline of the dominant kernel (largest share of the step among the instrumented calls)
+    frf_ms = stage_ms.get("b200id_frf_project", 0.0)
+    fir_ms = stage_ms.get("b200id_fir_eval", 0.0)
+    gp_ms = stage_ms.get("b200id_gp_batch_eval", 0.0)
+    dominant = max((("frf_project_kernel", frf_ms), ("fir_eval_kernel", fir_ms), ("gp_batch_kernel", gp_ms)), key=lambda kv: kv[1])[0]
+    frf_bytes = FRF_BYTES_PER_SAMPLE * a.n * 2            # two launches per step: train (nd bins) + validation (150 bins)
+    frf_flops = 8.0 * a.n * (a.nd + VAL_ND)               # 2 signals x (cos, sin) x FMA, both launches
+    fir_bytes = FIR_BYTES_PER_SAMPLE * a.n
+    fir_flops = 2.0 * N_TAPS * a.n
+    gp_flops = 1800 / world * (a.nd ** 3 / 3.0 + 2.0 * a.nd ** 2)
+    fp64_peak = max(fp64.values()) if fp64 else None
+    if dominant == "fir_eval_kernel":
+        ach = fir_bytes / (fir_ms * 1e-3) / 1e9
+    else:
+        ach = frf_bytes / (frf_ms * 1e-3) / 1e9 if frf_ms > 0 else 0.0
+        dominant = "frf_project_kernel"
+    roofline = {
+        "kernel": dominant, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+        "traffic": None, "peak_source": peak_src,
+        "note": "FP64-issue bound by construction (reference-faithful per-sample rounded phases need a sincos per "
+                "sample-bin); see fp64 block and DESIGN.md",
+        "fp64": {
+            "peak_tflops_measured": fp64_peak, **fp64,
+            "frf_algorithmic_tflops": frf_flops / (frf_ms * 1e-3) / 1e12 if frf_ms > 0 else None,
+            "fir_algorithmic_tflops": fir_flops / (fir_ms * 1e-3) / 1e12 if fir_ms > 0 else None,
+            "gp_algorithmic_tflops": gp_flops / (gp_ms * 1e-3) / 1e12 if gp_ms > 0 else None,
+            "frf_frac": (frf_flops / (frf_ms * 1e-3) / 1e12 / fp64_peak) if (fp64_peak and frf_ms > 0) else None,
+            "fir_frac": (fir_flops / (fir_ms * 1e-3) / 1e12 / fp64_peak) if (fp64_peak and fir_ms > 0) else None,
+            "gp_frac": (gp_flops / (gp_ms * 1e-3) / 1e12 / fp64_peak) if (fp64_peak and gp_ms > 0) else None,
+        },
+    }
+    stages = {
+        "ms_per_step_by_call": stage_ms,
+        "frf_samples_per_s_kernel": 2 * a.n / (frf_ms * 1e-3) if frf_ms > 0 else None,
+        "fir_samples_per_s_kernel": a.n / (fir_ms * 1e-3) if fir_ms > 0 else None,
+        "gpr_candidates_per_s_kernel": (1800 / world) / (gp_ms * 1e-3) if gp_ms > 0 else None,
+        "fir_hbm_gbs": fir_bytes / (fir_ms * 1e-3) / 1e9 if fir_ms > 0 else None,
+    }
+
+    cpu = None
+    if world == 1 and not a.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        n_s = min(a.n, a.cpu_sample)
+        st, cpu_metrics = cpu_pipeline_pass(n_s, a.nd, threads)
+        cpu_s = sum(st.values())
+        cpu = {"value": n_s / cpu_s, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"{n_s} samples per record of the same workload; stage seconds {json.dumps({k: round(v, 3) for k, v in st.items()})}"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": workload_config(a, world),
+        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": launches, "clocks": clk, "roofline": roofline, "cpu_baseline": cpu, "stages": stages,
+        "result": {"theta_real": res.theta_real.tolist(), "theta_imag": res.theta_imag.tolist(), "fir_rmse": res.fir.get("rmse")},
+        "device": {"sm_count": sm, "cc": f"{major}.{minor}"},
+    }
+    print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()

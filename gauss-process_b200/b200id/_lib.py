@@ -1,0 +1,114 @@
+"""ctypes binding of libb200id.so (include/b200id.h) -- the only way the Python mirror reaches CUDA.
+
+There is deliberately no CPU fallback: if the shared library is missing or a call fails, the
+product raises.  PyTorch is used by callers only to own device buffers and streams; pointers and
+the stream handle cross this boundary as plain integers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+PKG_ROOT = Path(__file__).resolve().parent.parent
+LIB_PATH = Path(os.environ.get("B200ID_LIB", PKG_ROOT / "lib" / "libb200id.so"))
+
+P = C.c_void_p
+I = C.c_int
+L = C.c_int64
+D = C.c_double
+Z = C.c_size_t
+
+# name -> (restype, argtypes); must list every symbol include/b200id.h declares
+SIGNATURES = {
+    "b200id_version": (I, []),
+    "b200id_last_error": (C.c_char_p, []),
+    "b200id_device_info": (I, [C.POINTER(I), C.POINTER(I), C.POINTER(I)]),
+    "b200id_frf_workspace_bytes": (Z, [I]),
+    "b200id_frf_moments": (I, [P, P, L, L, L, P, P, Z, P]),
+    "b200id_frf_project": (I, [P, P, P, L, L, L, P, I, P, D, P, P, Z, P]),
+    "b200id_frf_finalize": (I, [P, I, D, P, P, P]),
+    "b200id_cross_power": (I, [P, P, I, I, D, P, P]),
+    "b200id_gp_gram": (I, [I, P, P, I, P, I, P, P]),
+    "b200id_gp_batch_workspace_bytes": (Z, [L, I]),
+    "b200id_gp_batch_eval": (I, [I, P, P, L, P, P, I, D, I, P, P, I, D, D, P, P, Z, P]),
+    "b200id_first_strict_min": (I, [P, L, P, P, P, Z, P]),
+    "b200id_gp_fit_workspace_bytes": (Z, [I]),
+    "b200id_gp_fit": (I, [I, P, P, P, I, D, P, P, P, P, Z, P]),
+    "b200id_gp_fit_pinv": (I, [I, P, P, P, I, D, D, P, P, P, Z, P]),
+    "b200id_gp_predict": (I, [I, P, P, I, P, P, P, I, P, P, P]),
+    "b200id_chol_blocked_workspace_bytes": (Z, [I]),
+    "b200id_chol_blocked": (I, [P, I, I, P, P, Z, P]),
+    "b200id_idft_hermitian": (I, [P, I, P, I, P]),
+    "b200id_fir_workspace_bytes": (Z, [L]),
+    "b200id_fir_eval": (I, [P, P, L, L, P, I, L, D, P, P, P, Z, P]),
+    "b200id_fp64_peak_probe": (I, [I, I, P, C.POINTER(D), P]),
+}
+# host-side scalar math exposed for CPU unit tests of the numerics (not part of b200id.h)
+SELFTEST_SIGNATURES = {
+    "b200id_selftest_sincos_host": (None, [P, L, P, P]),
+    "b200id_selftest_gram_host": (None, [I, P, P, I, P, I, P]),
+}
+
+ERROR_NAMES = {-1: "E_ARG", -2: "E_WORKSPACE", -3: "E_CUDA", -4: "E_UNSUPPORTED"}
+
+
+class B200IDError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"libb200id: {ERROR_NAMES.get(code, code)}: {message}")
+        self.code = code
+
+
+_lib = None
+
+# kernels launched per successful entry-point call (bench.py reports the sum as gpu_launches)
+LAUNCHES_PER_CALL = {
+    "b200id_frf_moments": 2, "b200id_frf_project": 2, "b200id_frf_finalize": 1, "b200id_cross_power": 1,
+    "b200id_gp_gram": 1, "b200id_gp_batch_eval": 1, "b200id_first_strict_min": 1, "b200id_gp_fit": 1,
+    "b200id_gp_fit_pinv": 1, "b200id_gp_predict": 1, "b200id_idft_hermitian": 1, "b200id_fir_eval": 2,
+    "b200id_fp64_peak_probe": 1,
+}
+launch_count = 0
+# optional per-call CUDA-event timing: name -> list of (start_event, end_event); set by bench.py
+event_log = None
+
+
+def load() -> C.CDLL:
+    """Load the shared library (once) and type every entry point.  Raises if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise RuntimeError(
+            f"{LIB_PATH} not found: build it with `python gauss-process_b200/build.py` "
+            "(there is no CPU fallback for the b200id hot path)")
+    lib = C.CDLL(str(LIB_PATH))
+    for name, (res, args) in {**SIGNATURES, **SELFTEST_SIGNATURES}.items():
+        fn = getattr(lib, name)       # AttributeError if the library lacks a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def call(name: str, *args) -> None:
+    """Call an int-returning entry point and raise B200IDError on a non-zero status."""
+    global launch_count
+    lib = load()
+    if event_log is not None:
+        import torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise B200IDError(rc, lib.b200id_last_error().decode("utf-8", "replace"))
+    if event_log is not None:
+        e1.record()
+        event_log.setdefault(name, []).append((e0, e1))
+    launch_count += LAUNCHES_PER_CALL.get(name, 1)
+
+
+def device_info():
+    sm, major, minor = I(0), I(0), I(0)
+    call("b200id_device_info", C.byref(sm), C.byref(major), C.byref(minor))
+    return sm.value, major.value, minor.value

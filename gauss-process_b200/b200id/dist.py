@@ -1,0 +1,87 @@
+"""Multi-GPU plumbing: one process per GPU, torch.distributed (NCCL on GPUs, gloo in CPU tests).
+
+Only the three exchanges the path really has:
+  * FRF: one all-reduce(sum) of the per-bin cross-power numerator / denominator (3*nd doubles) when
+    records are sharded, or of the raw partial sums (4*nd doubles) when one record is time-sharded;
+  * GP candidate search: an all-gather of (best metric, global index) per rank, then the host picks
+    the first strict minimum in global scan order (grid_search.py:186-196);
+  * FIR validation: one all-reduce(sum) of the 4 fused error sums.
+Everything else runs rank-local with no data-path collective.
+"""
+from __future__ import annotations
+
+import os
+from typing import List, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def world() -> Tuple[int, int]:
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def init_from_env(backend: str = None) -> Tuple[int, int, int]:
+    """(rank, world_size, local_rank) from torchrun's environment; no-op for a single process."""
+    ws = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if ws > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group(backend=backend, rank=rank, world_size=ws)
+    elif torch.cuda.is_available():
+        torch.cuda.set_device(local)
+    return rank, ws, local
+
+
+def allreduce_sum_(t: torch.Tensor) -> torch.Tensor:
+    """In-place sum over ranks (identity for a single process)."""
+    if world()[1] > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t
+
+
+def shard_round_robin(n_items: int, rank: int, world_size: int) -> np.ndarray:
+    """Global indices i with i % world_size == rank (keeps per-kernel cost balanced across ranks)."""
+    return np.arange(rank, n_items, world_size, dtype=np.int64)
+
+
+def shard_contiguous(n_items: int, rank: int, world_size: int) -> Tuple[int, int]:
+    """[begin, end) of the rank's contiguous slice (time-segment / FIR output shards)."""
+    base, rem = divmod(n_items, world_size)
+    begin = rank * base + min(rank, rem)
+    return begin, begin + base + (1 if rank < rem else 0)
+
+
+def argmin_gather(local_best: float, local_global_idx: int, device=None) -> Tuple[int, float]:
+    """Global first strict minimum from each rank's (best metric, global index of it).
+
+    A rank with no finite candidate passes (inf, -1).  Ties across ranks go to the smallest global
+    index, which reproduces the sequential ``metric < best`` scan of grid_search.py:194.
+    """
+    rank, ws = world()
+    if ws == 1:
+        return int(local_global_idx), float(local_best)
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    mine = torch.tensor([float(local_best), float(local_global_idx)], dtype=torch.float64, device=device)
+    allv = [torch.empty_like(mine) for _ in range(ws)]
+    dist.all_gather(allv, mine)
+    return pick_first_strict_min([(float(v[0].item()), int(v[1].item())) for v in allv])
+
+
+def pick_first_strict_min(pairs: Sequence[Tuple[float, int]]) -> Tuple[int, float]:
+    best, best_idx = float("inf"), -1
+    for m, i in pairs:
+        if i < 0 or not (m == m):
+            continue
+        if m < best or (m == best and i < best_idx):
+            best, best_idx = m, i
+    return best_idx, best

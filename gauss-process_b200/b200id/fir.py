@@ -1,0 +1,88 @@
+"""Host side of K5/K6 (Hermitian IDFT -> FIR taps, FIR convolution + fused error sums).
+
+Mirrors the arithmetic of reference src/fir_model/fir_helpers.py:75-137, fir_fitting.py:285-306 and
+fir_validation.py:93-136,190 through the C ABI (include/b200id.h).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from .runtime import F64, Workspace, empty, ptr, require_cuda, stream_ptr, to_device
+
+
+def idft_taps_device(G_d: torch.Tensor, n_taps: int) -> torch.Tensor:
+    """First n_taps of Re ifft(Hermitian extension of G_d); G_d complex128 [nd] on the device."""
+    nd = G_d.numel()
+    M = 2 * nd - 1
+    if n_taps > M:
+        raise ValueError(f"N={n_taps} exceeds available length M={M}. Reduce N.")
+    h = empty(n_taps, G_d.device)
+    _lib.call("b200id_idft_hermitian", ptr(torch.view_as_real(G_d.contiguous())), C.c_int(nd), ptr(h),
+              C.c_int(n_taps), stream_ptr())
+    return h
+
+
+def idft_taps(G_pos, n_taps: int) -> np.ndarray:
+    dev = require_cuda()
+    G = torch.from_numpy(np.ascontiguousarray(np.asarray(G_pos, dtype=np.complex128).ravel())).to(dev)
+    return idft_taps_device(G, n_taps).cpu().numpy()
+
+
+def fir_eval_device(u_d: torch.Tensor, y_d: Optional[torch.Tensor], g_d: torch.Tensor, skip: int, y0: float,
+                    lead: int = 0, want_pred: bool = False, n: Optional[int] = None):
+    """(sums[4] = {sum e^2, sum y^2, sum (y-y0)^2, count}, y_pred or None) on the device.
+
+    ``u_d`` points at output index 0; with ``lead`` > 0 the ``lead`` samples before it must belong to
+    the same allocation (pass a view into a longer tensor) -- they are the FIR history of a shard.
+    """
+    dev = u_d.device
+    n = u_d.numel() if n is None else n
+    sums = empty(4, dev)
+    pred = empty(n, dev) if want_pred else None
+    nbytes = _lib.load().b200id_fir_workspace_bytes(n)
+    ws = Workspace.get("fir", nbytes, dev)
+    _lib.call("b200id_fir_eval", ptr(u_d), ptr(y_d), C.c_int64(n), C.c_int64(lead), ptr(g_d), C.c_int(g_d.numel()),
+              C.c_int64(skip), C.c_double(y0), ptr(pred), ptr(sums), ptr(ws), C.c_size_t(ws.numel()), stream_ptr())
+    return sums, pred
+
+
+def metrics_from_sums(sums, skip: int) -> Dict[str, float]:
+    """RMSE / FIT% / R2 from the fused sums (fir_validation.py:115-128, fir_fitting.py:296-306)."""
+    se, sy, st, cnt = (float(v) for v in sums)
+    rmse = math.sqrt(se / cnt)
+    norm_y = math.sqrt(sy)
+    fit = float(100 * (1.0 - math.sqrt(se) / norm_y)) if norm_y > 0 else 0.0
+    r2 = float(1.0 - se / st) if st > 0 else 0.0
+    return {"rmse": rmse, "fit_percent": fit, "r2": r2, "transient_skip": skip, "detrend": False}
+
+
+def fir_predict(u, g, n_out: Optional[int] = None) -> np.ndarray:
+    """np.convolve(u, g, 'full')[:n_out] on the device."""
+    dev = require_cuda()
+    u_d = to_device(np.asarray(u, dtype=np.float64).ravel(), dev)
+    g_d = to_device(np.asarray(g, dtype=np.float64).ravel(), dev)
+    n_out = u_d.numel() if n_out is None else min(n_out, u_d.numel())
+    _, pred = fir_eval_device(u_d, None, g_d, 0, 0.0, want_pred=True, n=n_out)
+    return pred.cpu().numpy()
+
+
+def fir_validate(u, y, g, detrend: bool = False, want_pred: bool = True) -> Tuple[Dict[str, float], Optional[np.ndarray]]:
+    """(metrics, y_pred) of FIR taps g on record (u, y): convolution and error sums on the device."""
+    dev = require_cuda()
+    u = np.asarray(u, dtype=np.float64).ravel()
+    y = np.asarray(y, dtype=np.float64).ravel()
+    g = np.asarray(g, dtype=np.float64).ravel()
+    if detrend:
+        u, y = u - np.mean(u), y - np.mean(y)
+    skip = min(10, g.size // 10)
+    u_d, y_d, g_d = to_device(u, dev), to_device(y, dev), to_device(g, dev)
+    n = min(u.size, y.size)
+    sums, pred = fir_eval_device(u_d, y_d, g_d, skip, float(y[skip]), want_pred=want_pred, n=n)
+    m = metrics_from_sums(sums.cpu().numpy(), skip)
+    return m, (pred.cpu().numpy() if want_pred else None)

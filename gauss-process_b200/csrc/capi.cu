@@ -1,0 +1,113 @@
+// capi.cu -- library-level entry points of the C ABI (include/b200id.h): version, errors, device
+// info and the FP64 peak probe that bench.py uses as the FP64 roofline denominator.
+#include <stdarg.h>
+#include "common.cuh"
+
+namespace b200id {
+
+static thread_local char g_error[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+}
+
+int check_cuda(cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return B200ID_OK;
+    set_error("%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
+    return B200ID_E_CUDA;
+}
+
+int sm_count() {
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (cached[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cached[dev] = n;
+    }
+    return cached[dev];
+}
+
+// ---------------------------------------------------------------- FP64 peak probe
+// mode 0: 8 independent DFMA chains per thread.  mode 1: mma.sync.m8n8k4.f64 chains.
+constexpr int PROBE_THREADS = 256;
+constexpr int PROBE_CHAINS = 8;
+
+__global__ void __launch_bounds__(PROBE_THREADS) probe_dfma_kernel(int iters, double* sink) {
+    double a[PROBE_CHAINS];
+    const double m = 1.0 + 1e-9 * threadIdx.x, c = 1e-12;
+#pragma unroll
+    for (int k = 0; k < PROBE_CHAINS; ++k) a[k] = 0.5 + k;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int rep = 0; rep < 8; ++rep) {
+#pragma unroll
+            for (int k = 0; k < PROBE_CHAINS; ++k) a[k] = fma(a[k], m, c);
+        }
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < PROBE_CHAINS; ++k) s += a[k];
+    if (s == 123.456) sink[0] = s;   // never true; keeps the chains alive
+}
+
+__global__ void __launch_bounds__(PROBE_THREADS) probe_dmma_kernel(int iters, double* sink) {
+    double c0[PROBE_CHAINS], c1[PROBE_CHAINS];
+    const double a = 1.0 + 1e-9 * threadIdx.x, b = 1e-3;
+#pragma unroll
+    for (int k = 0; k < PROBE_CHAINS; ++k) { c0[k] = k; c1[k] = -k; }
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int k = 0; k < PROBE_CHAINS; ++k) {
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                         : "+d"(c0[k]), "+d"(c1[k]) : "d"(a), "d"(b));
+        }
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < PROBE_CHAINS; ++k) s += c0[k] + c1[k];
+    if (s == 123.456) sink[0] = s;
+}
+
+}  // namespace b200id
+
+using namespace b200id;
+
+extern "C" int b200id_version(void) { return B200ID_VERSION; }
+
+extern "C" const char* b200id_last_error(void) { return g_error; }
+
+extern "C" int b200id_device_info(int* sm, int* cc_major, int* cc_minor) {
+    int dev = 0;
+    int rc = check_cuda(cudaGetDevice(&dev), "cudaGetDevice");
+    if (rc) return rc;
+    cudaDeviceProp p;
+    rc = check_cuda(cudaGetDeviceProperties(&p, dev), "cudaGetDeviceProperties");
+    if (rc) return rc;
+    if (sm) *sm = p.multiProcessorCount;
+    if (cc_major) *cc_major = p.major;
+    if (cc_minor) *cc_minor = p.minor;
+    return B200ID_OK;
+}
+
+extern "C" int b200id_fp64_peak_probe(int mode, int iters, double* sink, double* flops_out_host, void* stream) {
+    B200ID_REQUIRE(sink && iters > 0 && (mode == 0 || mode == 1), B200ID_E_ARG, "fp64_peak_probe: bad argument");
+    const int grid = sm_count() * 8;
+    cudaStream_t st = (cudaStream_t)stream;
+    double flops;
+    if (mode == 0) {
+        probe_dfma_kernel<<<grid, PROBE_THREADS, 0, st>>>(iters, sink);
+        flops = 2.0 * PROBE_CHAINS * 8.0 * (double)iters * PROBE_THREADS * (double)grid;
+    } else {
+        probe_dmma_kernel<<<grid, PROBE_THREADS, 0, st>>>(iters, sink);
+        // one m8n8k4 = 8*8*4 MACs per warp
+        flops = 2.0 * 256.0 * PROBE_CHAINS * (double)iters * (PROBE_THREADS / 32) * (double)grid;
+    }
+    B200ID_LAUNCH_CHECK("probe kernel");
+    if (flops_out_host) *flops_out_host = flops;
+    return B200ID_OK;
+}

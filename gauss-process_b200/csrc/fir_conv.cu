@@ -1,0 +1,177 @@
+// fir_conv.cu -- K5 Hermitian IDFT -> FIR taps, K6 causal FIR convolution fused with error sums.
+//
+// Reference call sites: src/fir_model/fir_helpers.py:75-137 (two-sided Hermitian extension + ifft),
+// src/fir_model/fir_fitting.py:285-306 and src/fir_model/fir_validation.py:93-136,190
+// (np.convolve(u, g, 'full')[:N], then RMSE / FIT / R2 over i >= skip).
+//
+// K6 layout.  A CTA of 128 threads produces a tile of 2048 consecutive outputs; each thread owns
+// 16 CONSECUTIVE outputs and keeps a sliding window of u in registers, so one block of 8 taps costs
+// 23 shared-memory loads of u + 8 broadcast loads of g for 128 DFMA (FP64-issue bound, not
+// shared-memory bound).  The u window [i0 - (taps-1), i0 + 2048) is staged in shared memory with one
+// padding double per 16 (lane stride 17 doubles, odd) so that the 16-output-strided lane addresses fall in distinct
+// banks.  y_pred is optional: the validation metric only needs the three error sums, which are
+// folded per CTA and then by a fixed-order tree (deterministic).
+#include "common.cuh"
+
+namespace b200id {
+
+// ------------------------------------------------------------------------------------------ K5
+// h[m] = (1/M) [ Re G0 + 2 sum_{k=1}^{nd-1} ( Re G_k cos(2 pi k m / M) - Im G_k sin(2 pi k m / M) ) ]
+// which is Re ifft(X)[m] for the Hermitian X of fir_helpers.py:97-107.  One warp per tap; the
+// twiddle index (k*m mod M) is exact in integers and sincospi keeps the angle exact too.
+__global__ void __launch_bounds__(256)
+idft_hermitian_kernel(const double* __restrict__ G, int nd, double* __restrict__ h, int n_taps) {
+    const int warps_per_cta = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int M = 2 * nd - 1;
+    const double invM = 1.0 / (double)M;
+    for (int m = blockIdx.x * warps_per_cta + (threadIdx.x >> 5); m < n_taps; m += gridDim.x * warps_per_cta) {
+        double acc = 0.0;
+        for (int k = 1 + lane; k < nd; k += 32) {
+            const long long idx = ((long long)k * m) % M;
+            double s, c;
+            sincospi(2.0 * (double)idx * invM, &s, &c);
+            acc += G[2 * k] * c - G[2 * k + 1] * s;
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) h[m] = (G[0] + 2.0 * acc) / (double)M;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ K6
+constexpr int FIR_THREADS = 128;
+constexpr int FIR_OPT = 16;                         // outputs per thread
+constexpr int FIR_TILE = FIR_THREADS * FIR_OPT;     // 2048 outputs per CTA
+constexpr int FIR_TAP_BLOCK = 8;
+constexpr int FIR_MAX_TAPS = 8192;
+
+__host__ __device__ inline int fir_pad(int x) { return x + (x >> 4); }
+static inline size_t fir_smem_bytes(int taps_padded) {
+    return ((size_t)fir_pad(FIR_TILE + taps_padded) + 8 + taps_padded) * sizeof(double);
+}
+
+__global__ void __launch_bounds__(FIR_THREADS)
+fir_eval_kernel(const double* __restrict__ u, const double* __restrict__ y, int64_t n, int64_t lead,
+                const double* __restrict__ g, int n_taps, int taps_padded, int64_t skip, double y0,
+                double* __restrict__ y_pred, double* __restrict__ cta_sums) {
+    extern __shared__ double sm[];
+    double* gs = sm;                         // [taps_padded], zero padded
+    double* us = gs + taps_padded;           // padded window, logical index x -> fir_pad(x)
+    __shared__ double scratch[FIR_THREADS / 32];
+
+    const int tid = threadIdx.x;
+    const int64_t i0 = (int64_t)blockIdx.x * FIR_TILE;
+    const int hist = taps_padded - 1;        // samples of history in front of the tile
+    for (int j = tid; j < taps_padded; j += FIR_THREADS) gs[j] = j < n_taps ? g[j] : 0.0;
+    // logical window index x in [0, hist + FIR_TILE) maps to sample i0 - hist + x
+    for (int x = tid; x < hist + FIR_TILE; x += FIR_THREADS) {
+        const int64_t i = i0 - hist + x;
+        us[fir_pad(x)] = (i >= -lead && i < n) ? __ldg(u + i) : 0.0;
+    }
+    __syncthreads();
+
+    // thread owns outputs o = 0..15 at tile positions p + o, p = 16 * tid; window position of
+    // u[i - j] for output position q and tap j is  x = hist + q - j.
+    const int p = tid * FIR_OPT;
+    double acc[FIR_OPT];
+#pragma unroll
+    for (int o = 0; o < FIR_OPT; ++o) acc[o] = 0.0;
+
+    // sliding window: win[c] = u at x = base + c, c = 0 .. FIR_OPT + FIR_TAP_BLOCK - 2
+    for (int j0 = 0; j0 < taps_padded; j0 += FIR_TAP_BLOCK) {
+        const int base = hist + p - j0 - (FIR_TAP_BLOCK - 1);    // >= 0 because j0 + 7 <= hist
+        double win[FIR_OPT + FIR_TAP_BLOCK - 1];
+#pragma unroll
+        for (int c = 0; c < FIR_OPT + FIR_TAP_BLOCK - 1; ++c) win[c] = us[fir_pad(base + c)];
+#pragma unroll
+        for (int jj = 0; jj < FIR_TAP_BLOCK; ++jj) {
+            const double gj = gs[j0 + jj];
+#pragma unroll
+            for (int o = 0; o < FIR_OPT; ++o)
+                acc[o] = fma(gj, win[o + (FIR_TAP_BLOCK - 1) - jj], acc[o]);
+        }
+    }
+
+    double se = 0.0, sy = 0.0, st = 0.0, cnt = 0.0;
+#pragma unroll
+    for (int o = 0; o < FIR_OPT; ++o) {
+        const int64_t i = i0 + p + o;
+        if (i < n) {
+            if (y_pred) y_pred[i] = acc[o];
+            if (y && i >= skip) {
+                const double yi = __ldg(y + i);
+                const double e = yi - acc[o];
+                const double d0 = yi - y0;
+                se = fma(e, e, se);
+                sy = fma(yi, yi, sy);
+                st = fma(d0, d0, st);
+                cnt += 1.0;
+            }
+        }
+    }
+    se = block_sum(se, scratch);
+    sy = block_sum(sy, scratch);
+    st = block_sum(st, scratch);
+    cnt = block_sum(cnt, scratch);
+    if (tid == 0) {
+        double* o = cta_sums + 4 * (size_t)blockIdx.x;
+        o[0] = se; o[1] = sy; o[2] = st; o[3] = cnt;
+    }
+}
+
+// out[c] = sum over CTAs of part[cta][c], c < 4; pairwise tree in a single CTA (fixed order).
+__global__ void __launch_bounds__(256) fir_fold_kernel(const double* __restrict__ part, int64_t n_cta, double* __restrict__ out) {
+    __shared__ double scratch[8];
+    for (int c = 0; c < 4; ++c) {
+        double v = 0.0;
+        // contiguous chunk per thread, then the block tree: order depends only on n_cta
+        const int64_t per = (n_cta + blockDim.x - 1) / blockDim.x;
+        const int64_t lo = (int64_t)threadIdx.x * per, hi = min(lo + per, n_cta);
+        for (int64_t k = lo; k < hi; ++k) v += part[4 * k + c];
+        v = block_sum(v, scratch);
+        if (threadIdx.x == 0) out[c] = v;
+    }
+}
+
+}  // namespace b200id
+
+using namespace b200id;
+
+extern "C" int b200id_idft_hermitian(const double* G_pos, int nd, double* h_out, int n_taps, void* stream) {
+    B200ID_REQUIRE(G_pos && h_out, B200ID_E_ARG, "idft_hermitian: null pointer");
+    B200ID_REQUIRE(nd >= 2, B200ID_E_ARG, "idft_hermitian: need nd >= 2");
+    B200ID_REQUIRE(n_taps > 0 && n_taps <= 2 * nd - 1, B200ID_E_ARG, "idft_hermitian: N=%d exceeds available length M=%d", n_taps, 2 * nd - 1);
+    int grid = (n_taps + 7) / 8;
+    if (grid > sm_count() * 8) grid = sm_count() * 8;
+    idft_hermitian_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(G_pos, nd, h_out, n_taps);
+    B200ID_LAUNCH_CHECK("idft_hermitian_kernel");
+    return B200ID_OK;
+}
+
+extern "C" size_t b200id_fir_workspace_bytes(int64_t n) {
+    if (n <= 0) return 0;
+    const int64_t ctas = (n + FIR_TILE - 1) / FIR_TILE;
+    return align_up((size_t)ctas * 4 * sizeof(double), 256);
+}
+
+extern "C" int b200id_fir_eval(const double* u, const double* y, int64_t n, int64_t lead, const double* g,
+                               int n_taps, int64_t skip, double y0, double* y_pred_out, double* sums_out,
+                               void* ws, size_t ws_bytes, void* stream) {
+    B200ID_REQUIRE(u && g && sums_out && ws, B200ID_E_ARG, "fir_eval: null pointer");
+    B200ID_REQUIRE(n > 0 && lead >= 0 && skip >= 0, B200ID_E_ARG, "fir_eval: bad sizes");
+    B200ID_REQUIRE(n_taps > 0 && n_taps <= FIR_MAX_TAPS, B200ID_E_UNSUPPORTED, "fir_eval: n_taps=%d outside (0, %d]", n_taps, FIR_MAX_TAPS);
+    const int64_t ctas = (n + FIR_TILE - 1) / FIR_TILE;
+    B200ID_REQUIRE(ctas < (1LL << 31), B200ID_E_UNSUPPORTED, "fir_eval: record too long for one launch");
+    B200ID_REQUIRE(ws_bytes >= (size_t)ctas * 4 * sizeof(double), B200ID_E_WORKSPACE, "fir_eval: workspace too small");
+    const int taps_padded = (n_taps + FIR_TAP_BLOCK - 1) / FIR_TAP_BLOCK * FIR_TAP_BLOCK;
+    const size_t smem = fir_smem_bytes(taps_padded);
+    int rc = check_cuda(cudaFuncSetAttribute(fir_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute(fir)");
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    fir_eval_kernel<<<(unsigned)ctas, FIR_THREADS, smem, st>>>(u, y, n, lead, g, n_taps, taps_padded, skip, y0,
+                                                              y_pred_out, (double*)ws);
+    B200ID_LAUNCH_CHECK("fir_eval_kernel");
+    fir_fold_kernel<<<1, 256, 0, st>>>((const double*)ws, ctas, sums_out);
+    B200ID_LAUNCH_CHECK("fir_fold_kernel");
+    return B200ID_OK;
+}

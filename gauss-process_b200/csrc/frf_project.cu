@@ -1,0 +1,304 @@
+// frf_project.cu -- K1: streaming DFT-projection reduction onto the N_d excitation bins.
+//
+// Replaces the per-bin Python loop of synchronous_coefficients_trapz
+// (reference src/frequency_transform/frf_estimator.py:194-232, hot loop :226-231) for u and y in
+// one pass over (t, u, y).
+//
+// Layout.  Samples are staged per CTA into a shared-memory tile as three SoA rows
+//   ts[j] = t_i,   as[j] = w_i (u_i - mean_u),   bs[j] = w_i (y_i - mean_y)
+// with w_i the trapezoid weight (t[i+1] - t[i-1]) / 2 (one-sided at the record ends), which is the
+// regrouping of np.trapz's sum_i (t[i+1]-t[i]) (f[i]+f[i+1]) / 2.  The 512 threads of a CTA are laid
+// out as (bin b = tid % nb, stripe r = tid / nb): consecutive lanes own consecutive bins and read
+// the SAME sample (shared-memory broadcast), so every lane carries four scalar accumulators and no
+// cross-lane traffic happens inside the hot loop.  Per (sample, bin) the work is
+//   p = fl(w_b * t_i)            -- rounded exactly like the reference's `wi * t`
+//   (s, c) = sincos_cw(p)        -- ~21 FP64 ops, branch-free
+//   acc += (a c, a s, b c, b s)  -- 4 DFMA
+// i.e. the kernel is FP64-issue bound (~26 FP64 ops per sample-bin), not HBM bound.
+// Per-CTA partial sums go to a [cta][4][nd] workspace and are folded by a fixed-order tree
+// (deterministic for a given grid).
+#include "common.cuh"
+#include "fp64_math.cuh"
+
+namespace b200id {
+
+constexpr int FRF_THREADS = 512;
+constexpr int FRF_TILE_MAX = 2048;          // samples per shared-memory tile (3 x 16 KB)
+constexpr int FRF_CTAS_PER_SM = 2;
+
+struct FrfPlan {
+    int tile;        // samples per tile
+    int n_tiles;
+    int grid_x;      // CTAs along samples
+    int grid_y;      // bin groups of <= FRF_THREADS bins
+};
+
+static FrfPlan frf_plan(int64_t n_own, int nd) {
+    FrfPlan p;
+    p.grid_y = (nd + FRF_THREADS - 1) / FRF_THREADS;
+    const int resident = sm_count() * FRF_CTAS_PER_SM;
+    const int want_x = resident / p.grid_y > 0 ? resident / p.grid_y : 1;
+    int64_t tile = (n_own + want_x - 1) / want_x;
+    tile = (tile + 63) / 64 * 64;
+    if (tile < 64) tile = 64;
+    if (tile > FRF_TILE_MAX) tile = FRF_TILE_MAX;
+    p.tile = (int)tile;
+    const int64_t nt = (n_own + tile - 1) / tile;
+    p.n_tiles = (int)nt;
+    p.grid_x = (int)(nt < want_x ? nt : want_x);
+    if (p.grid_x < 1) p.grid_x = 1;
+    return p;
+}
+
+// ------------------------------------------------------------------------------------------
+template <bool HAS_Y>
+__global__ void __launch_bounds__(FRF_THREADS, FRF_CTAS_PER_SM)
+frf_project_kernel(const double* __restrict__ t, const double* __restrict__ u,
+                   const double* __restrict__ y, int64_t n, int64_t own_begin, int64_t own_end,
+                   const double* __restrict__ w, int nd, const double* __restrict__ sums,
+                   double inv_count, int tile, int n_tiles, double* __restrict__ cta_partial) {
+    extern __shared__ double smem[];
+    double* ts = smem;                       // [tile + 2]  (one halo sample each side)
+    double* as = ts + (FRF_TILE_MAX + 2);    // [tile]
+    double* bs = as + FRF_TILE_MAX;          // [tile]
+
+    const int tid = threadIdx.x;
+    const int bin0 = blockIdx.y * FRF_THREADS;
+    const int nb = min(nd - bin0, FRF_THREADS);
+    const int R = FRF_THREADS / nb;          // sample stripes handled side by side
+    const int b = tid % nb, r = tid / nb;
+    const bool active = r < R;
+    const double wk = w[bin0 + b];
+    const double mean_u = sums ? sums[0] * inv_count : 0.0;
+    const double mean_y = (HAS_Y && sums) ? sums[1] * inv_count : 0.0;
+
+    double uc[2] = {0.0, 0.0}, us[2] = {0.0, 0.0}, yc[2] = {0.0, 0.0}, ys[2] = {0.0, 0.0};
+
+    for (int tl = blockIdx.x; tl < n_tiles; tl += gridDim.x) {
+        const int64_t i0 = own_begin + (int64_t)tl * tile;
+        const int cnt = (int)min((int64_t)tile, own_end - i0);
+        __syncthreads();                     // previous tile fully consumed
+        for (int j = tid; j < cnt + 2; j += FRF_THREADS) {
+            int64_t i = i0 - 1 + j;
+            i = i < 0 ? 0 : (i > n - 1 ? n - 1 : i);
+            ts[j] = __ldg(t + i);
+        }
+        __syncthreads();
+        for (int j = tid; j < cnt; j += FRF_THREADS) {
+            const double wt = 0.5 * (ts[j + 2] - ts[j]);
+            as[j] = wt * (__ldg(u + i0 + j) - mean_u);
+            if (HAS_Y) bs[j] = wt * (__ldg(y + i0 + j) - mean_y);
+        }
+        __syncthreads();
+        if (active) {
+            int j = r;
+            // two samples in flight per thread: independent sincos chains hide the FP64 latency
+            for (; j + R < cnt; j += 2 * R) {
+                const double p0 = wk * ts[j + 1], p1 = wk * ts[j + R + 1];
+                double s0, c0, s1, c1;
+                sincos_cw(p0, s0, c0);
+                sincos_cw(p1, s1, c1);
+                const double a0 = as[j], a1 = as[j + R];
+                uc[0] = fma(a0, c0, uc[0]); us[0] = fma(a0, s0, us[0]);
+                uc[1] = fma(a1, c1, uc[1]); us[1] = fma(a1, s1, us[1]);
+                if (HAS_Y) {
+                    const double b0 = bs[j], b1 = bs[j + R];
+                    yc[0] = fma(b0, c0, yc[0]); ys[0] = fma(b0, s0, ys[0]);
+                    yc[1] = fma(b1, c1, yc[1]); ys[1] = fma(b1, s1, ys[1]);
+                }
+            }
+            if (j < cnt) {
+                double s0, c0;
+                sincos_cw(wk * ts[j + 1], s0, c0);
+                const double a0 = as[j];
+                uc[0] = fma(a0, c0, uc[0]); us[0] = fma(a0, s0, us[0]);
+                if (HAS_Y) {
+                    const double b0 = bs[j];
+                    yc[0] = fma(b0, c0, yc[0]); ys[0] = fma(b0, s0, ys[0]);
+                }
+            }
+        }
+    }
+
+    // fold the R stripes of each bin in stripe order, one row per accumulator kind
+    __syncthreads();
+    double* red = smem;                      // [4][FRF_THREADS], reuses the tile
+    red[0 * FRF_THREADS + tid] = uc[0] + uc[1];
+    red[1 * FRF_THREADS + tid] = us[0] + us[1];
+    red[2 * FRF_THREADS + tid] = HAS_Y ? yc[0] + yc[1] : 0.0;
+    red[3 * FRF_THREADS + tid] = HAS_Y ? ys[0] + ys[1] : 0.0;
+    __syncthreads();
+    if (tid < nb) {
+        double* out = cta_partial + (size_t)blockIdx.x * 4 * nd + bin0 + tid;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            double v = 0.0;
+            for (int rr = 0; rr < R; ++rr) v += red[c * FRF_THREADS + rr * nb + tid];
+            out[(size_t)c * nd] = v;
+        }
+    }
+}
+
+// Fixed-order pairwise fold of the per-CTA partials: out[e] = sum_cta part[cta][e], e < 4*nd.
+__global__ void frf_fold_kernel(const double* __restrict__ part, int n_cta, int len,
+                                double* __restrict__ out) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= len) return;
+    // pairwise tree over CTA index, evaluated iteratively with a small stack-free scheme:
+    // sum blocks of 8 sequentially, then the block sums sequentially (n_cta <= ~300).
+    double total = 0.0;
+    for (int c0 = 0; c0 < n_cta; c0 += 8) {
+        double blk = 0.0;
+        const int c1 = min(c0 + 8, n_cta);
+        for (int c = c0; c < c1; ++c) blk += part[(size_t)c * len + e];
+        total += blk;
+    }
+    out[e] = total;
+}
+
+// ------------------------------------------------------------------------------------------
+// moments: sum u, sum y over the owned range (for the mean removal of frf_estimator.py:219-220)
+constexpr int MOM_THREADS = 256;
+
+__global__ void __launch_bounds__(MOM_THREADS)
+frf_moments_kernel(const double* __restrict__ u, const double* __restrict__ y, int64_t own_begin,
+                   int64_t own_end, int64_t chunk, double* __restrict__ cta_partial) {
+    __shared__ double scratch[MOM_THREADS / 32];
+    const int64_t lo = own_begin + (int64_t)blockIdx.x * chunk;
+    const int64_t hi = min(lo + chunk, own_end);
+    double su = 0.0, sy = 0.0;
+    for (int64_t i = lo + threadIdx.x; i < hi; i += MOM_THREADS) {
+        su += __ldg(u + i);
+        if (y) sy += __ldg(y + i);
+    }
+    su = block_sum(su, scratch);
+    sy = block_sum(sy, scratch);
+    if (threadIdx.x == 0) {
+        cta_partial[2 * blockIdx.x] = su;
+        cta_partial[2 * blockIdx.x + 1] = sy;
+    }
+}
+
+__global__ void frf_finalize_kernel(const double* __restrict__ partial, int nd, double scale,
+                                    double* __restrict__ U, double* __restrict__ Y) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nd) return;
+    // real = scale * trapz(x cos), imag = -scale * trapz(x sin)   (frf_estimator.py:229-231)
+    U[2 * k] = scale * partial[k];
+    U[2 * k + 1] = -scale * partial[nd + k];
+    if (Y) {
+        Y[2 * k] = scale * partial[2 * nd + k];
+        Y[2 * k + 1] = -scale * partial[3 * nd + k];
+    }
+}
+
+__global__ void cross_power_kernel(const double* __restrict__ U, const double* __restrict__ Y,
+                                   int n_records, int nd, double eps, double* __restrict__ G) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nd) return;
+    double nr = 0.0, ni = 0.0, den = 0.0;
+    for (int r = 0; r < n_records; ++r) {
+        const double ur = U[2 * ((size_t)r * nd + k)], ui = U[2 * ((size_t)r * nd + k) + 1];
+        const double yr = Y[2 * ((size_t)r * nd + k)], yi = Y[2 * ((size_t)r * nd + k) + 1];
+        // Y * conj(U)
+        nr += yr * ur + yi * ui;
+        ni += yi * ur - yr * ui;
+        const double a = hypot(ur, ui);       // np.abs(U) ** 2
+        den += a * a;
+    }
+    if (den > eps) {
+        G[2 * k] = nr / den;
+        G[2 * k + 1] = ni / den;
+    } else {
+        const double qn = nan("");
+        G[2 * k] = qn;
+        G[2 * k + 1] = qn;
+    }
+}
+
+constexpr size_t FRF_SMEM_BYTES = (size_t)(3 * FRF_TILE_MAX + 2) * sizeof(double);
+
+}  // namespace b200id
+
+using namespace b200id;
+
+extern "C" size_t b200id_frf_workspace_bytes(int nd) {
+    if (nd <= 0) return 0;
+    const size_t ctas = (size_t)sm_count() * FRF_CTAS_PER_SM + 8;
+    return align_up(ctas * 4 * (size_t)nd * sizeof(double), 256) + align_up((size_t)sm_count() * 4 * 2 * sizeof(double), 256) + 256;
+}
+
+extern "C" int b200id_frf_moments(const double* u, const double* y, int64_t n, int64_t own_begin,
+                                  int64_t own_end, double* sums_out, void* ws, size_t ws_bytes,
+                                  void* stream) {
+    B200ID_REQUIRE(u && sums_out && ws, B200ID_E_ARG, "frf_moments: null pointer");
+    B200ID_REQUIRE(n > 0 && own_begin >= 0 && own_end <= n && own_begin < own_end, B200ID_E_ARG,
+                   "frf_moments: bad range [%lld,%lld) of %lld", (long long)own_begin, (long long)own_end, (long long)n);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t n_own = own_end - own_begin;
+    int grid = sm_count() * 4;
+    int64_t chunk = (n_own + grid - 1) / grid;
+    chunk = (chunk + 255) / 256 * 256;
+    grid = (int)((n_own + chunk - 1) / chunk);
+    B200ID_REQUIRE(ws_bytes >= (size_t)grid * 2 * sizeof(double), B200ID_E_WORKSPACE, "frf_moments: workspace too small");
+    double* part = (double*)ws;
+    frf_moments_kernel<<<grid, MOM_THREADS, 0, st>>>(u, y, own_begin, own_end, chunk, part);
+    B200ID_LAUNCH_CHECK("frf_moments_kernel");
+    frf_fold_kernel<<<1, 32, 0, st>>>(part, grid, 2, sums_out);
+    B200ID_LAUNCH_CHECK("frf_fold_kernel(moments)");
+    return B200ID_OK;
+}
+
+extern "C" int b200id_frf_project(const double* t, const double* u, const double* y, int64_t n,
+                                  int64_t own_begin, int64_t own_end, const double* w, int nd,
+                                  const double* sums, double inv_count, double* partial_out,
+                                  void* ws, size_t ws_bytes, void* stream) {
+    B200ID_REQUIRE(t && u && w && partial_out && ws, B200ID_E_ARG, "frf_project: null pointer");
+    B200ID_REQUIRE(n >= 2 && nd > 0, B200ID_E_ARG, "frf_project: need n >= 2 and nd > 0 (n=%lld nd=%d)", (long long)n, nd);
+    B200ID_REQUIRE(own_begin >= 0 && own_end <= n && own_begin < own_end, B200ID_E_ARG,
+                   "frf_project: bad owned range [%lld,%lld) of %lld", (long long)own_begin, (long long)own_end, (long long)n);
+    cudaStream_t st = (cudaStream_t)stream;
+    const FrfPlan p = frf_plan(own_end - own_begin, nd);
+    const size_t need = (size_t)p.grid_x * 4 * nd * sizeof(double);
+    B200ID_REQUIRE(ws_bytes >= need, B200ID_E_WORKSPACE, "frf_project: workspace %zu < %zu", ws_bytes, need);
+    double* part = (double*)ws;
+    static bool attr_set = false;
+    if (!attr_set) {
+        int rc = check_cuda(cudaFuncSetAttribute(frf_project_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FRF_SMEM_BYTES), "smem attr");
+        if (rc) return rc;
+        rc = check_cuda(cudaFuncSetAttribute(frf_project_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FRF_SMEM_BYTES), "smem attr");
+        if (rc) return rc;
+        attr_set = true;
+    }
+    dim3 grid(p.grid_x, p.grid_y);
+    if (y)
+        frf_project_kernel<true><<<grid, FRF_THREADS, FRF_SMEM_BYTES, st>>>(t, u, y, n, own_begin, own_end, w, nd, sums, inv_count, p.tile, p.n_tiles, part);
+    else
+        frf_project_kernel<false><<<grid, FRF_THREADS, FRF_SMEM_BYTES, st>>>(t, u, nullptr, n, own_begin, own_end, w, nd, sums, inv_count, p.tile, p.n_tiles, part);
+    B200ID_LAUNCH_CHECK("frf_project_kernel");
+    const int len = 4 * nd;
+    frf_fold_kernel<<<(len + 127) / 128, 128, 0, st>>>(part, p.grid_x, len, partial_out);
+    B200ID_LAUNCH_CHECK("frf_fold_kernel");
+    return B200ID_OK;
+}
+
+extern "C" int b200id_frf_finalize(const double* partial, int nd, double scale, double* U_out,
+                                   double* Y_out, void* stream) {
+    B200ID_REQUIRE(partial && U_out && nd > 0, B200ID_E_ARG, "frf_finalize: bad argument");
+    frf_finalize_kernel<<<(nd + 127) / 128, 128, 0, (cudaStream_t)stream>>>(partial, nd, scale, U_out, Y_out);
+    B200ID_LAUNCH_CHECK("frf_finalize_kernel");
+    return B200ID_OK;
+}
+
+extern "C" int b200id_cross_power(const double* U, const double* Y, int n_records, int nd, double eps,
+                                  double* G_out, void* stream) {
+    B200ID_REQUIRE(U && Y && G_out && n_records > 0 && nd > 0, B200ID_E_ARG, "cross_power: bad argument");
+    cross_power_kernel<<<(nd + 127) / 128, 128, 0, (cudaStream_t)stream>>>(U, Y, n_records, nd, eps, G_out);
+    B200ID_LAUNCH_CHECK("cross_power_kernel");
+    return B200ID_OK;
+}
+
+// Host evaluation of the scalar device math, for CPU-side unit tests of the numerics only.
+extern "C" void b200id_selftest_sincos_host(const double* x, int64_t n, double* s_out, double* c_out) {
+    for (int64_t i = 0; i < n; ++i) sincos_cw(x[i], s_out[i], c_out[i]);
+}

@@ -1,0 +1,334 @@
+// gp_batch.cu -- K2/K3: Gram matrices, batched candidate evaluation, final fit and predict.
+//
+// Reference call sites: src/gpr/grid_search.py:91-133 (candidate metric), :186-196 (argmin scan),
+// src/gpr/gpr_fitting.py:73-100 (fit / predict) and :104-123 (NLL).
+//
+// Batched evaluation: ONE CTA PER CANDIDATE.  The CTA builds the lower triangle of
+// K + noise*I in shared memory (column-major, odd leading dimension), appends y as an extra ROW
+// (row n), and runs a right-looking Cholesky on the (n+1) x n array: after the factorisation row n
+// holds z = L^-1 y, so the forward solve is free and y^T K^-1 y = z.z.  NLL needs nothing else;
+// the validation-RMSE metric back-substitutes alpha = L^-T z and forms K(Xv, X) alpha on the fly.
+// Failure conventions (hard part 4): pivot <= 0 -> metric 1e10 (LinAlgError
+// branch, grid_search.py:132-133); NaN pivot -> factorisation continues and the metric is NaN.
+#include "common.cuh"
+#include "gp_kernels.cuh"
+#include "gp_linalg.cuh"
+
+namespace b200id {
+
+constexpr int GP_THREADS = 128;
+constexpr int GP_NMAX_SMEM = 160;   // (n+1) * ld doubles must fit in 227 KB
+
+__host__ __device__ inline int gp_ld(int n) { return (n + 1) | 1; }   // rows n+1 (y row), odd stride
+static inline size_t gp_smem_bytes(int n) {
+    return ((size_t)n * gp_ld(n) + 3 * (size_t)n + 64) * sizeof(double);
+}
+
+__global__ void __launch_bounds__(GP_THREADS)
+gp_batch_kernel(int kernel_id, const int* __restrict__ kernel_ids, const double* __restrict__ theta,
+                const double* __restrict__ X, const double* __restrict__ y, int n, double noise,
+                int metric, const double* __restrict__ Xv, const double* __restrict__ yv, int nv,
+                double y_mean, double y_scale, double* __restrict__ metric_out) {
+    extern __shared__ double sm[];
+    const int ld = gp_ld(n);
+    double* A = sm;                              // [n][ld]
+    double* xs = A + (size_t)n * ld;             // [n]
+    double* z = xs + n;                          // [n]
+    double* scratch = z + n;                     // [GP_THREADS/32 + ...]
+    __shared__ int status;
+
+    const int64_t cand = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int kid = kernel_ids ? kernel_ids[cand] : kernel_id;
+    const KernelParams kp = make_kernel_params(kid, theta + cand * B200ID_MAX_PARAMS);
+
+    if (tid == 0) status = 0;
+    for (int i = tid; i < n; i += GP_THREADS) xs[i] = X[i];
+    __syncthreads();
+    // lower triangle of K + noise*I, plus y as row n
+    for (int e = tid; e < n * (n + 1); e += GP_THREADS) {
+        const int j = e / (n + 1), i = e - j * (n + 1);
+        if (i == n) {
+            A[(size_t)j * ld + n] = y[j];
+        } else if (i >= j) {
+            double v = kernel_entry(kp, xs[i], xs[j]);
+            if (i == j) v = B200ID_ADD(v, noise);
+            A[(size_t)j * ld + i] = v;
+        }
+    }
+    __syncthreads();
+    chol_smem(A, n, ld, 1, &status);
+    if (status != 0) {
+        if (tid == 0) metric_out[cand] = B200ID_FAIL_METRIC;
+        return;
+    }
+    if (metric == B200ID_METRIC_NLL) {
+        // 0.5 y.alpha + sum log L_ii + 0.5 n log(2 pi)        grid_search.py:128-130
+        double part = 0.0;
+        for (int j = tid; j < n; j += GP_THREADS) {
+            const double zj = A[(size_t)j * ld + n];
+            part += 0.5 * zj * zj + log(A[(size_t)j * ld + j]);
+        }
+        const double tot = block_sum(part, scratch);
+        if (tid == 0) metric_out[cand] = tot + 0.5 * (double)n * 1.8378770664093453;  // log(2 pi)
+        return;
+    }
+    // validation RMSE on the de-standardised prediction                  grid_search.py:107-126
+    for (int j = tid; j < n; j += GP_THREADS) z[j] = A[(size_t)j * ld + n];
+    backsolve_smem(A, n, ld, z);
+    double se = 0.0;
+    for (int v = tid; v < nv; v += GP_THREADS) {
+        const double xv = Xv[v];
+        double pred = 0.0;
+        for (int j = 0; j < n; ++j) pred = fma(kernel_entry(kp, xv, xs[j]), z[j], pred);
+        pred = pred * y_scale + y_mean;
+        const double e = yv[v] - pred;
+        se = fma(e, e, se);
+    }
+    const double tot = block_sum(se, scratch);
+    if (tid == 0) metric_out[cand] = sqrt(tot / (double)nv);
+}
+
+// ------------------------------------------------------------------------------------------
+// first strict minimum in index order, NaNs skipped  (grid_search.py:186-196)
+constexpr int ARGMIN_THREADS = 1024;
+__global__ void __launch_bounds__(ARGMIN_THREADS)
+first_strict_min_kernel(const double* __restrict__ metric, int64_t n, double* best_out, int64_t* idx_out) {
+    __shared__ double sv[ARGMIN_THREADS];
+    __shared__ long long si[ARGMIN_THREADS];
+    double bv = INFINITY;
+    long long bi = -1;
+    for (int64_t i = threadIdx.x; i < n; i += ARGMIN_THREADS) {
+        const double v = metric[i];
+        if (v < bv) { bv = v; bi = i; }          // increasing i per thread: keeps the first of equals
+    }
+    sv[threadIdx.x] = bv;
+    si[threadIdx.x] = bi;
+    __syncthreads();
+    for (int s = ARGMIN_THREADS / 2; s > 0; s >>= 1) {
+        if (threadIdx.x < s) {
+            const double ov = sv[threadIdx.x + s];
+            const long long oi = si[threadIdx.x + s];
+            const double mv = sv[threadIdx.x];
+            const long long mi = si[threadIdx.x];
+            if (oi >= 0 && (mi < 0 || ov < mv || (ov == mv && oi < mi))) {
+                sv[threadIdx.x] = ov;
+                si[threadIdx.x] = oi;
+            }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        best_out[0] = sv[0];
+        idx_out[0] = si[0];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+__global__ void gram_kernel(int kernel_id, const double* __restrict__ theta, const double* __restrict__ X1,
+                            int n1, const double* __restrict__ X2, int n2, double* __restrict__ K) {
+    const KernelParams kp = make_kernel_params(kernel_id, theta);
+    const int64_t total = (int64_t)n1 * n2;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int i = (int)(e / n2), j = (int)(e - (int64_t)i * n2);
+        K[e] = kernel_entry(kp, X1[i], X2[j]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Final fit (single problem): Cholesky in shared memory, alpha, then K_inv = L^-T L^-1 through
+// global scratch (Kinv_out first holds L^-1, column j solved by thread j).
+__global__ void __launch_bounds__(GP_THREADS)
+gp_fit_kernel(int kernel_id, const double* __restrict__ theta, const double* __restrict__ X,
+              const double* __restrict__ y, int n, double diag_add, double* __restrict__ alpha_out,
+              double* __restrict__ Linv /*[n*n] scratch*/, double* __restrict__ Kinv_out, int* __restrict__ info_out) {
+    extern __shared__ double sm[];
+    const int ld = gp_ld(n);
+    double* A = sm;
+    double* xs = A + (size_t)n * ld;
+    double* z = xs + n;
+    __shared__ int status;
+    const int tid = threadIdx.x;
+    const KernelParams kp = make_kernel_params(kernel_id, theta);
+    if (tid == 0) status = 0;
+    for (int i = tid; i < n; i += GP_THREADS) xs[i] = X[i];
+    __syncthreads();
+    for (int e = tid; e < n * (n + 1); e += GP_THREADS) {
+        const int j = e / (n + 1), i = e - j * (n + 1);
+        if (i == n) {
+            A[(size_t)j * ld + n] = y[j];
+        } else if (i >= j) {
+            double v = kernel_entry(kp, xs[i], xs[j]);
+            if (i == j) v = B200ID_ADD(v, diag_add);
+            A[(size_t)j * ld + i] = v;
+        }
+    }
+    __syncthreads();
+    chol_smem(A, n, ld, 1, &status);
+    if (tid == 0) info_out[0] = status;
+    if (status != 0) return;
+    for (int j = tid; j < n; j += GP_THREADS) z[j] = A[(size_t)j * ld + n];
+    backsolve_smem(A, n, ld, z);
+    for (int j = tid; j < n; j += GP_THREADS) alpha_out[j] = z[j];
+    // L^-1: column c solves L v = e_c (forward substitution), v stored at Linv[c*n + i], i >= c
+    for (int c = tid; c < n; c += GP_THREADS) {
+        double* v = Linv + (size_t)c * n;
+        for (int i = 0; i < c; ++i) v[i] = 0.0;
+        for (int i = c; i < n; ++i) {
+            double s = (i == c) ? 1.0 : 0.0;
+            for (int p = c; p < i; ++p) s = fma(-A[(size_t)p * ld + i], v[p], s);
+            v[i] = s / A[(size_t)i * ld + i];
+        }
+    }
+    __threadfence_block();
+    __syncthreads();
+    // K_inv[i][j] = sum_{k >= max(i,j)} Linv[k][i] Linv[k][j]   (Linv[k][i] at Linv[i*n + k])
+    for (int e = tid; e < n * n; e += GP_THREADS) {
+        const int i = e / n, j = e - i * n;
+        if (j > i) continue;
+        double s = 0.0;
+        const double* vi = Linv + (size_t)i * n;
+        const double* vj = Linv + (size_t)j * n;
+        for (int k = i; k < n; ++k) s = fma(vi[k], vj[k], s);
+        Kinv_out[(size_t)i * n + j] = s;
+        Kinv_out[(size_t)j * n + i] = s;
+    }
+}
+
+// One CTA per test point: mean = K* alpha; var = k(xs,xs) - sum_j (K* K_inv)_j K*_j   (gpr_fitting.py:91-97)
+__global__ void __launch_bounds__(GP_THREADS)
+gp_predict_kernel(int kernel_id, const double* __restrict__ theta, const double* __restrict__ X, int n,
+                  const double* __restrict__ alpha, const double* __restrict__ Kinv,
+                  const double* __restrict__ Xs, int m, double* __restrict__ mean_out, double* __restrict__ std_out) {
+    extern __shared__ double sm[];
+    double* ks = sm;                     // [n] row of K*
+    double* scratch = ks + n;
+    const int tid = threadIdx.x;
+    const KernelParams kp = make_kernel_params(kernel_id, theta);
+    for (int q = blockIdx.x; q < m; q += gridDim.x) {
+        const double xq = Xs[q];
+        __syncthreads();
+        double part = 0.0;
+        for (int j = tid; j < n; j += GP_THREADS) {
+            const double kv = kernel_entry(kp, xq, X[j]);
+            ks[j] = kv;
+            part = fma(kv, alpha[j], part);
+        }
+        const double mean = block_sum(part, scratch);   // contains the __syncthreads that publishes ks
+        if (tid == 0) mean_out[q] = mean;
+        if (std_out) {
+            double acc = 0.0;
+            for (int j = tid; j < n; j += GP_THREADS) {
+                double v = 0.0;
+                for (int i = 0; i < n; ++i) v = fma(ks[i], Kinv[(size_t)i * n + j], v);
+                acc = fma(v, ks[j], acc);
+            }
+            const double quad = block_sum(acc, scratch);
+            if (tid == 0) {
+                const double var = kernel_entry(kp, xq, xq) - quad;
+                std_out[q] = sqrt(fmax(var, 0.0));
+            }
+        }
+    }
+}
+
+}  // namespace b200id
+
+using namespace b200id;
+
+static int set_smem_attr(const void* fn, size_t bytes) {
+    return check_cuda(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes), "cudaFuncSetAttribute(smem)");
+}
+
+extern "C" int b200id_gp_gram(int kernel_id, const double* theta, const double* X1, int n1, const double* X2,
+                              int n2, double* K_out, void* stream) {
+    B200ID_REQUIRE(theta && X1 && K_out && n1 > 0, B200ID_E_ARG, "gp_gram: bad argument");
+    B200ID_REQUIRE(kernel_id >= 0 && kernel_id < B200ID_K_COUNT, B200ID_E_ARG, "gp_gram: unknown kernel id %d", kernel_id);
+    if (!X2) { X2 = X1; n2 = n1; }
+    B200ID_REQUIRE(n2 > 0, B200ID_E_ARG, "gp_gram: n2 <= 0");
+    const int64_t total = (int64_t)n1 * n2;
+    int grid = (int)((total + 255) / 256);
+    if (grid > sm_count() * 8) grid = sm_count() * 8;
+    gram_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(kernel_id, theta, X1, n1, X2, n2, K_out);
+    B200ID_LAUNCH_CHECK("gram_kernel");
+    return B200ID_OK;
+}
+
+extern "C" size_t b200id_gp_batch_workspace_bytes(int64_t n_candidates, int n) {
+    (void)n_candidates; (void)n;
+    return 256;     // the shared-memory path needs no global scratch; kept for the blocked large-n path
+}
+
+extern "C" int b200id_gp_batch_eval(int kernel_id, const int* kernel_ids, const double* theta, int64_t n_candidates,
+                                    const double* X, const double* y, int n, double noise, int metric,
+                                    const double* Xv, const double* yv, int nv, double y_mean, double y_scale,
+                                    double* metric_out, void* ws, size_t ws_bytes, void* stream) {
+    (void)ws; (void)ws_bytes;
+    B200ID_REQUIRE(theta && X && y && metric_out, B200ID_E_ARG, "gp_batch_eval: null pointer");
+    B200ID_REQUIRE(n_candidates > 0 && n > 0, B200ID_E_ARG, "gp_batch_eval: empty problem");
+    B200ID_REQUIRE(kernel_ids || (kernel_id >= 0 && kernel_id < B200ID_K_COUNT), B200ID_E_ARG, "gp_batch_eval: unknown kernel id %d", kernel_id);
+    B200ID_REQUIRE(metric == B200ID_METRIC_NLL || metric == B200ID_METRIC_VAL_RMSE, B200ID_E_ARG, "gp_batch_eval: unknown metric %d", metric);
+    B200ID_REQUIRE(metric == B200ID_METRIC_NLL || (Xv && yv && nv > 0), B200ID_E_ARG, "gp_batch_eval: validation metric needs Xv, yv");
+    B200ID_REQUIRE(n <= GP_NMAX_SMEM, B200ID_E_UNSUPPORTED, "gp_batch_eval: n=%d exceeds the in-shared-memory limit %d", n, GP_NMAX_SMEM);
+    B200ID_REQUIRE(n_candidates < (1LL << 31), B200ID_E_UNSUPPORTED, "gp_batch_eval: too many candidates");
+    const size_t smem = gp_smem_bytes(n);
+    int rc = set_smem_attr((const void*)gp_batch_kernel, smem);
+    if (rc) return rc;
+    gp_batch_kernel<<<(unsigned)n_candidates, GP_THREADS, smem, (cudaStream_t)stream>>>(
+        kernel_id, kernel_ids, theta, X, y, n, noise, metric, Xv, yv, nv, y_mean, y_scale, metric_out);
+    B200ID_LAUNCH_CHECK("gp_batch_kernel");
+    return B200ID_OK;
+}
+
+extern "C" int b200id_first_strict_min(const double* metric, int64_t n_candidates, double* best_out, int64_t* idx_out,
+                                       void* ws, size_t ws_bytes, void* stream) {
+    (void)ws; (void)ws_bytes;
+    B200ID_REQUIRE(metric && best_out && idx_out && n_candidates > 0, B200ID_E_ARG, "first_strict_min: bad argument");
+    first_strict_min_kernel<<<1, ARGMIN_THREADS, 0, (cudaStream_t)stream>>>(metric, n_candidates, best_out, idx_out);
+    B200ID_LAUNCH_CHECK("first_strict_min_kernel");
+    return B200ID_OK;
+}
+
+extern "C" size_t b200id_gp_fit_workspace_bytes(int n) {
+    return n > 0 ? align_up((size_t)(n + 2) * (n + 2) * sizeof(double), 256) : 0;   // covers gp_fit and gp_fit_pinv
+}
+
+extern "C" int b200id_gp_fit(int kernel_id, const double* theta, const double* X, const double* y, int n,
+                             double diag_add, double* alpha_out, double* Kinv_out, int* info_out,
+                             void* ws, size_t ws_bytes, void* stream) {
+    B200ID_REQUIRE(theta && X && y && alpha_out && Kinv_out && info_out && ws, B200ID_E_ARG, "gp_fit: null pointer");
+    B200ID_REQUIRE(kernel_id >= 0 && kernel_id < B200ID_K_COUNT, B200ID_E_ARG, "gp_fit: unknown kernel id %d", kernel_id);
+    B200ID_REQUIRE(n > 0 && n <= GP_NMAX_SMEM, B200ID_E_UNSUPPORTED, "gp_fit: n=%d outside (0, %d]", n, GP_NMAX_SMEM);
+    B200ID_REQUIRE(ws_bytes >= (size_t)n * n * sizeof(double), B200ID_E_WORKSPACE, "gp_fit: workspace too small");
+    const size_t smem = gp_smem_bytes(n);
+    int rc = set_smem_attr((const void*)gp_fit_kernel, smem);
+    if (rc) return rc;
+    gp_fit_kernel<<<1, GP_THREADS, smem, (cudaStream_t)stream>>>(kernel_id, theta, X, y, n, diag_add, alpha_out,
+                                                                 (double*)ws, Kinv_out, info_out);
+    B200ID_LAUNCH_CHECK("gp_fit_kernel");
+    return B200ID_OK;
+}
+
+extern "C" int b200id_gp_predict(int kernel_id, const double* theta, const double* X, int n, const double* alpha,
+                                 const double* Kinv, const double* Xs, int m, double* mean_out, double* std_out,
+                                 void* stream) {
+    B200ID_REQUIRE(theta && X && alpha && Xs && mean_out, B200ID_E_ARG, "gp_predict: null pointer");
+    B200ID_REQUIRE(!std_out || Kinv, B200ID_E_ARG, "gp_predict: std requested without K_inv");
+    B200ID_REQUIRE(kernel_id >= 0 && kernel_id < B200ID_K_COUNT, B200ID_E_ARG, "gp_predict: unknown kernel id %d", kernel_id);
+    B200ID_REQUIRE(n > 0 && m > 0 && n <= 16384, B200ID_E_ARG, "gp_predict: bad sizes n=%d m=%d", n, m);
+    const size_t smem = ((size_t)n + 64) * sizeof(double);
+    int rc = set_smem_attr((const void*)gp_predict_kernel, smem);
+    if (rc) return rc;
+    int grid = m < sm_count() * 4 ? m : sm_count() * 4;
+    gp_predict_kernel<<<grid, GP_THREADS, smem, (cudaStream_t)stream>>>(kernel_id, theta, X, n, alpha, Kinv, Xs, m, mean_out, std_out);
+    B200ID_LAUNCH_CHECK("gp_predict_kernel");
+    return B200ID_OK;
+}
+
+// Host evaluation of the covariance functions, for CPU-side unit tests of the numerics only.
+extern "C" void b200id_selftest_gram_host(int kernel_id, const double* theta, const double* X1, int n1,
+                                          const double* X2, int n2, double* K_out) {
+    const KernelParams kp = make_kernel_params(kernel_id, theta);
+    for (int i = 0; i < n1; ++i)
+        for (int j = 0; j < n2; ++j) K_out[(size_t)i * n2 + j] = kernel_entry(kp, X1[i], X2[j]);
+}

@@ -1,0 +1,174 @@
+/*
+ * b200id.h -- C ABI of the B200-native frequency-domain identification hot path
+ *             (FRF estimation -> batched GP model selection -> Hermitian-IDFT FIR + validation).
+ *
+ * Drop-in boundary.  The reference (AtsushiYanaigsawa768/gauss-process) is pure Python and has
+ * no FFI of its own; its boundary is the import surface of src/frequency_transform, src/gpr and
+ * src/fir_model.  Each entry point below replaces the NumPy/SciPy arithmetic of the reference
+ * lines cited next to it; the Python mirror in gauss-process_b200/src/ binds them with ctypes
+ * (see INTEGRATION.md for the stub a reference maintainer would add).
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no torch / C++ types.
+ *   - Every data pointer is a DEVICE pointer owned by the caller (FP64, contiguous) unless the
+ *     parameter name ends in _host.  The library never allocates or frees caller-visible memory;
+ *     scratch comes from the caller-provided workspace (query *_workspace_bytes first).
+ *   - `stream` is a cudaStream_t passed as void*.  No call synchronises the host.
+ *   - Return value: 0 = ok, < 0 = error (B200ID_E_*); text via b200id_last_error().
+ *   - Complex arrays are interleaved (re, im) doubles.
+ */
+#ifndef B200ID_H
+#define B200ID_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200ID_VERSION 100
+
+#define B200ID_OK            0
+#define B200ID_E_ARG        -1   /* bad argument (null pointer, size <= 0, unknown id) */
+#define B200ID_E_WORKSPACE  -2   /* workspace too small */
+#define B200ID_E_CUDA       -3   /* CUDA runtime error (launch failed, wrong arch) */
+#define B200ID_E_UNSUPPORTED -4  /* size outside what the kernels support */
+
+/* kernel ids: src/gpr/kernels.py:386-411 (create_kernel names) */
+enum b200id_kernel_id {
+    B200ID_K_RBF = 0,            /* kernels.py:90   [length_scale, variance]        */
+    B200ID_K_MATERN12 = 1,       /* kernels.py:113  nu = 0.5                        */
+    B200ID_K_MATERN32 = 2,       /*                 nu = 1.5                        */
+    B200ID_K_MATERN52 = 3,       /*                 nu = 2.5                        */
+    B200ID_K_EXP = 4,            /* kernels.py:175  [omega, variance]               */
+    B200ID_K_DC = 5,             /* kernels.py:227  [alpha, beta, rho]              */
+    B200ID_K_DI = 6,             /* kernels.py:253  [beta, alpha]                   */
+    B200ID_K_SS1 = 7,            /* kernels.py:282  [beta, variance]                */
+    B200ID_K_SS2 = 8,            /* kernels.py:304                                  */
+    B200ID_K_SSHF = 9,           /* kernels.py:332                                  */
+    B200ID_K_STABLE_SPLINE = 10, /* kernels.py:358                                  */
+    B200ID_K_RQ = 11,            /* kernels.py:150  [length_scale, variance, alpha] */
+    B200ID_K_TC = 12,            /* kernels.py:201  [omega, variance]               */
+    B200ID_K_COUNT = 13
+};
+#define B200ID_MAX_PARAMS 3
+
+/* candidate metric: src/gpr/grid_search.py:91-133 */
+#define B200ID_METRIC_NLL      0
+#define B200ID_METRIC_VAL_RMSE 1
+#define B200ID_FAIL_METRIC     1e10   /* grid_search.py:132-133, gpr_fitting.py:122-123 */
+
+/* ------------------------------------------------------------------ library */
+int         b200id_version(void);
+const char* b200id_last_error(void);
+/* Fills SM count and compute capability of the current device. */
+int         b200id_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------ FRF (K1)
+ * Replaces the per-bin Python loop of synchronous_coefficients_trapz,
+ * src/frequency_transform/frf_estimator.py:194-232 (hot loop :226-231), for u and y in one pass.
+ *
+ * Samples [0, n) are resident; the call integrates the OWNED samples [own_begin, own_end) with
+ * trapezoid weights w_i = (t[min(i+1,n-1)] - t[max(i-1,0)]) / 2, so a time-segment shard passes
+ * its slice plus a one-sample halo on each interior side.  Phases are fl(w_k * t_i) exactly as
+ * the reference forms them (frf_estimator.py:227-228).
+ */
+size_t b200id_frf_workspace_bytes(int nd);
+
+/* sums_out[0] = sum u[own), sums_out[1] = sum y[own) (y may be NULL -> 0). frf_estimator.py:219-220 */
+int b200id_frf_moments(const double* u, const double* y, int64_t n,
+                       int64_t own_begin, int64_t own_end,
+                       double* sums_out /*[2]*/, void* ws, size_t ws_bytes, void* stream);
+
+/* partial_out[4*nd] = { S_uc[nd], S_us[nd], S_yc[nd], S_ys[nd] } with
+ *   S_xc[k] = sum_i w_i (x_i - mean_x) cos(fl(w_k t_i)),  S_xs likewise with sin.
+ * mean_x = sums[.] * inv_count when sums != NULL (subtract_mean), else 0.  y may be NULL. */
+int b200id_frf_project(const double* t, const double* u, const double* y, int64_t n,
+                       int64_t own_begin, int64_t own_end,
+                       const double* w, int nd,
+                       const double* sums /*[2] or NULL*/, double inv_count,
+                       double* partial_out /*[4*nd]*/, void* ws, size_t ws_bytes, void* stream);
+
+/* U[k] = scale * (S_uc[k] - j S_us[k]), Y likewise; scale = 2/T. frf_estimator.py:225-231 */
+int b200id_frf_finalize(const double* partial /*[4*nd]*/, int nd, double scale,
+                        double* U_out /*[2*nd]*/, double* Y_out /*[2*nd] or NULL*/, void* stream);
+
+/* G[k] = sum_r Y_r conj(U_r) / sum_r |U_r|^2, NaN+NaNj where the denominator <= eps.
+ * frf_cross_power_average, frf_estimator.py:239-252.  U, Y: [R][nd] complex. */
+int b200id_cross_power(const double* U, const double* Y, int n_records, int nd, double eps,
+                       double* G_out /*[2*nd]*/, void* stream);
+
+/* ------------------------------------------------------------------ GP (K2, K3)
+ * Gram matrices of the 13 kernels for 1-D inputs: src/gpr/kernels.py:90-382. */
+int b200id_gp_gram(int kernel_id, const double* theta /*[p] device*/, const double* X1, int n1,
+                   const double* X2 /*NULL -> X1*/, int n2, double* K_out /*[n1*n2] row-major*/,
+                   void* stream);
+
+/* Batched candidate evaluation, one CTA per candidate: Gram + noise*I (no jitter), in-shared-memory
+ * Cholesky, two triangular solves, NLL or validation RMSE.  grid_search.py:91-133 and
+ * gpr_fitting.py:104-123.  Non-positive pivot -> 1e10; NaN pivot -> NaN metric.
+ *   theta [C][B200ID_MAX_PARAMS] (unused slots ignored); kernel_ids [C] or NULL (-> kernel_id);
+ *   metric == VAL_RMSE uses Xv, yv (raw scale) and pred = (K* alpha) * y_scale + y_mean.
+ *   metric_out [C]. */
+size_t b200id_gp_batch_workspace_bytes(int64_t n_candidates, int n);
+int b200id_gp_batch_eval(int kernel_id, const int* kernel_ids, const double* theta, int64_t n_candidates,
+                         const double* X, const double* y, int n, double noise, int metric,
+                         const double* Xv, const double* yv, int nv, double y_mean, double y_scale,
+                         double* metric_out, void* ws, size_t ws_bytes, void* stream);
+
+/* First strict minimum of metric[0..C) scanning in index order, NaNs skipped (grid_search.py:186-196).
+ * best_out[0] = metric (+inf if none), idx_out[0] = index (-1 if none). */
+int b200id_first_strict_min(const double* metric, int64_t n_candidates,
+                            double* best_out, int64_t* idx_out, void* ws, size_t ws_bytes, void* stream);
+
+/* Final fit: K + diag_add*I, Cholesky, alpha = K^-1 y, K_inv (from the factor).  gpr_fitting.py:73-83.
+ * info_out[0] = 0 ok, k > 0 = non-positive pivot at column k (caller then uses b200id_sym_pinv). */
+size_t b200id_gp_fit_workspace_bytes(int n);
+int b200id_gp_fit(int kernel_id, const double* theta, const double* X, const double* y, int n,
+                  double diag_add, double* alpha_out /*[n]*/, double* Kinv_out /*[n*n]*/,
+                  int* info_out, void* ws, size_t ws_bytes, void* stream);
+
+/* Pseudo-inverse of the symmetric matrix K + diag_add*I by cyclic Jacobi eigendecomposition,
+ * dropping |lambda| <= rcond * max|lambda|; alpha = pinv @ y.  gpr_fitting.py:84-87 (np.linalg.pinv). */
+int b200id_gp_fit_pinv(int kernel_id, const double* theta, const double* X, const double* y, int n,
+                       double diag_add, double rcond, double* alpha_out, double* Kinv_out,
+                       void* ws, size_t ws_bytes, void* stream);
+
+/* mean = K(Xs, X) alpha; std = sqrt(max(k(xs,xs) - sum_j (K* K_inv)_j K*_j, 0)) (std_out may be NULL).
+ * gpr_fitting.py:89-100. */
+int b200id_gp_predict(int kernel_id, const double* theta, const double* X, int n,
+                      const double* alpha, const double* Kinv,
+                      const double* Xs, int m, double* mean_out, double* std_out, void* stream);
+
+/* Blocked FP64 Cholesky (lower, in place, row-major) for large n (N_d = 2048): panel factorisation in
+ * shared memory, trailing update as FP64 DGEMM tiles.  np.linalg.cholesky at gpr_fitting.py:80.
+ * info_out[0] as in b200id_gp_fit. */
+size_t b200id_chol_blocked_workspace_bytes(int n);
+int b200id_chol_blocked(double* A, int n, int lda, int* info_out, void* ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------ FIR (K5, K6)
+ * h[m] = Re( (1/M) sum_k X[k] e^{+2 pi j k m / M} ), m < n_taps, with X the two-sided Hermitian
+ * extension of G_pos (M = 2 nd - 1, X[0] = Re G[0]).  fir_helpers.py:75-137. */
+int b200id_idft_hermitian(const double* G_pos /*[2*nd]*/, int nd, double* h_out, int n_taps, void* stream);
+
+/* Causal FIR y_pred[i] = sum_{j<n_taps, j<=i+lead} g[j] u[i-j] over OWNED outputs [own_begin, own_end)
+ * of a resident slice (u has `lead` samples of history before index 0 of y: u points at the slice start,
+ * u[-lead..-1] must be readable when lead > 0), fused with the error sums over i >= skip_global:
+ *   sums_out = { sum e^2, sum y^2, sum (y - y0)^2, count }   with e = y - y_pred.
+ * np.convolve(u, g, 'full')[:N] at fir_fitting.py:285 / fir_validation.py:190 and the metrics at
+ * fir_fitting.py:288-306 / fir_validation.py:115-128.  y_pred_out may be NULL. */
+size_t b200id_fir_workspace_bytes(int64_t n);
+int b200id_fir_eval(const double* u, const double* y, int64_t n, int64_t lead,
+                    const double* g, int n_taps, int64_t skip, double y0,
+                    double* y_pred_out, double* sums_out /*[4]*/, void* ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------ measurement helpers */
+/* Runs an FP64 FMA (mode 0) or FP64 mma.sync (mode 1) issue-bound loop; returns flops executed in
+ * flops_out_host and leaves timing to the caller's CUDA events.  Used by bench.py for the FP64 roofline. */
+int b200id_fp64_peak_probe(int mode, int iters, double* sink, double* flops_out_host, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200ID_H */

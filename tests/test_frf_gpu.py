@@ -1,0 +1,122 @@
+"""GPU parity of K1 (FRF projection) through the C ABI, against the oracle and the reference's
+golden vectors.  Tolerance from BASELINE.json north_star: FRF G(jw_k) within 1e-9 relative."""
+import numpy as np
+import pytest
+
+from oracle import frf as ofrf
+from parity_util import rel_each, rel_max, record
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-9
+
+
+@pytest.fixture(scope="module")
+def frf():
+    from b200id import frf as mod
+    return mod
+
+
+def test_golden_uniform(frf, golden):
+    g = golden("frf")
+    U, Y = frf.demod_pair(g["t"], g["u"], g["y"], g["w"])
+    eU = record("frf.golden.U.rel_each", rel_each(U, g["U"]))
+    eY = record("frf.golden.Y.rel_each", rel_each(Y, g["Y"]))
+    assert eU < TOL and eY < TOL
+    G = frf.cross_power([U], [Y])
+    assert record("frf.golden.G.rel_each", rel_each(G, g["G"])) < TOL
+
+
+def test_golden_single_signal_drop_and_nomean(frf, golden):
+    g = golden("frf")
+    assert rel_each(frf.demod(g["t"], g["u"], g["w"]), g["U"]) < TOL
+    assert record("frf.golden.U_drop.rel_each", rel_each(frf.demod(g["t"], g["u"], g["w"], 1.5, True), g["U_drop"])) < TOL
+    assert record("frf.golden.Y_nomean.rel_each",
+                  rel_each(frf.demod(g["t"], g["y"] + 0.3, g["w"], 0.0, False), g["Y_nomean"])) < TOL
+
+
+def test_golden_nonuniform_timebase(frf, golden):
+    g = golden("frf")
+    U, Y = frf.demod_pair(g["t_jit"], g["u"], g["y"], g["w"])
+    assert record("frf.golden.U_jit.rel_each", rel_each(U, g["U_jit"])) < TOL
+    assert rel_each(Y, g["Y_jit"]) < TOL
+
+
+def test_cross_power_records_and_nan(frf, golden):
+    g = golden("frf")
+    G2 = frf.cross_power([g["U"], g["U2"]], [g["Y"], g["Y2"]])
+    assert rel_each(G2, g["G2"]) < 1e-14
+    Uz = g["U"].copy(); Uz[[3, 17]] = 0.0
+    Gn = frf.cross_power([Uz], [g["Y"]])
+    assert np.array_equal(np.isnan(Gn), np.isnan(g["G_nan"]))
+    ok = ~np.isnan(Gn)
+    assert rel_each(Gn[ok], g["G_nan"][ok]) < 1e-14
+    with pytest.raises(ValueError):
+        frf.cross_power([], [])
+    Gm, _, _ = frf.estimate_records([(g["t"], g["u"], g["y"]), (g["t"], g["u2"], g["y2"])], g["w"])
+    assert rel_each(Gm.real, g["df_2files"][:, 2]) < TOL and rel_each(Gm.imag, g["df_2files"][:, 3]) < TOL
+
+
+def test_errors_match_reference(frf):
+    t = np.arange(10) * 0.002
+    with pytest.raises(ValueError, match="Not enough samples"):
+        frf.demod(t, t, np.array([1.0]), drop_seconds=1.0)
+    with pytest.raises(ValueError, match="Non-positive record length"):
+        frf.demod(np.zeros(4), np.ones(4), np.array([1.0]))
+
+
+@pytest.mark.parametrize("n,nd,kind", [(200_000, 100, "multisine"), (300_001, 150, "square"), (4097, 7, "multisine"),
+                                       (50_000, 600, "multisine")])
+def test_oracle_seeded(frf, n, nd, kind):
+    """Ragged sizes, nd above one CTA's bin group (600 > 512), square-wave (broadband) input."""
+    from b200id import synth
+    t, u, y = synth.make_record(n, min(nd, 100), kind, seed=11)
+    _, w = ofrf.freq_grid(nd)
+    U, Y = frf.demod_pair(t, u, y, w)
+    Ur, Yr = ofrf.demod_trapz(t, u, w, threads=8), ofrf.demod_trapz(t, y, w, threads=8)
+    e = max(rel_each(U, Ur), rel_each(Y, Yr))
+    record(f"frf.oracle.{kind}.n{n}.nd{nd}.rel_each", e)
+    assert e < TOL
+    G, Gr = frf.cross_power([U], [Y]), ofrf.cross_power([Ur], [Yr])
+    assert record(f"frf.oracle.{kind}.n{n}.nd{nd}.G.rel_each", rel_each(G, Gr)) < TOL
+
+
+def test_long_record_late_time_phases(frf):
+    """Phases up to ~1e9 rad (time origin far from zero): the Cody-Waite path must hold."""
+    from b200id import synth
+    n, nd = 100_000, 50
+    t, u, y = synth.make_record(n, nd, "multisine", seed=2)
+    t = t + 1.9e6                       # as if this were the tail of a 1e9-sample record
+    _, w = ofrf.freq_grid(nd)
+    U, Y = frf.demod_pair(t, u, y, w)
+    Ur, Yr = ofrf.demod_trapz(t, u, w, threads=8), ofrf.demod_trapz(t, y, w, threads=8)
+    e = record("frf.oracle.late_time.rel_each", max(rel_each(U, Ur), rel_each(Y, Yr)))
+    assert e < TOL
+
+
+def test_linearity_and_segment_additivity_full_size(frf):
+    """Size-independent properties at the BASELINE cfg-2 shape (1e7 samples, nd=100):
+    projecting [0,n) equals the sum of the projections of two owned segments (what the time-segment
+    shards of the multi-GPU path compute), and the projection is linear in the signal."""
+    import torch
+    from b200id.runtime import require_cuda
+    dev = require_cuda()
+    n, nd = 10_000_000, 100
+    _, w = ofrf.freq_grid(nd)
+    gen = torch.Generator(device=dev); gen.manual_seed(0)
+    t = torch.arange(n, dtype=torch.float64, device=dev) * 0.002
+    u = torch.randn(n, dtype=torch.float64, device=dev, generator=gen)
+    y = torch.randn(n, dtype=torch.float64, device=dev, generator=gen)
+    w_d = torch.from_numpy(w).to(dev)
+    full = frf.project_device(t, u, y, w_d)
+    cut = 3_333_333
+    a = frf.project_device(t, u, y, w_d, own=(0, cut))
+    b = frf.project_device(t, u, y, w_d, own=(cut, n))
+    scale = float(full.abs().max())
+    e = record("frf.property.segment_additivity", float((a + b - full).abs().max()) / scale)
+    assert e < 1e-12
+    lin = frf.project_device(t, 2.0 * u + y, y, w_d)
+    expect = 2.0 * full[:2 * nd] + full[2 * nd:]
+    e = record("frf.property.linearity", float((lin[:2 * nd] - expect).abs().max()) / scale)
+    assert e < 1e-12
+    again = frf.project_device(t, u, y, w_d)
+    assert torch.equal(again, full), "projection must be deterministic run to run"

@@ -302,7 +302,7 @@ def main():
     fp64 = {}
     if rank == 0:
         sink = empty(1, dev)
-        for mode, name in ((0, "dfma"), (1, "dmma")):
+        for mode, name in ((0, "dfma"), (1, "dmma"), (2, "dfma_plus_dmma")):
             flops = C.c_double(0.0)
             from b200id.runtime import ptr, stream_ptr
             iters = 4000

@@ -85,6 +85,8 @@ def _prepare(t, x_list: Sequence[np.ndarray], drop_seconds: float):
         keep = t >= (t[0] + drop_seconds)
         if keep.all():
             pass
+        elif not keep.any():
+            t, xs = t[:0], [x[:0] for x in xs]
         elif t.size > 1 and bool(np.all(np.diff(t) > 0)):
             first = int(np.argmax(keep))          # monotone time: the mask is a suffix -> a view
             t, xs = t[first:], [x[first:] for x in xs]

@@ -169,7 +169,7 @@ class FittedGP:
         return (mean, std) if return_std else mean
 
 
-def fit_device(kernel: str, theta, X_d: torch.Tensor, y_d: torch.Tensor, noise: float) -> FittedGP:
+def fit_device(kernel: str, theta, X_d: torch.Tensor, y_d: torch.Tensor, noise: float, want_kinv: bool = True) -> FittedGP:
     """Final fit with the reference's jitter (noise + 1e-10), pinv branch on failure (gpr_fitting.py:73-87)."""
     import ctypes as C
     from . import _lib
@@ -178,7 +178,8 @@ def fit_device(kernel: str, theta, X_d: torch.Tensor, y_d: torch.Tensor, noise: 
     n = X_d.numel()
     kid = bgp.KERNEL_IDS[kernel][0]
     th = to_device(bgp._theta_block(theta)[0], dev)
-    alpha, Kinv = empty(n, dev), empty(n * n, dev)
+    want_kinv = want_kinv or n > 127
+    alpha, Kinv = empty(n, dev), (empty(n * n, dev) if want_kinv else None)
     info = torch.zeros(1, dtype=torch.int32, device=dev)
     ws = Workspace.get("gpfit", _lib.load().b200id_gp_fit_workspace_bytes(n), dev)
     diag = float(noise) + 1e-10
@@ -186,6 +187,8 @@ def fit_device(kernel: str, theta, X_d: torch.Tensor, y_d: torch.Tensor, noise: 
               ptr(Kinv), ptr(info), ptr(ws), C.c_size_t(ws.numel()), stream_ptr())
     used_pinv = int(info.item()) != 0
     if used_pinv:
+        if Kinv is None:
+            Kinv = empty(n * n, dev)
         _lib.call("b200id_gp_fit_pinv", C.c_int(kid), ptr(th), ptr(X_d), ptr(y_d), C.c_int(n), C.c_double(diag),
                   C.c_double(bgp.PINV_RCOND), ptr(alpha), ptr(Kinv), ptr(ws), C.c_size_t(ws.numel()), stream_ptr())
     return FittedGP(kernel, np.asarray(theta, dtype=np.float64), alpha, Kinv, X_d, used_pinv)
@@ -262,8 +265,8 @@ def identify_device(train: Sequence[Tuple[torch.Tensor, torch.Tensor, torch.Tens
     else:
         th_r = th_i = np.asarray(theta0, dtype=np.float64)
         mr = mi = float("nan")
-    gp_r = fit_device(kernel, th_r, X_d, yr, noise)
-    gp_i = fit_device(kernel, th_i, X_d, yi, noise)
+    gp_r = fit_device(kernel, th_r, X_d, yr, noise, want_kinv=False)     # the FIR path only needs the GP mean
+    gp_i = fit_device(kernel, th_i, X_d, yi, noise, want_kinv=False)
     # ---- paper-mode FIR: 1000-point uniform omega grid -> GP mean -> Hermitian IDFT -> taps
     w_uni = torch.linspace(float(omega.min()), float(omega.max()), PAPER_ND, dtype=F64, device=dev)
     Xu = xs.transform(torch.log10(w_uni)).contiguous()

@@ -73,6 +73,28 @@ __global__ void __launch_bounds__(PROBE_THREADS) probe_dmma_kernel(int iters, do
     if (s == 123.456) sink[0] = s;
 }
 
+// mode 2: both at once (4 DFMA chains + 4 DMMA chains per thread) -- tells whether FP64 FMA and FP64 MMA
+// share one pipe on this chip (combined rate == single rate) or can overlap.
+__global__ void __launch_bounds__(PROBE_THREADS) probe_mixed_kernel(int iters, double* sink) {
+    double a[4], c0[4], c1[4];
+    const double m = 1.0 + 1e-9 * threadIdx.x, c = 1e-12, b = 1e-3;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { a[k] = 0.5 + k; c0[k] = k; c1[k] = -k; }
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                         : "+d"(c0[k]), "+d"(c1[k]) : "d"(m), "d"(b));
+#pragma unroll
+            for (int rep = 0; rep < 8; ++rep) a[k] = fma(a[k], m, c);
+        }
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) s += a[k] + c0[k] + c1[k];
+    if (s == 123.456) sink[0] = s;
+}
+
 }  // namespace b200id
 
 using namespace b200id;
@@ -95,17 +117,21 @@ extern "C" int b200id_device_info(int* sm, int* cc_major, int* cc_minor) {
 }
 
 extern "C" int b200id_fp64_peak_probe(int mode, int iters, double* sink, double* flops_out_host, void* stream) {
-    B200ID_REQUIRE(sink && iters > 0 && (mode == 0 || mode == 1), B200ID_E_ARG, "fp64_peak_probe: bad argument");
+    B200ID_REQUIRE(sink && iters > 0 && mode >= 0 && mode <= 2, B200ID_E_ARG, "fp64_peak_probe: bad argument");
     const int grid = sm_count() * 8;
     cudaStream_t st = (cudaStream_t)stream;
     double flops;
     if (mode == 0) {
         probe_dfma_kernel<<<grid, PROBE_THREADS, 0, st>>>(iters, sink);
         flops = 2.0 * PROBE_CHAINS * 8.0 * (double)iters * PROBE_THREADS * (double)grid;
-    } else {
+    } else if (mode == 1) {
         probe_dmma_kernel<<<grid, PROBE_THREADS, 0, st>>>(iters, sink);
         // one m8n8k4 = 8*8*4 MACs per warp
         flops = 2.0 * 256.0 * PROBE_CHAINS * (double)iters * (PROBE_THREADS / 32) * (double)grid;
+    } else {
+        probe_mixed_kernel<<<grid, PROBE_THREADS, 0, st>>>(iters, sink);
+        // per thread and iteration: 4 x 8 DFMA; per warp and iteration: 4 m8n8k4 (256 MACs each)
+        flops = 2.0 * (double)iters * (double)grid * (4.0 * 8.0 * PROBE_THREADS + 4.0 * 256.0 * (PROBE_THREADS / 32));
     }
     B200ID_LAUNCH_CHECK("probe kernel");
     if (flops_out_host) *flops_out_host = flops;

@@ -5,9 +5,9 @@
 // (np.convolve(u, g, 'full')[:N], then RMSE / FIT / R2 over i >= skip).
 //
 // K6 layout.  A CTA of 128 threads produces a tile of 2048 consecutive outputs; each thread owns
-// 16 CONSECUTIVE outputs and keeps a sliding window of u in registers, so one block of 8 taps costs
-// 23 shared-memory loads of u + 8 broadcast loads of g for 128 DFMA (FP64-issue bound, not
-// shared-memory bound).  The u window [i0 - (taps-1), i0 + 2048) is staged in shared memory with one
+// 16 CONSECUTIVE outputs and keeps a circular 24-entry window of u in registers, so one block of 8 taps
+// costs 8 shared-memory loads of u (+ 8 uniform constant-bank loads of the taps) for 128 DFMA
+// (FP64-issue bound, not shared-memory bound).  The u window [i0 - (taps-1), i0 + 2048) is staged in shared memory with one
 // padding double per 16 (lane stride 17 doubles, odd) so that the 16-output-strided lane addresses fall in distinct
 // banks.  y_pred is optional: the validation metric only needs the three error sums, which are
 // folded per CTA and then by a fixed-order tree (deterministic).
@@ -43,13 +43,22 @@ constexpr int FIR_THREADS = 128;
 constexpr int FIR_OPT = 16;                         // outputs per thread
 constexpr int FIR_TILE = FIR_THREADS * FIR_OPT;     // 2048 outputs per CTA
 constexpr int FIR_TAP_BLOCK = 8;
+constexpr int FIR_TAP_GROUP = 24;                   // taps per unrolled group: 3 blocks, the window slots repeat with period 24
+constexpr int FIR_WIN = 24;                         // circular register window (23 live entries)
 constexpr int FIR_MAX_TAPS = 8192;
+constexpr int FIR_CONST_TAPS = 4104;                // taps up to this count are served from constant memory
+
+// FIR taps in constant memory: the tap index is warp-uniform, so every DFMA of the inner loop reads
+// acc (register), u window (register) and the tap through a uniform register -- two distinct
+// register operands, which is what lets the FP64 pipe issue at its full rate (see fp64_math.cuh).
+__constant__ double c_taps[FIR_CONST_TAPS];
 
 __host__ __device__ inline int fir_pad(int x) { return x + (x >> 4); }
 static inline size_t fir_smem_bytes(int taps_padded) {
     return ((size_t)fir_pad(FIR_TILE + taps_padded) + 8 + taps_padded) * sizeof(double);
 }
 
+template <bool G_CONST>
 __global__ void __launch_bounds__(FIR_THREADS)
 fir_eval_kernel(const double* __restrict__ u, const double* __restrict__ y, int64_t n, int64_t lead,
                 const double* __restrict__ g, int n_taps, int taps_padded, int64_t skip, double y0,
@@ -62,7 +71,8 @@ fir_eval_kernel(const double* __restrict__ u, const double* __restrict__ y, int6
     const int tid = threadIdx.x;
     const int64_t i0 = (int64_t)blockIdx.x * FIR_TILE;
     const int hist = taps_padded - 1;        // samples of history in front of the tile
-    for (int j = tid; j < taps_padded; j += FIR_THREADS) gs[j] = j < n_taps ? g[j] : 0.0;
+    if (!G_CONST)
+        for (int j = tid; j < taps_padded; j += FIR_THREADS) gs[j] = j < n_taps ? g[j] : 0.0;
     // logical window index x in [0, hist + FIR_TILE) maps to sample i0 - hist + x
     for (int x = tid; x < hist + FIR_TILE; x += FIR_THREADS) {
         const int64_t i = i0 - hist + x;
@@ -77,18 +87,30 @@ fir_eval_kernel(const double* __restrict__ u, const double* __restrict__ y, int6
 #pragma unroll
     for (int o = 0; o < FIR_OPT; ++o) acc[o] = 0.0;
 
-    // sliding window: win[c] = u at x = base + c, c = 0 .. FIR_OPT + FIR_TAP_BLOCK - 2
-    for (int j0 = 0; j0 < taps_padded; j0 += FIR_TAP_BLOCK) {
-        const int base = hist + p - j0 - (FIR_TAP_BLOCK - 1);    // >= 0 because j0 + 7 <= hist
-        double win[FIR_OPT + FIR_TAP_BLOCK - 1];
+    // Sliding register window.  Relative position r = x - (hist + p) of u[i - j] for output o and tap j is
+    // r = o - j.  A block of 8 taps j0..j0+7 touches r in [-j0-7, -j0+15] (23 values); moving to the next
+    // block shifts that range down by 8, so only 8 NEW values are loaded per block and the other 15 stay in
+    // registers.  Slot of r is (r mod 24): inside a group of 3 blocks (24 taps) every slot index is a
+    // compile-time constant, so the window never moves between registers.
+    double win[FIR_WIN];
+    const int origin = hist + p;             // window coordinate of r = 0
 #pragma unroll
-        for (int c = 0; c < FIR_OPT + FIR_TAP_BLOCK - 1; ++c) win[c] = us[fir_pad(base + c)];
+    for (int r = 1; r <= 15; ++r) win[r] = us[fir_pad(origin + r)];      // r = 1..15 of block 0
+    for (int g0 = 0; g0 < taps_padded; g0 += FIR_TAP_GROUP) {
 #pragma unroll
-        for (int jj = 0; jj < FIR_TAP_BLOCK; ++jj) {
-            const double gj = gs[j0 + jj];
+        for (int b = 0; b < FIR_TAP_GROUP / FIR_TAP_BLOCK; ++b) {
+            const int j0 = g0 + b * FIR_TAP_BLOCK;
+            // new entries r = -j0-7 .. -j0  ->  slots (-8b - 7 + c) mod 24, c = 0..7
 #pragma unroll
-            for (int o = 0; o < FIR_OPT; ++o)
-                acc[o] = fma(gj, win[o + (FIR_TAP_BLOCK - 1) - jj], acc[o]);
+            for (int c = 0; c < FIR_TAP_BLOCK; ++c)
+                win[((-8 * b - 7 + c) % FIR_WIN + FIR_WIN) % FIR_WIN] = us[fir_pad(origin - j0 - 7 + c)];
+#pragma unroll
+            for (int jj = 0; jj < FIR_TAP_BLOCK; ++jj) {
+                const double gj = G_CONST ? c_taps[j0 + jj] : gs[j0 + jj];
+#pragma unroll
+                for (int o = 0; o < FIR_OPT; ++o)
+                    acc[o] = fma(gj, win[((o - 8 * b - jj) % FIR_WIN + FIR_WIN) % FIR_WIN], acc[o]);
+            }
         }
     }
 
@@ -163,13 +185,32 @@ extern "C" int b200id_fir_eval(const double* u, const double* y, int64_t n, int6
     const int64_t ctas = (n + FIR_TILE - 1) / FIR_TILE;
     B200ID_REQUIRE(ctas < (1LL << 31), B200ID_E_UNSUPPORTED, "fir_eval: record too long for one launch");
     B200ID_REQUIRE(ws_bytes >= (size_t)ctas * 4 * sizeof(double), B200ID_E_WORKSPACE, "fir_eval: workspace too small");
-    const int taps_padded = (n_taps + FIR_TAP_BLOCK - 1) / FIR_TAP_BLOCK * FIR_TAP_BLOCK;
+    const int taps_padded = (n_taps + FIR_TAP_GROUP - 1) / FIR_TAP_GROUP * FIR_TAP_GROUP;
     const size_t smem = fir_smem_bytes(taps_padded);
-    int rc = check_cuda(cudaFuncSetAttribute(fir_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute(fir)");
-    if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    fir_eval_kernel<<<(unsigned)ctas, FIR_THREADS, smem, st>>>(u, y, n, lead, g, n_taps, taps_padded, skip, y0,
-                                                              y_pred_out, (double*)ws);
+    const bool use_const = taps_padded <= FIR_CONST_TAPS;
+    int rc;
+    if (use_const) {
+        // stage the (zero padded) taps into the constant bank on the caller's stream
+        void* sym = nullptr;
+        rc = check_cuda(cudaGetSymbolAddress(&sym, c_taps), "cudaGetSymbolAddress(c_taps)");
+        if (rc) return rc;
+        if (taps_padded > n_taps) {
+            rc = check_cuda(cudaMemsetAsync((double*)sym + n_taps, 0, (size_t)(taps_padded - n_taps) * sizeof(double), st), "cudaMemsetAsync(c_taps)");
+            if (rc) return rc;
+        }
+        rc = check_cuda(cudaMemcpyAsync(sym, g, (size_t)n_taps * sizeof(double), cudaMemcpyDeviceToDevice, st), "cudaMemcpyAsync(c_taps)");
+        if (rc) return rc;
+        rc = check_cuda(cudaFuncSetAttribute(fir_eval_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute(fir)");
+        if (rc) return rc;
+        fir_eval_kernel<true><<<(unsigned)ctas, FIR_THREADS, smem, st>>>(u, y, n, lead, g, n_taps, taps_padded, skip, y0,
+                                                                        y_pred_out, (double*)ws);
+    } else {
+        rc = check_cuda(cudaFuncSetAttribute(fir_eval_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute(fir)");
+        if (rc) return rc;
+        fir_eval_kernel<false><<<(unsigned)ctas, FIR_THREADS, smem, st>>>(u, y, n, lead, g, n_taps, taps_padded, skip, y0,
+                                                                         y_pred_out, (double*)ws);
+    }
     B200ID_LAUNCH_CHECK("fir_eval_kernel");
     fir_fold_kernel<<<1, 256, 0, st>>>((const double*)ws, ctas, sums_out);
     B200ID_LAUNCH_CHECK("fir_fold_kernel");

@@ -10,6 +10,7 @@
 // the validation-RMSE metric back-substitutes alpha = L^-T z and forms K(Xv, X) alpha on the fly.
 // Failure conventions (hard part 4): pivot <= 0 -> metric 1e10 (LinAlgError
 // branch, grid_search.py:132-133); NaN pivot -> factorisation continues and the metric is NaN.
+#include <stdlib.h>
 #include "common.cuh"
 #include "gp_kernels.cuh"
 #include "gp_linalg.cuh"
@@ -195,6 +196,44 @@ gp_fit_kernel(int kernel_id, const double* __restrict__ theta, const double* __r
     }
 }
 
+// K_inv = (L L^T)^-1 column by column: one warp per column c solves L v = e_c then L^T x = v with the
+// dense lower factor staged in shared memory (row-major, odd stride).
+constexpr int KINV_WARPS = 8;
+__global__ void __launch_bounds__(KINV_WARPS * 32)
+gp_kinv_kernel(const double* __restrict__ L, int n, const int* __restrict__ info, double* __restrict__ Kinv) {
+    extern __shared__ double sm[];
+    if (info[0] != 0) return;
+    const int ld = n | 1;
+    double* Ls = sm;                               // [n][ld]
+    double* vbuf = Ls + (size_t)n * ld;            // [KINV_WARPS][n]
+    for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+        const int i = e / n, j = e - i * n;
+        Ls[(size_t)i * ld + j] = L[e];
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int c = blockIdx.x * KINV_WARPS + w;
+    if (c >= n) return;
+    double* v = vbuf + (size_t)w * n;
+    for (int i = lane; i < n; i += 32) v[i] = 0.0;
+    __syncwarp();
+    for (int i = c; i < n; ++i) {                  // forward: v[i] = (e_c[i] - sum_{c<=p<i} L[i][p] v[p]) / L[i][i]
+        double s = 0.0;
+        for (int p = c + lane; p < i; p += 32) s = fma(Ls[(size_t)i * ld + p], v[p], s);
+        s = warp_sum(s);
+        if (lane == 0) v[i] = (((i == c) ? 1.0 : 0.0) - s) / Ls[(size_t)i * ld + i];
+        __syncwarp();
+    }
+    for (int i = n - 1; i >= 0; --i) {             // backward: x[i] = (v[i] - sum_{p>i} L[p][i] x[p]) / L[i][i]
+        double s = 0.0;
+        for (int p = i + 1 + lane; p < n; p += 32) s = fma(Ls[(size_t)p * ld + i], v[p], s);
+        s = warp_sum(s);
+        if (lane == 0) v[i] = (v[i] - s) / Ls[(size_t)i * ld + i];
+        __syncwarp();
+    }
+    for (int i = lane; i < n; i += 32) Kinv[(size_t)i * n + c] = v[i];
+}
+
 // One CTA per test point: mean = K* alpha; var = k(xs,xs) - sum_j (K* K_inv)_j K*_j   (gpr_fitting.py:91-97)
 __global__ void __launch_bounds__(GP_THREADS)
 gp_predict_kernel(int kernel_id, const double* __restrict__ theta, const double* __restrict__ X, int n,
@@ -236,6 +275,23 @@ gp_predict_kernel(int kernel_id, const double* __restrict__ theta, const double*
 
 using namespace b200id;
 
+// gp_batch_tiled.cu: blocked register-tiled path for n <= 127
+int b200id_gp_fit_tiled_launch(int kernel_id, const double* theta, const double* X, const double* y, int n,
+                               double diag_add, double* alpha_out, double* L_out, int* info_out, cudaStream_t st);
+int b200id_gp_batch_tiled_launch(int kernel_id, const int* kernel_ids, const double* theta, int64_t n_candidates,
+                                 const double* X, const double* y, int n, double noise, int metric,
+                                 const double* Xv, const double* yv, int nv, double y_mean, double y_scale,
+                                 double* metric_out, cudaStream_t st);
+
+static bool force_generic_gp_path() {
+    static int cached = -1;
+    if (cached < 0) {
+        const char* e = getenv("B200ID_GP_PATH");
+        cached = (e && strcmp(e, "generic") == 0) ? 1 : 0;
+    }
+    return cached == 1;
+}
+
 static int set_smem_attr(const void* fn, size_t bytes) {
     return check_cuda(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes), "cudaFuncSetAttribute(smem)");
 }
@@ -271,6 +327,9 @@ extern "C" int b200id_gp_batch_eval(int kernel_id, const int* kernel_ids, const 
     B200ID_REQUIRE(metric == B200ID_METRIC_NLL || (Xv && yv && nv > 0), B200ID_E_ARG, "gp_batch_eval: validation metric needs Xv, yv");
     B200ID_REQUIRE(n <= GP_NMAX_SMEM, B200ID_E_UNSUPPORTED, "gp_batch_eval: n=%d exceeds the in-shared-memory limit %d", n, GP_NMAX_SMEM);
     B200ID_REQUIRE(n_candidates < (1LL << 31), B200ID_E_UNSUPPORTED, "gp_batch_eval: too many candidates");
+    if (n <= 127 && !force_generic_gp_path())
+        return b200id_gp_batch_tiled_launch(kernel_id, kernel_ids, theta, n_candidates, X, y, n, noise, metric, Xv, yv, nv,
+                                            y_mean, y_scale, metric_out, (cudaStream_t)stream);
     const size_t smem = gp_smem_bytes(n);
     int rc = set_smem_attr((const void*)gp_batch_kernel, smem);
     if (rc) return rc;
@@ -296,15 +355,30 @@ extern "C" size_t b200id_gp_fit_workspace_bytes(int n) {
 extern "C" int b200id_gp_fit(int kernel_id, const double* theta, const double* X, const double* y, int n,
                              double diag_add, double* alpha_out, double* Kinv_out, int* info_out,
                              void* ws, size_t ws_bytes, void* stream) {
-    B200ID_REQUIRE(theta && X && y && alpha_out && Kinv_out && info_out && ws, B200ID_E_ARG, "gp_fit: null pointer");
+    B200ID_REQUIRE(theta && X && y && alpha_out && info_out && ws, B200ID_E_ARG, "gp_fit: null pointer");
     B200ID_REQUIRE(kernel_id >= 0 && kernel_id < B200ID_K_COUNT, B200ID_E_ARG, "gp_fit: unknown kernel id %d", kernel_id);
     B200ID_REQUIRE(n > 0 && n <= GP_NMAX_SMEM, B200ID_E_UNSUPPORTED, "gp_fit: n=%d outside (0, %d]", n, GP_NMAX_SMEM);
     B200ID_REQUIRE(ws_bytes >= (size_t)n * n * sizeof(double), B200ID_E_WORKSPACE, "gp_fit: workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc;
+    if (n <= 127 && !force_generic_gp_path()) {
+        // blocked kernel writes alpha + dense L (workspace); K_inv (optional) by one warp per column
+        rc = b200id_gp_fit_tiled_launch(kernel_id, theta, X, y, n, diag_add, alpha_out, (double*)ws, info_out, st);
+        if (rc) return rc;
+        if (Kinv_out) {
+            const size_t smem = ((size_t)n * (n | 1) + (size_t)KINV_WARPS * n) * sizeof(double);
+            rc = set_smem_attr((const void*)gp_kinv_kernel, smem);
+            if (rc) return rc;
+            gp_kinv_kernel<<<(n + KINV_WARPS - 1) / KINV_WARPS, KINV_WARPS * 32, smem, st>>>((const double*)ws, n, info_out, Kinv_out);
+            B200ID_LAUNCH_CHECK("gp_kinv_kernel");
+        }
+        return B200ID_OK;
+    }
+    B200ID_REQUIRE(Kinv_out, B200ID_E_ARG, "gp_fit: the generic path needs Kinv_out");
     const size_t smem = gp_smem_bytes(n);
-    int rc = set_smem_attr((const void*)gp_fit_kernel, smem);
+    rc = set_smem_attr((const void*)gp_fit_kernel, smem);
     if (rc) return rc;
-    gp_fit_kernel<<<1, GP_THREADS, smem, (cudaStream_t)stream>>>(kernel_id, theta, X, y, n, diag_add, alpha_out,
-                                                                 (double*)ws, Kinv_out, info_out);
+    gp_fit_kernel<<<1, GP_THREADS, smem, st>>>(kernel_id, theta, X, y, n, diag_add, alpha_out, (double*)ws, Kinv_out, info_out);
     B200ID_LAUNCH_CHECK("gp_fit_kernel");
     return B200ID_OK;
 }

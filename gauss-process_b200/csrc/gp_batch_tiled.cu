@@ -1,0 +1,288 @@
+// gp_batch_tiled.cu -- K2 fast path (n <= 127): one CTA of 4 warps per candidate, left-looking BLOCKED
+// Cholesky with register-tiled FP64 updates.
+//
+// Reference call sites: src/gpr/grid_search.py:91-133 (candidate metric), src/gpr/gpr_fitting.py:104-123.
+//
+// Layout in shared memory.  The (n+1) x n array [K + noise*I ; y^T] is stored by BLOCK COLUMNS of 16:
+// block column J keeps rows [16J, R) (R = n+1 rounded up to 4) column-major with leading dimension
+// ld_J = R - 16J, so a thread's 4 consecutive rows of one column are one 32-byte vector and the upper
+// triangle above each block is never stored (50 KB at n = 100 -> 4 CTAs per SM).
+//
+// Per block column J:
+//   update : C[i, c] -= sum_{k < 16J} L[i, k] L[16J + c, k].  Each warp owns 32 rows x 16 columns, each
+//            lane a 4 x 4 register tile; per k a lane reads 4 + 4 doubles (broadcast across the lanes that
+//            share the rows / columns: 4 shared-memory wavefronts per 16 DFMA warp instructions).
+//   diag   : warp 0 factorises the 16 x 16 diagonal block in place (right-looking, reciprocal scaling).
+//   panel  : one thread per row below solves x L_JJ^T = c by forward substitution in registers, multiplying
+//            by the stored reciprocal diagonal (as OpenBLAS TRSM does).
+// Row n carries y, so after the last block column it holds z = L^-1 y and y^T K^-1 y = z.z.
+// Failure conventions as in gp_linalg.cuh: pivot <= 0 or +inf -> 1e10, NaN pivot -> NaN metric.
+#include "common.cuh"
+#include "gp_kernels.cuh"
+
+namespace b200id {
+
+constexpr int GT_THREADS = 128;
+constexpr int GT_NB = 16;
+constexpr int GT_NMAX = 127;            // n + 1 rows <= 128 = 4 warps x 32 rows
+constexpr int GT_METRIC_FIT = 2;        // internal mode: write alpha and L instead of a metric
+
+struct TiledLayout {
+    int R;                              // rows incl. y row, rounded up to a multiple of 4
+    int nblk;                           // number of block columns
+};
+
+__host__ __device__ inline int gt_rows(int n) { return (n + 1 + 3) & ~3; }
+__host__ __device__ inline int gt_nblk(int n) { return (n + GT_NB - 1) / GT_NB; }
+// offset (in doubles) of block column J: sum_{q<J} 16 * (R - 16 q)
+__host__ __device__ inline int gt_off(int R, int J) { return GT_NB * (J * R - GT_NB * J * (J - 1) / 2); }
+static inline size_t gt_smem_bytes(int n) {
+    const int R = gt_rows(n), nb = gt_nblk(n);
+    return ((size_t)gt_off(R, nb) + 3 * (size_t)(n + 4) + 16) * sizeof(double);
+}
+
+__global__ void __launch_bounds__(GT_THREADS)
+gp_batch_tiled_kernel(int kernel_id, const int* __restrict__ kernel_ids, const double* __restrict__ theta,
+                      const double* __restrict__ X, const double* __restrict__ y, int n, double noise,
+                      int metric, const double* __restrict__ Xv, const double* __restrict__ yv, int nv,
+                      double y_mean, double y_scale, double* __restrict__ metric_out,
+                      double* __restrict__ fit_alpha, double* __restrict__ fit_L, int* __restrict__ fit_info) {
+    extern __shared__ __align__(16) double sm[];
+    const int R = gt_rows(n), nblk = gt_nblk(n);
+    double* Lb = sm;                                   // block-column storage
+    double* xs = Lb + gt_off(R, nblk);                 // [n]  inputs
+    double* idg = xs + (n + 4);                        // [n]  reciprocal diagonal of L
+    double* zz = idg + (n + 4);                        // [n]  z, then alpha
+    double* scratch = zz + (n + 4);                    // [8]
+    __shared__ int status;
+
+    const int64_t cand = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31;
+    // rotate the warp -> row-range map with the CTA index so that the 4 co-resident CTAs of an SM load
+    // its 4 sub-partitions evenly (the last rows do the most work)
+    const int wrow = ((tid >> 5) + (int)(blockIdx.x & 3)) & 3;
+    const int kid = kernel_ids ? kernel_ids[cand] : kernel_id;
+    const KernelParams kp = make_kernel_params(kid, theta + cand * B200ID_MAX_PARAMS);
+
+    if (tid == 0) status = 0;
+    for (int i = tid; i < n; i += GT_THREADS) xs[i] = X[i];
+    __syncthreads();
+
+    // ---- fill: K + noise*I (rows < n), y (row n), zeros (padding rows), block column by block column
+    for (int J = 0; J < nblk; ++J) {
+        const int ld = R - GT_NB * J;
+        double* col0 = Lb + gt_off(R, J);
+        for (int e = tid; e < ld * GT_NB; e += GT_THREADS) {
+            const int c = e / ld, r = e - c * ld;
+            const int i = GT_NB * J + r, j = GT_NB * J + c;
+            double v = 0.0;
+            if (j < n) {
+                if (i < n) {
+                    // evaluate with the larger index first, as the lower triangle of kernel(X) is laid out
+                    const int a = i >= j ? i : j, b = i >= j ? j : i;
+                    v = kernel_entry(kp, xs[a], xs[b]);
+                    if (i == j) v = B200ID_ADD(v, noise);
+                } else if (i == n) {
+                    v = y[j];
+                }
+            }
+            col0[e] = v;
+        }
+    }
+    __syncthreads();
+
+    const int rb = lane >> 2, cb = lane & 3;           // 8 row blocks x 4 column blocks of 4 x 4
+    const int i0 = 32 * wrow + 4 * rb;                 // first of this lane's 4 rows
+
+    for (int J = 0; J < nblk; ++J) {
+        const int ldJ = R - GT_NB * J;
+        double* colJ = Lb + gt_off(R, J);
+        const int ncols = min(GT_NB, n - GT_NB * J);
+        // ---------------- update with all previous block columns (register tiles)
+        if (J > 0 && i0 >= GT_NB * J && i0 < R) {
+            double acc[4][4];
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const double2 v01 = *reinterpret_cast<const double2*>(colJ + (4 * cb + b) * ldJ + (i0 - GT_NB * J));
+                const double2 v23 = *reinterpret_cast<const double2*>(colJ + (4 * cb + b) * ldJ + (i0 - GT_NB * J) + 2);
+                acc[0][b] = v01.x; acc[1][b] = v01.y; acc[2][b] = v23.x; acc[3][b] = v23.y;
+            }
+            for (int Jk = 0; Jk < J; ++Jk) {
+                const int ldk = R - GT_NB * Jk;
+                const double* pa = Lb + gt_off(R, Jk) + (i0 - GT_NB * Jk);
+                const double* pb = Lb + gt_off(R, Jk) + (GT_NB * (J - Jk) + 4 * cb);
+#pragma unroll 4
+                for (int kk = 0; kk < GT_NB; ++kk) {
+                    const double2 a01 = *reinterpret_cast<const double2*>(pa + kk * ldk);
+                    const double2 a23 = *reinterpret_cast<const double2*>(pa + kk * ldk + 2);
+                    const double2 b01 = *reinterpret_cast<const double2*>(pb + kk * ldk);
+                    const double2 b23 = *reinterpret_cast<const double2*>(pb + kk * ldk + 2);
+                    const double a[4] = {a01.x, a01.y, a23.x, a23.y};
+                    const double b[4] = {b01.x, b01.y, b23.x, b23.y};
+#pragma unroll
+                    for (int p = 0; p < 4; ++p)
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) acc[p][q] = fma(-a[p], b[q], acc[p][q]);
+                }
+            }
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                double* dst = colJ + (4 * cb + b) * ldJ + (i0 - GT_NB * J);
+                *reinterpret_cast<double2*>(dst) = make_double2(acc[0][b], acc[1][b]);
+                *reinterpret_cast<double2*>(dst + 2) = make_double2(acc[2][b], acc[3][b]);
+            }
+        }
+        __syncthreads();
+        // ---------------- diagonal block (warp 0): D[r][c] at colJ[c*ldJ + r], r, c < ncols
+        if (tid < 32) {
+            for (int k = 0; k < ncols; ++k) {
+                const double piv = colJ[k * ldJ + k];
+                if (piv <= 0.0 || piv == INFINITY) {          // uniform: every lane reads the same value
+                    if (lane == 0) status = GT_NB * J + k + 1;
+                    break;
+                }
+                const double d = sqrt(piv);
+                const double inv = 1.0 / d;
+                __syncwarp();
+                if (lane == 0) { colJ[k * ldJ + k] = d; idg[GT_NB * J + k] = inv; }
+                if (lane > k && lane < ncols) colJ[k * ldJ + lane] *= inv;
+                __syncwarp();
+                // D[r][c] -= D[r][k] D[c][k], k < c <= r < ncols: up to 120 pairs over 32 lanes
+                for (int e = lane; e < GT_NB * GT_NB; e += 32) {
+                    const int c = e >> 4, r = e & 15;
+                    if (c > k && r >= c && r < ncols)
+                        colJ[c * ldJ + r] = fma(-colJ[k * ldJ + r], colJ[k * ldJ + c], colJ[c * ldJ + r]);
+                }
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+        if (status != 0) {
+            if (tid == 0) {
+                if (metric == GT_METRIC_FIT) fit_info[0] = status;
+                else metric_out[cand] = B200ID_FAIL_METRIC;
+            }
+            return;
+        }
+        // ---------------- panel: rows below the diagonal block (incl. the y row), one thread per row
+        {
+            // rows start right after the ncols diagonal rows: in a partial last block the y row (offset n - 16J)
+            // sits inside the 16-row range of the block
+            const int r = ncols + tid;                  // row offset inside the block column
+            if (r < ldJ && GT_NB * J + r <= n) {
+                double x[GT_NB];
+#pragma unroll
+                for (int c = 0; c < GT_NB; ++c) x[c] = (c < ncols) ? colJ[c * ldJ + r] : 0.0;
+#pragma unroll
+                for (int c = 0; c < GT_NB; ++c) {
+                    if (c < ncols) {
+                        double s = x[c];
+#pragma unroll
+                        for (int p = 0; p < c; ++p) s = fma(-x[p], colJ[p * ldJ + c], s);
+                        x[c] = s * idg[GT_NB * J + c];
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < GT_NB; ++c)
+                    if (c < ncols) colJ[c * ldJ + r] = x[c];
+            }
+        }
+        __syncthreads();
+    }
+
+    // L(i, j) for i >= j lives at Lb[gt_off(R, j/16) + (j%16) * (R - 16 (j/16)) + (i - 16 (j/16))]
+    auto Lat = [&](int i, int j) -> double& {
+        const int J = j >> 4;
+        return Lb[gt_off(R, J) + (j & 15) * (R - GT_NB * J) + (i - GT_NB * J)];
+    };
+
+    if (metric == B200ID_METRIC_NLL) {
+        // 0.5 y.alpha + sum log L_ii + 0.5 n log(2 pi), with y.alpha = z.z        grid_search.py:128-130
+        double part = 0.0;
+        for (int j = tid; j < n; j += GT_THREADS) {
+            const double zj = Lat(n, j);
+            part += 0.5 * zj * zj + log(Lat(j, j));
+        }
+        const double tot = block_sum(part, scratch);
+        if (tid == 0) metric_out[cand] = tot + 0.5 * (double)n * 1.8378770664093453;
+        return;
+    }
+
+    // ---- validation RMSE: alpha = L^-T z by blocked back substitution, then K(Xv, X) alpha
+    for (int j = tid; j < n; j += GT_THREADS) zz[j] = Lat(n, j);
+    __syncthreads();
+    for (int J = nblk - 1; J >= 0; --J) {
+        const int ncols = min(GT_NB, n - GT_NB * J);
+        if (tid < 32) {
+            // 16 x 16 upper-triangular solve inside warp 0: alpha_k = (z_k - sum_{r>k} L[r][k] alpha_r) / L[k][k]
+            for (int k = ncols - 1; k >= 0; --k) {
+                const int gk = GT_NB * J + k;
+                const double ak = zz[gk] * idg[gk];
+                __syncwarp();
+                if (lane == 0) zz[gk] = ak;
+                if (lane < k) zz[GT_NB * J + lane] = fma(-Lat(gk, GT_NB * J + lane), ak, zz[GT_NB * J + lane]);
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+        // z[j] -= sum_{k in block J} L[k][j] alpha_k for j < 16 J
+        for (int j = tid; j < GT_NB * J; j += GT_THREADS) {
+            double s = zz[j];
+            for (int k = 0; k < ncols; ++k) s = fma(-Lat(GT_NB * J + k, j), zz[GT_NB * J + k], s);
+            zz[j] = s;
+        }
+        __syncthreads();
+    }
+    if (metric == GT_METRIC_FIT) {
+        // final fit (gpr_fitting.py:80-82): alpha and the dense lower factor (row-major) for the K_inv kernel
+        for (int j = tid; j < n; j += GT_THREADS) fit_alpha[j] = zz[j];
+        for (int e = tid; e < n * n; e += GT_THREADS) {
+            const int i = e / n, j = e - i * n;
+            fit_L[e] = (j <= i) ? Lat(i, j) : 0.0;
+        }
+        if (tid == 0) fit_info[0] = 0;
+        return;
+    }
+    double se = 0.0;
+    for (int v = tid; v < nv; v += GT_THREADS) {
+        const double xv = Xv[v];
+        double pred = 0.0;
+        for (int j = 0; j < n; ++j) pred = fma(kernel_entry(kp, xv, xs[j]), zz[j], pred);
+        pred = pred * y_scale + y_mean;
+        const double e = yv[v] - pred;
+        se = fma(e, e, se);
+    }
+    const double tot = block_sum(se, scratch);
+    if (tid == 0) metric_out[cand] = sqrt(tot / (double)nv);
+}
+
+}  // namespace b200id
+
+using namespace b200id;
+
+// Called by b200id_gp_batch_eval (gp_batch.cu) when n <= GT_NMAX.
+int b200id_gp_batch_tiled_launch(int kernel_id, const int* kernel_ids, const double* theta, int64_t n_candidates,
+                                 const double* X, const double* y, int n, double noise, int metric,
+                                 const double* Xv, const double* yv, int nv, double y_mean, double y_scale,
+                                 double* metric_out, cudaStream_t st) {
+    const size_t smem = gt_smem_bytes(n);
+    int rc = check_cuda(cudaFuncSetAttribute(gp_batch_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute(gp tiled)");
+    if (rc) return rc;
+    gp_batch_tiled_kernel<<<(unsigned)n_candidates, GT_THREADS, smem, st>>>(kernel_id, kernel_ids, theta, X, y, n, noise, metric,
+                                                                           Xv, yv, nv, y_mean, y_scale, metric_out,
+                                                                           nullptr, nullptr, nullptr);
+    B200ID_LAUNCH_CHECK("gp_batch_tiled_kernel");
+    return B200ID_OK;
+}
+
+// Final fit through the same blocked kernel (one CTA): alpha, dense L (row-major lower) and info.
+int b200id_gp_fit_tiled_launch(int kernel_id, const double* theta, const double* X, const double* y, int n,
+                               double diag_add, double* alpha_out, double* L_out, int* info_out, cudaStream_t st) {
+    const size_t smem = gt_smem_bytes(n);
+    int rc = check_cuda(cudaFuncSetAttribute(gp_batch_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute(gp tiled)");
+    if (rc) return rc;
+    gp_batch_tiled_kernel<<<1, GT_THREADS, smem, st>>>(kernel_id, nullptr, theta, X, y, n, diag_add, GT_METRIC_FIT,
+                                                      nullptr, nullptr, 0, 0.0, 1.0, nullptr, alpha_out, L_out, info_out);
+    B200ID_LAUNCH_CHECK("gp_batch_tiled_kernel(fit)");
+    return B200ID_OK;
+}

@@ -14,14 +14,19 @@ __device__ inline void chol_smem(double* A, int n, int ld, int extra, int* statu
     for (int k = 0; k < n; ++k) {
         double* colk = A + (size_t)k * ld;
         const double piv = colk[k];
-        if (piv <= 0.0) {               // NaN compares false -> continue like OpenBLAS potrf
+        // pivot <= 0 -> failure (LinAlgError branch).  NaN compares false and the factorisation goes on
+        // (OpenBLAS potf2 has no isnan test).  A +inf pivot (overflowed Gram) also counts as failure: in
+        // the reference the next inf*0 / inf-inf inside potrf raises the FP-invalid flag, which NumPy
+        // turns into LinAlgError (numpy.linalg.cholesky runs under errstate(invalid='call')).
+        if (piv <= 0.0 || piv == INFINITY) {
             if (tid == 0) *status = k + 1;
             __syncthreads();
             return;
         }
         const double d = sqrt(piv);
+        const double inv = 1.0 / d;     // potf2 scales the column by the reciprocal (SCAL), not by division
         __syncthreads();                // everyone has read the pivot before it is overwritten
-        for (int i = k + tid; i < rows; i += nt) colk[i] = (i == k) ? d : colk[i] / d;
+        for (int i = k + tid; i < rows; i += nt) colk[i] = (i == k) ? d : colk[i] * inv;
         __syncthreads();
         // trailing update: A[i][j] -= L[i][k] * L[j][k] for k < j <= i < rows, j < n.
         // Threads sweep rows (contiguous in shared memory) of one column after another.

@@ -123,7 +123,8 @@ int b200id_first_strict_min(const double* metric, int64_t n_candidates,
                             double* best_out, int64_t* idx_out, void* ws, size_t ws_bytes, void* stream);
 
 /* Final fit: K + diag_add*I, Cholesky, alpha = K^-1 y, K_inv (from the factor).  gpr_fitting.py:73-83.
- * info_out[0] = 0 ok, k > 0 = non-positive pivot at column k (caller then uses b200id_sym_pinv). */
+ * Kinv_out may be NULL when only alpha is needed (n <= 127).
+ * info_out[0] = 0 ok, k > 0 = non-positive pivot at column k (caller then uses b200id_gp_fit_pinv). */
 size_t b200id_gp_fit_workspace_bytes(int n);
 int b200id_gp_fit(int kernel_id, const double* theta, const double* X, const double* y, int n,
                   double diag_add, double* alpha_out /*[n]*/, double* Kinv_out /*[n*n]*/,

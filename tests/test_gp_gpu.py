@@ -36,19 +36,45 @@ def test_gram_golden(gp, golden, name):
     record(f"gp.gram.{name}.rel_each", worst)
 
 
-def _compare_metrics(got, ref, tag):
-    """Failure pattern (1e10), NaN pattern, and values of a metric vector against the reference's."""
+def _categories(v):
+    v = np.asarray(v)
+    return np.where(np.isnan(v), 2, np.where(v == 1e10, 1, np.where(np.isinf(v), 3, 0)))   # ok / fail / nan / inf
+
+
+def _cond_numbers(name, cands, X, noise):
+    """2-norm condition number of K + noise*I per candidate (oracle side, sets the error budget)."""
+    out = np.empty(len(cands))
+    with np.errstate(all="ignore"):
+        for i, th in enumerate(cands):
+            K = ogp.gram(name, th, X) + noise * np.eye(len(X))
+            out[i] = np.linalg.cond(K) if np.isfinite(K).all() else np.inf
+    return out
+
+
+def _compare_metrics(got, ref, tag, cond=None):
+    """Failure / NaN pattern and values of a metric vector against the reference's.
+
+    A candidate's NLL or validation RMSE is only defined to ~cond(K) * eps in the REFERENCE's own
+    arithmetic (it solves with K), so the 1e-8 budget of north_star applies to candidates with
+    cond(K) * eps << 1e-8; the others are checked against 100 * cond * eps."""
     got, ref = np.asarray(got), np.asarray(ref)
-    fail_g, fail_r = got == 1e10, ref == 1e10
-    nan_g, nan_r = np.isnan(got), np.isnan(ref)
-    flips = int(np.sum(fail_g != fail_r) + np.sum(nan_g != nan_r))
-    both = ~(fail_g | fail_r | nan_g | nan_r) & np.isfinite(ref) & np.isfinite(got)
-    err = np.abs(got[both] - ref[both]) / np.maximum(np.abs(ref[both]), 1e-300)
+    cg, cr = _categories(got), _categories(ref)
+    flips = int(np.sum(cg != cr))
+    both = (cg == 0) & (cr == 0)
+    err = np.abs(got - ref) / np.maximum(np.abs(ref), 1e-300)
     record(f"gp.metric.{tag}.flips", flips)
     record(f"gp.metric.{tag}.n_compared", int(both.sum()))
-    record(f"gp.metric.{tag}.rel_max", float(err.max()) if err.size else 0.0)
-    record(f"gp.metric.{tag}.rel_median", float(np.median(err)) if err.size else 0.0)
-    return flips, err
+    record(f"gp.metric.{tag}.rel_max", float(err[both].max()) if both.any() else 0.0)
+    record(f"gp.metric.{tag}.rel_median", float(np.median(err[both])) if both.any() else 0.0)
+    if cond is not None and both.any():
+        well = both & (cond < 1e6)
+        budget = np.maximum(TOL, 100.0 * cond * 2.2e-16)
+        record(f"gp.metric.{tag}.n_well_conditioned", int(well.sum()))
+        record(f"gp.metric.{tag}.rel_max_well_conditioned", float(err[well].max()) if well.any() else 0.0)
+        record(f"gp.metric.{tag}.n_over_cond_budget", int(np.sum(err[both] > budget[both])))
+        assert not well.any() or err[well].max() < TOL, (tag, float(err[well].max()))
+        assert np.sum(err[both] > budget[both]) <= max(1, int(0.01 * both.sum())), tag
+    return flips, err[both]
 
 
 @pytest.mark.parametrize("name", ogp.BASELINE_KERNELS)
@@ -57,37 +83,42 @@ def test_candidate_metrics_noise_1e6(gp, golden, name):
     g = golden("gp")
     C = g[f"cand_{name}"]
     X, y = g["X"], g["yr"]
+    cond = _cond_numbers(name, C, X, 1e-6)
     nll = gp.batch_eval(name, C, X, y, 1e-6)
-    flips, err = _compare_metrics(nll, g[f"nll_{name}"], f"nll.{name}")
-    assert flips == 0
-    # NLL of a candidate is conditioned like cond(K) * eps; the well-conditioned bulk meets 1e-8
-    assert np.median(err) < 1e-12 if err.size else True
-    assert (err < TOL).mean() > 0.97 if err.size else True
+    flips, _ = _compare_metrics(nll, g[f"nll_{name}"], f"nll.{name}", cond)
+    # overflowed Grams (inf entries) are the only place where the failure pattern may differ
+    overflow = ~np.isfinite(cond)
+    assert flips <= int(overflow.sum())
     vr = gp.batch_eval(name, C, X, y, 1e-6, Xv=g["Xv"], yv=g["yv_r"], y_mean=float(g["yr_mean"][0]),
                        y_scale=float(g["yr_scale"][0]))
-    flips, err = _compare_metrics(vr, g[f"vrmse_{name}"], f"vrmse.{name}")
-    assert flips == 0
-    assert (err < TOL).mean() > 0.97 if err.size else True
+    flips, _ = _compare_metrics(vr, g[f"vrmse_{name}"], f"vrmse.{name}", cond)
+    assert flips <= int(overflow.sum())
     vr0 = gp.batch_eval(name, C[:200], X, y, 1e-6, Xv=g["Xv"], yv=g["yv_r"])
-    _, err = _compare_metrics(vr0, g[f"vrmse_noscaler_{name}"], f"vrmse_noscaler.{name}")
-    assert (err < TOL).mean() > 0.97 if err.size else True
+    _compare_metrics(vr0, g[f"vrmse_noscaler_{name}"], f"vrmse_noscaler.{name}", cond[:200])
 
 
 @pytest.mark.parametrize("name", ogp.BASELINE_KERNELS)
 def test_candidate_metrics_noise_0_failure_pattern(gp, golden, name):
-    """run_baseline noise 0: singular Grams.  Pivot <= 0 -> 1e10, NaN pivot -> NaN.  Borderline
-    candidates may flip (SURVEY.md section 7 hard part 4); report how many."""
+    """run_baseline noise 0: singular Grams.  Pivot <= 0 -> 1e10, NaN pivot -> NaN.  Candidates with
+    cond(K) > 1e13 sit on the success/failure border (SURVEY.md section 7 hard part 4): count them."""
     g = golden("gp")
     C = g[f"cand_{name}"]
+    cond = _cond_numbers(name, C, g["X"], 0.0)
     nll0 = gp.batch_eval(name, C, g["X"], g["yr"], 0.0)
-    flips, _ = _compare_metrics(nll0, g[f"nll0_{name}"], f"nll0.{name}")
-    assert flips <= max(3, int(0.03 * len(C)))
+    cg, cr = _categories(nll0), _categories(g[f"nll0_{name}"])
+    flips = cg != cr
+    record(f"gp.metric.nll0.{name}.flips", int(flips.sum()))
+    record(f"gp.metric.nll0.{name}.flips_well_conditioned", int(np.sum(flips & (cond < 1e13))))
+    assert int(np.sum(flips & (cond < 1e13))) == 0
+    _compare_metrics(nll0, g[f"nll0_{name}"], f"nll0.{name}", cond)
 
 
 @pytest.mark.parametrize("name", ogp.BASELINE_KERNELS)
 @pytest.mark.parametrize("mode,tag,noise", [("nll", "n6", 1e-6), ("val", "n6", 1e-6), ("val", "n0", 0.0), ("nll", "n0", 0.0)])
 def test_selection_identical(gp, golden, name, mode, tag, noise):
-    """grid_search_hyperparameters end to end: the selected hyperparameters must be identical."""
+    """grid_search_hyperparameters end to end: the selected hyperparameters must be identical, unless
+    the reference's winner is itself decided by rounding noise (its cond(K) * eps exceeds the gap to the
+    runner-up), which is reported and xfailed, not hidden."""
     g = golden("gp")
     ref = g[f"sel_{name}_{mode}_{tag}"]
     cands = ogp.grid_candidates(name, 1500 if name == "dc" else 5000)     # host side, reference scan order
@@ -97,12 +128,18 @@ def test_selection_identical(gp, golden, name, mode, tag, noise):
     idx, best, metrics = gp.select(name, cands, g["X"], g["yr"], noise, **kw)
     same = idx >= 0 and np.array_equal(cands[idx], ref)
     record(f"gp.select.{name}.{mode}.{tag}.identical", bool(same))
-    if not same and noise == 0.0:
-        # noise 0 makes the winner a numerically singular candidate for some kernels; list, don't hide
+    if not same:
         i_ref = int(np.where((cands == ref).all(axis=1))[0][0])
+        with np.errstate(all="ignore"):
+            c_ref = float(np.linalg.cond(ogp.gram(name, ref, g["X"]) + noise * np.eye(len(g["X"]))))
+            c_our = float(np.linalg.cond(ogp.gram(name, cands[idx], g["X"]) + noise * np.eye(len(g["X"]))))
+        gap = abs(float(metrics[i_ref]) - best) / max(abs(best), 1e-300)
         record(f"gp.select.{name}.{mode}.{tag}.detail",
-               {"ours": cands[idx].tolist(), "ref": ref.tolist(), "our_metric": best, "our_metric_at_ref": float(metrics[i_ref])})
-        pytest.xfail("borderline-singular winner at noise 0 (documented in DESIGN.md)")
+               {"ours": cands[idx].tolist(), "ref": ref.tolist(), "our_metric": best, "our_metric_at_ref": float(metrics[i_ref]),
+                "cond_ref_winner": c_ref, "cond_our_winner": c_our, "relative_gap": gap})
+        noise_level = 100.0 * max(c_ref, c_our) * 2.2e-16
+        if gap < noise_level:
+            pytest.xfail(f"winner decided by rounding noise: gap {gap:.2e} < 100*cond*eps {noise_level:.2e}")
     assert same
 
 
@@ -169,3 +206,42 @@ def test_blocked_cholesky(gp, n):
     K2 = K.copy(); K2[n // 2, n // 2] = -1.0
     A2 = torch.from_numpy(K2).to(dev)
     assert gp.cholesky_blocked_device(A2) == n // 2 + 1
+
+
+@pytest.mark.parametrize("n", [5, 16, 17, 33, 100, 127, 128, 150])
+@pytest.mark.parametrize("name", ["matern52", "rbf", "dc"])
+def test_batch_paths_against_oracle_sizes(gp, n, name):
+    """Both batch paths (blocked register-tiled n <= 127, generic shared-memory n <= 160) and every
+    block-size edge (partial last block, y row inside the last block) against the oracle."""
+    rng = np.random.default_rng(n)
+    X = np.sort(rng.uniform(-1.7, 1.7, n)).reshape(-1, 1)
+    y = rng.standard_normal(n)
+    Xv = np.linspace(-1.6, 1.6, 37).reshape(-1, 1)
+    yv = rng.standard_normal(37)
+    thetas = ogp.restart_population(name, 24, 1e-6, seed=n)
+    noise = 1e-4
+    with np.errstate(all="ignore"):
+        ref_nll = np.array([ogp.candidate_metric(name, th, X, y, noise) for th in thetas])
+        ref_val = np.array([ogp.candidate_metric(name, th, X, y, noise, Xv, yv, 0.3, 1.7) for th in thetas])
+        cond = _cond_numbers(name, thetas, X, noise)
+    got_nll = gp.batch_eval(name, thetas, X, y, noise)
+    got_val = gp.batch_eval(name, thetas, X, y, noise, Xv=Xv, yv=yv, y_mean=0.3, y_scale=1.7)
+    _compare_metrics(got_nll, ref_nll, f"sizes.nll.{name}.n{n}", cond)
+    _compare_metrics(got_val, ref_val, f"sizes.val.{name}.n{n}", cond)
+    assert np.array_equal(_categories(got_nll), _categories(ref_nll))
+
+
+@pytest.mark.parametrize("n", [50, 100, 140])
+def test_fit_kinv_identity(gp, n):
+    """K_inv from the device fit times K is the identity to cond * eps; alpha solves K alpha = y."""
+    rng = np.random.default_rng(n)
+    X = np.linspace(-1.7, 1.7, n).reshape(-1, 1)
+    y = rng.standard_normal(n)
+    th = [0.4, 1.3]
+    alpha, Kinv, used_pinv = gp.fit(ogp.KERNELS["matern32"][0], th, X, y, 1e-4)
+    assert not used_pinv
+    K = ogp.gram("matern32", th, X) + 1e-4 * np.eye(n)
+    cond = np.linalg.cond(K)
+    e_id = record(f"gp.fit.kinv_identity.n{n}", float(np.max(np.abs(Kinv @ K - np.eye(n)))))
+    e_al = record(f"gp.fit.alpha_residual.n{n}", float(np.max(np.abs(K @ alpha - y)) / np.max(np.abs(y))))
+    assert e_id < 50 * cond * 2.2e-16 and e_al < 50 * cond * 2.2e-16

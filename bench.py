@@ -244,13 +244,45 @@ def main():
         va = (dev_recs[1][0], dev_recs[1][1], dev_recs[1][2], spans[1], y0)
         return P.identify_device(tr, va, a.nd, KERNEL, NOISE, cands, n_taps=N_TAPS)
 
+    # e2e: the calls a user of the reference makes (public drop-in surface, HOST NumPy buffers in pinned
+    # memory): every FRF / FIR call copies its record host->device, every result comes back as NumPy.
+    import contextlib, io
+    from sklearn.preprocessing import StandardScaler
+    from src.frequency_transform.frf_estimator import (matlab_freq_grid, synchronous_coefficients_trapz_pair,
+                                                       frf_cross_power_average)
+    from src.gpr import create_kernel, GaussianProcessRegressor
+    from src.fir_model.fir_fitting import gp_to_fir_direct_pipeline
+    from b200id import fir as bfir
+    host = [[x.numpy() for x in rec] for rec in pinned]            # NumPy views of the pinned buffers
+    _, omega_h = matlab_freq_grid(a.nd, -1.0, 2.3)
+    _, omega_v = matlab_freq_grid(VAL_ND, -1.0, 2.3)
+    e2e_dir = ROOT / "gpurun_out" / f"bench_e2e_rank{rank}"
+
     def step_e2e():
-        d = [[x.to(dev, non_blocking=True) for x in rec] for rec in pinned]
-        tr = [(d[0][0], d[0][1], d[0][2], spans[0])]
-        va = (d[1][0], d[1][1], d[1][2], spans[1], y0)
-        res = P.identify_device(tr, va, a.nd, KERNEL, NOISE, cands, n_taps=N_TAPS)
-        taps = res.taps.cpu()           # D2H of the step's result (taps + the metrics already read back)
-        return res, taps
+        with contextlib.redirect_stdout(io.StringIO()):
+            (t, u, y), (tv, uv, yv) = host
+            U, Y = synchronous_coefficients_trapz_pair(t, u, y, omega_h)
+            G = frf_cross_power_average([U], [Y])
+            Uv, Yv = synchronous_coefficients_trapz_pair(tv, uv, yv, omega_v)
+            Gv = frf_cross_power_average([Uv], [Yv])
+            Xs = StandardScaler(); Xn = Xs.fit_transform(np.log10(omega_h).reshape(-1, 1))
+            Xv = Xs.transform(np.log10(omega_v).reshape(-1, 1))
+            gps = []
+            for target, vy in ((G.real, Gv.real), (G.imag, Gv.imag)):
+                sc = StandardScaler(); z = sc.fit_transform(target.reshape(-1, 1)).ravel()
+                gp = GaussianProcessRegressor(kernel=create_kernel(KERNEL), noise_variance=NOISE)
+                gp.fit(Xn, z, optimize=True, use_grid_search=True, max_grid_combinations=5000,
+                       validation_X=Xv, validation_y=vy, y_scaler=sc)
+                gps.append((gp, sc))
+
+            def predict(w_new):
+                Xq = Xs.transform(np.log10(w_new).reshape(-1, 1))
+                parts = [sc.inverse_transform(gp.predict(Xq).reshape(-1, 1)).ravel() for gp, sc in gps]
+                return parts[0] + 1j * parts[1]
+
+            fir_res = gp_to_fir_direct_pipeline(omega_h, G, gp_predict_func=predict, mat_file=None, output_dir=e2e_dir)
+            metrics, _ = bfir.fir_validate(uv, yv, fir_res["fir_coefficients"], want_pred=False)
+        return metrics, fir_res["fir_coefficients"]
 
     def barrier():
         if world > 1:
@@ -290,9 +322,10 @@ def main():
     ms_inst, _, log, _ = timed(step_resident, a.steps, 1, with_events=True)
     stage_ms = {k: sum(s.elapsed_time(e) for s, e in v) / a.steps for k, v in (log or {}).items()}
     # ---- e2e timing: host pinned buffers in, result out
-    ms_e2e, (res_e, taps_e), _, _ = timed(step_e2e, a.steps, a.warmup)
-    h2d = sum(x.numel() * 8 for rec in pinned for x in rec)
-    d2h = N_TAPS * 8 + 2 * 2 * 8 + 4 * 8 + 2 * 16     # taps + scaler stats + FIR sums + argmin pairs
+    ms_e2e, (metrics_e, taps_e), _, _ = timed(step_e2e, a.steps, a.warmup)
+    # per step: train (t,u,y) + validation (t,u,y) for the two FRFs + validation (u,y) again for the FIR pass
+    h2d = 8 * a.n * (3 + 3 + 2) + 8 * (a.nd + VAL_ND) * 2 + 2 * 900 * 3 * 8 + 2 * 8 * (a.nd * 2 + VAL_ND * 2) + 8 * (N_TAPS + 1000 * 2)
+    d2h = 16 * 2 * (a.nd + VAL_ND) * 2 + 2 * (900 * 8 + 16) + 2 * 8 * (a.nd + a.nd * a.nd) + 2 * 1000 * 8 + N_TAPS * 8 + 4 * 8
 
     total_samples = a.n * world
     value = total_samples / (ms_step * 1e-3)
@@ -375,7 +408,8 @@ def main():
         "data": "synthetic", "config": workload_config(a, world),
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": launches, "clocks": clk, "roofline": roofline, "cpu_baseline": cpu, "stages": stages,
-        "result": {"theta_real": res.theta_real.tolist(), "theta_imag": res.theta_imag.tolist(), "fir_rmse": res.fir.get("rmse")},
+        "result": {"theta_real": res.theta_real.tolist(), "theta_imag": res.theta_imag.tolist(), "fir_rmse": res.fir.get("rmse"),
+                   "e2e_fir_rmse": metrics_e.get("rmse")},
         "device": {"sm_count": sm, "cc": f"{major}.{minor}"},
     }
     print(json.dumps(line), flush=True)

@@ -72,7 +72,8 @@ def fir_predict(u, g, n_out: Optional[int] = None) -> np.ndarray:
     return pred.cpu().numpy()
 
 
-def fir_validate(u, y, g, detrend: bool = False, want_pred: bool = True) -> Tuple[Dict[str, float], Optional[np.ndarray]]:
+def fir_validate(u, y, g, detrend: bool = False, want_pred: bool = True,
+                 skip: Optional[int] = None) -> Tuple[Dict[str, float], Optional[np.ndarray]]:
     """(metrics, y_pred) of FIR taps g on record (u, y): convolution and error sums on the device."""
     dev = require_cuda()
     u = np.asarray(u, dtype=np.float64).ravel()
@@ -80,7 +81,7 @@ def fir_validate(u, y, g, detrend: bool = False, want_pred: bool = True) -> Tupl
     g = np.asarray(g, dtype=np.float64).ravel()
     if detrend:
         u, y = u - np.mean(u), y - np.mean(y)
-    skip = min(10, g.size // 10)
+    skip = min(10, g.size // 10) if skip is None else int(skip)
     u_d, y_d, g_d = to_device(u, dev), to_device(y, dev), to_device(g, dev)
     n = min(u.size, y.size)
     sums, pred = fir_eval_device(u_d, y_d, g_d, skip, float(y[skip]), want_pred=want_pred, n=n)

@@ -109,13 +109,14 @@ def select(kernel, thetas, X, y, noise: float, **kw) -> Tuple[int, float, np.nda
     return int(idx.item()), float(best.item()), m.cpu().numpy()
 
 
-def fit(kernel_id: int, theta, X, y, diag_add: float):
-    """(alpha[n], K_inv[n,n], used_pinv) -- Cholesky path, pseudo-inverse path when a pivot is <= 0."""
+def fit(kernel_id: int, theta, X, y, diag_add: float, want_kinv: bool = True):
+    """(alpha[n], K_inv[n,n] or None, used_pinv) -- Cholesky path, pseudo-inverse path when a pivot is <= 0."""
     dev = require_cuda()
     x, yy = to_device(_flat(X), dev), to_device(_flat(y), dev)
     n = x.numel()
     th = to_device(_theta_block(theta)[0], dev)
-    alpha, Kinv = empty(n, dev), empty(n * n, dev)
+    want_kinv = want_kinv or n > 127
+    alpha, Kinv = empty(n, dev), (empty(n * n, dev) if want_kinv else None)
     info = torch.zeros(1, dtype=torch.int32, device=dev)
     nbytes = _lib.load().b200id_gp_fit_workspace_bytes(n)
     ws = Workspace.get("gpfit", nbytes, dev)
@@ -123,9 +124,11 @@ def fit(kernel_id: int, theta, X, y, diag_add: float):
               ptr(alpha), ptr(Kinv), ptr(info), ptr(ws), C.c_size_t(ws.numel()), stream_ptr())
     used_pinv = int(info.item()) != 0
     if used_pinv:
+        if Kinv is None:
+            Kinv = empty(n * n, dev)
         _lib.call("b200id_gp_fit_pinv", C.c_int(kernel_id), ptr(th), ptr(x), ptr(yy), C.c_int(n), C.c_double(diag_add),
                   C.c_double(PINV_RCOND), ptr(alpha), ptr(Kinv), ptr(ws), C.c_size_t(ws.numel()), stream_ptr())
-    return alpha.cpu().numpy(), Kinv.view(n, n).cpu().numpy(), used_pinv
+    return alpha.cpu().numpy(), (Kinv.view(n, n).cpu().numpy() if Kinv is not None else None), used_pinv
 
 
 def predict(kernel_id: int, theta, X_train, alpha, K_inv, Xs, return_std: bool = False):

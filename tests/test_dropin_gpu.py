@@ -1,0 +1,169 @@
+"""GPU parity of the drop-in Python surface (gauss-process_b200/src) against the reference's golden
+vectors: the same calls main.py / run_baseline.py make, with the reference's names and arguments."""
+import io
+import contextlib
+
+import numpy as np
+import pytest
+
+from parity_util import rel_each, rel_max, record
+
+pytestmark = pytest.mark.gpu
+
+
+def quiet(fn, *a, **k):
+    with contextlib.redirect_stdout(io.StringIO()):
+        return fn(*a, **k)
+
+
+@pytest.fixture(scope="module")
+def mats(tmp_path_factory, golden):
+    from b200id import synth
+    g = golden("frf")
+    d = tmp_path_factory.mktemp("mats")
+    a = synth.write_mat(d / "a.mat", g["t"], g["u"], g["y"])
+    b = synth.write_mat(d / "b.mat", g["t"], g["u2"], g["y2"])
+    return a, b
+
+
+def test_estimate_frequency_response(mats, golden):
+    from src.frequency_transform import estimate_frequency_response
+    g = golden("frf")
+    df = estimate_frequency_response([str(mats[0]), str(mats[1])], method="frf", nd=50, n_files=2)
+    assert list(df.columns) == ["omega_rad_s", "freq_Hz", "ReG", "ImG", "absG", "phase_rad"]
+    got, ref = df.to_numpy(), g["df_2files"]
+    assert np.array_equal(got[:, :2], ref[:, :2])                      # omega / Hz bits identical (host grid)
+    assert record("dropin.frf.df_2files.rel_each", rel_each(got[:, 2:], ref[:, 2:])) < 1e-9
+    df = estimate_frequency_response([str(mats[0])], method="frf", nd=30, time_duration=7.0, drop_seconds=1.0, n_files=1)
+    assert record("dropin.frf.df_window.rel_each", rel_each(df.to_numpy()[:, 2:], g["df_window"][:, 2:])) < 1e-9
+    with pytest.raises(FileNotFoundError):
+        estimate_frequency_response(["/nonexistent/*.mat"])
+    with pytest.raises(ValueError, match="Unknown method"):
+        estimate_frequency_response([str(mats[0])], method="wavelet")
+    with pytest.raises(ValueError, match="No data in"):
+        estimate_frequency_response([str(mats[0])], time_duration=1.0, drop_seconds=1e6)
+
+
+def test_reference_function_names(golden):
+    from src.frequency_transform.frf_estimator import synchronous_coefficients_trapz, frf_cross_power_average
+    g = golden("frf")
+    U = synchronous_coefficients_trapz(g["t"], g["u"], g["w"])
+    Y = synchronous_coefficients_trapz(g["t"], g["y"], g["w"], drop_seconds=0.0, subtract_mean=True)
+    assert U.dtype == np.complex128 and U.shape == g["w"].shape
+    assert rel_each(U, g["U"]) < 1e-9 and rel_each(Y, g["Y"]) < 1e-9
+    assert rel_each(frf_cross_power_average([U], [Y]), g["G"]) < 1e-9
+
+
+@pytest.mark.parametrize("name", ["matern52", "rbf", "ss2", "exp", "dc"])
+def test_gpr_grid_search_selection(golden, name):
+    """GaussianProcessRegressor.fit(use_grid_search=True) with an sklearn y_scaler: selected
+    hyperparameters identical to the reference's, posterior mean within 1e-8."""
+    from sklearn.preprocessing import StandardScaler
+    from src.gpr import create_kernel, GaussianProcessRegressor
+    g = golden("gp")
+    scaler = StandardScaler().fit(g["G"].real.reshape(-1, 1))
+    gp = GaussianProcessRegressor(kernel=create_kernel(name), noise_variance=1e-6)
+    quiet(gp.fit, g["X"], g["yr"], optimize=True, use_grid_search=True, max_grid_combinations=1500 if name == "dc" else 5000,
+          validation_X=g["Xv"], validation_y=g["yv_r"], y_scaler=scaler)
+    assert np.array_equal(gp.kernel.get_params(), g[f"sel_{name}_val_n6"])
+    mean, std = gp.predict(g["X"], return_std=True)
+    assert mean.shape == (50,) and std.shape == (50,) and gp.K_inv.shape == (50, 50) and gp.alpha.shape == (50,)
+    e = record(f"dropin.gpr.{name}.mean.rel_max", rel_max(mean, g[f"sel_mean_{name}_val_n6"]))
+    # alpha of the selected model is conditioned like cond(K)*eps (the ss2 winner has cond(K) ~ 1e32: its
+    # posterior mean is only defined to ~1e-5 in the reference's own arithmetic); see test_gp_gpu for the
+    # conditioning-aware 1e-8 checks
+    assert e < (1e-4 if name == "ss2" else 1e-6)
+
+
+def test_gpr_plain_fit_predict_and_errors(golden):
+    from src.gpr import create_kernel, GaussianProcessRegressor, Kernel
+    g = golden("gp")
+    k = create_kernel("matern", nu=2.5)
+    assert isinstance(k, Kernel) and k.n_params == 2 and k.bounds == [(1e-3, 1e3), (1e-3, 1e3)]
+    k.set_params(g["theta_matern52"][0])
+    gp = GaussianProcessRegressor(kernel=k, noise_variance=1e-6)
+    gp.fit(g["X"], g["yr"], optimize=False)
+    m = gp.predict(g["Xs_new"])
+    assert record("dropin.gpr.plain.mean.rel_max", rel_max(m, g["fit_mean_new_matern52"])) < 1e-8
+    K = k(g["X"][:24])
+    np.testing.assert_allclose(K, g["gram_matern52_0"], rtol=2e-15)
+    with pytest.raises(ValueError, match="Unknown kernel type"):
+        create_kernel("laplace")
+    with pytest.raises(NotImplementedError):
+        create_kernel("matern", nu=0.7)(g["X"][:4])
+
+
+def test_gpr_lbfgs_path(golden):
+    """--optimize without --grid-search: SciPy L-BFGS-B on device NLL evaluations, seeded like
+    run_baseline.py:129.  Same optimum within optimiser tolerance (SURVEY.md section 7 hard part 6)."""
+    from src.gpr import create_kernel, GaussianProcessRegressor
+    from b200id import gp as bgp
+    g = golden("gp")
+    np.random.seed(42)
+    gp = GaussianProcessRegressor(kernel=create_kernel("matern52"), noise_variance=1e-6)
+    gp.fit(g["X"], g["yr"], optimize=True, n_restarts=3)
+    nll = float(bgp.batch_eval("matern52", gp.kernel.get_params(), g["X"], g["yr"], gp.noise_variance)[0])
+    ref = float(g["lbfgs_nll_matern52"])
+    record("dropin.gpr.lbfgs.nll", {"ours": nll, "ref": ref, "theta": gp.kernel.get_params().tolist(),
+                                     "theta_ref": g["lbfgs_theta_matern52"].tolist()})
+    assert nll <= ref + 1e-3 * abs(ref) + 1e-3
+
+
+def test_fir_pipeline_and_validation(tmp_path, golden):
+    from b200id import synth
+    from src.fir_model.fir_fitting import gp_to_fir_direct_pipeline
+    from src.fir_model.fir_validation import validate_fir_with_mat, compute_time_domain_metrics, load_mat_time_series
+    from src.fir_model.fir_helpers import build_two_sided_hermitian_from_positive, idft_to_fir_coeffs_two_sided
+    g = golden("fir")
+    p = synth.write_mat(tmp_path / "val.mat", g["t"], g["u"], g["y"])
+    r = quiet(gp_to_fir_direct_pipeline, g["w"], g["G"], gp_predict_func=synth.plant_response, mat_file=p,
+              output_dir=tmp_path / "o1")
+    for key in ("paper_mode", "Nd", "M_idft", "fir_order", "fir_coefficients", "method", "omega_range", "rmse",
+                "fit_percent", "r2", "Ts", "transient_skip", "detrend"):
+        assert key in r, key
+    assert (r["Nd"], r["M_idft"], r["fir_order"], r["method"]) == (1000, 1999, 1024, "gp_paper_mode")
+    assert record("dropin.fir.taps.rel_max", rel_max(r["fir_coefficients"], g["pipe_taps"])) < 1e-12
+    got = np.array([r["rmse"], r["fit_percent"], r["r2"], r["transient_skip"], r["Ts"]])
+    assert record("dropin.fir.metrics.rel_each", rel_each(got, g["pipe_metrics"])) < 1e-11
+    r2 = quiet(gp_to_fir_direct_pipeline, g["w"], g["G"], gp_predict_func=None, mat_file=p, output_dir=tmp_path / "o2",
+               fir_order=300)
+    assert rel_max(r2["fir_coefficients"], g["pipe_interp_taps"]) < 1e-12
+    v = quiet(validate_fir_with_mat, r["fir_coefficients"], p, output_dir=None, detrend=False)
+    assert rel_each(np.array([v["rmse"], v["fit_percent"], v["r2"]]), g["validate_metrics"][:3]) < 1e-11
+    assert v["validation_file"] == str(p) and v["detrend"] is False
+    ts = load_mat_time_series(p)
+    m = compute_time_domain_metrics(ts["y"], g["y_pred"], fir_length=1024)
+    assert rel_each(np.array([m["rmse"], m["fit_percent"], m["r2"]]), g["validate_metrics"][:3]) < 1e-11
+    X = build_two_sided_hermitian_from_positive(g["G"][:9])
+    assert np.array_equal(X, g["herm_small"])
+    h, full = idft_to_fir_coeffs_two_sided(X, 11)
+    assert rel_max(h, g["taps_small"]) < 1e-13 and rel_max(full, g["hfull_small"]) < 1e-13
+    with pytest.raises(ValueError, match="exceeds available length"):
+        idft_to_fir_coeffs_two_sided(X, 18)
+
+
+@pytest.mark.parametrize("tag,kernel,opt,grid,noise", [("m52_plain", "matern52", False, False, 1e-6),
+                                                       ("m52_grid", "matern52", True, True, 1e-6)])
+def test_whole_pipeline_against_reference_run(tmp_path, golden, tag, kernel, opt, grid, noise):
+    """The reference's run_gp_pipeline output on synthetic .mat files (README command line shape) vs the
+    same sequence of public calls on the drop-in surface."""
+    from b200id import synth
+    import pipeline_flow
+    g = golden("pipeline")
+    n, nd = int(g["n"]), int(g["nd"])
+    tt, ut, yt = synth.make_record(n, nd, "multisine", seed=0)
+    tv, uv, yv = synth.make_record(n, nd, "square", seed=1)
+    ptrain = synth.write_mat(tmp_path / "train.mat", tt, ut, yt)
+    pval = synth.write_mat(tmp_path / "val.mat", tv, uv, yv)
+    np.random.seed(42)
+    res = quiet(pipeline_flow.run, ptrain, pval, tmp_path / tag, kernel=kernel, nd=nd, noise=noise, optimize=opt, grid=grid)
+    assert record(f"dropin.pipeline.{tag}.frf.rel_each", rel_each(res["frf"][:, 2:4], g[f"{tag}_frf"][:, 2:4])) < 1e-9
+    assert np.array_equal(np.array(res["kernel_params"]["real"]), g[f"{tag}_theta_real"])
+    assert np.array_equal(np.array(res["kernel_params"]["imag"]), g[f"{tag}_theta_imag"])
+    gp_m = np.array([res["real"]["rmse"], res["imag"]["rmse"], res["real"]["r2"], res["imag"]["r2"]])
+    record(f"dropin.pipeline.{tag}.gp_metrics.rel_each", rel_each(gp_m, g[f"{tag}_gp_rmse"]))
+    f = res["fir_extraction"]
+    e_taps = record(f"dropin.pipeline.{tag}.taps.rel_max", rel_max(f["fir_coefficients"], g[f"{tag}_taps"]))
+    e_fir = record(f"dropin.pipeline.{tag}.fir_metrics.rel_each",
+                   rel_each(np.array([f["rmse"], f["fit_percent"], f["r2"]]), g[f"{tag}_fir"]))
+    assert e_taps < 1e-7 and e_fir < 1e-7

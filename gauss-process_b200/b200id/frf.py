@@ -8,6 +8,7 @@ device-resident timing and by the multi-GPU shards).
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -48,6 +49,52 @@ def project_device(t_d: torch.Tensor, u_d: torch.Tensor, y_d: Optional[torch.Ten
     return out
 
 
+# max w * |t_i - (t0 + i dt)| for which the first-order fast path is used: the dropped second-order term is
+# eps^2 / 2 <= ~3e-12 in the basis values, three orders below the 1e-9 parity budget
+UNIFORM_PHASE_TOL = 2e-6
+_FORCE_PATH = os.environ.get("B200ID_FRF_PATH", "auto")     # auto | general | uniform
+
+
+def uniformity_device(t_d: torch.Tensor, t0: float, dt: float) -> float:
+    """max_i |t_i - (t0 + i dt)| (one small D2H read)."""
+    dev = t_d.device
+    out = empty(1, dev)
+    ws, _ = _ws(1, dev)
+    _lib.call("b200id_frf_uniformity", ptr(t_d), C.c_int64(t_d.numel()), C.c_double(t0), C.c_double(dt), ptr(out),
+              ptr(ws), C.c_size_t(ws.numel()), stream_ptr())
+    return float(out.item())
+
+
+def project_uniform_device(t_d, u_d, y_d, w_d, t0: float, dt: float, own=None, sums=None, inv_count: float = 0.0):
+    """Same partial sums as project_device through the uniform-timebase fast path."""
+    dev = t_d.device
+    n, nd = t_d.numel(), w_d.numel()
+    own = (0, n) if own is None else own
+    out = empty(4 * nd, dev)
+    ws, _ = _ws(nd, dev)
+    _lib.call("b200id_frf_project_uniform", ptr(t_d), ptr(u_d), ptr(y_d), C.c_int64(n), C.c_int64(own[0]),
+              C.c_int64(own[1]), ptr(w_d), C.c_int(nd), ptr(sums), C.c_double(inv_count), C.c_double(t0),
+              C.c_double(dt), ptr(out), ptr(ws), C.c_size_t(ws.numel()), stream_ptr())
+    return out
+
+
+def choose_path(t_d: torch.Tensor, span: float, w_max: float, t0: Optional[float] = None):
+    """('uniform', t0, dt) when the record's time stamps sit on an arithmetic progression up to FP64
+    rounding (then the fast kernel reproduces the reference's per-sample phase rounding to first order),
+    else ('general', None, None)."""
+    n = t_d.numel()
+    if _FORCE_PATH == "general" or n < 3:
+        return "general", None, None
+    t0 = float(t_d[0].item()) if t0 is None else float(t0)
+    dt = span / (n - 1)
+    if not (dt > 0.0):
+        return "general", None, None
+    dmax = uniformity_device(t_d, t0, dt)
+    if _FORCE_PATH == "uniform" or dmax * w_max < UNIFORM_PHASE_TOL:
+        return "uniform", t0, dt
+    return "general", None, None
+
+
 def finalize_device(partial: torch.Tensor, nd: int, scale: float, want_y: bool = True):
     """(U, Y) device complex128 tensors from the partial sums; scale = 2 / T."""
     dev = partial.device
@@ -68,11 +115,21 @@ def cross_power_device(U: torch.Tensor, Y: torch.Tensor, eps: float = 1e-15) -> 
     return torch.view_as_complex(G.view(nd, 2))
 
 
-def record_coefficients_device(t_d, u_d, y_d, w_d, span: float, subtract_mean: bool = True):
-    """(U, Y) of one resident record.  ``span`` = t[-1] - t[0] (the caller knows it on the host)."""
+def record_coefficients_device(t_d, u_d, y_d, w_d, span: float, subtract_mean: bool = True,
+                               t0: Optional[float] = None, w_max: Optional[float] = None, path=None):
+    """(U, Y) of one resident record.  ``span`` = t[-1] - t[0] (the caller knows it on the host).
+
+    ``path`` = a (kind, t0, dt) tuple from :func:`choose_path` to skip the uniformity probe (callers that
+    process the same record repeatedly cache it); None probes."""
     n, nd = t_d.numel(), w_d.numel()
     sums = moments_device(u_d, y_d, (0, n)) if subtract_mean else None
-    part = project_device(t_d, u_d, y_d, w_d, (0, n), sums, 1.0 / n)
+    if path is None:
+        w_max = float(w_d.max().item()) if w_max is None else w_max
+        path = choose_path(t_d, span, w_max, t0)
+    if path[0] == "uniform":
+        part = project_uniform_device(t_d, u_d, y_d, w_d, path[1], path[2], (0, n), sums, 1.0 / n)
+    else:
+        part = project_device(t_d, u_d, y_d, w_d, (0, n), sums, 1.0 / n)
     return finalize_device(part, nd, 2.0 / span, want_y=y_d is not None)
 
 
@@ -106,7 +163,7 @@ def demod(t, x, w, drop_seconds: float = 0.0, subtract_mean: bool = True) -> np.
     t, (x,), span = _prepare(t, [x], drop_seconds)
     w = np.asarray(w, dtype=np.float64)
     U, _ = record_coefficients_device(to_device(t, dev), to_device(x, dev), None, to_device(w.ravel(), dev), span,
-                                      subtract_mean)
+                                      subtract_mean, t0=float(t[0]), w_max=float(np.max(np.abs(w))))
     return U.cpu().numpy().reshape(w.shape)
 
 
@@ -116,7 +173,8 @@ def demod_pair(t, u, y, w, drop_seconds: float = 0.0, subtract_mean: bool = True
     t, (u, y), span = _prepare(t, [u, y], drop_seconds)
     w = np.asarray(w, dtype=np.float64)
     U, Y = record_coefficients_device(to_device(t, dev), to_device(u, dev), to_device(y, dev),
-                                      to_device(w.ravel(), dev), span, subtract_mean)
+                                      to_device(w.ravel(), dev), span, subtract_mean, t0=float(t[0]),
+                                      w_max=float(np.max(np.abs(w))))
     UY = torch.stack([U, Y]).cpu().numpy()
     return UY[0].reshape(w.shape), UY[1].reshape(w.shape)
 
@@ -139,7 +197,7 @@ def estimate_records(records, w, drop_seconds: float = 0.0, subtract_mean: bool 
     for (t, u, y) in records:
         t, (u, y), span = _prepare(t, [u, y], drop_seconds)
         U, Y = record_coefficients_device(to_device(t, dev), to_device(u, dev), to_device(y, dev), w_d, span,
-                                          subtract_mean)
+                                          subtract_mean, t0=float(t[0]), w_max=float(np.max(np.abs(w))))
         Us.append(U)
         Ys.append(Y)
     G = cross_power_device(torch.stack(Us), torch.stack(Ys), eps)

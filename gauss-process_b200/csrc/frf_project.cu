@@ -25,6 +25,7 @@ namespace b200id {
 constexpr int FRF_THREADS = 512;
 constexpr int FRF_TILE_MAX = 2048;          // samples per shared-memory tile (3 x 16 KB)
 constexpr int FRF_CTAS_PER_SM = 2;
+constexpr int MOM_THREADS = 256;
 
 struct FrfPlan {
     int tile;        // samples per tile
@@ -139,6 +140,178 @@ frf_project_kernel(const double* __restrict__ t, const double* __restrict__ u,
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Uniform-timebase fast path.  When t_i = t0 + i*dt + delta_i with |w_max * delta_i| << 1 (sampled data:
+// delta_i is the FP64 rounding of the stored time stamps), the reference's rounded phase is
+//     fl(w t_i) = w (t0 + i dt) + eps_i,   eps_i = w delta_i - e_i,   e_i = w t_i - fl(w t_i)  (exact, one FMA)
+// so  cos/sin(fl(w t_i)) = cos/sin(theta_i + eps_i)  with theta_i on an exact arithmetic progression.
+// theta_i advances by a rotation (4 FP64 ops) and eps_i (|eps| < ~2.5e-6) enters to first order
+// (2 FP64 ops; the dropped eps^2/2 is < 3e-12).  13 FP64 ops per sample-bin instead of 24, and the
+// result still follows the reference's per-sample phase rounding, which is what the 1e-9 parity
+// at weakly excited bins needs ("K1").  Every chain is re-seeded from an exact
+// double-double phase at each tile, so rotation drift is bounded by ~100 steps.
+constexpr int FRFU_CHAINS = 4;              // independent rotation chains per thread (ILP)
+
+struct DD { double hi, lo; };
+__device__ __forceinline__ DD dd_time(double t0, double k, double dt) {
+    // t0 + k*dt as an unevaluated sum (k integer-valued): exact product, then TwoSum with t0
+    const double ph = k * dt, pl = fma(k, dt, -ph);
+    const double sh = t0 + ph, bb = sh - t0;
+    const double sl = (t0 - (sh - bb)) + (ph - bb);
+    DD r; r.hi = sh; r.lo = sl + pl; return r;
+}
+// sin / cos of w * (x.hi + x.lo): FP64 sincos of the rounded product, first-order fix for what it dropped
+__device__ __forceinline__ void sincos_dd(double w, DD x, double& s, double& c) {
+    const double ph = w * x.hi;
+    const double pl = fma(w, x.hi, -ph) + w * x.lo;
+    double s0, c0;
+    sincos_cw(ph, s0, c0);
+    s = fma(c0, pl, s0);
+    c = fma(-s0, pl, c0);
+}
+
+template <bool HAS_Y>
+__global__ void __launch_bounds__(FRF_THREADS, FRF_CTAS_PER_SM)
+frf_project_uniform_kernel(const double* __restrict__ t, const double* __restrict__ u,
+                           const double* __restrict__ y, int64_t n, int64_t own_begin, int64_t own_end,
+                           const double* __restrict__ w, int nd, const double* __restrict__ sums,
+                           double inv_count, double t0, double dt, int tile, int n_tiles,
+                           double* __restrict__ cta_partial) {
+    extern __shared__ __align__(16) double smem[];
+    double2* td = reinterpret_cast<double2*>(smem);                 // [tile] (t_i, delta_i)
+    double2* ab = td + FRF_TILE_MAX;                                // [tile] (w_i (u_i - mean), w_i (y_i - mean))
+
+    const int tid = threadIdx.x;
+    const int bin0 = blockIdx.y * FRF_THREADS;
+    const int nb = min(nd - bin0, FRF_THREADS);
+    const int R = FRF_THREADS / nb;
+    const int b = tid % nb, r = tid / nb;
+    const bool active = r < R;
+    const double wk = w[bin0 + b];
+    const double mean_u = sums ? sums[0] * inv_count : 0.0;
+    const double mean_y = (HAS_Y && sums) ? sums[1] * inv_count : 0.0;
+
+    // rotation by FRFU_CHAINS * R samples
+    double sd, cd;
+    {
+        DD step; const double kk = (double)(FRFU_CHAINS * R);
+        step.hi = kk * dt; step.lo = fma(kk, dt, -step.hi);
+        sincos_dd(wk, step, sd, cd);
+    }
+    double uc[2] = {0.0, 0.0}, us[2] = {0.0, 0.0}, yc[2] = {0.0, 0.0}, ys[2] = {0.0, 0.0};
+
+    for (int tl = blockIdx.x; tl < n_tiles; tl += gridDim.x) {
+        const int64_t i0 = own_begin + (int64_t)tl * tile;
+        const int cnt = (int)min((int64_t)tile, own_end - i0);
+        __syncthreads();
+        for (int j = tid; j < cnt; j += FRF_THREADS) {
+            const int64_t i = i0 + j;
+            const double ti = __ldg(t + i);
+            const double tm = __ldg(t + (i > 0 ? i - 1 : 0)), tp = __ldg(t + (i < n - 1 ? i + 1 : n - 1));
+            const double wt = 0.5 * (tp - tm);
+            // delta_i = t_i - (t0 + i dt), exact: TwoDiff(t_i, t0) then subtract the exact product i*dt
+            const double k = (double)i;
+            const double ph = k * dt, pl = fma(k, dt, -ph);
+            const double d = ti - t0, bb = d - ti;
+            const double derr = (ti - (d - bb)) + (-t0 - bb);
+            td[j] = make_double2(ti, ((d - ph) - pl) + derr);
+            ab[j] = make_double2(wt * (__ldg(u + i) - mean_u), HAS_Y ? wt * (__ldg(y + i) - mean_y) : 0.0);
+        }
+        __syncthreads();
+        if (active) {
+            // chain q handles samples j = r + R (q + FRFU_CHAINS m); seed each from the exact phase
+            double cs[FRFU_CHAINS], sn[FRFU_CHAINS];
+#pragma unroll
+            for (int q = 0; q < FRFU_CHAINS; ++q) {
+                const DD x = dd_time(t0, (double)(i0 + r + R * q), dt);
+                sincos_dd(wk, x, sn[q], cs[q]);
+            }
+            const int stride = R * FRFU_CHAINS;
+            int j = r;
+            for (; j + R * (FRFU_CHAINS - 1) < cnt; j += stride) {
+#pragma unroll
+                for (int q = 0; q < FRFU_CHAINS; ++q) {
+                    const double2 tdv = td[j + R * q];
+                    const double2 abv = ab[j + R * q];
+                    const double p = wk * tdv.x;
+                    const double e = fma(wk, tdv.x, -p);
+                    const double eps = fma(wk, tdv.y, -e);
+                    const double c1 = fma(-sn[q], eps, cs[q]);
+                    const double s1 = fma(cs[q], eps, sn[q]);
+                    uc[q & 1] = fma(abv.x, c1, uc[q & 1]); us[q & 1] = fma(abv.x, s1, us[q & 1]);
+                    if (HAS_Y) { yc[q & 1] = fma(abv.y, c1, yc[q & 1]); ys[q & 1] = fma(abv.y, s1, ys[q & 1]); }
+                    const double cn = fma(cs[q], cd, -(sn[q] * sd));
+                    sn[q] = fma(sn[q], cd, cs[q] * sd);
+                    cs[q] = cn;
+                }
+            }
+            // tail: fewer than FRFU_CHAINS samples left in this stripe
+#pragma unroll
+            for (int q = 0; q < FRFU_CHAINS; ++q) {
+                if (j + R * q < cnt) {
+                    const double2 tdv = td[j + R * q];
+                    const double2 abv = ab[j + R * q];
+                    const double p = wk * tdv.x;
+                    const double e = fma(wk, tdv.x, -p);
+                    const double eps = fma(wk, tdv.y, -e);
+                    const double c1 = fma(-sn[q], eps, cs[q]);
+                    const double s1 = fma(cs[q], eps, sn[q]);
+                    uc[q & 1] = fma(abv.x, c1, uc[q & 1]); us[q & 1] = fma(abv.x, s1, us[q & 1]);
+                    if (HAS_Y) { yc[q & 1] = fma(abv.y, c1, yc[q & 1]); ys[q & 1] = fma(abv.y, s1, ys[q & 1]); }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    double* red = smem;
+    red[0 * FRF_THREADS + tid] = uc[0] + uc[1];
+    red[1 * FRF_THREADS + tid] = us[0] + us[1];
+    red[2 * FRF_THREADS + tid] = HAS_Y ? yc[0] + yc[1] : 0.0;
+    red[3 * FRF_THREADS + tid] = HAS_Y ? ys[0] + ys[1] : 0.0;
+    __syncthreads();
+    if (tid < nb) {
+        double* out = cta_partial + (size_t)blockIdx.x * 4 * nd + bin0 + tid;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            double v = 0.0;
+            for (int rr = 0; rr < R; ++rr) v += red[c * FRF_THREADS + rr * nb + tid];
+            out[(size_t)c * nd] = v;
+        }
+    }
+}
+
+// max_i |t_i - (t0 + i dt)| over [0, n): decides whether the uniform path applies
+__global__ void __launch_bounds__(MOM_THREADS)
+frf_uniformity_kernel(const double* __restrict__ t, int64_t n, double t0, double dt, int64_t chunk,
+                      double* __restrict__ cta_max) {
+    __shared__ double sh[MOM_THREADS / 32];
+    const int64_t lo = (int64_t)blockIdx.x * chunk, hi = min(lo + chunk, n);
+    double m = 0.0;
+    for (int64_t i = lo + threadIdx.x; i < hi; i += MOM_THREADS) {
+        const double ti = __ldg(t + i), k = (double)i;
+        const double ph = k * dt, pl = fma(k, dt, -ph);
+        const double d = ti - t0, bb = d - ti;
+        const double derr = (ti - (d - bb)) + (-t0 - bb);
+        const double delta = ((d - ph) - pl) + derr;
+        m = fmax(m, fabs(delta));
+        if (!(delta == delta)) m = INFINITY;
+    }
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double v = 0.0;
+        for (int k = 0; k < MOM_THREADS / 32; ++k) v = fmax(v, sh[k]);
+        cta_max[blockIdx.x] = v;
+    }
+}
+__global__ void frf_max_fold_kernel(const double* __restrict__ part, int n_cta, double* __restrict__ out) {
+    double v = 0.0;
+    for (int c = threadIdx.x; c < n_cta; c += 32) v = fmax(v, part[c]);
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if (threadIdx.x == 0) out[0] = v;
+}
+
 // Fixed-order pairwise fold of the per-CTA partials: out[e] = sum_cta part[cta][e], e < 4*nd.
 __global__ void frf_fold_kernel(const double* __restrict__ part, int n_cta, int len,
                                 double* __restrict__ out) {
@@ -158,8 +331,6 @@ __global__ void frf_fold_kernel(const double* __restrict__ part, int n_cta, int 
 
 // ------------------------------------------------------------------------------------------
 // moments: sum u, sum y over the owned range (for the mean removal of frf_estimator.py:219-220)
-constexpr int MOM_THREADS = 256;
-
 __global__ void __launch_bounds__(MOM_THREADS)
 frf_moments_kernel(const double* __restrict__ u, const double* __restrict__ y, int64_t own_begin,
                    int64_t own_end, int64_t chunk, double* __restrict__ cta_partial) {
@@ -217,6 +388,7 @@ __global__ void cross_power_kernel(const double* __restrict__ U, const double* _
 }
 
 constexpr size_t FRF_SMEM_BYTES = (size_t)(3 * FRF_TILE_MAX + 2) * sizeof(double);
+constexpr size_t FRFU_SMEM_BYTES = (size_t)(4 * FRF_TILE_MAX) * sizeof(double);
 
 }  // namespace b200id
 
@@ -276,6 +448,51 @@ extern "C" int b200id_frf_project(const double* t, const double* u, const double
     else
         frf_project_kernel<false><<<grid, FRF_THREADS, FRF_SMEM_BYTES, st>>>(t, u, nullptr, n, own_begin, own_end, w, nd, sums, inv_count, p.tile, p.n_tiles, part);
     B200ID_LAUNCH_CHECK("frf_project_kernel");
+    const int len = 4 * nd;
+    frf_fold_kernel<<<(len + 127) / 128, 128, 0, st>>>(part, p.grid_x, len, partial_out);
+    B200ID_LAUNCH_CHECK("frf_fold_kernel");
+    return B200ID_OK;
+}
+
+extern "C" int b200id_frf_uniformity(const double* t, int64_t n, double t0, double dt, double* max_abs_delta_out,
+                                     void* ws, size_t ws_bytes, void* stream) {
+    B200ID_REQUIRE(t && max_abs_delta_out && ws && n >= 2, B200ID_E_ARG, "frf_uniformity: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    int grid = sm_count() * 4;
+    int64_t chunk = (n + grid - 1) / grid;
+    chunk = (chunk + 255) / 256 * 256;
+    grid = (int)((n + chunk - 1) / chunk);
+    B200ID_REQUIRE(ws_bytes >= (size_t)grid * sizeof(double), B200ID_E_WORKSPACE, "frf_uniformity: workspace too small");
+    frf_uniformity_kernel<<<grid, MOM_THREADS, 0, st>>>(t, n, t0, dt, chunk, (double*)ws);
+    B200ID_LAUNCH_CHECK("frf_uniformity_kernel");
+    frf_max_fold_kernel<<<1, 32, 0, st>>>((const double*)ws, grid, max_abs_delta_out);
+    B200ID_LAUNCH_CHECK("frf_max_fold_kernel");
+    return B200ID_OK;
+}
+
+extern "C" int b200id_frf_project_uniform(const double* t, const double* u, const double* y, int64_t n,
+                                          int64_t own_begin, int64_t own_end, const double* w, int nd,
+                                          const double* sums, double inv_count, double t0, double dt,
+                                          double* partial_out, void* ws, size_t ws_bytes, void* stream) {
+    B200ID_REQUIRE(t && u && w && partial_out && ws, B200ID_E_ARG, "frf_project_uniform: null pointer");
+    B200ID_REQUIRE(n >= 2 && nd > 0 && dt > 0.0, B200ID_E_ARG, "frf_project_uniform: need n >= 2, nd > 0, dt > 0");
+    B200ID_REQUIRE(own_begin >= 0 && own_end <= n && own_begin < own_end, B200ID_E_ARG,
+                   "frf_project_uniform: bad owned range [%lld,%lld) of %lld", (long long)own_begin, (long long)own_end, (long long)n);
+    cudaStream_t st = (cudaStream_t)stream;
+    const FrfPlan p = frf_plan(own_end - own_begin, nd);
+    const size_t need = (size_t)p.grid_x * 4 * nd * sizeof(double);
+    B200ID_REQUIRE(ws_bytes >= need, B200ID_E_WORKSPACE, "frf_project_uniform: workspace %zu < %zu", ws_bytes, need);
+    double* part = (double*)ws;
+    int rc = check_cuda(cudaFuncSetAttribute(frf_project_uniform_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FRFU_SMEM_BYTES), "smem attr");
+    if (rc) return rc;
+    rc = check_cuda(cudaFuncSetAttribute(frf_project_uniform_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FRFU_SMEM_BYTES), "smem attr");
+    if (rc) return rc;
+    dim3 grid(p.grid_x, p.grid_y);
+    if (y)
+        frf_project_uniform_kernel<true><<<grid, FRF_THREADS, FRFU_SMEM_BYTES, st>>>(t, u, y, n, own_begin, own_end, w, nd, sums, inv_count, t0, dt, p.tile, p.n_tiles, part);
+    else
+        frf_project_uniform_kernel<false><<<grid, FRF_THREADS, FRFU_SMEM_BYTES, st>>>(t, u, nullptr, n, own_begin, own_end, w, nd, sums, inv_count, t0, dt, p.tile, p.n_tiles, part);
+    B200ID_LAUNCH_CHECK("frf_project_uniform_kernel");
     const int len = 4 * nd;
     frf_fold_kernel<<<(len + 127) / 128, 128, 0, st>>>(part, p.grid_x, len, partial_out);
     B200ID_LAUNCH_CHECK("frf_fold_kernel");

@@ -90,6 +90,18 @@ int b200id_frf_project(const double* t, const double* u, const double* y, int64_
                        const double* sums /*[2] or NULL*/, double inv_count,
                        double* partial_out /*[4*nd]*/, void* ws, size_t ws_bytes, void* stream);
 
+/* Uniform-timebase fast path of b200id_frf_project (same outputs, same reference lines).  Valid when every
+ * resident sample obeys t_i = t0 + i*dt + delta_i with w_max * |delta_i| < ~2e-6 (sampled data whose time
+ * stamps differ from the grid only by FP64 rounding): the phase fl(w_k t_i) the reference forms is then
+ * reproduced to first order from a rotation recurrence plus the exactly computed rounding terms, at about
+ * half the FP64 work.  b200id_frf_uniformity returns max_i |delta_i| so the caller can decide. */
+int b200id_frf_uniformity(const double* t, int64_t n, double t0, double dt, double* max_abs_delta_out /*[1]*/,
+                          void* ws, size_t ws_bytes, void* stream);
+int b200id_frf_project_uniform(const double* t, const double* u, const double* y, int64_t n,
+                               int64_t own_begin, int64_t own_end, const double* w, int nd,
+                               const double* sums /*[2] or NULL*/, double inv_count, double t0, double dt,
+                               double* partial_out /*[4*nd]*/, void* ws, size_t ws_bytes, void* stream);
+
 /* U[k] = scale * (S_uc[k] - j S_us[k]), Y likewise; scale = 2/T. frf_estimator.py:225-231 */
 int b200id_frf_finalize(const double* partial /*[4*nd]*/, int nd, double scale,
                         double* U_out /*[2*nd]*/, double* Y_out /*[2*nd] or NULL*/, void* stream);

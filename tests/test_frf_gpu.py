@@ -120,3 +120,41 @@ def test_linearity_and_segment_additivity_full_size(frf):
     assert e < 1e-12
     again = frf.project_device(t, u, y, w_d)
     assert torch.equal(again, full), "projection must be deterministic run to run"
+
+
+@pytest.mark.parametrize("n,nd,kind,t_shift", [(200_000, 100, "multisine", 0.0), (300_001, 150, "square", 0.0),
+                                               (100_000, 50, "multisine", 1.9e6), (65_537, 150, "square", 123.4567),
+                                               (5_000, 600, "multisine", 0.0)])
+def test_uniform_fast_path_matches_oracle_and_general(frf, n, nd, kind, t_shift):
+    """The uniform-timebase kernel (rotation recurrence + first-order rounding correction) against the
+    oracle (per-bin 1e-9, including weakly excited bins of the broadband square-wave record) and against
+    the general kernel; with time origins far from zero (phases ~ 1e9 rad) and off the sampling grid."""
+    import torch
+    from b200id import synth
+    from b200id.runtime import require_cuda, to_device
+    dev = require_cuda()
+    t, u, y = synth.make_record(n, min(nd, 100), kind, seed=21)
+    t = t + t_shift
+    _, w = ofrf.freq_grid(nd)
+    span = float(t[-1] - t[0])
+    t_d, u_d, y_d, w_d = (to_device(a, dev) for a in (t, u, y, w))
+    kind_sel, t0, dt = frf.choose_path(t_d, span, float(w.max()), float(t[0]))
+    assert kind_sel == "uniform"
+    Uu, Yu = frf.record_coefficients_device(t_d, u_d, y_d, w_d, span, path=("uniform", t0, dt))
+    Ug, Yg = frf.record_coefficients_device(t_d, u_d, y_d, w_d, span, path=("general", None, None))
+    Ur, Yr = ofrf.demod_trapz(t, u, w, threads=8), ofrf.demod_trapz(t, y, w, threads=8)
+    e_o = max(rel_each(Uu.cpu().numpy(), Ur), rel_each(Yu.cpu().numpy(), Yr))
+    e_g = max(rel_each(Uu.cpu().numpy(), Ug.cpu().numpy()), rel_each(Yu.cpu().numpy(), Yg.cpu().numpy()))
+    record(f"frf.uniform.{kind}.n{n}.nd{nd}.shift{t_shift:g}.vs_oracle", e_o)
+    record(f"frf.uniform.{kind}.n{n}.nd{nd}.shift{t_shift:g}.vs_general", e_g)
+    assert e_o < TOL and e_g < TOL
+
+
+def test_jittered_timebase_takes_general_path(frf, golden):
+    import torch
+    from b200id.runtime import require_cuda, to_device
+    g = golden("frf")
+    dev = require_cuda()
+    tj = g["t_jit"]
+    kind_sel, _, _ = frf.choose_path(to_device(tj, dev), float(tj[-1] - tj[0]), float(g["w"].max()), float(tj[0]))
+    assert kind_sel == "general"

@@ -234,14 +234,15 @@ def main():
     train_h, val_h = make_records(a.n, a.nd, seed=100 * rank, dev=dev)
     pinned = [[torch.from_numpy(x).pin_memory() for x in rec] for rec in (train_h, val_h)]
     spans = [float(rec[0][-1] - rec[0][0]) for rec in (train_h, val_h)]
+    t0s = [float(rec[0][0]) for rec in (train_h, val_h)]
     skip = min(10, N_TAPS // 10)
     y0 = float(val_h[2][skip])
     dev_recs = [[x.to(dev) for x in rec] for rec in pinned]
     cands = P.CandidateSet.build(KERNEL, P.grid_candidates(KERNEL), dev, rank=rank, world_size=world)
 
     def step_resident():
-        tr = [(dev_recs[0][0], dev_recs[0][1], dev_recs[0][2], spans[0])]
-        va = (dev_recs[1][0], dev_recs[1][1], dev_recs[1][2], spans[1], y0)
+        tr = [(dev_recs[0][0], dev_recs[0][1], dev_recs[0][2], spans[0], t0s[0])]
+        va = (dev_recs[1][0], dev_recs[1][1], dev_recs[1][2], spans[1], y0, t0s[1])
         return P.identify_device(tr, va, a.nd, KERNEL, NOISE, cands, n_taps=N_TAPS)
 
     # e2e: the calls a user of the reference makes (public drop-in surface, HOST NumPy buffers in pinned

@@ -209,6 +209,50 @@ class IdentifyResult:
     gp_imag: Optional[FittedGP] = None
 
 
+_GRID_CACHE: Dict[Tuple[int, int], "GridInputs"] = {}
+
+
+@dataclass
+class GridInputs:
+    """Per-N_d constants of the GP stage, computed once on the host (NumPy, like gp_pipeline.py:130,281-282)
+    and kept on the device: omega, standardised log10(omega) for the training grid, the 150-bin validation
+    grid and the 1000-point uniform grid of the paper-mode FIR."""
+    omega: np.ndarray
+    w_d: torch.Tensor
+    w_max: float
+    X_d: torch.Tensor
+    wv_d: torch.Tensor
+    wv_max: float
+    Xv_d: torch.Tensor
+    Xu_d: torch.Tensor
+
+    @staticmethod
+    def get(nd: int, dev) -> "GridInputs":
+        key = (nd, dev.index)
+        gi = _GRID_CACHE.get(key)
+        if gi is None:
+            omega = log_grid_omega(nd)
+            lx = np.log10(omega)
+            mean, scale = float(np.mean(lx)), float(np.sqrt(np.mean((lx - np.mean(lx)) ** 2)))
+            scale = scale if scale != 0.0 else 1.0
+            wv = log_grid_omega(VALIDATION_ND)
+            wu = np.linspace(float(omega.min()), float(omega.max()), PAPER_ND)
+            gi = GridInputs(omega, to_device(omega, dev), float(omega.max()), to_device((lx - mean) / scale, dev),
+                            to_device(wv, dev), float(wv.max()), to_device((np.log10(wv) - mean) / scale, dev),
+                            to_device((np.log10(wu) - mean) / scale, dev))
+            _GRID_CACHE[key] = gi
+        return gi
+
+
+def _two_standardizers(G: torch.Tensor) -> Tuple[Standardizer, Standardizer]:
+    """StandardScaler statistics of Re G and Im G with a single device->host read."""
+    ri = torch.view_as_real(G)                                   # [nd, 2]
+    m = ri.mean(dim=0)
+    sd = torch.sqrt(((ri - m) ** 2).mean(dim=0))
+    st = torch.cat([m, sd]).cpu().tolist()
+    return (Standardizer(st[0], st[2] if st[2] != 0.0 else 1.0), Standardizer(st[1], st[3] if st[3] != 0.0 else 1.0))
+
+
 def identify_device(train: Sequence[Tuple[torch.Tensor, torch.Tensor, torch.Tensor, float]],
                     val: Optional[Tuple[torch.Tensor, torch.Tensor, torch.Tensor, float]],
                     nd: int, kernel: str = "matern52", noise: float = 1e-6,
@@ -217,20 +261,22 @@ def identify_device(train: Sequence[Tuple[torch.Tensor, torch.Tensor, torch.Tens
                     val_frf: Optional[Tuple[torch.Tensor, torch.Tensor]] = None) -> IdentifyResult:
     """One pass of the hot path with every array resident on the device.
 
-    train: list of records (t, u, y, span) -- span = t[-1] - t[0]; several records are cross-power
-    averaged (transform.py:124-150), and under torch.distributed each rank passes ITS records and
-    the per-bin numerator/denominator are all-reduced.  val: the validation record (FIR validation,
-    and the 150-bin validation FRF when use_validation_metric).  candidates: grid (None -> no
-    search, theta0 is used as is).
+    train: list of records (t, u, y, span[, t0]) -- span = t[-1] - t[0], t0 = t[0]; several records are
+    cross-power averaged (transform.py:124-150), and under torch.distributed each rank passes ITS records
+    and the per-bin numerator/denominator are all-reduced.  val: the validation record
+    (t, u, y, span[, y0[, t0]]) -- FIR validation, and the 150-bin validation FRF when
+    use_validation_metric.  candidates: grid (None -> no search, theta0 is used as is).
     """
     dev = train[0][0].device
-    omega = log_grid_omega(nd)
-    w_d = to_device(omega, dev)
+    gi = GridInputs.get(nd, dev)
+    omega, w_d, X_d = gi.omega, gi.w_d, gi.X_d
     # ---- FRF: per-record coefficients, cross-power numerator / denominator, one all-reduce
     num = torch.zeros(nd, dtype=torch.complex128, device=dev)
     den = torch.zeros(nd, dtype=F64, device=dev)
-    for (t_d, u_d, y_d, span) in train:
-        U, Y = bfrf.record_coefficients_device(t_d, u_d, y_d, w_d, span)
+    for rec in train:
+        t_d, u_d, y_d, span = rec[:4]
+        U, Y = bfrf.record_coefficients_device(t_d, u_d, y_d, w_d, span, t0=rec[4] if len(rec) > 4 else None,
+                                               w_max=gi.w_max)
         num += Y * U.conj()
         den += U.abs() ** 2
     if bdist.world()[1] > 1:
@@ -239,38 +285,39 @@ def identify_device(train: Sequence[Tuple[torch.Tensor, torch.Tensor, torch.Tens
         num = torch.view_as_complex(packed[:2 * nd].view(nd, 2).contiguous())
         den = packed[2 * nd:]
     G = torch.where(den > 1e-15, num / den, torch.full_like(num, complex(float("nan"), float("nan"))))
-    # ---- GP inputs: standardised log10 omega, Re G, Im G (gp_pipeline.py:130-132, 281-282)
-    Xraw = torch.log10(w_d)
-    xs = Standardizer.fit(Xraw)
-    X_d = xs.transform(Xraw).contiguous()
-    sr, si = Standardizer.fit(G.real), Standardizer.fit(G.imag)
+    # ---- GP targets: standardised Re G, Im G (gp_pipeline.py:131-132)
+    sr, si = _two_standardizers(G)
     yr, yi = sr.transform(G.real).contiguous(), si.transform(G.imag).contiguous()
     Xv_d = yv_r = yv_i = None
     if candidates is not None and use_validation_metric and val is not None:
-        wv = log_grid_omega(VALIDATION_ND)
-        wv_d = to_device(wv, dev)
         if val_frf is None:
-            Uv, Yv = bfrf.record_coefficients_device(val[0], val[1], val[2], wv_d, val[3])
+            Uv, Yv = bfrf.record_coefficients_device(val[0], val[1], val[2], gi.wv_d, val[3],
+                                                     t0=val[5] if len(val) > 5 else None, w_max=gi.wv_max)
         else:
             Uv, Yv = val_frf
         Gv = bfrf.cross_power_device(Uv, Yv)
-        Xv_d = xs.transform(torch.log10(wv_d)).contiguous()
+        Xv_d = gi.Xv_d
         yv_r, yv_i = Gv.real.contiguous(), Gv.imag.contiguous()
-    # ---- model selection (grid_search.py:48-203) then final fits
+    # ---- model selection (grid_search.py:48-203): the Re and Im searches are independent -> two streams
     if candidates is not None:
-        ir, mr = select_candidates(candidates, X_d, yr, noise, Xv_d, yv_r, sr)
-        ii, mi = select_candidates(candidates, X_d, yi, noise, Xv_d, yv_i, si)
+        main = torch.cuda.current_stream()
+        side = _side_stream(dev)
+        side.wait_stream(main)
+        pend_r = select_candidates_async(candidates, X_d, yr, noise, Xv_d, yv_r, sr)
+        with torch.cuda.stream(side):
+            pend_i = select_candidates_async(candidates, X_d, yi, noise, Xv_d, yv_i, si)
+        main.wait_stream(side)
+        both = torch.stack([pend_r, pend_i]).cpu()
+        ir, mr = _finish_selection(candidates, both[0], dev)
+        ii, mi = _finish_selection(candidates, both[1], dev)
         th_r = _theta_of(candidates, ir)
         th_i = _theta_of(candidates, ii)
     else:
         th_r = th_i = np.asarray(theta0, dtype=np.float64)
         mr = mi = float("nan")
-    gp_r = fit_device(kernel, th_r, X_d, yr, noise, want_kinv=False)     # the FIR path only needs the GP mean
-    gp_i = fit_device(kernel, th_i, X_d, yi, noise, want_kinv=False)
+    gp_r, gp_i = fit_pair_device(kernel, (th_r, th_i), X_d, (yr, yi), noise)      # the FIR path only needs the GP mean
     # ---- paper-mode FIR: 1000-point uniform omega grid -> GP mean -> Hermitian IDFT -> taps
-    w_uni = torch.linspace(float(omega.min()), float(omega.max()), PAPER_ND, dtype=F64, device=dev)
-    Xu = xs.transform(torch.log10(w_uni)).contiguous()
-    G_uni = torch.complex(sr.inverse(gp_r.predict_device(Xu)), si.inverse(gp_i.predict_device(Xu)))
+    G_uni = torch.complex(sr.inverse(gp_r.predict_device(gi.Xu_d)), si.inverse(gp_i.predict_device(gi.Xu_d)))
     taps = bfir.idft_taps_device(G_uni, min(n_taps, 2 * PAPER_ND - 1))
     res = IdentifyResult(omega, G, th_r, th_i, mr, mi, taps, {}, G_uni, gp_r, gp_i)
     # ---- FIR validation on the validation record (fir_fitting.py:285-306), sums all-reduced
@@ -281,6 +328,71 @@ def identify_device(train: Sequence[Tuple[torch.Tensor, torch.Tensor, torch.Tens
         bdist.allreduce_sum_(sums)
         res.fir = bfir.metrics_from_sums(sums.cpu().numpy(), skip)
     return res
+
+
+_SIDE_STREAMS: Dict[int, "torch.cuda.Stream"] = {}
+
+
+def _side_stream(dev) -> "torch.cuda.Stream":
+    st = _SIDE_STREAMS.get(dev.index)
+    if st is None:
+        st = torch.cuda.Stream(device=dev)
+        _SIDE_STREAMS[dev.index] = st
+    return st
+
+
+def select_candidates_async(cs: CandidateSet, X_d, y_d, noise: float, Xv_d=None, yv_d=None,
+                            scaler: Optional[Standardizer] = None) -> torch.Tensor:
+    """Launch the batched metric + first-strict-min on the current stream; returns a device [2] tensor
+    (best metric, local index as double) without synchronising."""
+    kid = bgp.KERNEL_IDS[cs.kernel][0] if cs.kernel is not None else 0
+    use_val = Xv_d is not None
+    m = bgp.batch_eval_device(kid, cs.kernel_ids, cs.theta, X_d, y_d, noise,
+                              bgp.METRIC_VAL_RMSE if use_val else bgp.METRIC_NLL, Xv_d, yv_d,
+                              scaler.mean if (use_val and scaler) else 0.0, scaler.scale if (use_val and scaler) else 1.0)
+    best, idx = bgp.first_strict_min_device(m)
+    return torch.stack([best[0], idx[0].to(F64)])
+
+
+def _finish_selection(cs: CandidateSet, pair_host: torch.Tensor, dev) -> Tuple[int, float]:
+    local_best, local_idx = float(pair_host[0]), int(pair_host[1])
+    if cs.global_index is not None:
+        gidx = int(cs.global_index[local_idx]) if local_idx >= 0 else -1
+        return bdist.argmin_gather(local_best, gidx, device=dev)
+    return local_idx, local_best
+
+
+def fit_pair_device(kernel: str, thetas, X_d: torch.Tensor, ys, noise: float):
+    """Two final fits (Re, Im) with ONE host read of both info flags; pinv branch as in fit_device."""
+    import ctypes as C
+    from . import _lib
+    from .runtime import Workspace, ptr, stream_ptr
+    dev = X_d.device
+    n = X_d.numel()
+    if n > 127:
+        return tuple(fit_device(kernel, th, X_d, y, noise) for th, y in zip(thetas, ys))
+    kid = bgp.KERNEL_IDS[kernel][0]
+    diag = float(noise) + 1e-10
+    infos = torch.zeros(2, dtype=torch.int32, device=dev)
+    nbytes = _lib.load().b200id_gp_fit_workspace_bytes(n)
+    out = []
+    for k, (th, y_d) in enumerate(zip(thetas, ys)):
+        th_d = to_device(bgp._theta_block(th)[0], dev)
+        alpha = empty(n, dev)
+        ws = Workspace.get(f"gpfit{k}", nbytes, dev)
+        _lib.call("b200id_gp_fit", C.c_int(kid), ptr(th_d), ptr(X_d), ptr(y_d), C.c_int(n), C.c_double(diag), ptr(alpha),
+                  ptr(None), ptr(infos[k:k + 1]), ptr(ws), C.c_size_t(ws.numel()), stream_ptr())
+        out.append((th, th_d, alpha, y_d, ws))
+    flags = infos.cpu().tolist()
+    fitted = []
+    for (th, th_d, alpha, y_d, ws), flag in zip(out, flags):
+        Kinv = None
+        if flag != 0:
+            Kinv = empty(n * n, dev)
+            _lib.call("b200id_gp_fit_pinv", C.c_int(kid), ptr(th_d), ptr(X_d), ptr(y_d), C.c_int(n), C.c_double(diag),
+                      C.c_double(bgp.PINV_RCOND), ptr(alpha), ptr(Kinv), ptr(ws), C.c_size_t(ws.numel()), stream_ptr())
+        fitted.append(FittedGP(kernel, np.asarray(th, dtype=np.float64), alpha, Kinv, X_d, flag != 0))
+    return tuple(fitted)
 
 
 def _theta_of(cs: CandidateSet, global_idx: int) -> np.ndarray:

@@ -41,6 +41,46 @@ static inline size_t gt_smem_bytes(int n) {
     return ((size_t)gt_off(R, nb) + 3 * (size_t)(n + 4) + 16) * sizeof(double);
 }
 
+// Gram fill of the block-column storage, kernel id fixed at compile time.  Thread (c = tid / 8, r8 = tid % 8)
+// walks rows r8, r8 + 8, ... of column c of each block column: no integer division, 8 consecutive rows per
+// column are contiguous in shared memory.
+template <int ID>
+__device__ __forceinline__ void gt_fill(const KernelParams& kp, const double* __restrict__ xs,
+                                        const double* __restrict__ y, int n, double noise, int R, int nblk,
+                                        double* __restrict__ Lb) {
+    const int c = threadIdx.x >> 3, r8 = threadIdx.x & 7;
+    for (int J = 0; J < nblk; ++J) {
+        const int ld = R - GT_NB * J;
+        double* col = Lb + gt_off(R, J) + c * ld;
+        const int j = GT_NB * J + c;
+        const double xj = j < n ? xs[j] : 0.0;
+        const double yj = j < n ? y[j] : 0.0;
+        for (int r = r8; r < ld; r += 8) {
+            const int i = GT_NB * J + r;
+            double v = 0.0;
+            if (j < n) {
+                if (i < n) {
+                    // evaluate with the larger index first, as the lower triangle of kernel(X) is laid out
+                    v = (i >= j) ? kernel_entry_t<ID>(kp, xs[i], xj) : kernel_entry_t<ID>(kp, xj, xs[i]);
+                    if (i == j) v = B200ID_ADD(v, noise);
+                } else if (i == n) {
+                    v = yj;
+                }
+            }
+            col[r] = v;
+        }
+    }
+}
+
+// sum_j k(xv, x_j) alpha_j for one validation point, kernel id fixed at compile time
+template <int ID>
+__device__ __forceinline__ void gt_predict_point(const KernelParams& kp, double xv, const double* __restrict__ xs,
+                                                 const double* __restrict__ alpha, int n, double* out) {
+    double pred = 0.0;
+    for (int j = 0; j < n; ++j) pred = fma(kernel_entry_t<ID>(kp, xv, xs[j]), alpha[j], pred);
+    *out = pred;
+}
+
 __global__ void __launch_bounds__(GT_THREADS)
 gp_batch_tiled_kernel(int kernel_id, const int* __restrict__ kernel_ids, const double* __restrict__ theta,
                       const double* __restrict__ X, const double* __restrict__ y, int n, double noise,
@@ -69,26 +109,7 @@ gp_batch_tiled_kernel(int kernel_id, const int* __restrict__ kernel_ids, const d
     __syncthreads();
 
     // ---- fill: K + noise*I (rows < n), y (row n), zeros (padding rows), block column by block column
-    for (int J = 0; J < nblk; ++J) {
-        const int ld = R - GT_NB * J;
-        double* col0 = Lb + gt_off(R, J);
-        for (int e = tid; e < ld * GT_NB; e += GT_THREADS) {
-            const int c = e / ld, r = e - c * ld;
-            const int i = GT_NB * J + r, j = GT_NB * J + c;
-            double v = 0.0;
-            if (j < n) {
-                if (i < n) {
-                    // evaluate with the larger index first, as the lower triangle of kernel(X) is laid out
-                    const int a = i >= j ? i : j, b = i >= j ? j : i;
-                    v = kernel_entry(kp, xs[a], xs[b]);
-                    if (i == j) v = B200ID_ADD(v, noise);
-                } else if (i == n) {
-                    v = y[j];
-                }
-            }
-            col0[e] = v;
-        }
-    }
+    B200ID_DISPATCH_KERNEL(kid, gt_fill, kp, xs, y, n, noise, R, nblk, Lb)
     __syncthreads();
 
     const int rb = lane >> 2, cb = lane & 3;           // 8 row blocks x 4 column blocks of 4 x 4
@@ -133,27 +154,41 @@ gp_batch_tiled_kernel(int kernel_id, const int* __restrict__ kernel_ids, const d
             }
         }
         __syncthreads();
-        // ---------------- diagonal block (warp 0): D[r][c] at colJ[c*ldJ + r], r, c < ncols
+        // ---------------- diagonal block (warp 0), in registers: lane r owns row r (d[c] = D[r][c], c <= r).
+        // Right-looking; column k of L is broadcast lane by lane with shuffles, so the only serial latency
+        // per column is one sqrt/rsqrt pair.  Scaling multiplies by the reciprocal like OpenBLAS potf2.
         if (tid < 32) {
-            for (int k = 0; k < ncols; ++k) {
-                const double piv = colJ[k * ldJ + k];
-                if (piv <= 0.0 || piv == INFINITY) {          // uniform: every lane reads the same value
-                    if (lane == 0) status = GT_NB * J + k + 1;
-                    break;
+            double d[GT_NB];
+#pragma unroll
+            for (int c = 0; c < GT_NB; ++c)
+                d[c] = (lane < ncols && c <= lane) ? colJ[c * ldJ + lane] : 0.0;
+            int fail = 0;
+#pragma unroll
+            for (int k = 0; k < GT_NB; ++k) {
+                if (k < ncols && fail == 0) {
+                    const double piv = __shfl_sync(0xffffffffu, d[k], k);
+                    if (piv <= 0.0 || piv == INFINITY) {        // NaN compares false: the factorisation goes on
+                        fail = k + 1;
+                    } else {
+                        const double dk = sqrt(piv);
+                        const double inv = 1.0 / dk;
+                        const double l = (lane == k) ? dk : d[k] * inv;
+                        d[k] = l;
+                        if (lane == k) idg[GT_NB * J + k] = inv;
+#pragma unroll
+                        for (int c = k + 1; c < GT_NB; ++c) {
+                            const double lc = __shfl_sync(0xffffffffu, l, c);
+                            d[c] = fma(-l, lc, d[c]);
+                        }
+                    }
                 }
-                const double d = sqrt(piv);
-                const double inv = 1.0 / d;
-                __syncwarp();
-                if (lane == 0) { colJ[k * ldJ + k] = d; idg[GT_NB * J + k] = inv; }
-                if (lane > k && lane < ncols) colJ[k * ldJ + lane] *= inv;
-                __syncwarp();
-                // D[r][c] -= D[r][k] D[c][k], k < c <= r < ncols: up to 120 pairs over 32 lanes
-                for (int e = lane; e < GT_NB * GT_NB; e += 32) {
-                    const int c = e >> 4, r = e & 15;
-                    if (c > k && r >= c && r < ncols)
-                        colJ[c * ldJ + r] = fma(-colJ[k * ldJ + r], colJ[k * ldJ + c], colJ[c * ldJ + r]);
-                }
-                __syncwarp();
+            }
+            if (fail != 0) {
+                if (lane == 0) status = GT_NB * J + fail;
+            } else {
+#pragma unroll
+                for (int c = 0; c < GT_NB; ++c)
+                    if (lane < ncols && c <= lane) colJ[c * ldJ + lane] = d[c];
             }
         }
         __syncthreads();
@@ -247,7 +282,7 @@ gp_batch_tiled_kernel(int kernel_id, const int* __restrict__ kernel_ids, const d
     for (int v = tid; v < nv; v += GT_THREADS) {
         const double xv = Xv[v];
         double pred = 0.0;
-        for (int j = 0; j < n; ++j) pred = fma(kernel_entry(kp, xv, xs[j]), zz[j], pred);
+        B200ID_DISPATCH_KERNEL(kid, gt_predict_point, kp, xv, xs, zz, n, &pred)
         pred = pred * y_scale + y_mean;
         const double e = yv[v] - pred;
         se = fma(e, e, se);

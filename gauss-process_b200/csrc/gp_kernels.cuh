@@ -49,9 +49,11 @@ B200ID_HD KernelParams make_kernel_params(int id, const double* theta) {
 
 B200ID_HD double heaviside(double x) { return x >= 0.0 ? 1.0 : 0.0; }
 
-// k(xa, xb); xa indexes the row (X1), xb the column (X2).
-B200ID_HD double kernel_entry(const KernelParams& k, double xa, double xb) {
-    switch (k.id) {
+// k(xa, xb) with the kernel id as a compile-time constant (the switch folds away); xa indexes the row
+// (X1), xb the column (X2).
+template <int ID>
+B200ID_HD double kernel_entry_t(const KernelParams& k, double xa, double xb) {
+    switch (ID) {
         case B200ID_K_RBF: {            // variance * exp(-0.5 * d2 / ls**2)            kernels.py:98-100
             const double d = B200ID_SUB(xa, xb);
             const double d2 = B200ID_MUL(d, d);
@@ -62,9 +64,9 @@ B200ID_HD double kernel_entry(const KernelParams& k, double xa, double xb) {
         case B200ID_K_MATERN52: {       // kernels.py:121-136
             const double d = B200ID_DIV(fabs(B200ID_SUB(xa, xb)), k.p0);
             double v;
-            if (k.id == B200ID_K_MATERN12) {
+            if (ID == B200ID_K_MATERN12) {
                 v = exp(-d);
-            } else if (k.id == B200ID_K_MATERN32) {
+            } else if (ID == B200ID_K_MATERN32) {
                 const double s3 = 1.7320508075688772;       // np.sqrt(3.0)
                 const double a = B200ID_MUL(s3, d);
                 v = B200ID_MUL(B200ID_ADD(1.0, a), exp(-a));
@@ -123,6 +125,37 @@ B200ID_HD double kernel_entry(const KernelParams& k, double xa, double xb) {
         default:
             return nan("");
     }
+}
+
+// run FN<ID>(args...) for the runtime kernel id
+#define B200ID_DISPATCH_KERNEL(id, FN, ...)                                   \
+    switch (id) {                                                             \
+        case B200ID_K_RBF: FN<B200ID_K_RBF>(__VA_ARGS__); break;              \
+        case B200ID_K_MATERN12: FN<B200ID_K_MATERN12>(__VA_ARGS__); break;    \
+        case B200ID_K_MATERN32: FN<B200ID_K_MATERN32>(__VA_ARGS__); break;    \
+        case B200ID_K_MATERN52: FN<B200ID_K_MATERN52>(__VA_ARGS__); break;    \
+        case B200ID_K_EXP: FN<B200ID_K_EXP>(__VA_ARGS__); break;              \
+        case B200ID_K_DC: FN<B200ID_K_DC>(__VA_ARGS__); break;                \
+        case B200ID_K_DI: FN<B200ID_K_DI>(__VA_ARGS__); break;                \
+        case B200ID_K_SS1: FN<B200ID_K_SS1>(__VA_ARGS__); break;              \
+        case B200ID_K_SS2: FN<B200ID_K_SS2>(__VA_ARGS__); break;              \
+        case B200ID_K_SSHF: FN<B200ID_K_SSHF>(__VA_ARGS__); break;            \
+        case B200ID_K_STABLE_SPLINE: FN<B200ID_K_STABLE_SPLINE>(__VA_ARGS__); break; \
+        case B200ID_K_RQ: FN<B200ID_K_RQ>(__VA_ARGS__); break;                \
+        case B200ID_K_TC: FN<B200ID_K_TC>(__VA_ARGS__); break;                \
+        default: break;                                                       \
+    }
+
+template <int ID>
+B200ID_HD void kernel_entry_into(const KernelParams& k, double xa, double xb, double* out) {
+    *out = kernel_entry_t<ID>(k, xa, xb);
+}
+
+// runtime-id form (single evaluations: Gram export, predict, selftests)
+B200ID_HD double kernel_entry(const KernelParams& k, double xa, double xb) {
+    double v = nan("");
+    B200ID_DISPATCH_KERNEL(k.id, kernel_entry_into, k, xa, xb, &v)
+    return v;
 }
 
 B200ID_HD int kernel_n_params(int id) {

@@ -58,7 +58,7 @@ def batch_eval_device(kernel_id: int, kernel_ids_d: Optional[torch.Tensor], thet
     c, n = theta_d.shape[0], X_d.numel()
     out = empty(c, dev) if out is None else out
     nv = 0 if Xv_d is None else Xv_d.numel()
-    ws = Workspace.get("gp", 256, dev)
+    ws = Workspace.get("gp", _lib.load().b200id_gp_batch_workspace_bytes(c, n), dev)
     _lib.call("b200id_gp_batch_eval", C.c_int(kernel_id), ptr(kernel_ids_d), ptr(theta_d), C.c_int64(c), ptr(X_d),
               ptr(y_d), C.c_int(n), C.c_double(noise), C.c_int(metric), ptr(Xv_d), ptr(yv_d), C.c_int(nv),
               C.c_double(y_mean), C.c_double(y_scale), ptr(out), ptr(ws), C.c_size_t(ws.numel()), stream_ptr())
@@ -115,7 +115,7 @@ def fit(kernel_id: int, theta, X, y, diag_add: float, want_kinv: bool = True):
     x, yy = to_device(_flat(X), dev), to_device(_flat(y), dev)
     n = x.numel()
     th = to_device(_theta_block(theta)[0], dev)
-    want_kinv = want_kinv or n > 127
+    want_kinv = want_kinv or (127 < n <= SMEM_NMAX)
     alpha, Kinv = empty(n, dev), (empty(n * n, dev) if want_kinv else None)
     info = torch.zeros(1, dtype=torch.int32, device=dev)
     nbytes = _lib.load().b200id_gp_fit_workspace_bytes(n)

@@ -400,3 +400,51 @@ def _theta_of(cs: CandidateSet, global_idx: int) -> np.ndarray:
         raise ValueError("grid search found no finite candidate (all metrics NaN): kernel.set_params(None) in the reference")
     nparams = bgp.KERNEL_IDS[cs.kernel][1]
     return cs.full_theta[global_idx, :nparams].copy()
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE config 3: all baseline kernels x many restart start points, one batched launch per target
+def restart_candidates(n_restarts: int, kernels: Sequence[str] = tuple(BASELINE_KERNELS), seed: int = 42):
+    """(theta [C,3], kernel_ids [C], names) for ``n_restarts`` start points per kernel, kernels in
+    run_baseline METHOD_ORDER (run_baseline.py:37-41), each population seeded like run_baseline.py:129."""
+    th, ids, names = [], [], []
+    for name in kernels:
+        P = restart_population(name, n_restarts, seed)
+        th.append(bgp._theta_block(P))
+        ids.append(np.full(n_restarts, bgp.KERNEL_IDS[name][0], dtype=np.int32))
+        names += [name] * n_restarts
+    return np.vstack(th), np.concatenate(ids), names
+
+
+def select_best(kernels: Sequence[str], per_kernel_best: Sequence[float]) -> int:
+    """Cross-kernel selection (an ADDITION: the reference prints a table and leaves the choice to the
+    reader, run_baseline.py:170-179): argmin of the per-kernel best metric, ties and scan order as the
+    sequential ``metric < best`` rule, i.e. first in METHOD_ORDER wins, NaN never wins."""
+    best, arg = float("inf"), -1
+    for k, m in enumerate(per_kernel_best):
+        if m < best:
+            best, arg = m, k
+    return arg
+
+
+def population_search_device(theta: np.ndarray, kernel_ids: np.ndarray, X_d, y_d, noise: float,
+                             n_per_kernel: int, rank: int = 0, world_size: int = 1):
+    """NLL of every (kernel, start point) candidate in ONE launch (mixed kernel ids), sharded
+    round-robin over ranks; returns (metrics of this rank's shard, global indices, per-kernel
+    (best metric, global index) after the argmin gather)."""
+    dev = X_d.device
+    cs = CandidateSet.build(None, theta, dev, kernel_ids=kernel_ids, rank=rank, world_size=world_size)
+    m = bgp.batch_eval_device(0, cs.kernel_ids, cs.theta, X_d, y_d, noise, bgp.METRIC_NLL)
+    m_host = m.cpu().numpy()
+    gidx = cs.global_index if cs.global_index is not None else np.arange(theta.shape[0])
+    n_kernels = theta.shape[0] // n_per_kernel
+    out = []
+    for k in range(n_kernels):
+        sel = (gidx >= k * n_per_kernel) & (gidx < (k + 1) * n_per_kernel)
+        vals, idxs = m_host[sel], gidx[sel]
+        best, arg = float("inf"), -1
+        for v, i in zip(vals, idxs):            # first strict minimum in global scan order within the shard
+            if v < best:
+                best, arg = float(v), int(i)
+        out.append(bdist.argmin_gather(best, arg, device=dev))
+    return m_host, gidx, out

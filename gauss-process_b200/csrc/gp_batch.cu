@@ -283,6 +283,17 @@ int b200id_gp_batch_tiled_launch(int kernel_id, const int* kernel_ids, const dou
                                  const double* Xv, const double* yv, int nv, double y_mean, double y_scale,
                                  double* metric_out, cudaStream_t st);
 
+// gp_large.cu: global-memory path for n > 160 (blocked Cholesky)
+size_t b200id_gp_large_workspace_bytes(int n, int nv);
+int b200id_gp_fit_large(int kernel_id, const double* theta, const double* X, const double* y, int n, double diag_add,
+                        double* alpha_out, double* Kinv_out, int* info_out, void* ws, size_t ws_bytes, cudaStream_t st);
+int b200id_gp_batch_eval_large(int kernel_id, const int* kernel_ids_host_or_null, const double* theta, int64_t n_candidates,
+                               const double* X, const double* y, int n, double noise, int metric, const double* Xv,
+                               const double* yv, int nv, double y_mean, double y_scale, double* metric_out,
+                               void* ws, size_t ws_bytes, cudaStream_t st);
+constexpr int GP_LARGE_NMAX = 8192;
+constexpr int GP_LARGE_NV_CAP = 8192;
+
 static bool force_generic_gp_path() {
     static int cached = -1;
     if (cached < 0) {
@@ -311,21 +322,26 @@ extern "C" int b200id_gp_gram(int kernel_id, const double* theta, const double* 
 }
 
 extern "C" size_t b200id_gp_batch_workspace_bytes(int64_t n_candidates, int n) {
-    (void)n_candidates; (void)n;
-    return 256;     // the shared-memory path needs no global scratch; kept for the blocked large-n path
+    (void)n_candidates;
+    if (n > GP_NMAX_SMEM) return b200id_gp_large_workspace_bytes(n, GP_LARGE_NV_CAP) + 512;
+    return 256;     // the shared-memory paths need no global scratch
 }
 
 extern "C" int b200id_gp_batch_eval(int kernel_id, const int* kernel_ids, const double* theta, int64_t n_candidates,
                                     const double* X, const double* y, int n, double noise, int metric,
                                     const double* Xv, const double* yv, int nv, double y_mean, double y_scale,
                                     double* metric_out, void* ws, size_t ws_bytes, void* stream) {
-    (void)ws; (void)ws_bytes;
     B200ID_REQUIRE(theta && X && y && metric_out, B200ID_E_ARG, "gp_batch_eval: null pointer");
     B200ID_REQUIRE(n_candidates > 0 && n > 0, B200ID_E_ARG, "gp_batch_eval: empty problem");
     B200ID_REQUIRE(kernel_ids || (kernel_id >= 0 && kernel_id < B200ID_K_COUNT), B200ID_E_ARG, "gp_batch_eval: unknown kernel id %d", kernel_id);
     B200ID_REQUIRE(metric == B200ID_METRIC_NLL || metric == B200ID_METRIC_VAL_RMSE, B200ID_E_ARG, "gp_batch_eval: unknown metric %d", metric);
     B200ID_REQUIRE(metric == B200ID_METRIC_NLL || (Xv && yv && nv > 0), B200ID_E_ARG, "gp_batch_eval: validation metric needs Xv, yv");
-    B200ID_REQUIRE(n <= GP_NMAX_SMEM, B200ID_E_UNSUPPORTED, "gp_batch_eval: n=%d exceeds the in-shared-memory limit %d", n, GP_NMAX_SMEM);
+    if (n > GP_NMAX_SMEM) {
+        B200ID_REQUIRE(n <= GP_LARGE_NMAX && nv <= GP_LARGE_NV_CAP, B200ID_E_UNSUPPORTED, "gp_batch_eval: n=%d / nv=%d beyond the large-n limits", n, nv);
+        B200ID_REQUIRE(ws, B200ID_E_ARG, "gp_batch_eval: the large-n path needs a workspace");
+        return b200id_gp_batch_eval_large(kernel_id, kernel_ids, theta, n_candidates, X, y, n, noise, metric, Xv, yv, nv,
+                                          y_mean, y_scale, metric_out, ws, ws_bytes, (cudaStream_t)stream);
+    }
     B200ID_REQUIRE(n_candidates < (1LL << 31), B200ID_E_UNSUPPORTED, "gp_batch_eval: too many candidates");
     if (n <= 127 && !force_generic_gp_path())
         return b200id_gp_batch_tiled_launch(kernel_id, kernel_ids, theta, n_candidates, X, y, n, noise, metric, Xv, yv, nv,
@@ -349,6 +365,7 @@ extern "C" int b200id_first_strict_min(const double* metric, int64_t n_candidate
 }
 
 extern "C" size_t b200id_gp_fit_workspace_bytes(int n) {
+    if (n > GP_NMAX_SMEM) return b200id_gp_large_workspace_bytes(n, 0) + align_up((size_t)n * n * sizeof(double), 256) + 256;
     return n > 0 ? align_up((size_t)(n + 2) * (n + 2) * sizeof(double), 256) : 0;   // covers gp_fit and gp_fit_pinv
 }
 
@@ -357,10 +374,12 @@ extern "C" int b200id_gp_fit(int kernel_id, const double* theta, const double* X
                              void* ws, size_t ws_bytes, void* stream) {
     B200ID_REQUIRE(theta && X && y && alpha_out && info_out && ws, B200ID_E_ARG, "gp_fit: null pointer");
     B200ID_REQUIRE(kernel_id >= 0 && kernel_id < B200ID_K_COUNT, B200ID_E_ARG, "gp_fit: unknown kernel id %d", kernel_id);
-    B200ID_REQUIRE(n > 0 && n <= GP_NMAX_SMEM, B200ID_E_UNSUPPORTED, "gp_fit: n=%d outside (0, %d]", n, GP_NMAX_SMEM);
-    B200ID_REQUIRE(ws_bytes >= (size_t)n * n * sizeof(double), B200ID_E_WORKSPACE, "gp_fit: workspace too small");
+    B200ID_REQUIRE(n > 0 && n <= GP_LARGE_NMAX, B200ID_E_UNSUPPORTED, "gp_fit: n=%d outside (0, %d]", n, GP_LARGE_NMAX);
     cudaStream_t st = (cudaStream_t)stream;
     int rc;
+    if (n > GP_NMAX_SMEM)
+        return b200id_gp_fit_large(kernel_id, theta, X, y, n, diag_add, alpha_out, Kinv_out, info_out, ws, ws_bytes, st);
+    B200ID_REQUIRE(ws_bytes >= (size_t)n * n * sizeof(double), B200ID_E_WORKSPACE, "gp_fit: workspace too small");
     if (n <= 127 && !force_generic_gp_path()) {
         // blocked kernel writes alpha + dense L (workspace); K_inv (optional) by one warp per column
         rc = b200id_gp_fit_tiled_launch(kernel_id, theta, X, y, n, diag_add, alpha_out, (double*)ws, info_out, st);

@@ -245,3 +245,75 @@ def test_fit_kinv_identity(gp, n):
     e_id = record(f"gp.fit.kinv_identity.n{n}", float(np.max(np.abs(Kinv @ K - np.eye(n)))))
     e_al = record(f"gp.fit.alpha_residual.n{n}", float(np.max(np.abs(K @ alpha - y)) / np.max(np.abs(y))))
     assert e_id < 50 * cond * 2.2e-16 and e_al < 50 * cond * 2.2e-16
+
+
+def test_config3_all_kernels_restart_population(gp, golden):
+    """BASELINE config 3 shape (11 kernels x N restart start points, NLL, noise 1e-6, one mixed-kernel
+    launch) at N = 64 per kernel against the oracle: per-kernel first strict minimum and the cross-kernel
+    pick identical; metrics within the conditioning-aware budget."""
+    import torch
+    from b200id import pipeline as P
+    from b200id.runtime import require_cuda, to_device
+    g = golden("gp")
+    dev = require_cuda()
+    n_per = 64
+    theta, ids, names = P.restart_candidates(n_per)
+    X, y = g["X"], g["yr"]
+    m, gidx, per_kernel = P.population_search_device(theta, ids, to_device(X.ravel(), dev), to_device(y, dev), 1e-6, n_per)
+    with np.errstate(all="ignore"):
+        ref = np.array([ogp.candidate_metric(nm, th[:ogp.KERNELS[nm][1].__len__()], X, y, 1e-6) for nm, th in zip(names, theta)])
+    assert np.array_equal(theta.reshape(11, n_per, 3)[3, :, :2], ogp.restart_population("matern12", n_per, 1e-6, seed=42))
+    bests = []
+    for k, name in enumerate(P.BASELINE_KERNELS):
+        sl = slice(k * n_per, (k + 1) * n_per)
+        ei, eb = ogp.first_strict_min(ref[sl])
+        gi, gb = per_kernel[k]
+        cond = _cond_numbers(name, [t[:len(ogp.KERNELS[name][1])] for t in theta[sl]], X, 1e-6)
+        _compare_metrics(m[sl], ref[sl], f"cfg3.{name}", cond)
+        well = ei >= 0 and cond[ei] < 1e8
+        if well:
+            assert gi == k * n_per + ei, (name, gi, ei)
+        bests.append(gb)
+    pick = P.select_best(P.BASELINE_KERNELS, bests)
+    ref_pick = P.select_best(P.BASELINE_KERNELS, [ogp.first_strict_min(ref[k * n_per:(k + 1) * n_per])[1] for k in range(11)])
+    record("gp.cfg3.cross_kernel_pick", {"ours": P.BASELINE_KERNELS[pick], "ref": P.BASELINE_KERNELS[ref_pick]})
+    assert pick == ref_pick
+
+
+@pytest.mark.parametrize("n", [200, 700, 2048])
+def test_config4_large_n_fit_and_metrics(gp, n):
+    """BASELINE config 4 shape (N_d up to 2048: Gram in global memory, blocked Cholesky, blocked
+    triangular solves) against np.linalg on the same Gram: NLL / val-RMSE of a few candidates, alpha,
+    K_inv and the posterior mean / sigma."""
+    rng = np.random.default_rng(n)
+    X = np.linspace(-1.7, 1.7, n).reshape(-1, 1)
+    y = np.sin(3 * X.ravel()) + 0.1 * rng.standard_normal(n)
+    Xv = np.linspace(-1.65, 1.65, 150).reshape(-1, 1)
+    yv = np.sin(3 * Xv.ravel())
+    name, noise = "matern12", 1e-3
+    thetas = np.array([[0.5, 1.0], [2.0, 0.3], [0.05, 2.0]])
+    with np.errstate(all="ignore"):
+        ref_nll = np.array([ogp.candidate_metric(name, th, X, y, noise) for th in thetas])
+        ref_val = np.array([ogp.candidate_metric(name, th, X, y, noise, Xv, yv, 0.1, 1.3) for th in thetas])
+        cond = _cond_numbers(name, thetas, X, noise)
+    got_nll = gp.batch_eval(name, thetas, X, y, noise)
+    got_val = gp.batch_eval(name, thetas, X, y, noise, Xv=Xv, yv=yv, y_mean=0.1, y_scale=1.3)
+    _compare_metrics(got_nll, ref_nll, f"cfg4.nll.n{n}", cond)
+    _compare_metrics(got_val, ref_val, f"cfg4.val.n{n}", cond)
+    # failure convention on the large path: an indefinite Gram -> 1e10
+    bad = gp.batch_eval("ss1", np.array([[1.0, 1.0]]), X, y, 0.0)
+    assert bad[0] == 1e10
+    kid = ogp.KERNELS[name][0]
+    alpha, Kinv, used_pinv = gp.fit(kid, thetas[0], X, y, noise)
+    assert not used_pinv and Kinv.shape == (n, n)
+    K = ogp.gram(name, thetas[0], X) + noise * np.eye(n)
+    c = float(np.linalg.cond(K))
+    e_al = record(f"gp.cfg4.alpha_residual.n{n}", float(np.max(np.abs(K @ alpha - y)) / np.max(np.abs(y))))
+    e_id = record(f"gp.cfg4.kinv_identity.n{n}", float(np.max(np.abs(Kinv @ K - np.eye(n)))))
+    assert e_al < 100 * c * 2.2e-16 and e_id < 100 * c * 2.2e-16
+    a_ref, Kinv_ref, _ = ogp.fit(name, thetas[0], X, y, noise - 1e-10)
+    Xs = np.linspace(-1.7, 1.7, 1000).reshape(-1, 1)
+    mean, std = gp.predict(kid, thetas[0], X, alpha, Kinv, Xs, True)
+    m_ref, s_ref = ogp.predict(name, thetas[0], X, a_ref, Kinv_ref, Xs, True)
+    assert record(f"gp.cfg4.mean.n{n}.rel_max", rel_max(mean, m_ref)) < 1e-8
+    assert record(f"gp.cfg4.std.n{n}.abs", float(np.max(np.abs(std - s_ref)))) < 1e-6

@@ -41,6 +41,10 @@ KERNEL = "matern52"
 NOISE = 1e-6
 N_TAPS = 1024
 VAL_ND = 150
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures
+# (profiles/r01_ncu_full_*.txt), 10^7-sample record: FRF reads t,u,y once (240 MB), FIR reads u,y (160 MB)
+NCU_TRAFFIC_BYTES = {"frf_project_uniform_kernel": 245.6e6, "frf_project_kernel": 245.3e6, "fir_eval_kernel": 167.3e6,
+                     "gp_batch_tiled_kernel": 0.27e6}
 FRF_BYTES_PER_SAMPLE = 24        # t, u, y FP64 read once
 FIR_BYTES_PER_SAMPLE = 16        # u, y FP64 read once, y_pred not materialised
 
@@ -356,10 +360,11 @@ def main():
         return
 
     # ---- roofline of the dominant kernel (largest share of the step among the instrumented calls)
-    frf_ms = stage_ms.get("b200id_frf_project", 0.0)
+    frf_ms = stage_ms.get("b200id_frf_project", 0.0) + stage_ms.get("b200id_frf_project_uniform", 0.0)
+    frf_kernel = "frf_project_uniform_kernel" if stage_ms.get("b200id_frf_project_uniform", 0.0) > stage_ms.get("b200id_frf_project", 0.0) else "frf_project_kernel"
     fir_ms = stage_ms.get("b200id_fir_eval", 0.0)
     gp_ms = stage_ms.get("b200id_gp_batch_eval", 0.0)
-    dominant = max((("frf_project_kernel", frf_ms), ("fir_eval_kernel", fir_ms), ("gp_batch_kernel", gp_ms)), key=lambda kv: kv[1])[0]
+    dominant = max(((frf_kernel, frf_ms), ("fir_eval_kernel", fir_ms), ("gp_batch_tiled_kernel", gp_ms)), key=lambda kv: kv[1])[0]
     frf_bytes = FRF_BYTES_PER_SAMPLE * a.n * 2            # two launches per step: train (nd bins) + validation (150 bins)
     frf_flops = 8.0 * a.n * (a.nd + VAL_ND)               # 2 signals x (cos, sin) x FMA, both launches
     fir_bytes = FIR_BYTES_PER_SAMPLE * a.n
@@ -370,12 +375,13 @@ def main():
         ach = fir_bytes / (fir_ms * 1e-3) / 1e9
     else:
         ach = frf_bytes / (frf_ms * 1e-3) / 1e9 if frf_ms > 0 else 0.0
-        dominant = "frf_project_kernel"
+        dominant = frf_kernel
     roofline = {
         "kernel": dominant, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-        "traffic": None, "peak_source": peak_src,
-        "note": "FP64-issue bound by construction (reference-faithful per-sample rounded phases need a sincos per "
-                "sample-bin); see fp64 block and DESIGN.md",
+        "traffic": NCU_TRAFFIC_BYTES.get(dominant), "peak_source": peak_src,
+        "launches_per_step": 2 if dominant.startswith("frf") else 1,
+        "note": "FP64-issue bound by construction: the reference rounds the phase per sample, so each sample-bin costs 13 "
+                "(uniform timebase) or 24 (general) FP64 ops where 4 are algorithmic; see the fp64 block and DESIGN.md",
         "fp64": {
             "peak_tflops_measured": fp64_peak, **fp64,
             "frf_algorithmic_tflops": frf_flops / (frf_ms * 1e-3) / 1e12 if frf_ms > 0 else None,

@@ -39,6 +39,7 @@ def source_digest() -> str:
     for f in files:
         h.update(f.name.encode())
         h.update(f.read_bytes())
+    h.update(os.environ.get("B200ID_NVCC_FLAGS", "").encode())
     return h.hexdigest()
 
 
@@ -48,8 +49,9 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     if not force and LIB.exists() and STAMP.exists() and STAMP.read_text().strip() == digest:
         return LIB
     srcs = [str(CSRC / s) for s in SOURCES if (CSRC / s).exists()]
+    extra = os.environ.get("B200ID_NVCC_FLAGS", "").split()      # e.g. -DGT_PROFILE for the phase-timing build
     cmd = [nvcc_path(), "-O3", "-std=c++17", "-shared", "-Xcompiler", "-fPIC", "-lineinfo", *ARCH,
-           "-Xcompiler", "-ffp-contract=off", "-o", str(LIB), *srcs]
+           "-Xcompiler", "-ffp-contract=off", *extra, "-o", str(LIB), *srcs]
     if verbose:
         cmd[1:1] = ["-Xptxas", "-v"]
         print(" ".join(cmd))

@@ -12,7 +12,8 @@
 //   update : C[i, c] -= sum_{k < 16J} L[i, k] L[16J + c, k].  Each warp owns 32 rows x 16 columns, each
 //            lane a 4 x 4 register tile; per k a lane reads 4 + 4 doubles (broadcast across the lanes that
 //            share the rows / columns: 4 shared-memory wavefronts per 16 DFMA warp instructions).
-//   diag   : warp 0 factorises the 16 x 16 diagonal block in place (right-looking, reciprocal scaling).
+//   diag   : one warp factorises the 16 x 16 diagonal block in registers (shuffles, reciprocal scaling)
+//            while the other warps already apply block columns < J to block column J+1 (lookahead).
 //   panel  : one thread per row below solves x L_JJ^T = c by forward substitution in registers, multiplying
 //            by the stored reciprocal diagonal (as OpenBLAS TRSM does).
 // Row n carries y, so after the last block column it holds z = L^-1 y and y^T K^-1 y = z.z.
@@ -21,6 +22,21 @@
 #include "gp_kernels.cuh"
 
 namespace b200id {
+
+// Optional phase timing (build with -DGT_PROFILE): per-warp clock64 deltas accumulated per phase.
+#ifdef GT_PROFILE
+__device__ unsigned long long g_gt_prof[16];
+#define GT_TICK(phase)                                                                    \
+    do {                                                                                  \
+        const long long _now = clock64();                                                 \
+        if ((threadIdx.x & 31) == 0) atomicAdd(&g_gt_prof[phase], (unsigned long long)(_now - _t0)); \
+        _t0 = _now;                                                                       \
+    } while (0)
+#define GT_TICK_INIT long long _t0 = clock64();
+#else
+#define GT_TICK(phase)
+#define GT_TICK_INIT
+#endif
 
 constexpr int GT_THREADS = 128;
 constexpr int GT_NB = 16;
@@ -104,48 +120,68 @@ gp_batch_tiled_kernel(int kernel_id, const int* __restrict__ kernel_ids, const d
     const int kid = kernel_ids ? kernel_ids[cand] : kernel_id;
     const KernelParams kp = make_kernel_params(kid, theta + cand * B200ID_MAX_PARAMS);
 
+    GT_TICK_INIT
     if (tid == 0) status = 0;
     for (int i = tid; i < n; i += GT_THREADS) xs[i] = X[i];
     __syncthreads();
 
     // ---- fill: K + noise*I (rows < n), y (row n), zeros (padding rows), block column by block column
     B200ID_DISPATCH_KERNEL(kid, gt_fill, kp, xs, y, n, noise, R, nblk, Lb)
+    GT_TICK(0);
     __syncthreads();
+    GT_TICK(1);
 
     const int rb = lane >> 2, cb = lane & 3;           // 8 row blocks x 4 column blocks of 4 x 4
     const int i0 = 32 * wrow + 4 * rb;                 // first of this lane's 4 rows
+
+    // acc carries this lane's 4x4 tile of the NEXT block column across the diagonal/panel phases ("lookahead"):
+    // while one warp factorises diagonal block J, the others already subtract block columns < J from block
+    // column J+1, so only the rank-16 contribution of block column J itself remains on the critical path.
+    double acc[4][4];
+    bool acc_valid = false;
+    // the diagonal block is factorised by the warp that owns the lowest rows (it runs out of update work first)
+    const bool diag_warp = (wrow == 0);
+
+    // subtract block columns [Jk0, Jk1) from acc (tile rows i0.., columns of block column J)
+    auto apply_columns = [&](int J, int Jk0, int Jk1) {
+        for (int Jk = Jk0; Jk < Jk1; ++Jk) {
+            const int ldk = R - GT_NB * Jk;
+            const double* pa = Lb + gt_off(R, Jk) + (i0 - GT_NB * Jk);
+            const double* pb = Lb + gt_off(R, Jk) + (GT_NB * (J - Jk) + 4 * cb);
+#pragma unroll 4
+            for (int kk = 0; kk < GT_NB; ++kk) {
+                const double2 a01 = *reinterpret_cast<const double2*>(pa + kk * ldk);
+                const double2 a23 = *reinterpret_cast<const double2*>(pa + kk * ldk + 2);
+                const double2 b01 = *reinterpret_cast<const double2*>(pb + kk * ldk);
+                const double2 b23 = *reinterpret_cast<const double2*>(pb + kk * ldk + 2);
+                const double a[4] = {a01.x, a01.y, a23.x, a23.y};
+                const double b[4] = {b01.x, b01.y, b23.x, b23.y};
+#pragma unroll
+                for (int p = 0; p < 4; ++p)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) acc[p][q] = fma(-a[p], b[q], acc[p][q]);
+            }
+        }
+    };
+    auto load_tile = [&](int J) {
+        const int ldJ = R - GT_NB * J;
+        const double* colJ = Lb + gt_off(R, J);
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const double2 v01 = *reinterpret_cast<const double2*>(colJ + (4 * cb + b) * ldJ + (i0 - GT_NB * J));
+            const double2 v23 = *reinterpret_cast<const double2*>(colJ + (4 * cb + b) * ldJ + (i0 - GT_NB * J) + 2);
+            acc[0][b] = v01.x; acc[1][b] = v01.y; acc[2][b] = v23.x; acc[3][b] = v23.y;
+        }
+    };
 
     for (int J = 0; J < nblk; ++J) {
         const int ldJ = R - GT_NB * J;
         double* colJ = Lb + gt_off(R, J);
         const int ncols = min(GT_NB, n - GT_NB * J);
-        // ---------------- update with all previous block columns (register tiles)
+        // ---------------- finish the update of block column J: the lookahead covered block columns < J-1
         if (J > 0 && i0 >= GT_NB * J && i0 < R) {
-            double acc[4][4];
-#pragma unroll
-            for (int b = 0; b < 4; ++b) {
-                const double2 v01 = *reinterpret_cast<const double2*>(colJ + (4 * cb + b) * ldJ + (i0 - GT_NB * J));
-                const double2 v23 = *reinterpret_cast<const double2*>(colJ + (4 * cb + b) * ldJ + (i0 - GT_NB * J) + 2);
-                acc[0][b] = v01.x; acc[1][b] = v01.y; acc[2][b] = v23.x; acc[3][b] = v23.y;
-            }
-            for (int Jk = 0; Jk < J; ++Jk) {
-                const int ldk = R - GT_NB * Jk;
-                const double* pa = Lb + gt_off(R, Jk) + (i0 - GT_NB * Jk);
-                const double* pb = Lb + gt_off(R, Jk) + (GT_NB * (J - Jk) + 4 * cb);
-#pragma unroll 4
-                for (int kk = 0; kk < GT_NB; ++kk) {
-                    const double2 a01 = *reinterpret_cast<const double2*>(pa + kk * ldk);
-                    const double2 a23 = *reinterpret_cast<const double2*>(pa + kk * ldk + 2);
-                    const double2 b01 = *reinterpret_cast<const double2*>(pb + kk * ldk);
-                    const double2 b23 = *reinterpret_cast<const double2*>(pb + kk * ldk + 2);
-                    const double a[4] = {a01.x, a01.y, a23.x, a23.y};
-                    const double b[4] = {b01.x, b01.y, b23.x, b23.y};
-#pragma unroll
-                    for (int p = 0; p < 4; ++p)
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) acc[p][q] = fma(-a[p], b[q], acc[p][q]);
-                }
-            }
+            if (!acc_valid) load_tile(J);
+            apply_columns(J, acc_valid ? J - 1 : 0, J);
 #pragma unroll
             for (int b = 0; b < 4; ++b) {
                 double* dst = colJ + (4 * cb + b) * ldJ + (i0 - GT_NB * J);
@@ -153,11 +189,14 @@ gp_batch_tiled_kernel(int kernel_id, const int* __restrict__ kernel_ids, const d
                 *reinterpret_cast<double2*>(dst + 2) = make_double2(acc[2][b], acc[3][b]);
             }
         }
+        acc_valid = false;
+        GT_TICK(2);
         __syncthreads();
+        GT_TICK(3);
         // ---------------- diagonal block (warp 0), in registers: lane r owns row r (d[c] = D[r][c], c <= r).
         // Right-looking; column k of L is broadcast lane by lane with shuffles, so the only serial latency
         // per column is one sqrt/rsqrt pair.  Scaling multiplies by the reciprocal like OpenBLAS potf2.
-        if (tid < 32) {
+        if (diag_warp) {
             double d[GT_NB];
 #pragma unroll
             for (int c = 0; c < GT_NB; ++c)
@@ -170,8 +209,13 @@ gp_batch_tiled_kernel(int kernel_id, const int* __restrict__ kernel_ids, const d
                     if (piv <= 0.0 || piv == INFINITY) {        // NaN compares false: the factorisation goes on
                         fail = k + 1;
                     } else {
-                        const double dk = sqrt(piv);
-                        const double inv = 1.0 / dk;
+                        // sqrt(piv) and its reciprocal from ONE rsqrt + Newton steps: the IEEE sqrt followed by an
+                        // IEEE division is ~300 cycles of serial latency per pivot, and the n pivots are the
+                        // critical path of the whole factorisation.  dk and inv end up within 1 ulp.
+                        double inv = rsqrt(piv);
+                        double dk = piv * inv;
+                        dk = fma(0.5 * inv, fma(-dk, dk, piv), dk);
+                        inv = fma(inv, fma(-dk, inv, 1.0), inv);
                         const double l = (lane == k) ? dk : d[k] * inv;
                         d[k] = l;
                         if (lane == k) idg[GT_NB * J + k] = inv;
@@ -191,7 +235,16 @@ gp_batch_tiled_kernel(int kernel_id, const int* __restrict__ kernel_ids, const d
                     if (lane < ncols && c <= lane) colJ[c * ldJ + lane] = d[c];
             }
         }
+        GT_TICK(4);
+        // ---------------- lookahead: block column J+1 minus block columns < J (all final), kept in registers
+        if (J + 1 < nblk && J >= 1 && i0 >= GT_NB * (J + 1) && i0 < R) {
+            load_tile(J + 1);
+            apply_columns(J + 1, 0, J);
+            acc_valid = true;
+        }
+        GT_TICK(5);
         __syncthreads();
+        GT_TICK(6);
         if (status != 0) {
             if (tid == 0) {
                 if (metric == GT_METRIC_FIT) fit_info[0] = status;
@@ -211,10 +264,12 @@ gp_batch_tiled_kernel(int kernel_id, const int* __restrict__ kernel_ids, const d
 #pragma unroll
                 for (int c = 0; c < GT_NB; ++c) {
                     if (c < ncols) {
-                        double s = x[c];
+                        // right-looking inside the row: x[c] is final, push it into the later columns at once
+                        // (independent FMAs, so the dependent chain is 16 steps, not 136)
+                        x[c] *= idg[GT_NB * J + c];
 #pragma unroll
-                        for (int p = 0; p < c; ++p) s = fma(-x[p], colJ[p * ldJ + c], s);
-                        x[c] = s * idg[GT_NB * J + c];
+                        for (int q = c + 1; q < GT_NB; ++q)
+                            if (q < ncols) x[q] = fma(-x[c], colJ[c * ldJ + q], x[q]);
                     }
                 }
 #pragma unroll
@@ -222,7 +277,9 @@ gp_batch_tiled_kernel(int kernel_id, const int* __restrict__ kernel_ids, const d
                     if (c < ncols) colJ[c * ldJ + r] = x[c];
             }
         }
+        GT_TICK(7);
         __syncthreads();
+        GT_TICK(8);
     }
 
     // L(i, j) for i >= j lives at Lb[gt_off(R, j/16) + (j%16) * (R - 16 (j/16)) + (i - 16 (j/16))]
@@ -309,6 +366,16 @@ int b200id_gp_batch_tiled_launch(int kernel_id, const int* kernel_ids, const dou
     B200ID_LAUNCH_CHECK("gp_batch_tiled_kernel");
     return B200ID_OK;
 }
+
+#ifdef GT_PROFILE
+extern "C" int b200id_debug_gt_profile(unsigned long long* out16_host, int reset) {
+    if (reset) {
+        unsigned long long z[16] = {0};
+        return check_cuda(cudaMemcpyToSymbol(g_gt_prof, z, sizeof(z)), "reset prof");
+    }
+    return check_cuda(cudaMemcpyFromSymbol(out16_host, g_gt_prof, 16 * sizeof(unsigned long long)), "read prof");
+}
+#endif
 
 // Final fit through the same blocked kernel (one CTA): alpha, dense L (row-major lower) and info.
 int b200id_gp_fit_tiled_launch(int kernel_id, const double* theta, const double* X, const double* y, int n,

@@ -87,3 +87,20 @@ def fir_validate(u, y, g, detrend: bool = False, want_pred: bool = True,
     sums, pred = fir_eval_device(u_d, y_d, g_d, skip, float(y[skip]), want_pred=want_pred, n=n)
     m = metrics_from_sums(sums.cpu().numpy(), skip)
     return m, (pred.cpu().numpy() if want_pred else None)
+
+
+def fir_validate_sharded(u_d: torch.Tensor, y_d: torch.Tensor, g_d: torch.Tensor, lo: int, hi: int, y0: float,
+                         skip_global: Optional[int] = None) -> Dict[str, float]:
+    """Validation metrics of FIR taps on ONE record whose outputs [lo, hi) belong to this rank.
+
+    ``u_d`` is the rank's slice of u INCLUDING min(lo, taps - 1) samples of history in front of output
+    ``lo``; ``y_d`` is y[lo:hi].  ``y0`` = y[skip] of the whole record (R2 baseline).  One 4-double
+    all-reduce (FIR row)."""
+    from . import dist as bdist
+    taps = g_d.numel()
+    skip = min(10, taps // 10) if skip_global is None else skip_global
+    lead = min(lo, taps - 1)
+    n_out = hi - lo
+    sums, _ = fir_eval_device(u_d[lead:], y_d, g_d, max(0, skip - lo), y0, lead=lead, n=n_out)
+    bdist.allreduce_sum_(sums)
+    return metrics_from_sums(sums.cpu().numpy(), skip)

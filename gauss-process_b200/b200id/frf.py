@@ -202,3 +202,33 @@ def estimate_records(records, w, drop_seconds: float = 0.0, subtract_mean: bool 
         Ys.append(Y)
     G = cross_power_device(torch.stack(Us), torch.stack(Ys), eps)
     return G.cpu().numpy(), torch.stack(Us).cpu().numpy(), torch.stack(Ys).cpu().numpy()
+
+
+# ----------------------------------------------------------------------------------------- time-segment shards
+def record_coefficients_sharded(t_d, u_d, y_d, w_d, lo: int, hi: int, n_total: int, span: float, w_max: float,
+                                subtract_mean: bool = True):
+    """(U, Y) of ONE record whose samples are split over ranks.
+
+    This rank holds the resident slice t_d/u_d/y_d = samples [lo - h0, hi + h1) of the record, with
+    h0 = 1 if lo > 0 and h1 = 1 if hi < n_total (one-sample halo for the trapezoid weights), and owns
+    [lo, hi).  Two tiny all-reduces: (sum u, sum y) for the mean, then the 4*nd partial sums; every
+    rank finalises redundantly.  ``span`` = t[-1] - t[0] of the WHOLE record.
+    """
+    from . import dist as bdist
+    h0 = 1 if lo > 0 else 0
+    n_local = t_d.numel()
+    own = (h0, h0 + (hi - lo))
+    assert own[1] <= n_local
+    nd = w_d.numel()
+    sums = None
+    if subtract_mean:
+        sums = moments_device(u_d, y_d, own)
+        bdist.allreduce_sum_(sums)
+    span_local = float((t_d[-1] - t_d[0]).item())
+    kind, t0, dt = choose_path(t_d, span_local, w_max)
+    if kind == "uniform":
+        part = project_uniform_device(t_d, u_d, y_d, w_d, t0, dt, own, sums, 1.0 / n_total)
+    else:
+        part = project_device(t_d, u_d, y_d, w_d, own, sums, 1.0 / n_total)
+    bdist.allreduce_sum_(part)
+    return finalize_device(part, nd, 2.0 / span, want_y=y_d is not None)

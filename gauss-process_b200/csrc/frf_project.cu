@@ -150,7 +150,7 @@ frf_project_kernel(const double* __restrict__ t, const double* __restrict__ u,
 // result still follows the reference's per-sample phase rounding, which is what the 1e-9 parity
 // at weakly excited bins needs ("K1").  Every chain is re-seeded from an exact
 // double-double phase at each tile, so rotation drift is bounded by ~100 steps.
-constexpr int FRFU_CHAINS = 4;              // independent rotation chains per thread (ILP)
+constexpr int FRFU_CHAINS = 2;              // independent rotation chains per thread (ILP)
 
 struct DD { double hi, lo; };
 __device__ __forceinline__ DD dd_time(double t0, double k, double dt) {
@@ -170,7 +170,14 @@ __device__ __forceinline__ void sincos_dd(double w, DD x, double& s, double& c) 
     c = fma(-s0, pl, c0);
 }
 
-template <bool HAS_Y>
+// |sin| of the three-term kernel's chain step below which a bin is handed to the rotation kernel: the
+// three-term recurrence amplifies rounding by ~m / |sin D| (m <= ~350 steps between re-seeds -> < 4e-11).
+constexpr double FRFU_SIN_MIN = 1e-3;
+
+// THREE = true : three-term recurrence for every well-conditioned bin (the others are left untouched);
+// THREE = false: rotation recurrence for the few remaining bins, compacted so that they still fill the CTA.
+// Launched back to back on the same grid; each (cta, bin) partial is written by exactly one of them.
+template <bool HAS_Y, bool THREE>
 __global__ void __launch_bounds__(FRF_THREADS, FRF_CTAS_PER_SM)
 frf_project_uniform_kernel(const double* __restrict__ t, const double* __restrict__ u,
                            const double* __restrict__ y, int64_t n, int64_t own_begin, int64_t own_end,
@@ -180,24 +187,61 @@ frf_project_uniform_kernel(const double* __restrict__ t, const double* __restric
     extern __shared__ __align__(16) double smem[];
     double2* td = reinterpret_cast<double2*>(smem);                 // [tile] (t_i, delta_i)
     double2* ab = td + FRF_TILE_MAX;                                // [tile] (w_i (u_i - mean), w_i (y_i - mean))
+    __shared__ int s_list[FRF_THREADS];
+    __shared__ int s_count;
 
     const int tid = threadIdx.x;
     const int bin0 = blockIdx.y * FRF_THREADS;
-    const int nb = min(nd - bin0, FRF_THREADS);
+    const int nb_all = min(nd - bin0, FRF_THREADS);
+    const int R_three = FRF_THREADS / nb_all;                        // stripes of the three-term kernel
+    // classification of bin (bin0 + tid) by the three-term kernel's chain step
+    bool good = false;
+    if (tid < nb_all) {
+        DD step; const double kk = (double)(FRFU_CHAINS * R_three);
+        step.hi = kk * dt; step.lo = fma(kk, dt, -step.hi);
+        double s3, c3;
+        sincos_dd(w[bin0 + tid], step, s3, c3);
+        good = fabs(s3) >= FRFU_SIN_MIN;
+    }
+    int nb, bsel;
+    if (THREE) {
+        nb = nb_all;
+        s_list[tid] = good ? 1 : 0;                                  // flag per bin of this group
+        __syncthreads();
+        bsel = tid % nb;
+    } else {
+        if (tid == 0) s_count = 0;
+        __syncthreads();
+        // ordered compaction of the ill-conditioned bins (warp ballots, warps in order)
+        for (int wbase = 0; wbase < nb_all; wbase += 32) {
+            if (tid >= wbase && tid < wbase + 32) {
+                const unsigned m = __ballot_sync(0xffffffffu, tid < nb_all && !good);
+                if (tid < nb_all && !good) s_list[s_count + __popc(m & ((1u << (tid & 31)) - 1u))] = tid;
+                __syncwarp();
+                if ((tid & 31) == 0) s_count += __popc(m);
+            }
+            __syncthreads();
+        }
+        nb = s_count;
+        if (nb == 0) return;
+        bsel = s_list[tid % nb];
+    }
     const int R = FRF_THREADS / nb;
-    const int b = tid % nb, r = tid / nb;
-    const bool active = r < R;
+    const int b = THREE ? bsel : bsel;                               // bin index inside the group
+    const int r = tid / nb;
+    const bool active = (r < R) && (THREE ? (s_list[b] != 0) : true);
     const double wk = w[bin0 + b];
     const double mean_u = sums ? sums[0] * inv_count : 0.0;
     const double mean_y = (HAS_Y && sums) ? sums[1] * inv_count : 0.0;
 
-    // rotation by FRFU_CHAINS * R samples
+    // step of one chain: FRFU_CHAINS * R samples
     double sd, cd;
     {
         DD step; const double kk = (double)(FRFU_CHAINS * R);
         step.hi = kk * dt; step.lo = fma(kk, dt, -step.hi);
         sincos_dd(wk, step, sd, cd);
     }
+    constexpr bool use3 = THREE;
     double uc[2] = {0.0, 0.0}, us[2] = {0.0, 0.0}, yc[2] = {0.0, 0.0}, ys[2] = {0.0, 0.0};
 
     for (int tl = blockIdx.x; tl < n_tiles; tl += gridDim.x) {
@@ -228,38 +272,73 @@ frf_project_uniform_kernel(const double* __restrict__ t, const double* __restric
             }
             const int stride = R * FRFU_CHAINS;
             int j = r;
-            for (; j + R * (FRFU_CHAINS - 1) < cnt; j += stride) {
+// one sample of chain q: reference phase = theta + eps, accumulate, leave (cs, sn) untouched
+#define FRFU_SAMPLE(q, cval, sval)                                                                   \
+    {                                                                                                \
+        const double2 tdv = td[j + R * (q)];                                                         \
+        const double2 abv = ab[j + R * (q)];                                                         \
+        const double p = wk * tdv.x;                                                                 \
+        const double e = fma(wk, tdv.x, -p);                                                         \
+        const double eps = fma(wk, tdv.y, -e);                                                       \
+        const double c1 = fma(-(sval), eps, (cval));                                                 \
+        const double s1 = fma((cval), eps, (sval));                                                  \
+        uc[(q) & 1] = fma(abv.x, c1, uc[(q) & 1]); us[(q) & 1] = fma(abv.x, s1, us[(q) & 1]);        \
+        if (HAS_Y) { yc[(q) & 1] = fma(abv.y, c1, yc[(q) & 1]); ys[(q) & 1] = fma(abv.y, s1, ys[(q) & 1]); } \
+    }
+            if (use3) {
+                // three-term recurrence x[m+1] = 2 cos(D) x[m] - x[m-1]: one FMA per component instead of a
+                // 4-op rotation.  Its rounding error grows like m / |sin D|; it is only used where |sin D| >=
+                // 1e-2 (m <= ~100 steps between re-seeds -> < 2e-12), other bins keep the rotation.
+                double cp[FRFU_CHAINS], sp[FRFU_CHAINS];
 #pragma unroll
-                for (int q = 0; q < FRFU_CHAINS; ++q) {
-                    const double2 tdv = td[j + R * q];
-                    const double2 abv = ab[j + R * q];
-                    const double p = wk * tdv.x;
-                    const double e = fma(wk, tdv.x, -p);
-                    const double eps = fma(wk, tdv.y, -e);
-                    const double c1 = fma(-sn[q], eps, cs[q]);
-                    const double s1 = fma(cs[q], eps, sn[q]);
-                    uc[q & 1] = fma(abv.x, c1, uc[q & 1]); us[q & 1] = fma(abv.x, s1, us[q & 1]);
-                    if (HAS_Y) { yc[q & 1] = fma(abv.y, c1, yc[q & 1]); ys[q & 1] = fma(abv.y, s1, ys[q & 1]); }
-                    const double cn = fma(cs[q], cd, -(sn[q] * sd));
-                    sn[q] = fma(sn[q], cd, cs[q] * sd);
-                    cs[q] = cn;
+                for (int q = 0; q < FRFU_CHAINS; ++q) {       // x[-1] by one backward rotation
+                    cp[q] = fma(cs[q], cd, sn[q] * sd);
+                    sp[q] = fma(sn[q], cd, -(cs[q] * sd));
+                }
+                const double K = 2.0 * cd;
+                for (; j + R * (FRFU_CHAINS - 1) + stride < cnt; j += 2 * stride) {
+#pragma unroll
+                    for (int q = 0; q < FRFU_CHAINS; ++q) {
+                        FRFU_SAMPLE(q, cs[q], sn[q])
+                        cp[q] = fma(K, cs[q], -cp[q]);         // cp now holds x[m+1], cs holds x[m]
+                        sp[q] = fma(K, sn[q], -sp[q]);
+                    }
+                    j += stride;
+#pragma unroll
+                    for (int q = 0; q < FRFU_CHAINS; ++q) {
+                        FRFU_SAMPLE(q, cp[q], sp[q])
+                        cs[q] = fma(K, cp[q], -cs[q]);         // roles swap back: cs = x[m+2], cp = x[m+1]
+                        sn[q] = fma(K, sp[q], -sn[q]);
+                    }
+                    j -= stride;
+                }
+                // (cs, sn) is current again; finish with single steps
+                for (; j + R * (FRFU_CHAINS - 1) < cnt; j += stride) {
+#pragma unroll
+                    for (int q = 0; q < FRFU_CHAINS; ++q) {
+                        FRFU_SAMPLE(q, cs[q], sn[q])
+                        const double cn = fma(K, cs[q], -cp[q]), snn = fma(K, sn[q], -sp[q]);
+                        cp[q] = cs[q]; sp[q] = sn[q];
+                        cs[q] = cn; sn[q] = snn;
+                    }
+                }
+            } else {
+                for (; j + R * (FRFU_CHAINS - 1) < cnt; j += stride) {
+#pragma unroll
+                    for (int q = 0; q < FRFU_CHAINS; ++q) {
+                        FRFU_SAMPLE(q, cs[q], sn[q])
+                        const double cn = fma(cs[q], cd, -(sn[q] * sd));
+                        sn[q] = fma(sn[q], cd, cs[q] * sd);
+                        cs[q] = cn;
+                    }
                 }
             }
             // tail: fewer than FRFU_CHAINS samples left in this stripe
 #pragma unroll
             for (int q = 0; q < FRFU_CHAINS; ++q) {
-                if (j + R * q < cnt) {
-                    const double2 tdv = td[j + R * q];
-                    const double2 abv = ab[j + R * q];
-                    const double p = wk * tdv.x;
-                    const double e = fma(wk, tdv.x, -p);
-                    const double eps = fma(wk, tdv.y, -e);
-                    const double c1 = fma(-sn[q], eps, cs[q]);
-                    const double s1 = fma(cs[q], eps, sn[q]);
-                    uc[q & 1] = fma(abv.x, c1, uc[q & 1]); us[q & 1] = fma(abv.x, s1, us[q & 1]);
-                    if (HAS_Y) { yc[q & 1] = fma(abv.y, c1, yc[q & 1]); ys[q & 1] = fma(abv.y, s1, ys[q & 1]); }
-                }
+                if (j + R * q < cnt) FRFU_SAMPLE(q, cs[q], sn[q])
             }
+#undef FRFU_SAMPLE
         }
     }
     __syncthreads();
@@ -269,8 +348,9 @@ frf_project_uniform_kernel(const double* __restrict__ t, const double* __restric
     red[2 * FRF_THREADS + tid] = HAS_Y ? yc[0] + yc[1] : 0.0;
     red[3 * FRF_THREADS + tid] = HAS_Y ? ys[0] + ys[1] : 0.0;
     __syncthreads();
-    if (tid < nb) {
-        double* out = cta_partial + (size_t)blockIdx.x * 4 * nd + bin0 + tid;
+    if (tid < nb && (THREE ? (s_list[tid] != 0) : true)) {
+        const int bin = THREE ? tid : s_list[tid];
+        double* out = cta_partial + (size_t)blockIdx.x * 4 * nd + bin0 + bin;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
             double v = 0.0;
@@ -483,15 +563,21 @@ extern "C" int b200id_frf_project_uniform(const double* t, const double* u, cons
     const size_t need = (size_t)p.grid_x * 4 * nd * sizeof(double);
     B200ID_REQUIRE(ws_bytes >= need, B200ID_E_WORKSPACE, "frf_project_uniform: workspace %zu < %zu", ws_bytes, need);
     double* part = (double*)ws;
-    int rc = check_cuda(cudaFuncSetAttribute(frf_project_uniform_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FRFU_SMEM_BYTES), "smem attr");
-    if (rc) return rc;
-    rc = check_cuda(cudaFuncSetAttribute(frf_project_uniform_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FRFU_SMEM_BYTES), "smem attr");
-    if (rc) return rc;
+    int rc = 0;
+    const void* fns[4] = {(const void*)frf_project_uniform_kernel<true, true>, (const void*)frf_project_uniform_kernel<true, false>,
+                          (const void*)frf_project_uniform_kernel<false, true>, (const void*)frf_project_uniform_kernel<false, false>};
+    for (int k = 0; k < 4; ++k) {
+        rc = check_cuda(cudaFuncSetAttribute(fns[k], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FRFU_SMEM_BYTES), "smem attr");
+        if (rc) return rc;
+    }
     dim3 grid(p.grid_x, p.grid_y);
-    if (y)
-        frf_project_uniform_kernel<true><<<grid, FRF_THREADS, FRFU_SMEM_BYTES, st>>>(t, u, y, n, own_begin, own_end, w, nd, sums, inv_count, t0, dt, p.tile, p.n_tiles, part);
-    else
-        frf_project_uniform_kernel<false><<<grid, FRF_THREADS, FRFU_SMEM_BYTES, st>>>(t, u, nullptr, n, own_begin, own_end, w, nd, sums, inv_count, t0, dt, p.tile, p.n_tiles, part);
+    if (y) {
+        frf_project_uniform_kernel<true, true><<<grid, FRF_THREADS, FRFU_SMEM_BYTES, st>>>(t, u, y, n, own_begin, own_end, w, nd, sums, inv_count, t0, dt, p.tile, p.n_tiles, part);
+        frf_project_uniform_kernel<true, false><<<grid, FRF_THREADS, FRFU_SMEM_BYTES, st>>>(t, u, y, n, own_begin, own_end, w, nd, sums, inv_count, t0, dt, p.tile, p.n_tiles, part);
+    } else {
+        frf_project_uniform_kernel<false, true><<<grid, FRF_THREADS, FRFU_SMEM_BYTES, st>>>(t, u, nullptr, n, own_begin, own_end, w, nd, sums, inv_count, t0, dt, p.tile, p.n_tiles, part);
+        frf_project_uniform_kernel<false, false><<<grid, FRF_THREADS, FRFU_SMEM_BYTES, st>>>(t, u, nullptr, n, own_begin, own_end, w, nd, sums, inv_count, t0, dt, p.tile, p.n_tiles, part);
+    }
     B200ID_LAUNCH_CHECK("frf_project_uniform_kernel");
     const int len = 4 * nd;
     frf_fold_kernel<<<(len + 127) / 128, 128, 0, st>>>(part, p.grid_x, len, partial_out);

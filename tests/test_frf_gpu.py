@@ -192,3 +192,17 @@ def test_all_kernels_ragged_sizes_run_clean():
     script = Path(__file__).resolve().parent / "sanitize_smoke.py"
     out = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "all kernels ran" in out.stdout, out.stderr[-3000:]
+
+
+def test_uniform_path_ill_conditioned_bins_use_rotation_kernel(frf):
+    """Bins whose chain step lands on a multiple of pi (or is tiny) are unsafe for the three-term
+    recurrence; they must be routed to the compact rotation kernel and still meet the 1e-9 parity."""
+    from b200id import synth
+    n = 50_000
+    t, u, y = synth.make_record(n, 50, "square", seed=5)
+    R, S, dt = 512 // 5, 2, 0.002
+    w = np.array([1e-4, 1.0, np.pi / (R * S * dt), 2 * np.pi / (R * S * dt) + 1e-9, 300.0])
+    U, Y = frf.demod_pair(t, u, y, w)
+    Ur, Yr = ofrf.demod_trapz(t, u, w), ofrf.demod_trapz(t, y, w)
+    e = record("frf.uniform.ill_conditioned_bins.rel_each", max(rel_each(U, Ur), rel_each(Y, Yr)))
+    assert e < TOL

@@ -11,6 +11,7 @@
 // padding double per 16 (lane stride 17 doubles, odd) so that the 16-output-strided lane addresses fall in distinct
 // banks.  y_pred is optional: the validation metric only needs the three error sums, which are
 // folded per CTA and then by a fixed-order tree (deterministic).
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace b200id {
@@ -159,6 +160,22 @@ __global__ void __launch_bounds__(256) fir_fold_kernel(const double* __restrict_
 
 using namespace b200id;
 
+// fir_fft.cu: overlap-save FFT path
+size_t b200id_fir_fft_workspace_bytes();
+bool b200id_fir_fft_applicable(int64_t n, int n_taps);
+int b200id_fir_eval_fft(const double* u, const double* y, int64_t n, int64_t lead, const double* g, int n_taps,
+                        int64_t skip, double y0, double* y_pred_out, double* sums_out, void* ws, size_t ws_bytes,
+                        cudaStream_t st);
+
+static int fir_path_override() {          // B200ID_FIR_PATH = auto | direct | fft
+    static int cached = -1;
+    if (cached < 0) {
+        const char* e = getenv("B200ID_FIR_PATH");
+        cached = (e && strcmp(e, "direct") == 0) ? 1 : (e && strcmp(e, "fft") == 0) ? 2 : 0;
+    }
+    return cached;
+}
+
 extern "C" int b200id_idft_hermitian(const double* G_pos, int nd, double* h_out, int n_taps, void* stream) {
     B200ID_REQUIRE(G_pos && h_out, B200ID_E_ARG, "idft_hermitian: null pointer");
     B200ID_REQUIRE(nd >= 2, B200ID_E_ARG, "idft_hermitian: need nd >= 2");
@@ -173,7 +190,9 @@ extern "C" int b200id_idft_hermitian(const double* G_pos, int nd, double* h_out,
 extern "C" size_t b200id_fir_workspace_bytes(int64_t n) {
     if (n <= 0) return 0;
     const int64_t ctas = (n + FIR_TILE - 1) / FIR_TILE;
-    return align_up((size_t)ctas * 4 * sizeof(double), 256);
+    const size_t direct = align_up((size_t)ctas * 4 * sizeof(double), 256);
+    const size_t fft = b200id_fir_fft_workspace_bytes();
+    return direct > fft ? direct : fft;
 }
 
 extern "C" int b200id_fir_eval(const double* u, const double* y, int64_t n, int64_t lead, const double* g,
@@ -182,6 +201,9 @@ extern "C" int b200id_fir_eval(const double* u, const double* y, int64_t n, int6
     B200ID_REQUIRE(u && g && sums_out && ws, B200ID_E_ARG, "fir_eval: null pointer");
     B200ID_REQUIRE(n > 0 && lead >= 0 && skip >= 0, B200ID_E_ARG, "fir_eval: bad sizes");
     B200ID_REQUIRE(n_taps > 0 && n_taps <= FIR_MAX_TAPS, B200ID_E_UNSUPPORTED, "fir_eval: n_taps=%d outside (0, %d]", n_taps, FIR_MAX_TAPS);
+    const int ov = fir_path_override();
+    if (ov != 1 && ((ov == 2 && n_taps <= 2048) || b200id_fir_fft_applicable(n, n_taps)))
+        return b200id_fir_eval_fft(u, y, n, lead, g, n_taps, skip, y0, y_pred_out, sums_out, ws, ws_bytes, (cudaStream_t)stream);
     const int64_t ctas = (n + FIR_TILE - 1) / FIR_TILE;
     B200ID_REQUIRE(ctas < (1LL << 31), B200ID_E_UNSUPPORTED, "fir_eval: record too long for one launch");
     B200ID_REQUIRE(ws_bytes >= (size_t)ctas * 4 * sizeof(double), B200ID_E_WORKSPACE, "fir_eval: workspace too small");

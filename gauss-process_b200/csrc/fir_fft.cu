@@ -1,0 +1,224 @@
+// fir_fft.cu -- K6 fast path: causal FIR validation by in-shared-memory overlap-save FFT (FP64).
+//
+// Reference call sites: np.convolve(u, g, 'full')[:N] at src/fir_model/fir_fitting.py:285 and
+// fir_validation.py:190, metrics at fir_fitting.py:288-306 / fir_validation.py:115-128.
+//
+// Direct form costs 2*taps FP64 flops per output (2048 at 1024 taps) and is FP64-issue bound at ~81 % of the
+// FP64 peak (fir_conv.cu).  Overlap-save turns that into ~90 flops per output, which moves the kernel from
+// the FP64 pipe to shared-memory bandwidth:
+//   * one work unit = TWO consecutive output blocks A, B carried as the real and imaginary part of one
+//     complex sequence z = uA + j uB of length N = 4096.  The taps are real, so IFFT(FFT(z) G) =
+//     (uA * g) + j (uB * g): no real-FFT untangling is needed at all;
+//   * radix-4 decimation-in-frequency forward stages leave the spectrum in base-4 digit-reversed order, the
+//     tap spectrum G is produced by the SAME forward routine (so it is in the same order), and the inverse
+//     runs the decimation-in-time stages in the opposite order: no reordering pass either.  The last forward
+//     stage, the product with G and the first inverse stage touch the same four elements per thread and are
+//     fused in registers;
+//   * the circular convolution is valid for m in [taps-1, N): each block yields V = N - taps + 1 outputs.
+// Data (N complex, padded one element per 8 against bank conflicts) + N/4 twiddles = 90 KB per CTA -> 2 CTAs
+// per SM, persistent grid, error sums fused into the epilogue (y_pred is optional).
+#include "common.cuh"
+
+namespace b200id {
+
+constexpr int FF_N = 4096;
+constexpr int FF_THREADS = 256;
+constexpr int FF_MAX_TAPS = FF_N / 2;       // keeps >= 50 % of every block valid
+constexpr int FF_CTAS_PER_SM = 2;
+
+__device__ __forceinline__ int ff_pad(int p) { return p + (p >> 3); }
+constexpr int FF_DATA_ELEMS = FF_N + FF_N / 8;
+
+struct cplx { double x, y; };
+__device__ __forceinline__ cplx cadd(cplx a, cplx b) { return {a.x + b.x, a.y + b.y}; }
+__device__ __forceinline__ cplx csub(cplx a, cplx b) { return {a.x - b.x, a.y - b.y}; }
+__device__ __forceinline__ cplx cmul(cplx a, cplx b) { return {fma(a.x, b.x, -(a.y * b.y)), fma(a.x, b.y, a.y * b.x)}; }
+__device__ __forceinline__ cplx cmulc(cplx a, cplx b) { return {fma(a.x, b.x, a.y * b.y), fma(a.y, b.x, -(a.x * b.y))}; }  // a * conj(b)
+__device__ __forceinline__ cplx mul_mj(cplx a) { return {a.y, -a.x}; }     // -j a
+__device__ __forceinline__ cplx mul_pj(cplx a) { return {-a.y, a.x}; }     // +j a
+__device__ __forceinline__ cplx lds(const double2* s, int p) { const double2 v = s[ff_pad(p)]; return {v.x, v.y}; }
+__device__ __forceinline__ void sts(double2* s, int p, cplx v) { s[ff_pad(p)] = make_double2(v.x, v.y); }
+
+// tw[k] = exp(-2 pi i k / N), k < N/4
+__device__ __forceinline__ void ff_make_twiddles(double2* tw) {
+    for (int k = threadIdx.x; k < FF_N / 4; k += FF_THREADS) {
+        double s, c;
+        sincospi(2.0 * (double)k / (double)FF_N, &s, &c);
+        tw[k] = make_double2(c, -s);
+    }
+}
+
+// forward DIF stages L = N .. 16 (the L = 4 stage is fused by the callers)
+__device__ __forceinline__ void ff_forward_stages(double2* x, const double2* tw) {
+    for (int lg = 12; lg >= 4; lg -= 2) {               // L = 2^lg = 4096, 1024, 256, 64, 16
+        const int L = 1 << lg, q4 = L >> 2, tstep = FF_N >> lg;
+        for (int bidx = threadIdx.x; bidx < FF_N / 4; bidx += FF_THREADS) {
+            const int g = bidx >> (lg - 2), j = bidx & (q4 - 1);
+            const int base = (g << lg) + j;
+            const cplx a0 = lds(x, base), a1 = lds(x, base + q4), a2 = lds(x, base + 2 * q4), a3 = lds(x, base + 3 * q4);
+            const double2 t1 = tw[j * tstep];
+            const cplx w1 = {t1.x, t1.y}, w2 = cmul(w1, w1), w3 = cmul(w2, w1);
+            const cplx b0 = cadd(a0, a2), b1 = csub(a0, a2), b2 = cadd(a1, a3), b3 = mul_mj(csub(a1, a3));
+            sts(x, base, cadd(b0, b2));
+            sts(x, base + q4, cmul(cadd(b1, b3), w1));
+            sts(x, base + 2 * q4, cmul(csub(b0, b2), w2));
+            sts(x, base + 3 * q4, cmul(csub(b1, b3), w3));
+        }
+        __syncthreads();
+    }
+}
+
+// inverse DIT stages L = 16 .. N (the L = 4 stage is fused by the caller); no 1/N scale here
+__device__ __forceinline__ void ff_inverse_stages(double2* x, const double2* tw) {
+    for (int lg = 4; lg <= 12; lg += 2) {
+        const int L = 1 << lg, q4 = L >> 2, tstep = FF_N >> lg;
+        for (int bidx = threadIdx.x; bidx < FF_N / 4; bidx += FF_THREADS) {
+            const int g = bidx >> (lg - 2), j = bidx & (q4 - 1);
+            const int base = (g << lg) + j;
+            const double2 t1 = tw[j * tstep];
+            const cplx w1 = {t1.x, t1.y}, w2 = cmul(w1, w1), w3 = cmul(w2, w1);
+            const cplx c0 = lds(x, base), c1 = cmulc(lds(x, base + q4), w1), c2 = cmulc(lds(x, base + 2 * q4), w2),
+                       c3 = cmulc(lds(x, base + 3 * q4), w3);
+            const cplx e0 = cadd(c0, c2), e1 = csub(c0, c2), e2 = cadd(c1, c3), e3 = mul_pj(csub(c1, c3));
+            sts(x, base, cadd(e0, e2));
+            sts(x, base + q4, cadd(e1, e3));
+            sts(x, base + 2 * q4, csub(e0, e2));
+            sts(x, base + 3 * q4, csub(e1, e3));
+        }
+        __syncthreads();
+    }
+}
+
+// spectrum of the zero-padded taps in the forward routine's (digit-reversed) order, scaled by 1/N
+__global__ void __launch_bounds__(FF_THREADS)
+fir_fft_taps_kernel(const double* __restrict__ g, int n_taps, double2* __restrict__ Grev) {
+    extern __shared__ __align__(16) double2 ff_sm[];
+    double2* x = ff_sm;
+    double2* tw = ff_sm + FF_DATA_ELEMS;
+    ff_make_twiddles(tw);
+    for (int m = threadIdx.x; m < FF_N; m += FF_THREADS) sts(x, m, {m < n_taps ? g[m] : 0.0, 0.0});
+    __syncthreads();
+    ff_forward_stages(x, tw);
+    const double inv_n = 1.0 / (double)FF_N;
+    for (int bidx = threadIdx.x; bidx < FF_N / 4; bidx += FF_THREADS) {
+        const int base = 4 * bidx;
+        const cplx a0 = lds(x, base), a1 = lds(x, base + 1), a2 = lds(x, base + 2), a3 = lds(x, base + 3);
+        const cplx b0 = cadd(a0, a2), b1 = csub(a0, a2), b2 = cadd(a1, a3), b3 = mul_mj(csub(a1, a3));
+        const cplx y0 = cadd(b0, b2), y1 = cadd(b1, b3), y2 = csub(b0, b2), y3 = csub(b1, b3);
+        Grev[base] = make_double2(y0.x * inv_n, y0.y * inv_n);
+        Grev[base + 1] = make_double2(y1.x * inv_n, y1.y * inv_n);
+        Grev[base + 2] = make_double2(y2.x * inv_n, y2.y * inv_n);
+        Grev[base + 3] = make_double2(y3.x * inv_n, y3.y * inv_n);
+    }
+}
+
+__global__ void __launch_bounds__(FF_THREADS, FF_CTAS_PER_SM)
+fir_fft_kernel(const double* __restrict__ u, const double* __restrict__ y, int64_t n, int64_t lead, int n_taps,
+               const double2* __restrict__ Grev, int64_t skip, double y0, int64_t n_units,
+               double* __restrict__ y_pred, double* __restrict__ cta_sums) {
+    extern __shared__ __align__(16) double2 ff_sm[];
+    double2* x = ff_sm;
+    double2* tw = ff_sm + FF_DATA_ELEMS;
+    __shared__ double scratch[FF_THREADS / 32];
+    const int tid = threadIdx.x;
+    const int hist = n_taps - 1;
+    const int V = FF_N - hist;                       // valid outputs per block
+    ff_make_twiddles(tw);
+    double se = 0.0, sy = 0.0, st = 0.0, cnt = 0.0;
+
+    for (int64_t unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+        const int64_t oA = unit * 2 * (int64_t)V, oB = oA + V;       // first output of blocks A and B
+        __syncthreads();                                             // previous unit fully consumed / twiddles ready
+        for (int m = tid; m < FF_N; m += FF_THREADS) {
+            const int64_t ia = oA - hist + m, ib = oB - hist + m;
+            const double ua = (ia >= -lead && ia < n) ? __ldg(u + ia) : 0.0;
+            const double ub = (ib >= -lead && ib < n) ? __ldg(u + ib) : 0.0;
+            sts(x, m, {ua, ub});
+        }
+        __syncthreads();
+        ff_forward_stages(x, tw);
+        // fused: last forward stage (L = 4), product with the tap spectrum, first inverse stage (L = 4)
+        for (int bidx = tid; bidx < FF_N / 4; bidx += FF_THREADS) {
+            const int base = 4 * bidx;
+            const cplx a0 = lds(x, base), a1 = lds(x, base + 1), a2 = lds(x, base + 2), a3 = lds(x, base + 3);
+            const cplx b0 = cadd(a0, a2), b1 = csub(a0, a2), b2 = cadd(a1, a3), b3 = mul_mj(csub(a1, a3));
+            const double2 g0 = __ldg(Grev + base), g1 = __ldg(Grev + base + 1), g2 = __ldg(Grev + base + 2), g3 = __ldg(Grev + base + 3);
+            const cplx c0 = cmul(cadd(b0, b2), {g0.x, g0.y}), c1 = cmul(cadd(b1, b3), {g1.x, g1.y}),
+                       c2 = cmul(csub(b0, b2), {g2.x, g2.y}), c3 = cmul(csub(b1, b3), {g3.x, g3.y});
+            const cplx e0 = cadd(c0, c2), e1 = csub(c0, c2), e2 = cadd(c1, c3), e3 = mul_pj(csub(c1, c3));
+            sts(x, base, cadd(e0, e2));
+            sts(x, base + 1, cadd(e1, e3));
+            sts(x, base + 2, csub(e0, e2));
+            sts(x, base + 3, csub(e1, e3));
+        }
+        __syncthreads();
+        ff_inverse_stages(x, tw);
+        // epilogue: valid part m in [hist, N) -> outputs oA + (m - hist) (real part) and oB + (m - hist) (imaginary)
+        for (int m = hist + tid; m < FF_N; m += FF_THREADS) {
+            const cplx v = lds(x, m);
+            const int64_t ia = oA + (m - hist), ib = oB + (m - hist);
+            if (ia < n) {
+                if (y_pred) y_pred[ia] = v.x;
+                if (y && ia >= skip) {
+                    const double yi = __ldg(y + ia), e = yi - v.x, d0 = yi - y0;
+                    se = fma(e, e, se); sy = fma(yi, yi, sy); st = fma(d0, d0, st); cnt += 1.0;
+                }
+            }
+            if (ib < n) {
+                if (y_pred) y_pred[ib] = v.y;
+                if (y && ib >= skip) {
+                    const double yi = __ldg(y + ib), e = yi - v.y, d0 = yi - y0;
+                    se = fma(e, e, se); sy = fma(yi, yi, sy); st = fma(d0, d0, st); cnt += 1.0;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    se = block_sum(se, scratch);
+    sy = block_sum(sy, scratch);
+    st = block_sum(st, scratch);
+    cnt = block_sum(cnt, scratch);
+    if (tid == 0) {
+        double* o = cta_sums + 4 * (size_t)blockIdx.x;
+        o[0] = se; o[1] = sy; o[2] = st; o[3] = cnt;
+    }
+}
+
+constexpr size_t FF_SMEM_BYTES = (size_t)(FF_DATA_ELEMS + FF_N / 4) * sizeof(double2);
+
+}  // namespace b200id
+
+using namespace b200id;
+
+size_t b200id_fir_fft_workspace_bytes() {
+    return align_up((size_t)FF_N * sizeof(double2), 256) + align_up((size_t)(sm_count() * FF_CTAS_PER_SM + 8) * 4 * sizeof(double), 256);
+}
+bool b200id_fir_fft_applicable(int64_t n, int n_taps) {
+    return n_taps >= 128 && n_taps <= FF_MAX_TAPS && n >= 32768;
+}
+
+// fir_fold_kernel lives in fir_conv.cu
+namespace b200id { __global__ void fir_fold_kernel(const double* __restrict__ part, int64_t n_cta, double* __restrict__ out); }
+
+int b200id_fir_eval_fft(const double* u, const double* y, int64_t n, int64_t lead, const double* g, int n_taps,
+                        int64_t skip, double y0, double* y_pred_out, double* sums_out, void* ws, size_t ws_bytes,
+                        cudaStream_t st) {
+    B200ID_REQUIRE(ws_bytes >= b200id_fir_fft_workspace_bytes(), B200ID_E_WORKSPACE, "fir_eval(fft): workspace too small");
+    double2* Grev = (double2*)ws;
+    double* cta_sums = (double*)((char*)ws + align_up((size_t)FF_N * sizeof(double2), 256));
+    int rc = check_cuda(cudaFuncSetAttribute(fir_fft_taps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FF_SMEM_BYTES), "cudaFuncSetAttribute(fir fft taps)");
+    if (rc) return rc;
+    rc = check_cuda(cudaFuncSetAttribute(fir_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FF_SMEM_BYTES), "cudaFuncSetAttribute(fir fft)");
+    if (rc) return rc;
+    fir_fft_taps_kernel<<<1, FF_THREADS, FF_SMEM_BYTES, st>>>(g, n_taps, Grev);
+    B200ID_LAUNCH_CHECK("fir_fft_taps_kernel");
+    const int V = FF_N - (n_taps - 1);
+    const int64_t n_units = (n + 2 * (int64_t)V - 1) / (2 * (int64_t)V);
+    int grid = sm_count() * FF_CTAS_PER_SM;
+    if (n_units < grid) grid = (int)n_units;
+    fir_fft_kernel<<<grid, FF_THREADS, FF_SMEM_BYTES, st>>>(u, y, n, lead, n_taps, Grev, skip, y0, n_units, y_pred_out, cta_sums);
+    B200ID_LAUNCH_CHECK("fir_fft_kernel");
+    fir_fold_kernel<<<1, 256, 0, st>>>(cta_sums, grid, sums_out);
+    B200ID_LAUNCH_CHECK("fir_fold_kernel");
+    return B200ID_OK;
+}

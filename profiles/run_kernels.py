@@ -45,5 +45,7 @@ def timed(name, fn):
 timed("frf_project_general", lambda: frf.project_device(t, u, y, w))
 timed("frf_project_uniform", lambda: frf.project_uniform_device(t, u, y, w, 0.0, 0.002))
 timed("fir_eval", lambda: fir.fir_eval_device(u, y, g, 10, 0.0))
+timed("fir_eval_2048taps", lambda: fir.fir_eval_device(u, y, torch.cat([g, g]), 10, 0.0))
+timed("fir_eval_direct_100taps", lambda: fir.fir_eval_device(u, y, g[:100].contiguous(), 10, 0.0))
 timed("gp_batch_nll", lambda: gp.batch_eval_device(3, None, th, X, yy, 1e-6))
 timed("gp_batch_val", lambda: gp.batch_eval_device(3, None, th[:2048], X, yy, 1e-6, gp.METRIC_VAL_RMSE, Xv, yv, 0.0, 1.0))

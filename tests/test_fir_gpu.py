@@ -44,7 +44,10 @@ def test_convolution_and_metrics_golden(fir, golden):
 
 
 @pytest.mark.parametrize("n,taps", [(1, 1), (5, 3), (2047, 1024), (2048, 1024), (2049, 7), (100_003, 1024),
-                                    (50_000, 300), (4096, 1999), (10_000, 2500)])
+                                    (50_000, 300), (4096, 1999), (10_000, 2500),
+                                    # overlap-save FFT path (n >= 32768, 128 <= taps <= 2048), block-edge cases
+                                    (32_768, 128), (40_000, 2048), (3073 * 2 * 6, 1024), (3073 * 2 * 6 + 1, 1024),
+                                    (250_001, 1025), (70_000, 127), (70_000, 2049)])
 def test_convolution_oracle_ragged(fir, n, taps):
     rng = np.random.default_rng(n + taps)
     u = rng.standard_normal(n); g = rng.standard_normal(taps) / taps
@@ -77,7 +80,9 @@ def test_shard_history_matches_whole(fir):
     cut = 4_321_987
     a, pa = fir.fir_eval_device(u[:cut], y[:cut], g, skip, y0, want_pred=True)
     b, pb = fir.fir_eval_device(u[cut:], y[cut:], g, 0, y0, lead=taps - 1, want_pred=True)
-    assert torch.equal(pa, pred[:cut]) and torch.equal(pb, pred[cut:])
+    # the overlap-save path blocks the record from each slice's own origin: equal to rounding, not bitwise
+    scale = float(pred.abs().max())
+    assert float((pa - pred[:cut]).abs().max()) < 1e-13 * scale and float((pb - pred[cut:]).abs().max()) < 1e-13 * scale
     e = record("fir.property.shard_additivity", float(((a + b - whole).abs() / whole.abs()).max()))
     assert e < 1e-12
     # linearity in the taps, and idempotence (deterministic run to run)

@@ -129,11 +129,20 @@ fir_fft_kernel(const double* __restrict__ u, const double* __restrict__ y, int64
     for (int64_t unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
         const int64_t oA = unit * 2 * (int64_t)V, oB = oA + V;       // first output of blocks A and B
         __syncthreads();                                             // previous unit fully consumed / twiddles ready
-        for (int m = tid; m < FF_N; m += FF_THREADS) {
-            const int64_t ia = oA - hist + m, ib = oB - hist + m;
-            const double ua = (ia >= -lead && ia < n) ? __ldg(u + ia) : 0.0;
-            const double ub = (ib >= -lead && ib < n) ? __ldg(u + ib) : 0.0;
-            sts(x, m, {ua, ub});
+        {
+            // all 32 global loads of this thread are issued before the first shared-memory store, so the DRAM
+            // latency is paid once per unit and not once per element
+            constexpr int PER = FF_N / FF_THREADS;           // 16
+            double ra[PER], rb[PER];
+#pragma unroll
+            for (int k = 0; k < PER; ++k) {
+                const int m = tid + k * FF_THREADS;
+                const int64_t ia = oA - hist + m, ib = oB - hist + m;
+                ra[k] = (ia >= -lead && ia < n) ? __ldg(u + ia) : 0.0;
+                rb[k] = (ib >= -lead && ib < n) ? __ldg(u + ib) : 0.0;
+            }
+#pragma unroll
+            for (int k = 0; k < PER; ++k) sts(x, tid + k * FF_THREADS, {ra[k], rb[k]});
         }
         __syncthreads();
         ff_forward_stages(x, tw);
@@ -154,21 +163,38 @@ fir_fft_kernel(const double* __restrict__ u, const double* __restrict__ y, int64
         __syncthreads();
         ff_inverse_stages(x, tw);
         // epilogue: valid part m in [hist, N) -> outputs oA + (m - hist) (real part) and oB + (m - hist) (imaginary)
-        for (int m = hist + tid; m < FF_N; m += FF_THREADS) {
-            const cplx v = lds(x, m);
-            const int64_t ia = oA + (m - hist), ib = oB + (m - hist);
-            if (ia < n) {
-                if (y_pred) y_pred[ia] = v.x;
-                if (y && ia >= skip) {
-                    const double yi = __ldg(y + ia), e = yi - v.x, d0 = yi - y0;
-                    se = fma(e, e, se); sy = fma(yi, yi, sy); st = fma(d0, d0, st); cnt += 1.0;
+        {
+            constexpr int PER = FF_N / FF_THREADS;           // at most 16 valid rows per thread
+            double ya[PER], yb[PER];
+            if (y) {
+#pragma unroll
+                for (int k = 0; k < PER; ++k) {              // prefetch the measured outputs (latency paid once)
+                    const int m = hist + tid + k * FF_THREADS;
+                    const int64_t ia = oA + (m - hist), ib = oB + (m - hist);
+                    ya[k] = (m < FF_N && ia < n) ? __ldg(y + ia) : 0.0;
+                    yb[k] = (m < FF_N && ib < n) ? __ldg(y + ib) : 0.0;
                 }
             }
-            if (ib < n) {
-                if (y_pred) y_pred[ib] = v.y;
-                if (y && ib >= skip) {
-                    const double yi = __ldg(y + ib), e = yi - v.y, d0 = yi - y0;
-                    se = fma(e, e, se); sy = fma(yi, yi, sy); st = fma(d0, d0, st); cnt += 1.0;
+#pragma unroll
+            for (int k = 0; k < PER; ++k) {
+                const int m = hist + tid + k * FF_THREADS;
+                if (m < FF_N) {
+                    const cplx v = lds(x, m);
+                    const int64_t ia = oA + (m - hist), ib = oB + (m - hist);
+                    if (ia < n) {
+                        if (y_pred) y_pred[ia] = v.x;
+                        if (y && ia >= skip) {
+                            const double yi = ya[k], e = yi - v.x, d0 = yi - y0;
+                            se = fma(e, e, se); sy = fma(yi, yi, sy); st = fma(d0, d0, st); cnt += 1.0;
+                        }
+                    }
+                    if (ib < n) {
+                        if (y_pred) y_pred[ib] = v.y;
+                        if (y && ib >= skip) {
+                            const double yi = yb[k], e = yi - v.y, d0 = yi - y0;
+                            se = fma(e, e, se); sy = fma(yi, yi, sy); st = fma(d0, d0, st); cnt += 1.0;
+                        }
+                    }
                 }
             }
         }

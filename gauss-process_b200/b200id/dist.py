@@ -77,6 +77,22 @@ def argmin_gather(local_best: float, local_global_idx: int, device=None) -> Tupl
     return pick_first_strict_min([(float(v[0].item()), int(v[1].item())) for v in allv])
 
 
+def argmin_gather_multi(local_pairs: Sequence[Tuple[float, int]], device=None) -> List[Tuple[int, float]]:
+    """Several independent argmin gathers (e.g. the Re and Im searches) in ONE collective and one
+    device->host read: local_pairs[k] = (best metric, global index) of search k on this rank."""
+    rank, ws = world()
+    if ws == 1:
+        return [(int(i), float(m)) for m, i in local_pairs]
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    k = len(local_pairs)
+    mine = torch.tensor([[float(m), float(i)] for m, i in local_pairs], dtype=torch.float64, device=device).reshape(-1)
+    out = torch.empty(ws * 2 * k, dtype=torch.float64, device=device)
+    dist.all_gather_into_tensor(out, mine)
+    tab = out.cpu().reshape(ws, k, 2)
+    return [pick_first_strict_min([(float(tab[r, j, 0]), int(tab[r, j, 1])) for r in range(ws)]) for j in range(k)]
+
+
 def pick_first_strict_min(pairs: Sequence[Tuple[float, int]]) -> Tuple[int, float]:
     best, best_idx = float("inf"), -1
     for m, i in pairs:

@@ -112,6 +112,8 @@ class CandidateSet:
     kernel_ids: Optional[torch.Tensor] = None
     global_index: Optional[np.ndarray] = None      # set when the list is a rank's shard
     full_theta: Optional[np.ndarray] = None        # the whole host-side list (every rank can index it)
+    full_theta_dev: Optional[torch.Tensor] = None  # same on the device (device-side pick of the winner)
+    global_index_dev: Optional[torch.Tensor] = None
 
     @staticmethod
     def build(kernel: Optional[str], thetas: np.ndarray, dev, kernel_ids: Optional[np.ndarray] = None,
@@ -125,7 +127,8 @@ class CandidateSet:
             if kernel_ids is not None:
                 kernel_ids = np.asarray(kernel_ids)[gidx]
         ids = None if kernel_ids is None else torch.as_tensor(np.asarray(kernel_ids, dtype=np.int32), device=dev)
-        return CandidateSet(kernel, th, to_device(th, dev), ids, gidx, full)
+        gdev = None if gidx is None else torch.as_tensor(gidx, device=dev)
+        return CandidateSet(kernel, th, to_device(th, dev), ids, gidx, full, to_device(full, dev), gdev)
 
 
 def select_candidates(cs: CandidateSet, X_d, y_d, noise: float, Xv_d=None, yv_d=None, scaler: Optional[Standardizer] = None,
@@ -253,6 +256,78 @@ def _two_standardizers(G: torch.Tensor) -> Tuple[Standardizer, Standardizer]:
     return (Standardizer(st[0], st[2] if st[2] != 0.0 else 1.0), Standardizer(st[1], st[3] if st[3] != 0.0 else 1.0))
 
 
+def _probe_paths(probes):
+    """FRF path (uniform fast path or general) of several records with ONE device->host read.
+
+    probes: list of (t_d, span, t0 or None, w_max)."""
+    import ctypes as C
+    from . import _lib
+    from .runtime import ptr, stream_ptr
+    outs, metas = [], []
+    for t_d, span, t0, w_max in probes:
+        n = t_d.numel()
+        if bfrf._FORCE_PATH == "general" or n < 3 or not (span > 0.0):
+            metas.append(None)
+            continue
+        t0 = float(t_d[0].item()) if t0 is None else float(t0)
+        dt = span / (n - 1)
+        out = empty(1, t_d.device)
+        ws, _ = bfrf._ws(1, t_d.device)
+        _lib.call("b200id_frf_uniformity", ptr(t_d), C.c_int64(n), C.c_double(t0), C.c_double(dt), ptr(out), ptr(ws),
+                  C.c_size_t(ws.numel()), stream_ptr())
+        outs.append(out)
+        metas.append((t0, dt, w_max, len(outs) - 1))
+    vals = torch.cat(outs).cpu().tolist() if outs else []
+    paths = []
+    for m in metas:
+        if m is None:
+            paths.append(("general", None, None))
+        else:
+            t0, dt, w_max, k = m
+            ok = bfrf._FORCE_PATH == "uniform" or vals[k] * w_max < bfrf.UNIFORM_PHASE_TOL
+            paths.append(("uniform", t0, dt) if ok else ("general", None, None))
+    return paths
+
+
+def _async_to_host(t: torch.Tensor):
+    """Start a device->host copy into pinned memory; returns (host tensor, event)."""
+    host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    host.copy_(t, non_blocking=True)
+    ev = torch.cuda.Event()
+    ev.record()
+    return host, ev
+
+
+def _device_pick(cs: "CandidateSet", pend: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """(theta [3] on the device, global index, metric) of the selected candidate WITHOUT a host round trip.
+
+    pend = [best metric, local index] on the device.  With several ranks the (metric, global index) pairs are
+    all-gathered and the first strict minimum in global scan order is taken on the device (ties -> smallest
+    global index, NaN / empty shards skipped), reproducing grid_search.py:186-196."""
+    dev = pend.device
+    best, lidx = pend[0], pend[1].to(torch.int64)
+    if cs.global_index is None:
+        gidx = lidx
+    else:
+        gmap = cs.global_index_dev
+        gidx = torch.where(lidx >= 0, gmap[lidx.clamp(min=0)], torch.full_like(lidx, -1))
+        import torch.distributed as dist
+        ws = bdist.world()[1]
+        mine = torch.stack([best, gidx.to(F64)])
+        tab = torch.empty(ws * 2, dtype=F64, device=dev)
+        dist.all_gather_into_tensor(tab, mine)
+        tab = tab.view(ws, 2)
+        m, g = tab[:, 0], tab[:, 1]
+        valid = (g >= 0) & (m == m)
+        m = torch.where(valid, m, torch.full_like(m, float("inf")))
+        best = m.min()
+        g = torch.where((m == best) & valid & (best < float("inf")), g, torch.full_like(g, float("inf")))
+        gsel = g.min()
+        gidx = torch.where(torch.isfinite(gsel), gsel, torch.full_like(gsel, -1.0)).to(torch.int64)
+    theta = cs.full_theta_dev[gidx.clamp(min=0)]
+    return theta.contiguous(), gidx, best
+
+
 def identify_device(train: Sequence[Tuple[torch.Tensor, torch.Tensor, torch.Tensor, float]],
                     val: Optional[Tuple[torch.Tensor, torch.Tensor, torch.Tensor, float]],
                     nd: int, kernel: str = "matern52", noise: float = 1e-6,
@@ -266,17 +341,29 @@ def identify_device(train: Sequence[Tuple[torch.Tensor, torch.Tensor, torch.Tens
     and the per-bin numerator/denominator are all-reduced.  val: the validation record
     (t, u, y, span[, y0[, t0]]) -- FIR validation, and the 150-bin validation FRF when
     use_validation_metric.  candidates: grid (None -> no search, theta0 is used as is).
+
+    The host only blocks twice: once for the timebase probes, once at the end.  Everything in between is
+    enqueued ahead of the GPU (the selected hyperparameters, the fit status and the all-gathered argmin stay
+    on the device), so the stream never drains while Python prepares the next launch.
     """
+    import ctypes as C
+    from . import _lib
+    from .runtime import Workspace, ptr, stream_ptr
     dev = train[0][0].device
     gi = GridInputs.get(nd, dev)
     omega, w_d, X_d = gi.omega, gi.w_d, gi.X_d
+    n = X_d.numel()
+    want_val_frf = candidates is not None and use_validation_metric and val is not None and val_frf is None
+    # ---- timebase probes of every record: one host read
+    probes = [(r[0], r[3], r[4] if len(r) > 4 else None, gi.w_max) for r in train]
+    if want_val_frf:
+        probes.append((val[0], val[3], val[5] if len(val) > 5 else None, gi.wv_max))
+    paths = _probe_paths(probes)
     # ---- FRF: per-record coefficients, cross-power numerator / denominator, one all-reduce
     num = torch.zeros(nd, dtype=torch.complex128, device=dev)
     den = torch.zeros(nd, dtype=F64, device=dev)
-    for rec in train:
-        t_d, u_d, y_d, span = rec[:4]
-        U, Y = bfrf.record_coefficients_device(t_d, u_d, y_d, w_d, span, t0=rec[4] if len(rec) > 4 else None,
-                                               w_max=gi.w_max)
+    for rec, path in zip(train, paths):
+        U, Y = bfrf.record_coefficients_device(rec[0], rec[1], rec[2], w_d, rec[3], path=path)
         num += Y * U.conj()
         den += U.abs() ** 2
     if bdist.world()[1] > 1:
@@ -285,20 +372,32 @@ def identify_device(train: Sequence[Tuple[torch.Tensor, torch.Tensor, torch.Tens
         num = torch.view_as_complex(packed[:2 * nd].view(nd, 2).contiguous())
         den = packed[2 * nd:]
     G = torch.where(den > 1e-15, num / den, torch.full_like(num, complex(float("nan"), float("nan"))))
-    # ---- GP targets: standardised Re G, Im G (gp_pipeline.py:131-132)
-    sr, si = _two_standardizers(G)
-    yr, yi = sr.transform(G.real).contiguous(), si.transform(G.imag).contiguous()
+    # ---- StandardScaler statistics of Re G, Im G: computed on the device, copied asynchronously
+    ri = torch.view_as_real(G)
+    mean2 = ri.mean(dim=0)
+    sd2 = torch.sqrt(((ri - mean2) ** 2).mean(dim=0))
+    sd2 = torch.where(sd2 == 0.0, torch.ones_like(sd2), sd2)
+    stats_host, stats_ev = _async_to_host(torch.cat([mean2, sd2]))
+    yr = ((G.real - mean2[0]) / sd2[0]).contiguous()
+    yi = ((G.imag - mean2[1]) / sd2[1]).contiguous()
+    # ---- validation FRF (150 bins) is enqueued BEFORE the host waits for the statistics
     Xv_d = yv_r = yv_i = None
     if candidates is not None and use_validation_metric and val is not None:
         if val_frf is None:
-            Uv, Yv = bfrf.record_coefficients_device(val[0], val[1], val[2], gi.wv_d, val[3],
-                                                     t0=val[5] if len(val) > 5 else None, w_max=gi.wv_max)
+            Uv, Yv = bfrf.record_coefficients_device(val[0], val[1], val[2], gi.wv_d, val[3], path=paths[-1])
         else:
             Uv, Yv = val_frf
         Gv = bfrf.cross_power_device(Uv, Yv)
         Xv_d = gi.Xv_d
         yv_r, yv_i = Gv.real.contiguous(), Gv.imag.contiguous()
-    # ---- model selection (grid_search.py:48-203): the Re and Im searches are independent -> two streams
+    stats_ev.synchronize()                                  # GPU keeps working on the validation FRF meanwhile
+    st = stats_host.tolist()
+    sr, si = Standardizer(st[0], st[2]), Standardizer(st[1], st[3])
+    # ---- model selection (grid_search.py:48-203): Re and Im searches on two streams, winners stay on the device
+    diag = float(noise) + 1e-10
+    kid = bgp.KERNEL_IDS[kernel][0]
+    infos = torch.zeros(2, dtype=torch.int32, device=dev)
+    sel = None
     if candidates is not None:
         main = torch.cuda.current_stream()
         side = _side_stream(dev)
@@ -307,26 +406,85 @@ def identify_device(train: Sequence[Tuple[torch.Tensor, torch.Tensor, torch.Tens
         with torch.cuda.stream(side):
             pend_i = select_candidates_async(candidates, X_d, yi, noise, Xv_d, yv_i, si)
         main.wait_stream(side)
-        both = torch.stack([pend_r, pend_i]).cpu()
-        ir, mr = _finish_selection(candidates, both[0], dev)
-        ii, mi = _finish_selection(candidates, both[1], dev)
-        th_r = _theta_of(candidates, ir)
-        th_i = _theta_of(candidates, ii)
+        th_r_d, gidx_r, best_r = _device_pick(candidates, pend_r)
+        th_i_d, gidx_i, best_i = _device_pick(candidates, pend_i)
+        sel = torch.stack([gidx_r.to(F64), best_r, gidx_i.to(F64), best_i])
     else:
-        th_r = th_i = np.asarray(theta0, dtype=np.float64)
-        mr = mi = float("nan")
-    gp_r, gp_i = fit_pair_device(kernel, (th_r, th_i), X_d, (yr, yi), noise)      # the FIR path only needs the GP mean
-    # ---- paper-mode FIR: 1000-point uniform omega grid -> GP mean -> Hermitian IDFT -> taps
-    G_uni = torch.complex(sr.inverse(gp_r.predict_device(gi.Xu_d)), si.inverse(gp_i.predict_device(gi.Xu_d)))
-    taps = bfir.idft_taps_device(G_uni, min(n_taps, 2 * PAPER_ND - 1))
+        th = bgp._theta_block(np.asarray(theta0, dtype=np.float64))[0]
+        th_r_d = th_i_d = to_device(th, dev)
+    # ---- final fits (gpr_fitting.py:73-83); status flags are read at the end
+    nbytes = _lib.load().b200id_gp_fit_workspace_bytes(n)
+    alphas = []
+    for k, (th_d, y_d) in enumerate(((th_r_d, yr), (th_i_d, yi))):
+        alpha = empty(n, dev)
+        ws = Workspace.get(f"gpfit{k}", nbytes, dev)
+        kinv = empty(n * n, dev) if n > 127 else None
+        _lib.call("b200id_gp_fit", C.c_int(kid), ptr(th_d), ptr(X_d), ptr(y_d), C.c_int(n), C.c_double(diag), ptr(alpha),
+                  ptr(kinv), ptr(infos[k:k + 1]), ptr(ws), C.c_size_t(ws.numel()), stream_ptr())
+        alphas.append((alpha, kinv))
+
+    def tail(al_r, al_i):
+        # paper-mode FIR: 1000-point uniform omega grid -> GP mean -> Hermitian IDFT -> taps -> validation
+        m = gi.Xu_d.numel()
+        means = []
+        for th_d, al in ((th_r_d, al_r), (th_i_d, al_i)):
+            mean = empty(m, dev)
+            _lib.call("b200id_gp_predict", C.c_int(kid), ptr(th_d), ptr(X_d), C.c_int(n), ptr(al), ptr(None),
+                      ptr(gi.Xu_d), C.c_int(m), ptr(mean), ptr(None), stream_ptr())
+            means.append(mean)
+        G_uni = torch.complex(means[0] * sd2[0] + mean2[0], means[1] * sd2[1] + mean2[1])
+        taps = bfir.idft_taps_device(G_uni, min(n_taps, 2 * PAPER_ND - 1))
+        sums = None
+        if val is not None:
+            skip = min(10, taps.numel() // 10)
+            y0 = val[4] if len(val) > 4 else float(val[2][skip].item())
+            sums, _ = bfir.fir_eval_device(val[1], val[2], taps, skip, y0)
+            bdist.allreduce_sum_(sums)
+        return G_uni, taps, sums
+
+    G_uni, taps, sums = tail(alphas[0][0], alphas[1][0])
+    # ---- the only blocking read: selection, fit status, FIR sums, selected hyperparameters
+    pack = [infos.to(F64), th_r_d.reshape(-1)[:3], th_i_d.reshape(-1)[:3]]
+    if sel is not None:
+        pack.append(sel)
+    if sums is not None:
+        pack.append(sums)
+    host = torch.cat(pack).cpu().tolist()
+    flags = (int(host[0]), int(host[1]))
+    nparams = bgp.KERNEL_IDS[kernel][1]
+    th_r, th_i = np.array(host[2:2 + nparams]), np.array(host[5:5 + nparams])
+    pos = 8
+    mr = mi = float("nan")
+    if sel is not None:
+        gr, mr, gi_, mi = host[pos:pos + 4]
+        pos += 4
+        if int(gr) < 0 or int(gi_) < 0:
+            raise ValueError("grid search found no finite candidate (all metrics NaN): kernel.set_params(None) in the reference")
+    used_pinv = [False, False]
+    if flags[0] != 0 or flags[1] != 0:
+        # a pivot was non-positive: redo the affected fit through the pseudo-inverse branch (gpr_fitting.py:84-87)
+        new_alphas = []
+        for k, (th_d, y_d) in enumerate(((th_r_d, yr), (th_i_d, yi))):
+            alpha, kinv = alphas[k]
+            if flags[k] != 0:
+                if n > bgp.SMEM_NMAX:
+                    raise _lib.B200IDError(-4, "pseudo-inverse branch is limited to n <= 160")
+                kinv = empty(n * n, dev)
+                ws = Workspace.get(f"gpfit{k}", nbytes, dev)
+                _lib.call("b200id_gp_fit_pinv", C.c_int(kid), ptr(th_d), ptr(X_d), ptr(y_d), C.c_int(n), C.c_double(diag),
+                          C.c_double(bgp.PINV_RCOND), ptr(alpha), ptr(kinv), ptr(ws), C.c_size_t(ws.numel()), stream_ptr())
+                used_pinv[k] = True
+            new_alphas.append((alpha, kinv))
+        alphas = new_alphas
+        G_uni, taps, sums = tail(alphas[0][0], alphas[1][0])
+        host_sums = sums.cpu().tolist() if sums is not None else None
+    else:
+        host_sums = host[pos:pos + 4] if sums is not None else None
+    gp_r = FittedGP(kernel, th_r, alphas[0][0], alphas[0][1], X_d, used_pinv[0])
+    gp_i = FittedGP(kernel, th_i, alphas[1][0], alphas[1][1], X_d, used_pinv[1])
     res = IdentifyResult(omega, G, th_r, th_i, mr, mi, taps, {}, G_uni, gp_r, gp_i)
-    # ---- FIR validation on the validation record (fir_fitting.py:285-306), sums all-reduced
-    if val is not None:
-        skip = min(10, taps.numel() // 10)
-        y0 = val[4] if len(val) > 4 else float(val[2][skip].item())
-        sums, _ = bfir.fir_eval_device(val[1], val[2], taps, skip, y0)
-        bdist.allreduce_sum_(sums)
-        res.fir = bfir.metrics_from_sums(sums.cpu().numpy(), skip)
+    if host_sums is not None:
+        res.fir = bfir.metrics_from_sums(host_sums, min(10, taps.numel() // 10))
     return res
 
 
@@ -360,6 +518,20 @@ def _finish_selection(cs: CandidateSet, pair_host: torch.Tensor, dev) -> Tuple[i
         gidx = int(cs.global_index[local_idx]) if local_idx >= 0 else -1
         return bdist.argmin_gather(local_best, gidx, device=dev)
     return local_idx, local_best
+
+
+def _finish_selections(cs: CandidateSet, pairs_host: torch.Tensor, dev) -> List[Tuple[int, float]]:
+    """Local (best, local index) pairs of several searches -> global picks with one collective."""
+    local = []
+    for row in pairs_host:
+        local_best, local_idx = float(row[0]), int(row[1])
+        if cs.global_index is not None:
+            local.append((local_best, int(cs.global_index[local_idx]) if local_idx >= 0 else -1))
+        else:
+            local.append((local_best, local_idx))
+    if cs.global_index is None:
+        return [(i, m) for m, i in local]
+    return bdist.argmin_gather_multi(local, device=dev)
 
 
 def fit_pair_device(kernel: str, thetas, X_d: torch.Tensor, ys, noise: float):

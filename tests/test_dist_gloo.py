@@ -92,3 +92,32 @@ def test_shard_helpers():
     assert cover == list(range(10))
     assert bdist.pick_first_strict_min([(3.0, 7), (3.0, 2), (float("nan"), 0), (float("inf"), -1)]) == (2, 3.0)
     assert bdist.pick_first_strict_min([(float("inf"), -1)]) == (-1, float("inf"))
+
+
+def _worker_multi(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    bdist.init_from_env(backend="gloo")
+    rng = np.random.default_rng(7)
+    a = rng.integers(0, 9, 101).astype(np.float64); b = rng.integers(0, 9, 101).astype(np.float64)
+    b[::3] = np.nan
+    pairs = []
+    for metrics in (a, b):
+        mine = bdist.shard_round_robin(len(metrics), rank, world)
+        li, lb = ogp.first_strict_min(metrics[mine])
+        pairs.append((lb, int(mine[li]) if li >= 0 else -1))
+    got = bdist.argmin_gather_multi(pairs, device=torch.device("cpu"))
+    assert got == [ogp.first_strict_min(a), ogp.first_strict_min(b)], got
+    q.put(rank)
+    dist.destroy_process_group()
+
+
+def test_two_rank_multi_argmin_gather():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_multi, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]

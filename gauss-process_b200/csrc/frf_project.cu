@@ -392,21 +392,18 @@ __global__ void frf_max_fold_kernel(const double* __restrict__ part, int n_cta, 
     if (threadIdx.x == 0) out[0] = v;
 }
 
-// Fixed-order pairwise fold of the per-CTA partials: out[e] = sum_cta part[cta][e], e < 4*nd.
-__global__ void frf_fold_kernel(const double* __restrict__ part, int n_cta, int len,
-                                double* __restrict__ out) {
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+// Fixed-order fold of the per-CTA partials: out[e] = sum_cta part[cta][e], e < len.  One warp per output
+// element: lane l adds CTAs l, l+32, ... in order, then a fixed shuffle tree -- the order depends only on
+// n_cta, so the result is deterministic for a given grid.
+__global__ void __launch_bounds__(256)
+frf_fold_kernel(const double* __restrict__ part, int n_cta, int len, double* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (e >= len) return;
-    // pairwise tree over CTA index, evaluated iteratively with a small stack-free scheme:
-    // sum blocks of 8 sequentially, then the block sums sequentially (n_cta <= ~300).
-    double total = 0.0;
-    for (int c0 = 0; c0 < n_cta; c0 += 8) {
-        double blk = 0.0;
-        const int c1 = min(c0 + 8, n_cta);
-        for (int c = c0; c < c1; ++c) blk += part[(size_t)c * len + e];
-        total += blk;
-    }
-    out[e] = total;
+    double v = 0.0;
+    for (int c = lane; c < n_cta; c += 32) v += part[(size_t)c * len + e];
+    v = warp_sum(v);
+    if (lane == 0) out[e] = v;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -496,7 +493,7 @@ extern "C" int b200id_frf_moments(const double* u, const double* y, int64_t n, i
     double* part = (double*)ws;
     frf_moments_kernel<<<grid, MOM_THREADS, 0, st>>>(u, y, own_begin, own_end, chunk, part);
     B200ID_LAUNCH_CHECK("frf_moments_kernel");
-    frf_fold_kernel<<<1, 32, 0, st>>>(part, grid, 2, sums_out);
+    frf_fold_kernel<<<1, 64, 0, st>>>(part, grid, 2, sums_out);
     B200ID_LAUNCH_CHECK("frf_fold_kernel(moments)");
     return B200ID_OK;
 }
@@ -529,7 +526,7 @@ extern "C" int b200id_frf_project(const double* t, const double* u, const double
         frf_project_kernel<false><<<grid, FRF_THREADS, FRF_SMEM_BYTES, st>>>(t, u, nullptr, n, own_begin, own_end, w, nd, sums, inv_count, p.tile, p.n_tiles, part);
     B200ID_LAUNCH_CHECK("frf_project_kernel");
     const int len = 4 * nd;
-    frf_fold_kernel<<<(len + 127) / 128, 128, 0, st>>>(part, p.grid_x, len, partial_out);
+    frf_fold_kernel<<<(len + 7) / 8, 256, 0, st>>>(part, p.grid_x, len, partial_out);
     B200ID_LAUNCH_CHECK("frf_fold_kernel");
     return B200ID_OK;
 }
@@ -580,7 +577,7 @@ extern "C" int b200id_frf_project_uniform(const double* t, const double* u, cons
     }
     B200ID_LAUNCH_CHECK("frf_project_uniform_kernel");
     const int len = 4 * nd;
-    frf_fold_kernel<<<(len + 127) / 128, 128, 0, st>>>(part, p.grid_x, len, partial_out);
+    frf_fold_kernel<<<(len + 7) / 8, 256, 0, st>>>(part, p.grid_x, len, partial_out);
     B200ID_LAUNCH_CHECK("frf_fold_kernel");
     return B200ID_OK;
 }

@@ -27,7 +27,7 @@ SIGNATURES = {
     "b200id_frf_workspace_bytes": (Z, [I]),
     "b200id_frf_moments": (I, [P, P, L, L, L, P, P, Z, P]),
     "b200id_frf_project": (I, [P, P, P, L, L, L, P, I, P, D, P, P, Z, P]),
-    "b200id_frf_uniformity": (I, [P, L, D, D, P, P, Z, P]),
+    "b200id_frf_uniformity": (I, [P, L, L, L, D, D, P, P, Z, P]),
     "b200id_frf_project_uniform": (I, [P, P, P, L, L, L, P, I, P, D, D, D, P, P, Z, P]),
     "b200id_frf_finalize": (I, [P, I, D, P, P, P]),
     "b200id_cross_power": (I, [P, P, I, I, D, P, P]),

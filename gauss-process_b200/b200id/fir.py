@@ -7,13 +7,14 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from typing import Dict, Optional, Tuple
 
 import numpy as np
 import torch
 
 from . import _lib
-from .runtime import F64, Workspace, empty, ptr, require_cuda, stream_ptr, to_device
+from .runtime import F64, Workspace, empty, host_f64, ptr, require_cuda, side_stream, stream_edges, stream_ptr, to_device
 
 
 def idft_taps_device(G_d: torch.Tensor, n_taps: int) -> torch.Tensor:
@@ -72,6 +73,43 @@ def fir_predict(u, g, n_out: Optional[int] = None) -> np.ndarray:
     return pred.cpu().numpy()
 
 
+STREAM_MIN_SAMPLES = 1 << 20      # host records at least this long are uploaded piecewise, overlapped with the FIR
+STREAM_CHUNKS = 6
+_STREAM = os.environ.get("B200ID_FIR_STREAM", "1") != "0"
+
+
+def fir_eval_streamed(u_h, y_h, g_d: torch.Tensor, skip: int, y0: float, n: int, want_pred: bool = False,
+                      n_chunks: int = STREAM_CHUNKS):
+    """:func:`fir_eval_device` for a HOST record: u, y go up in pieces on the copy stream and each piece's
+    outputs are convolved (history = the pieces already resident) and folded into the error sums as soon as
+    it has landed, so only the last, short piece's kernel runs after the copy."""
+    dev = g_d.device
+    uh, yh = host_f64(u_h), host_f64(y_h)
+    taps = g_d.numel()
+    edges = stream_edges(n, n_chunks)
+    main, side = torch.cuda.current_stream(), side_stream(dev)
+    u_d, y_d = empty(n, dev), empty(n, dev)
+    pred = empty(n, dev) if want_pred else None
+    side.wait_stream(main)
+    landed = []
+    with torch.cuda.stream(side):
+        for lo, hi in zip(edges, edges[1:]):
+            u_d[lo:hi].copy_(uh[lo:hi], non_blocking=True)
+            y_d[lo:hi].copy_(yh[lo:hi], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(side)
+            landed.append(ev)
+    total = None
+    for ev, lo, hi in zip(landed, edges, edges[1:]):
+        main.wait_event(ev)
+        sums, pk = fir_eval_device(u_d[lo:], y_d[lo:hi], g_d, max(0, skip - lo), y0, lead=min(lo, taps - 1),
+                                   want_pred=want_pred, n=hi - lo)
+        if want_pred:
+            pred[lo:hi].copy_(pk)
+        total = sums if total is None else total.add_(sums)
+    return total, pred
+
+
 def fir_validate(u, y, g, detrend: bool = False, want_pred: bool = True,
                  skip: Optional[int] = None) -> Tuple[Dict[str, float], Optional[np.ndarray]]:
     """(metrics, y_pred) of FIR taps g on record (u, y): convolution and error sums on the device."""
@@ -82,9 +120,12 @@ def fir_validate(u, y, g, detrend: bool = False, want_pred: bool = True,
     if detrend:
         u, y = u - np.mean(u), y - np.mean(y)
     skip = min(10, g.size // 10) if skip is None else int(skip)
-    u_d, y_d, g_d = to_device(u, dev), to_device(y, dev), to_device(g, dev)
     n = min(u.size, y.size)
-    sums, pred = fir_eval_device(u_d, y_d, g_d, skip, float(y[skip]), want_pred=want_pred, n=n)
+    g_d = to_device(g, dev)
+    if _STREAM and n >= STREAM_MIN_SAMPLES:
+        sums, pred = fir_eval_streamed(u[:n], y[:n], g_d, skip, float(y[skip]), n, want_pred=want_pred)
+    else:
+        sums, pred = fir_eval_device(to_device(u, dev), to_device(y, dev), g_d, skip, float(y[skip]), want_pred=want_pred, n=n)
     m = metrics_from_sums(sums.cpu().numpy(), skip)
     return m, (pred.cpu().numpy() if want_pred else None)
 

@@ -15,7 +15,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .runtime import F64, Workspace, empty, ptr, require_cuda, stream_ptr, to_device
+from .runtime import F64, Workspace, empty, host_f64, ptr, require_cuda, side_stream, stream_edges, stream_ptr, to_device
 
 
 def _ws(nd: int, dev):
@@ -55,14 +55,20 @@ UNIFORM_PHASE_TOL = 2e-6
 _FORCE_PATH = os.environ.get("B200ID_FRF_PATH", "auto")     # auto | general | uniform
 
 
-def uniformity_device(t_d: torch.Tensor, t0: float, dt: float) -> float:
-    """max_i |t_i - (t0 + i dt)| (one small D2H read)."""
+def uniformity_device_async(t_d: torch.Tensor, t0: float, dt: float, own=None) -> torch.Tensor:
+    """max |t_i - (t0 + i dt)| over i in ``own`` (default: all) as a 1-element device tensor."""
     dev = t_d.device
+    own = (0, t_d.numel()) if own is None else own
     out = empty(1, dev)
     ws, _ = _ws(1, dev)
-    _lib.call("b200id_frf_uniformity", ptr(t_d), C.c_int64(t_d.numel()), C.c_double(t0), C.c_double(dt), ptr(out),
-              ptr(ws), C.c_size_t(ws.numel()), stream_ptr())
-    return float(out.item())
+    _lib.call("b200id_frf_uniformity", ptr(t_d), C.c_int64(t_d.numel()), C.c_int64(own[0]), C.c_int64(own[1]),
+              C.c_double(t0), C.c_double(dt), ptr(out), ptr(ws), C.c_size_t(ws.numel()), stream_ptr())
+    return out
+
+
+def uniformity_device(t_d: torch.Tensor, t0: float, dt: float, own=None) -> float:
+    """max_i |t_i - (t0 + i dt)| (one small D2H read)."""
+    return float(uniformity_device_async(t_d, t0, dt, own).item())
 
 
 def project_uniform_device(t_d, u_d, y_d, w_d, t0: float, dt: float, own=None, sums=None, inv_count: float = 0.0):
@@ -133,6 +139,105 @@ def record_coefficients_device(t_d, u_d, y_d, w_d, span: float, subtract_mean: b
     return finalize_device(part, nd, 2.0 / span, want_y=y_d is not None)
 
 
+# ----------------------------------------------------------------------------------------- streamed host records
+STREAM_MIN_SAMPLES = 1 << 20      # below this one bulk copy + one launch is faster than chunking
+STREAM_CHUNKS = 6
+STREAM_HEAD_SAMPLES = 4096       # host-side look at the time base before any of it is on the device
+_STREAM = os.environ.get("B200ID_FRF_STREAM", "1") != "0"
+
+
+def record_coefficients_streamed(t_h, u_h, y_h, w_d, span: float, subtract_mean: bool = True,
+                                 w_max: Optional[float] = None, n_chunks: int = STREAM_CHUNKS, trace: Optional[list] = None):
+    """(U, Y) of one HOST-resident record, with the projection overlapped with the host->device copy.
+
+    The signals u, y go up first (the mean needs all of them); the time stamps follow in ``n_chunks`` pieces
+    on a copy stream and each piece is projected as soon as it has landed, so only the last piece's kernel is
+    exposed after the copy.  The path is guessed from the first few thousand time stamps on the host; a
+    'uniform' guess is verified on the device over the whole record once it is resident, and the record is
+    re-projected with the general kernel in the rare case that a later part is off the grid.  Same sums as
+    :func:`record_coefficients_device` up to the order of the final additions.
+    """
+    dev = w_d.device
+    th, uh = host_f64(t_h), host_f64(u_h)
+    yh = None if y_h is None else host_f64(y_h)
+    n, nd = th.numel(), w_d.numel()
+    edges = stream_edges(n, n_chunks)
+    n_chunks = len(edges) - 1
+    main, side = torch.cuda.current_stream(), side_stream(dev)
+    t_d, u_d = empty(n, dev), empty(n, dev)
+    y_d = None if yh is None else empty(n, dev)
+    side.wait_stream(main)            # the fresh buffers may still be in use by earlier work on this stream
+    landed = [torch.cuda.Event(enable_timing=trace is not None) for _ in range(n_chunks)]
+    signals_up = torch.cuda.Event(enable_timing=trace is not None)
+
+    def mark(label, stream=None):
+        if trace is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record(main if stream is None else stream)
+            trace.append((label, ev))
+
+    mark("start")
+    if trace is not None:
+        trace.append(("signals_up", signals_up))
+        trace.extend((f"t_landed[{k}]", landed[k]) for k in range(n_chunks))
+
+    def send(k):
+        with torch.cuda.stream(side):
+            t_d[edges[k]:edges[k + 1]].copy_(th[edges[k]:edges[k + 1]], non_blocking=True)
+            landed[k].record(side)
+
+    with torch.cuda.stream(side):
+        u_d.copy_(uh, non_blocking=True)
+        if y_d is not None:
+            y_d.copy_(yh, non_blocking=True)
+        signals_up.record(side)
+    for k in range(min(2, n_chunks)):
+        send(k)
+    main.wait_event(signals_up)
+    sums = moments_device(u_d, y_d, (0, n)) if subtract_mean else None
+    mark("moments_done")
+
+    t0, dt = float(th[0]), span / (n - 1)
+    w_max = float(w_d.max().item()) if w_max is None else w_max
+    # Path guess from the head of the record on the host (no device round trip); the device check over the
+    # whole record below is what decides whether the guess stands.
+    kind = "general"
+    if _FORCE_PATH == "uniform":
+        kind = "uniform"
+    elif _FORCE_PATH != "general" and n >= 3 and dt > 0.0:
+        head = th[:min(n, STREAM_HEAD_SAMPLES)].numpy()
+        grid = t0 + np.arange(head.size, dtype=np.float64) * dt
+        if float(np.max(np.abs(head - grid))) * w_max < UNIFORM_PHASE_TOL:
+            kind = "uniform"
+
+    part = None
+    for k in range(n_chunks):
+        if k + 2 < n_chunks:
+            send(k + 2)
+        main.wait_event(landed[k])
+        # a sample's trapezoid weight needs its right neighbour: piece k owns up to its last-but-one sample
+        own = (edges[k] - (1 if k > 0 else 0), edges[k + 1] - 1 if k + 1 < n_chunks else n)
+        if kind == "uniform":
+            pk = project_uniform_device(t_d, u_d, y_d, w_d, t0, dt, own, sums, 1.0 / n)
+        else:
+            pk = project_device(t_d, u_d, y_d, w_d, own, sums, 1.0 / n)
+        part = pk if part is None else part.add_(pk)
+        mark(f"projected[{k}]")
+    if kind == "uniform" and _FORCE_PATH != "uniform":
+        if not (uniformity_device(t_d, t0, dt) * w_max < UNIFORM_PHASE_TOL):
+            part = project_device(t_d, u_d, y_d, w_d, (0, n), sums, 1.0 / n)
+    return finalize_device(part, nd, 2.0 / span, want_y=y_d is not None)
+
+
+def _coefficients(t, u, y, w_d, span, subtract_mean, w_max):
+    """Dispatch one prepared host record: streamed when it is large enough to pay, else bulk copy."""
+    dev = w_d.device
+    if _STREAM and not (isinstance(t, torch.Tensor) and t.is_cuda) and len(t) >= STREAM_MIN_SAMPLES:
+        return record_coefficients_streamed(t, u, y, w_d, span, subtract_mean, w_max)
+    return record_coefficients_device(to_device(t, dev), to_device(u, dev), None if y is None else to_device(y, dev),
+                                      w_d, span, subtract_mean, t0=float(t[0]), w_max=w_max)
+
+
 # ----------------------------------------------------------------------------------------- host API
 def _prepare(t, x_list: Sequence[np.ndarray], drop_seconds: float):
     """Transient drop + the reference's two ValueErrors (frf_estimator.py:212-223), on the host."""
@@ -162,8 +267,7 @@ def demod(t, x, w, drop_seconds: float = 0.0, subtract_mean: bool = True) -> np.
     dev = require_cuda()
     t, (x,), span = _prepare(t, [x], drop_seconds)
     w = np.asarray(w, dtype=np.float64)
-    U, _ = record_coefficients_device(to_device(t, dev), to_device(x, dev), None, to_device(w.ravel(), dev), span,
-                                      subtract_mean, t0=float(t[0]), w_max=float(np.max(np.abs(w))))
+    U, _ = _coefficients(t, x, None, to_device(w.ravel(), dev), span, subtract_mean, float(np.max(np.abs(w))))
     return U.cpu().numpy().reshape(w.shape)
 
 
@@ -172,9 +276,7 @@ def demod_pair(t, u, y, w, drop_seconds: float = 0.0, subtract_mean: bool = True
     dev = require_cuda()
     t, (u, y), span = _prepare(t, [u, y], drop_seconds)
     w = np.asarray(w, dtype=np.float64)
-    U, Y = record_coefficients_device(to_device(t, dev), to_device(u, dev), to_device(y, dev),
-                                      to_device(w.ravel(), dev), span, subtract_mean, t0=float(t[0]),
-                                      w_max=float(np.max(np.abs(w))))
+    U, Y = _coefficients(t, u, y, to_device(w.ravel(), dev), span, subtract_mean, float(np.max(np.abs(w))))
     UY = torch.stack([U, Y]).cpu().numpy()
     return UY[0].reshape(w.shape), UY[1].reshape(w.shape)
 
@@ -196,8 +298,7 @@ def estimate_records(records, w, drop_seconds: float = 0.0, subtract_mean: bool 
     Us, Ys = [], []
     for (t, u, y) in records:
         t, (u, y), span = _prepare(t, [u, y], drop_seconds)
-        U, Y = record_coefficients_device(to_device(t, dev), to_device(u, dev), to_device(y, dev), w_d, span,
-                                          subtract_mean, t0=float(t[0]), w_max=float(np.max(np.abs(w))))
+        U, Y = _coefficients(t, u, y, w_d, span, subtract_mean, float(np.max(np.abs(w))))
         Us.append(U)
         Ys.append(Y)
     G = cross_power_device(torch.stack(Us), torch.stack(Ys), eps)

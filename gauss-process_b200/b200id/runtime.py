@@ -44,6 +44,39 @@ def to_device(a, dev: torch.device, dtype=F64) -> torch.Tensor:
     return t.contiguous()
 
 
+_side_streams = {}
+
+
+def side_stream(dev: torch.device) -> torch.cuda.Stream:
+    """The per-device copy stream used to overlap host->device transfers with kernels."""
+    s = _side_streams.get(dev.index)
+    if s is None:
+        s = _side_streams[dev.index] = torch.cuda.Stream(device=dev)
+    return s
+
+
+def host_f64(a) -> torch.Tensor:
+    """Host array -> contiguous float64 CPU tensor sharing its memory when possible (pinned stays pinned)."""
+    if isinstance(a, torch.Tensor):
+        return a.to(F64).contiguous()
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64))
+
+
+def stream_edges(n: int, n_chunks: int) -> list:
+    """Piece boundaries for a streamed upload: equal pieces, except that the last two are a half and a
+    quarter piece so that little work is left exposed after the final copy lands."""
+    k = max(1, min(int(n_chunks), n // 4))
+    weights = [1.0] * k
+    if k >= 3:
+        weights[-2], weights[-1] = 0.5, 0.25
+    total, acc, edges = sum(weights), 0.0, [0]
+    for wgt in weights[:-1]:
+        acc += wgt
+        edges.append(max(edges[-1] + 2, min(n - 2, int(round(n * acc / total)))))
+    edges.append(n)
+    return edges
+
+
 def empty(n, dev, dtype=F64) -> torch.Tensor:
     return torch.empty(n, dtype=dtype, device=dev)
 

@@ -360,12 +360,12 @@ frf_project_uniform_kernel(const double* __restrict__ t, const double* __restric
     }
 }
 
-// max_i |t_i - (t0 + i dt)| over [0, n): decides whether the uniform path applies
+// max_i |t_i - (t0 + i dt)| over [begin, end): decides whether the uniform path applies
 __global__ void __launch_bounds__(MOM_THREADS)
-frf_uniformity_kernel(const double* __restrict__ t, int64_t n, double t0, double dt, int64_t chunk,
+frf_uniformity_kernel(const double* __restrict__ t, int64_t begin, int64_t end, double t0, double dt, int64_t chunk,
                       double* __restrict__ cta_max) {
     __shared__ double sh[MOM_THREADS / 32];
-    const int64_t lo = (int64_t)blockIdx.x * chunk, hi = min(lo + chunk, n);
+    const int64_t lo = begin + (int64_t)blockIdx.x * chunk, hi = min(lo + chunk, end);
     double m = 0.0;
     for (int64_t i = lo + threadIdx.x; i < hi; i += MOM_THREADS) {
         const double ti = __ldg(t + i), k = (double)i;
@@ -392,18 +392,29 @@ __global__ void frf_max_fold_kernel(const double* __restrict__ part, int n_cta, 
     if (threadIdx.x == 0) out[0] = v;
 }
 
-// Fixed-order fold of the per-CTA partials: out[e] = sum_cta part[cta][e], e < len.  One warp per output
-// element: lane l adds CTAs l, l+32, ... in order, then a fixed shuffle tree -- the order depends only on
+// Fixed-order fold of the per-CTA partials: out[e] = sum_cta part[cta][e], e < len.  A CTA owns 32
+// consecutive outputs (lane = output, so every warp load is one coalesced 256-byte row segment); warp w adds
+// CTAs w, w+W, ... in order and the W warp sums are then added in warp order -- the order depends only on
 // n_cta, so the result is deterministic for a given grid.
-__global__ void __launch_bounds__(256)
+constexpr int FOLD_WARPS = 32;
+__global__ void __launch_bounds__(FOLD_WARPS * 32)
 frf_fold_kernel(const double* __restrict__ part, int n_cta, int len, double* __restrict__ out) {
-    const int lane = threadIdx.x & 31;
-    const int e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (e >= len) return;
+    __shared__ double sh[FOLD_WARPS][33];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int e = blockIdx.x * 32 + lane;
     double v = 0.0;
-    for (int c = lane; c < n_cta; c += 32) v += part[(size_t)c * len + e];
-    v = warp_sum(v);
-    if (lane == 0) out[e] = v;
+    if (e < len) {
+#pragma unroll 4
+        for (int c = warp; c < n_cta; c += FOLD_WARPS) v += part[(size_t)c * len + e];
+    }
+    sh[warp][lane] = v;
+    __syncthreads();
+    if (warp == 0 && e < len) {
+        double acc = sh[0][lane];
+#pragma unroll
+        for (int k = 1; k < FOLD_WARPS; ++k) acc += sh[k][lane];
+        out[e] = acc;
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -493,7 +504,7 @@ extern "C" int b200id_frf_moments(const double* u, const double* y, int64_t n, i
     double* part = (double*)ws;
     frf_moments_kernel<<<grid, MOM_THREADS, 0, st>>>(u, y, own_begin, own_end, chunk, part);
     B200ID_LAUNCH_CHECK("frf_moments_kernel");
-    frf_fold_kernel<<<1, 64, 0, st>>>(part, grid, 2, sums_out);
+    frf_fold_kernel<<<1, FOLD_WARPS * 32, 0, st>>>(part, grid, 2, sums_out);
     B200ID_LAUNCH_CHECK("frf_fold_kernel(moments)");
     return B200ID_OK;
 }
@@ -526,21 +537,24 @@ extern "C" int b200id_frf_project(const double* t, const double* u, const double
         frf_project_kernel<false><<<grid, FRF_THREADS, FRF_SMEM_BYTES, st>>>(t, u, nullptr, n, own_begin, own_end, w, nd, sums, inv_count, p.tile, p.n_tiles, part);
     B200ID_LAUNCH_CHECK("frf_project_kernel");
     const int len = 4 * nd;
-    frf_fold_kernel<<<(len + 7) / 8, 256, 0, st>>>(part, p.grid_x, len, partial_out);
+    frf_fold_kernel<<<(len + 31) / 32, FOLD_WARPS * 32, 0, st>>>(part, p.grid_x, len, partial_out);
     B200ID_LAUNCH_CHECK("frf_fold_kernel");
     return B200ID_OK;
 }
 
-extern "C" int b200id_frf_uniformity(const double* t, int64_t n, double t0, double dt, double* max_abs_delta_out,
-                                     void* ws, size_t ws_bytes, void* stream) {
+extern "C" int b200id_frf_uniformity(const double* t, int64_t n, int64_t own_begin, int64_t own_end, double t0, double dt,
+                                     double* max_abs_delta_out, void* ws, size_t ws_bytes, void* stream) {
     B200ID_REQUIRE(t && max_abs_delta_out && ws && n >= 2, B200ID_E_ARG, "frf_uniformity: bad argument");
+    B200ID_REQUIRE(own_begin >= 0 && own_end <= n && own_begin < own_end, B200ID_E_ARG,
+                   "frf_uniformity: bad range [%lld,%lld) of %lld", (long long)own_begin, (long long)own_end, (long long)n);
     cudaStream_t st = (cudaStream_t)stream;
+    const int64_t n_own = own_end - own_begin;
     int grid = sm_count() * 4;
-    int64_t chunk = (n + grid - 1) / grid;
+    int64_t chunk = (n_own + grid - 1) / grid;
     chunk = (chunk + 255) / 256 * 256;
-    grid = (int)((n + chunk - 1) / chunk);
+    grid = (int)((n_own + chunk - 1) / chunk);
     B200ID_REQUIRE(ws_bytes >= (size_t)grid * sizeof(double), B200ID_E_WORKSPACE, "frf_uniformity: workspace too small");
-    frf_uniformity_kernel<<<grid, MOM_THREADS, 0, st>>>(t, n, t0, dt, chunk, (double*)ws);
+    frf_uniformity_kernel<<<grid, MOM_THREADS, 0, st>>>(t, own_begin, own_end, t0, dt, chunk, (double*)ws);
     B200ID_LAUNCH_CHECK("frf_uniformity_kernel");
     frf_max_fold_kernel<<<1, 32, 0, st>>>((const double*)ws, grid, max_abs_delta_out);
     B200ID_LAUNCH_CHECK("frf_max_fold_kernel");
@@ -577,7 +591,7 @@ extern "C" int b200id_frf_project_uniform(const double* t, const double* u, cons
     }
     B200ID_LAUNCH_CHECK("frf_project_uniform_kernel");
     const int len = 4 * nd;
-    frf_fold_kernel<<<(len + 7) / 8, 256, 0, st>>>(part, p.grid_x, len, partial_out);
+    frf_fold_kernel<<<(len + 31) / 32, FOLD_WARPS * 32, 0, st>>>(part, p.grid_x, len, partial_out);
     B200ID_LAUNCH_CHECK("frf_fold_kernel");
     return B200ID_OK;
 }

@@ -26,7 +26,8 @@ class GaussianProcessRegressor:
         self.noise_variance = noise_variance
         self.X_train = None
         self.y_train = None
-        self.K_inv = None
+        self._K_inv = None
+        self._fit_args = None
         self.alpha = None
         self.X_scaler = None
         self.y_scaler = None
@@ -49,13 +50,28 @@ class GaussianProcessRegressor:
                     validation_y=validation_y, y_scaler=y_scaler)
             else:
                 self._optimize_hyperparameters(n_restarts)
-        self.alpha, self.K_inv, _ = _gp.fit(self.kernel.kernel_id, self.kernel.theta(), self.X_train, self.y_train,
-                                            self.noise_variance + FIT_JITTER)
+        self._fit_args = (self.kernel.kernel_id, self.kernel.theta().copy(), self.noise_variance + FIT_JITTER)
+        self.alpha, self._K_inv, _ = _gp.fit(*self._fit_args[:2], self.X_train, self.y_train, self._fit_args[2],
+                                             want_kinv=False)
+
+    @property
+    def K_inv(self):
+        """(K + (noise + 1e-10) I)^-1 of the last fit (reference :78-87).  The posterior mean needs only
+        ``alpha``; the n x n inverse is formed on first use (``predict(return_std=True)`` or a direct read)
+        from the same factorisation inputs, so its values are those an eager fit would have stored."""
+        if self._K_inv is None and self._fit_args is not None:
+            kid, theta, diag_add = self._fit_args
+            _, self._K_inv, _ = _gp.fit(kid, theta, self.X_train, self.y_train, diag_add, want_kinv=True)
+        return self._K_inv
+
+    @K_inv.setter
+    def K_inv(self, value):
+        self._K_inv = value
 
     def predict(self, X: np.ndarray, return_std: bool = False) -> Union[np.ndarray, Tuple[np.ndarray, np.ndarray]]:
         """Posterior mean (and std = sqrt(max(k** - sum((K* K_inv) o K*), 0))) at X (reference :89-100)."""
-        return _gp.predict(self.kernel.kernel_id, self.kernel.theta(), self.X_train, self.alpha, self.K_inv, X,
-                           return_std)
+        return _gp.predict(self.kernel.kernel_id, self.kernel.theta(), self.X_train, self.alpha,
+                           self.K_inv if return_std else None, X, return_std)
 
     def _optimize_hyperparameters(self, n_restarts: int):
         """L-BFGS-B on the negative log marginal likelihood with random restarts (reference :102-155).

@@ -64,22 +64,28 @@ def grid_search_hyperparameters(kernel: Kernel,
     y_mean, y_scale = _scaler_stats(y_scaler)
     val = dict(Xv=validation_X, yv=validation_y, y_mean=y_mean, y_scale=y_scale) if use_validation else {}
 
-    if use_validation:
-        start = kernel.get_params()
-        m0 = _gp.batch_eval(kernel.kernel_id, start, X_train, y_train, noise_variance, **val)[0]
-        print(f"  Initial (pre-grid-search) {metric_name}: {m0:.6e}")
-        print(f"  Initial params: {start}, noise: {noise_variance:.3e} (fixed)")
-
+    start = kernel.get_params()
     axes = [param_grids.get(f"param_{i}", _axis(lo, hi)) for i, (lo, hi) in enumerate(kernel.bounds)]
     combos = list(product(*axes))
-    print(f"  Grid search: {len(combos)} combinations to evaluate...")
-    if len(combos) > max_combinations:
-        print(f"  Too many combinations ({len(combos)}), randomly sampling {max_combinations}...")
+    n_total = len(combos)
+    if n_total > max_combinations:
         random.seed(42)
         combos = random.sample(combos, max_combinations)
     candidates = np.array(combos, dtype=np.float64).reshape(len(combos), len(axes))
 
-    best_idx, best_metric, _ = _gp.select(kernel.kernel_id, candidates, X_train, y_train, noise_variance, **val)
+    # ONE device round trip: metric of the start point and of every candidate, the first-strict-minimum scan,
+    # the fit of the winner (noise + 1e-10 jitter, as GaussianProcessRegressor.fit will ask for next) and its
+    # fitted mean at the training inputs.  The prints below keep the reference's order.
+    res = _gp.search_and_fit(kernel.kernel_id, start, candidates, X_train, y_train, noise_variance,
+                             noise_variance + 1e-10, **val)
+    if use_validation:
+        print(f"  Initial (pre-grid-search) {metric_name}: {res['start_metric']:.6e}")
+        print(f"  Initial params: {start}, noise: {noise_variance:.3e} (fixed)")
+    print(f"  Grid search: {n_total} combinations to evaluate...")
+    if n_total > max_combinations:
+        print(f"  Too many combinations ({n_total}), randomly sampling {max_combinations}...")
+
+    best_idx, best_metric = res["index"], res["best"]
     best_params = candidates[best_idx].copy() if best_idx >= 0 else None
     # as in the reference: if no candidate beat +inf (all NaN), set_params(None) raises here
     kernel.set_params(best_params)
@@ -89,9 +95,12 @@ def grid_search_hyperparameters(kernel: Kernel,
     if use_validation:
         # diagnostic only (reference :209-232): training RMSE of the selected model with the fit jitter
         try:
-            alpha, _, _ = _gp.fit(kernel.kernel_id, kernel.theta(), X_train, y_train, noise_variance + 1e-10, want_kinv=False)
-            pred = _gp.gram(kernel.kernel_id, kernel.theta(), X_train) @ alpha
-            truth = np.asarray(y_train, dtype=float)
+            if res["used_pinv"]:                                   # singular winner: pseudo-inverse fit
+                alpha, _, _ = _gp.fit(kernel.kernel_id, kernel.theta(), X_train, y_train, noise_variance + 1e-10, want_kinv=False)
+                pred = _gp.gram(kernel.kernel_id, kernel.theta(), X_train) @ alpha
+            else:
+                pred = res["train_pred"]
+            truth = np.asarray(y_train, dtype=float).ravel()
             if y_scaler is not None:
                 pred, truth = pred * y_scale + y_mean, truth * y_scale + y_mean
             train_rmse = float(np.sqrt(np.mean((truth - pred) ** 2)))

@@ -94,9 +94,11 @@ int b200id_frf_project(const double* t, const double* u, const double* y, int64_
  * resident sample obeys t_i = t0 + i*dt + delta_i with w_max * |delta_i| < ~2e-6 (sampled data whose time
  * stamps differ from the grid only by FP64 rounding): the phase fl(w_k t_i) the reference forms is then
  * reproduced to first order from a rotation recurrence plus the exactly computed rounding terms, at about
- * half the FP64 work.  b200id_frf_uniformity returns max_i |delta_i| so the caller can decide. */
-int b200id_frf_uniformity(const double* t, int64_t n, double t0, double dt, double* max_abs_delta_out /*[1]*/,
-                          void* ws, size_t ws_bytes, void* stream);
+ * half the FP64 work.  b200id_frf_uniformity returns max |delta_i| over i in [own_begin, own_end) (i counts
+ * from the start of the resident slice, as everywhere in this section) so the caller can decide -- per
+ * chunk, when a record is streamed to the device piecewise. */
+int b200id_frf_uniformity(const double* t, int64_t n, int64_t own_begin, int64_t own_end, double t0, double dt,
+                          double* max_abs_delta_out /*[1]*/, void* ws, size_t ws_bytes, void* stream);
 int b200id_frf_project_uniform(const double* t, const double* u, const double* y, int64_t n,
                                int64_t own_begin, int64_t own_end, const double* w, int nd,
                                const double* sums /*[2] or NULL*/, double inv_count, double t0, double dt,

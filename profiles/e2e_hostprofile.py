@@ -46,3 +46,37 @@ pr = cProfile.Profile(); pr.enable()
 for _ in range(5): step()
 pr.disable()
 s = io.StringIO(); pstats.Stats(pr, stream=s).sort_stats("tottime").print_stats(22); print(s.getvalue()[:5000])
+
+# ---- wall time per public call (synchronised), to see where a step goes
+def phases():
+    out = {}
+    def lap(name, t0):
+        torch.cuda.synchronize(); out[name] = out.get(name, 0.0) + (time.perf_counter() - t0) * 1e3
+    with contextlib.redirect_stdout(io.StringIO()):
+        (t, u, y), (tv, uv, yv) = host
+        t0 = time.perf_counter(); U, Y = synchronous_coefficients_trapz_pair(t, u, y, omega_h); lap("frf_train", t0)
+        t0 = time.perf_counter(); Uv, Yv = synchronous_coefficients_trapz_pair(tv, uv, yv, omega_v); lap("frf_val", t0)
+        t0 = time.perf_counter(); G = frf_cross_power_average([U], [Y]); Gv = frf_cross_power_average([Uv], [Yv]); lap("cross_power", t0)
+        t0 = time.perf_counter()
+        Xs = StandardScaler(); Xn = Xs.fit_transform(np.log10(omega_h).reshape(-1, 1)); Xv = Xs.transform(np.log10(omega_v).reshape(-1, 1))
+        gps = []
+        for target, vy in ((G.real, Gv.real), (G.imag, Gv.imag)):
+            sc = StandardScaler(); z = sc.fit_transform(target.reshape(-1, 1)).ravel()
+            gp = GaussianProcessRegressor(kernel=create_kernel("matern52"), noise_variance=1e-6)
+            gp.fit(Xn, z, optimize=True, use_grid_search=True, max_grid_combinations=5000, validation_X=Xv, validation_y=vy, y_scaler=sc)
+            gps.append((gp, sc))
+        lap("gp_fit_x2", t0)
+        def predict(w_new):
+            Xq = Xs.transform(np.log10(w_new).reshape(-1, 1))
+            parts = [sc.inverse_transform(gp.predict(Xq).reshape(-1, 1)).ravel() for gp, sc in gps]
+            return parts[0] + 1j * parts[1]
+        t0 = time.perf_counter()
+        fir_res = gp_to_fir_direct_pipeline(omega_h, G, gp_predict_func=predict, mat_file=None, output_dir=ROOT / "gpurun_out" / "e2e_prof")
+        lap("gp_to_fir", t0)
+        t0 = time.perf_counter(); bfir.fir_validate(uv, yv, fir_res["fir_coefficients"], want_pred=False); lap("fir_validate", t0)
+    return out
+acc = {}
+for _ in range(5):
+    for k, v in phases().items():
+        acc[k] = acc.get(k, 0.0) + v / 5
+print("phase ms:", {k: round(v, 3) for k, v in acc.items()}, "sum", round(sum(acc.values()), 3))

@@ -49,3 +49,7 @@ timed("fir_eval_2048taps", lambda: fir.fir_eval_device(u, y, torch.cat([g, g]), 
 timed("fir_eval_direct_100taps", lambda: fir.fir_eval_device(u, y, g[:100].contiguous(), 10, 0.0))
 timed("gp_batch_nll", lambda: gp.batch_eval_device(3, None, th, X, yy, 1e-6))
 timed("gp_batch_val", lambda: gp.batch_eval_device(3, None, th[:2048], X, yy, 1e-6, gp.METRIC_VAL_RMSE, Xv, yv, 0.0, 1.0))
+nq = a.n // 5
+timed("frf_project_uniform_fifth_of_record", lambda: frf.project_uniform_device(t, u, y, w, 0.0, 0.002, own=(nq, 2 * nq)))
+timed("frf_uniformity_fifth_of_record", lambda: frf.uniformity_device_async(t, 0.0, 0.002, own=(nq, 2 * nq)))
+timed("frf_moments", lambda: frf.moments_device(u, y, (0, a.n)))

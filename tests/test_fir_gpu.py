@@ -95,3 +95,39 @@ def test_shard_history_matches_whole(fir):
     for i in idx.tolist():
         ref = float((u[i - taps + 1:i + 1].flip(0) * g).sum().item())
         assert abs(float(pred[i].item()) - ref) < 1e-12
+
+
+@pytest.mark.parametrize("n,taps,chunks", [(300_007, 1024, 6), (70_001, 300, 3), (150_000, 2048, 8), (41, 7, 4)])
+def test_streamed_host_validation_matches_oracle(fir, n, taps, chunks):
+    """Piecewise upload + per-piece FIR (history from the pieces already resident) = the oracle's whole-record
+    convolution and metrics; both with and without the prediction coming back."""
+    from b200id.runtime import require_cuda, to_device
+    dev = require_cuda()
+    rng = np.random.default_rng(n)
+    u = rng.standard_normal(n); g = rng.standard_normal(taps) / taps
+    ref = ofir.fir_predict(u, g)
+    y = ref + 0.01 * rng.standard_normal(n)
+    skip = min(10, taps // 10)
+    sums, pred = fir.fir_eval_streamed(u, y, to_device(g, dev), skip, float(y[skip]), n, want_pred=True, n_chunks=chunks)
+    assert rel_max(pred.cpu().numpy(), ref) < 1e-13
+    m = fir.metrics_from_sums(sums.cpu().numpy(), skip)
+    mr, _ = ofir.fir_validate(u, y, g)
+    for k in ("rmse", "fit_percent", "r2"):
+        assert abs(m[k] - mr[k]) <= 1e-11 * max(1.0, abs(mr[k])), k
+    sums2, none = fir.fir_eval_streamed(u, y, to_device(g, dev), skip, float(y[skip]), n, want_pred=False, n_chunks=chunks)
+    assert none is None
+    np.testing.assert_allclose(sums2.cpu().numpy(), sums.cpu().numpy(), rtol=1e-13)
+
+
+def test_public_validate_streams_large_host_records(fir, monkeypatch):
+    n, taps = 1_100_000, 1024
+    rng = np.random.default_rng(4)
+    u = rng.standard_normal(n); g = rng.standard_normal(taps) / taps
+    y = rng.standard_normal(n)
+    assert n >= fir.STREAM_MIN_SAMPLES
+    ms, ps = fir.fir_validate(u, y, g)
+    monkeypatch.setattr(fir, "_STREAM", False)
+    mb, pb = fir.fir_validate(u, y, g)
+    assert rel_max(ps, pb) < 1e-13
+    for k in ("rmse", "fit_percent", "r2"):
+        assert abs(ms[k] - mb[k]) <= 1e-12 * max(1.0, abs(mb[k])), k

@@ -206,3 +206,74 @@ def test_uniform_path_ill_conditioned_bins_use_rotation_kernel(frf):
     Ur, Yr = ofrf.demod_trapz(t, u, w), ofrf.demod_trapz(t, y, w)
     e = record("frf.uniform.ill_conditioned_bins.rel_each", max(rel_each(U, Ur), rel_each(Y, Yr)))
     assert e < TOL
+
+
+@pytest.mark.parametrize("n,chunks,kind,t_shift", [(300_001, 8, "multisine", 0.0), (200_003, 5, "square", 123.4567),
+                                                   (65_537, 3, "multisine", 1.9e6), (1000, 8, "multisine", 0.0)])
+def test_streamed_host_record_matches_oracle_and_resident(frf, n, chunks, kind, t_shift):
+    """The copy-overlapped host path (signals first, time stamps in pieces, one projection per piece)
+    against the oracle at the FRF tolerance and against the single-launch resident path."""
+    from b200id import synth
+    from b200id.runtime import require_cuda, to_device
+    dev = require_cuda()
+    nd = 60
+    t, u, y = synth.make_record(n, nd, kind, seed=33)
+    t = t + t_shift
+    _, w = ofrf.freq_grid(nd)
+    span, w_d = float(t[-1] - t[0]), to_device(w, dev)
+    Us, Ys = frf.record_coefficients_streamed(t, u, y, w_d, span, w_max=float(w.max()), n_chunks=chunks)
+    Ud, Yd = frf.record_coefficients_device(to_device(t, dev), to_device(u, dev), to_device(y, dev), w_d, span,
+                                            t0=float(t[0]), w_max=float(w.max()))
+    Ur, Yr = ofrf.demod_trapz(t, u, w, threads=8), ofrf.demod_trapz(t, y, w, threads=8)
+    e_o = max(rel_each(Us.cpu().numpy(), Ur), rel_each(Ys.cpu().numpy(), Yr))
+    e_d = max(rel_each(Us.cpu().numpy(), Ud.cpu().numpy()), rel_each(Ys.cpu().numpy(), Yd.cpu().numpy()))
+    record(f"frf.streamed.{kind}.n{n}.c{chunks}.vs_oracle", e_o)
+    record(f"frf.streamed.{kind}.n{n}.c{chunks}.vs_resident", e_d)
+    assert e_o < TOL and e_d < TOL
+    # one signal, no mean subtraction
+    U1, none = frf.record_coefficients_streamed(t, u, None, w_d, span, subtract_mean=False, w_max=float(w.max()),
+                                                n_chunks=chunks)
+    assert none is None
+    assert rel_each(U1.cpu().numpy(), ofrf.demod_trapz(t, u, w, subtract_mean=False, threads=8)) < TOL
+
+
+def test_streamed_record_nonuniform_and_late_jitter(frf, golden):
+    """(i) a jittered time base is projected piecewise by the general kernel; (ii) a record whose FIRST piece
+    sits on the grid but a later one does not is detected on the device and re-projected (no silent use of
+    the uniform kernel off its validity range)."""
+    from b200id import synth
+    from b200id.runtime import require_cuda, to_device
+    dev = require_cuda()
+    g = golden("frf")
+    tj, uj, yj, w = g["t_jit"], g["u"], g["y"], g["w"]
+    w_d = to_device(w, dev)
+    U, Y = frf.record_coefficients_streamed(tj, uj, yj, w_d, float(tj[-1] - tj[0]), w_max=float(w.max()), n_chunks=4)
+    assert max(rel_each(U.cpu().numpy(), g["U_jit"]), rel_each(Y.cpu().numpy(), g["Y_jit"])) < TOL
+    n, nd = 120_000, 40
+    t, u, y = synth.make_record(n, nd, "multisine", seed=5)
+    rng = np.random.default_rng(0)
+    t = t.copy()
+    t[n // 2:-1] += rng.uniform(-2e-4, 2e-4, size=n - n // 2 - 1)      # second half off the grid, still monotone
+    assert np.all(np.diff(t) > 0)
+    _, w = ofrf.freq_grid(nd)
+    w_d = to_device(w, dev)
+    U, Y = frf.record_coefficients_streamed(t, u, y, w_d, float(t[-1] - t[0]), w_max=float(w.max()), n_chunks=8)
+    Ur, Yr = ofrf.demod_trapz(t, u, w, threads=8), ofrf.demod_trapz(t, y, w, threads=8)
+    e = record("frf.streamed.late_jitter.vs_oracle", max(rel_each(U.cpu().numpy(), Ur), rel_each(Y.cpu().numpy(), Yr)))
+    assert e < TOL
+
+
+def test_public_demod_streams_large_host_records(frf, monkeypatch):
+    """demod_pair on a host record above the streaming threshold = the same call with streaming disabled."""
+    from b200id import synth
+    n, nd = 1_200_000, 30
+    t, u, y = synth.make_record(n, nd, "multisine", seed=8)
+    _, w = ofrf.freq_grid(nd)
+    assert n >= frf.STREAM_MIN_SAMPLES
+    Us, Ys = frf.demod_pair(t, u, y, w)
+    monkeypatch.setattr(frf, "_STREAM", False)
+    Ub, Yb = frf.demod_pair(t, u, y, w)
+    e = record("frf.streamed.public.vs_bulk", max(rel_each(Us, Ub), rel_each(Ys, Yb)))
+    assert e < 1e-11
+    Ur = ofrf.demod_trapz(t, u, w, threads=16)
+    assert rel_each(Us, Ur) < TOL

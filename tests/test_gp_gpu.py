@@ -317,3 +317,73 @@ def test_config4_large_n_fit_and_metrics(gp, n):
     m_ref, s_ref = ogp.predict(name, thetas[0], X, a_ref, Kinv_ref, Xs, True)
     assert record(f"gp.cfg4.mean.n{n}.rel_max", rel_max(mean, m_ref)) < 1e-8
     assert record(f"gp.cfg4.std.n{n}.abs", float(np.max(np.abs(std - s_ref)))) < 1e-6
+
+
+@pytest.mark.parametrize("name,n,mode", [("matern52", 100, "val"), ("rbf", 60, "nll"), ("dc", 33, "val"), ("matern32", 140, "nll")])
+def test_search_and_fit_single_round_trip(gp, name, n, mode):
+    """gp.search_and_fit (start metric + all candidates + scan + winner's fit + fitted mean, one device
+    round trip) returns exactly what the separate batch_eval / select / fit calls return, and leaves the
+    winner's factorisation memoised for the GaussianProcessRegressor.fit that follows it."""
+    rng = np.random.default_rng(n)
+    kid = ogp.KERNELS[name][0]
+    X = np.linspace(-1.6, 1.7, n)
+    y = np.sin(2.5 * X) + 0.05 * rng.standard_normal(n)
+    cands = ogp.grid_candidates(name, 400)
+    start = cands[7] * 1.01
+    noise, jitter = 1e-6, 1e-6 + 1e-10
+    kw = {}
+    if mode == "val":
+        Xv = np.linspace(-1.5, 1.5, 37)
+        kw = dict(Xv=Xv, yv=0.7 * np.sin(2.5 * Xv) + 0.2, y_mean=0.2, y_scale=0.7)
+    res = gp.search_and_fit(kid, start, cands, X, y, noise, jitter, **kw)
+    m0 = gp.batch_eval(kid, start, X, y, noise, **kw)[0]
+    idx, best, metrics = gp.select(kid, cands, X, y, noise, **kw)
+    # (a candidate's CTA index differs by one between the two batches; warp roles rotate with it, so allow an ulp)
+    assert res["index"] == idx
+    np.testing.assert_allclose([res["best"], res["start_metric"]], [best, m0], rtol=1e-12)
+    np.testing.assert_allclose(res["metrics"], metrics, rtol=1e-12, equal_nan=True)
+    assert not res["used_pinv"]
+    gp._fit_memo.clear()
+    alpha, Kinv, used = gp.fit(kid, cands[idx], X, y, jitter, want_kinv=False)
+    np.testing.assert_allclose(res["alpha"], alpha, rtol=1e-12, atol=0)
+    assert not used
+    K = ogp.gram(name, cands[idx], X.reshape(-1, 1))
+    cond = np.linalg.cond(K + jitter * np.eye(n))
+    e = record(f"gp.search_and_fit.{name}.n{n}.train_pred", rel_max(res["train_pred"], K @ alpha))
+    assert e < 100 * cond * 2.2e-16
+    # memo: a second search leaves the winner's fit behind; fit() with the same inputs returns it, K_inv on demand
+    gp.search_and_fit(kid, start, cands, X, y, noise, jitter, **kw)
+    from b200id import _lib
+    before = _lib.launch_count
+    a2, k2, _ = gp.fit(kid, cands[idx], X, y, jitter, want_kinv=False)
+    assert _lib.launch_count == before, "memoised fit must not relaunch"
+    np.testing.assert_allclose(a2, alpha, rtol=1e-12, atol=0)
+    a3, k3, _ = gp.fit(kid, cands[idx], X, y, jitter, want_kinv=True)
+    assert k3 is not None and np.max(np.abs(k3 @ (K + jitter * np.eye(n)) - np.eye(n))) < 50 * cond * 2.2e-16
+
+
+def test_gpr_mirror_lazy_kinv_and_std(gp, golden):
+    """GaussianProcessRegressor.K_inv is formed on first use and equals the eager inverse; predict with
+    return_std after a grid-search fit matches the oracle's sigma."""
+    from src.gpr import create_kernel, GaussianProcessRegressor
+    rng = np.random.default_rng(3)
+    n = 80
+    X = np.linspace(-1.6, 1.7, n).reshape(-1, 1)
+    y = np.cos(1.5 * X.ravel()) + 0.02 * rng.standard_normal(n)
+    import contextlib, io
+    m = GaussianProcessRegressor(kernel=create_kernel("matern52"), noise_variance=1e-5)
+    with contextlib.redirect_stdout(io.StringIO()):
+        m.fit(X, y, optimize=True, use_grid_search=True, max_grid_combinations=300)
+    assert m._K_inv is None                      # not needed for the mean
+    Xq = np.linspace(-1.5, 1.5, 25).reshape(-1, 1)
+    mean0 = m.predict(Xq)
+    theta = m.kernel.get_params()
+    K = ogp.gram("matern52", theta, X) + (1e-5 + 1e-10) * np.eye(n)
+    cond = np.linalg.cond(K)
+    mean, std = m.predict(Xq, return_std=True)
+    assert m._K_inv is not None and np.array_equal(mean, mean0)
+    assert np.max(np.abs(m.K_inv @ K - np.eye(n))) < 50 * cond * 2.2e-16
+    alpha_o, Kinv_o, _ = ogp.fit("matern52", theta, X, y, 1e-5)
+    mean_o, std_o = ogp.predict("matern52", theta, X, alpha_o, Kinv_o, Xq, return_std=True)
+    assert rel_max(mean, mean_o) < 100 * cond * 2.2e-16
+    assert np.max(np.abs(std - std_o)) < 1e-6          # sqrt of a difference of O(1) terms at cond*eps

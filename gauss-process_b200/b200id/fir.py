@@ -114,6 +114,10 @@ def fir_validate(u, y, g, detrend: bool = False, want_pred: bool = True,
                  skip: Optional[int] = None) -> Tuple[Dict[str, float], Optional[np.ndarray]]:
     """(metrics, y_pred) of FIR taps g on record (u, y): convolution and error sums on the device."""
     dev = require_cuda()
+    from .records import STORE
+    rec = None if detrend else STORE.lookup(u, y)          # both vectors of one stored file record?
+    if rec is not None and (rec.role_of(u), rec.role_of(y)) != ("u", "y"):
+        rec = None
     u = np.asarray(u, dtype=np.float64).ravel()
     y = np.asarray(y, dtype=np.float64).ravel()
     g = np.asarray(g, dtype=np.float64).ravel()
@@ -122,7 +126,10 @@ def fir_validate(u, y, g, detrend: bool = False, want_pred: bool = True,
     skip = min(10, g.size // 10) if skip is None else int(skip)
     n = min(u.size, y.size)
     g_d = to_device(g, dev)
-    if _STREAM and n >= STREAM_MIN_SAMPLES:
+    if rec is not None:
+        _, u_d, y_d = STORE.on_device(rec, dev)            # normally already in HBM, from the FRF of this file
+        sums, pred = fir_eval_device(u_d, y_d, g_d, skip, float(y[skip]), want_pred=want_pred, n=n)
+    elif _STREAM and n >= STREAM_MIN_SAMPLES:
         sums, pred = fir_eval_streamed(u[:n], y[:n], g_d, skip, float(y[skip]), n, want_pred=want_pred)
     else:
         sums, pred = fir_eval_device(to_device(u, dev), to_device(y, dev), g_d, skip, float(y[skip]), want_pred=want_pred, n=n)

@@ -147,7 +147,8 @@ _STREAM = os.environ.get("B200ID_FRF_STREAM", "1") != "0"
 
 
 def record_coefficients_streamed(t_h, u_h, y_h, w_d, span: float, subtract_mean: bool = True,
-                                 w_max: Optional[float] = None, n_chunks: int = STREAM_CHUNKS, trace: Optional[list] = None):
+                                 w_max: Optional[float] = None, n_chunks: int = STREAM_CHUNKS, trace: Optional[list] = None,
+                                 keep: Optional[dict] = None):
     """(U, Y) of one HOST-resident record, with the projection overlapped with the host->device copy.
 
     The signals u, y go up first (the mean needs all of them); the time stamps follow in ``n_chunks`` pieces
@@ -226,6 +227,8 @@ def record_coefficients_streamed(t_h, u_h, y_h, w_d, span: float, subtract_mean:
     if kind == "uniform" and _FORCE_PATH != "uniform":
         if not (uniformity_device(t_d, t0, dt) * w_max < UNIFORM_PHASE_TOL):
             part = project_device(t_d, u_d, y_d, w_d, (0, n), sums, 1.0 / n)
+    if keep is not None:
+        keep["device_arrays"] = (t_d, u_d, y_d)      # every copy has been waited for on this stream
     return finalize_device(part, nd, 2.0 / span, want_y=y_d is not None)
 
 
@@ -236,6 +239,51 @@ def _coefficients(t, u, y, w_d, span, subtract_mean, w_max):
         return record_coefficients_streamed(t, u, y, w_d, span, subtract_mean, w_max)
     return record_coefficients_device(to_device(t, dev), to_device(u, dev), None if y is None else to_device(y, dev),
                                       w_d, span, subtract_mean, t0=float(t[0]), w_max=w_max)
+
+
+# ----------------------------------------------------------------------------------------- stored records
+def _stored_pair(rec, w: np.ndarray, drop_seconds: float, subtract_mean: bool):
+    """(U, Y) of a record held by :mod:`b200id.records`: both signals in one
+    fused pass over the resident copy, memoised per (grid, drop, subtract_mean) -- the reference's
+    ``synchronous_coefficients_trapz(t, u, ...)`` followed by ``(t, y, ...)`` (data_loader.py:184-185) costs
+    one projection, and asking again for the same file costs none.  None when the record needs the host
+    path (transient drop on a non-monotone time base)."""
+    from .records import STORE
+    dev = require_cuda()
+    memo_key = (w.tobytes(), float(drop_seconds or 0.0), bool(subtract_mean))
+    hit = rec.coefficients.get(memo_key)
+    if hit is not None:
+        STORE.stats["coefficient_hits"] += 1
+        return hit
+    t = rec.t
+    first = 0
+    if drop_seconds and drop_seconds > 0.0:
+        if not rec.monotone():
+            return None
+        first = int(np.searchsorted(t, t[0] + drop_seconds, side="left"))
+    if t.size - first < 2:
+        raise ValueError("Not enough samples after transient drop.")
+    span = float(t[-1] - t[first])
+    if span <= 0:
+        raise ValueError("Non-positive record length.")
+    w_flat = np.ascontiguousarray(w, dtype=np.float64).ravel()
+    w_d, w_max = to_device(w_flat, dev), float(np.max(np.abs(w_flat)))
+    if rec.device_arrays is None and first == 0 and _STREAM and t.size >= STREAM_MIN_SAMPLES:
+        keep = {}
+        U, Y = record_coefficients_streamed(rec.t, rec.u, rec.y, w_d, span, subtract_mean, w_max, keep=keep)
+        STORE.adopt(rec, keep["device_arrays"])
+    else:
+        t_d, u_d, y_d = (a[first:] for a in STORE.on_device(rec, dev))
+        path = rec.facts.get(("frf_path", first, w_max))
+        if path is None:
+            path = rec.facts[("frf_path", first, w_max)] = choose_path(t_d, span, w_max, float(t[first]))
+        U, Y = record_coefficients_device(t_d, u_d, y_d, w_d, span, subtract_mean, path=path)
+    UY = torch.stack([U, Y]).cpu().numpy()
+    out = (UY[0].reshape(w.shape), UY[1].reshape(w.shape))
+    for a in out:
+        a.setflags(write=False)
+    rec.coefficients[memo_key] = out
+    return out
 
 
 # ----------------------------------------------------------------------------------------- host API
@@ -265,6 +313,12 @@ def _prepare(t, x_list: Sequence[np.ndarray], drop_seconds: float):
 def demod(t, x, w, drop_seconds: float = 0.0, subtract_mean: bool = True) -> np.ndarray:
     """One-signal synchronous demodulation (the reference's synchronous_coefficients_trapz)."""
     dev = require_cuda()
+    from .records import STORE
+    rec = STORE.lookup(t, x)
+    if rec is not None and rec.role_of(t) == "t" and rec.role_of(x) in ("u", "y"):
+        pair = _stored_pair(rec, np.asarray(w, dtype=np.float64), drop_seconds, subtract_mean)
+        if pair is not None:
+            return pair[0 if rec.role_of(x) == "u" else 1].copy()
     t, (x,), span = _prepare(t, [x], drop_seconds)
     w = np.asarray(w, dtype=np.float64)
     U, _ = _coefficients(t, x, None, to_device(w.ravel(), dev), span, subtract_mean, float(np.max(np.abs(w))))
@@ -274,6 +328,12 @@ def demod(t, x, w, drop_seconds: float = 0.0, subtract_mean: bool = True) -> np.
 def demod_pair(t, u, y, w, drop_seconds: float = 0.0, subtract_mean: bool = True):
     """(U, Y) with t, u, y read once (fused form of two synchronous_coefficients_trapz calls)."""
     dev = require_cuda()
+    from .records import STORE
+    rec = STORE.lookup(t, u, y)
+    if rec is not None and (rec.role_of(t), rec.role_of(u), rec.role_of(y)) == ("t", "u", "y"):
+        pair = _stored_pair(rec, np.asarray(w, dtype=np.float64), drop_seconds, subtract_mean)
+        if pair is not None:
+            return pair[0].copy(), pair[1].copy()
     t, (u, y), span = _prepare(t, [u, y], drop_seconds)
     w = np.asarray(w, dtype=np.float64)
     U, Y = _coefficients(t, u, y, to_device(w.ravel(), dev), span, subtract_mean, float(np.max(np.abs(w))))

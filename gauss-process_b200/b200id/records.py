@@ -1,0 +1,216 @@
+"""File-keyed store of time-domain records: parse once, upload once, reuse on the device.
+
+SURVEY.md section 8(f) rank 1.  The reference re-reads the same ``.mat`` file up to three times per kernel
+(validation FRF ``data_loader.py:170``, paper-mode FIR ``fir_fitting.py:267``, ``fir_validation.py:163``)
+and ``run_baseline.py`` repeats that for every kernel; each read is a ``loadmat`` of the whole record and,
+behind this package, a host->device copy of it.  The store keeps
+
+  * the parsed ``loadmat`` dict per file (key = resolved path + mtime + size, so a rewritten file misses),
+  * per (file, loader) the contiguous FP64 ``t, u, y`` host arrays, made READ-ONLY so that object identity
+    implies unchanged contents, and -- once something on the device has asked for them -- their HBM copies,
+  * per record the synchronous-demodulation coefficients already computed for a given frequency grid.
+
+The mirrors under ``src/`` hand out the store's arrays from their loaders and look incoming arrays up by
+identity, so the reference's own call sequences (``load_time_u_y`` -> ``synchronous_coefficients_trapz`` for
+u, then for y; ``load_mat_time_series`` -> convolution) run on resident data without any change on the
+caller's side.  Both levels are LRU-bounded; ``B200ID_RECORD_CACHE=0`` turns the store off.
+"""
+from __future__ import annotations
+
+import os
+from collections import OrderedDict
+from pathlib import Path
+from typing import Callable, Dict, Optional, Tuple
+
+import numpy as np
+import torch
+
+from .runtime import from_numpy
+
+ENABLED = os.environ.get("B200ID_RECORD_CACHE", "1") != "0"
+HOST_BUDGET = int(float(os.environ.get("B200ID_RECORD_CACHE_HOST_GB", "8")) * 2**30)
+DEVICE_BUDGET = int(float(os.environ.get("B200ID_RECORD_CACHE_DEVICE_GB", "32")) * 2**30)
+
+
+def file_key(path) -> Tuple[str, int, int]:
+    p = Path(path).resolve()
+    st = p.stat()
+    return str(p), st.st_mtime_ns, st.st_size
+
+
+def _freeze(a: np.ndarray) -> np.ndarray:
+    a.setflags(write=False)
+    return a
+
+
+class Record:
+    """One (file, loader) record: read-only host arrays, lazily uploaded device copies, derived facts."""
+
+    def __init__(self, key, t: np.ndarray, u: np.ndarray, y: np.ndarray):
+        self.key = key
+        self.t, self.u, self.y = (_freeze(np.ascontiguousarray(a, dtype=np.float64)) for a in (t, u, y))
+        self.device_arrays: Optional[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]] = None
+        self.facts: Dict[object, object] = {}      # monotone flag, chosen FRF path per start index, ...
+        self.coefficients: Dict[object, Tuple[np.ndarray, np.ndarray]] = {}
+
+    @property
+    def host_bytes(self) -> int:
+        return self.t.nbytes + self.u.nbytes + self.y.nbytes
+
+    @property
+    def device_bytes(self) -> int:
+        return 0 if self.device_arrays is None else sum(a.numel() * 8 for a in self.device_arrays)
+
+    def role_of(self, arr) -> Optional[str]:
+        for name in ("t", "u", "y"):
+            if getattr(self, name) is arr:
+                return name
+        return None
+
+    def monotone(self) -> bool:
+        if "monotone" not in self.facts:
+            self.facts["monotone"] = bool(self.t.size < 2 or np.all(np.diff(self.t) > 0))
+        return self.facts["monotone"]
+
+
+class RecordStore:
+    def __init__(self, host_budget: int = HOST_BUDGET, device_budget: int = DEVICE_BUDGET):
+        self.host_budget, self.device_budget = host_budget, device_budget
+        self.mats: "OrderedDict[tuple, Tuple[dict, int]]" = OrderedDict()
+        self.records: "OrderedDict[tuple, Record]" = OrderedDict()
+        self.by_id: Dict[int, Record] = {}
+        self.file_facts: "OrderedDict[tuple, object]" = OrderedDict()      # small per-file results (e.g. Ts)
+        self.stats = {"mat_hits": 0, "mat_misses": 0, "record_hits": 0, "record_misses": 0, "uploads": 0,
+                      "coefficient_hits": 0, "record_aliases": 0}
+
+    # ------------------------------------------------------------------ files
+    def loadmat(self, path) -> dict:
+        """``scipy.io.loadmat(path)``, parsed once per (path, mtime, size); the arrays are read-only."""
+        from scipy.io import loadmat
+        if not ENABLED:
+            return loadmat(path)
+        key = file_key(path)
+        hit = self.mats.get(key)
+        if hit is not None:
+            self.mats.move_to_end(key)
+            self.stats["mat_hits"] += 1
+            return hit[0]
+        self.stats["mat_misses"] += 1
+        data = loadmat(path)
+        nbytes = 0
+        for v in data.values():
+            if isinstance(v, np.ndarray):
+                nbytes += v.nbytes
+                try:
+                    v.setflags(write=False)
+                except ValueError:
+                    pass
+        self.mats[key] = (data, nbytes)
+        self._trim()
+        return data
+
+    def record(self, path, tag, extract: Callable[[dict], Tuple[np.ndarray, np.ndarray, np.ndarray]]) -> Record:
+        """The (t, u, y) record ``extract(loadmat(path))`` yields, built once per (file, tag)."""
+        if not ENABLED:
+            return Record(None, *extract(self.loadmat(path)))
+        key = (file_key(path), tag)
+        rec = self.records.get(key)
+        if rec is not None:
+            self.records.move_to_end(key)
+            self.stats["record_hits"] += 1
+            return rec
+        self.stats["record_misses"] += 1
+        t, u, y = extract(self.loadmat(path))
+        # two loaders that pull the same vectors out of one file (the usual 3xN ``output`` layout) share one
+        # record, hence one set of host arrays and one HBM copy
+        for (fk, _), other in self.records.items():
+            if fk == key[0] and all(np.shape(a) == b.shape and np.array_equal(a, b) for a, b in ((t, other.t), (u, other.u), (y, other.y))):
+                self.records[key] = other
+                self.stats["record_aliases"] += 1
+                return other
+        rec = Record(key, t, u, y)
+        self.records[key] = rec
+        for a in (rec.t, rec.u, rec.y):
+            self.by_id[id(a)] = rec
+        self._trim(keep=key)
+        return rec
+
+    def file_fact(self, path, tag, compute: Callable[[dict], object]):
+        """``compute(loadmat(path))`` once per (file, tag) -- for small derived values such as the sampling
+        period; at most 256 are kept."""
+        if not ENABLED:
+            return compute(self.loadmat(path))
+        key = (file_key(path), tag)
+        if key in self.file_facts:
+            self.file_facts.move_to_end(key)
+            return self.file_facts[key]
+        value = compute(self.loadmat(path))
+        self.file_facts[key] = value
+        while len(self.file_facts) > 256:
+            self.file_facts.popitem(last=False)
+        return value
+
+    def lookup(self, *arrays) -> Optional[Record]:
+        """The record ALL of ``arrays`` belong to (by object identity), else None."""
+        if not ENABLED or not arrays:
+            return None
+        rec = self.by_id.get(id(arrays[0]))
+        if rec is None:
+            return None
+        for a in arrays:
+            if rec.role_of(a) is None:
+                return None
+        return rec
+
+    # ------------------------------------------------------------------ device
+    def on_device(self, rec: Record, dev: torch.device):
+        """(t_d, u_d, y_d) of ``rec`` in HBM, uploaded on first use."""
+        if rec.device_arrays is None or rec.device_arrays[0].device != dev:
+            rec.device_arrays = tuple(from_numpy(a).to(dev, non_blocking=True) for a in (rec.t, rec.u, rec.y))
+            self.stats["uploads"] += 1
+            self._trim(keep=rec.key)
+        return rec.device_arrays
+
+    def adopt(self, rec: Record, arrays) -> None:
+        """Keep device copies that a streamed first pass has just produced."""
+        rec.device_arrays = tuple(arrays)
+        self.stats["uploads"] += 1
+        self._trim(keep=rec.key)
+
+    # ------------------------------------------------------------------ housekeeping
+    def _trim(self, keep=None) -> None:
+        while self.mats and sum(n for _, n in self.mats.values()) > self.host_budget:
+            self.mats.popitem(last=False)
+        def totals():
+            uniq = {id(r): r for r in self.records.values()}.values()
+            return sum(r.host_bytes for r in uniq), sum(r.device_bytes for r in uniq)
+        host, device = totals()
+        for key in list(self.records):
+            if host <= self.host_budget and device <= self.device_budget:
+                break
+            if key == keep:
+                continue
+            rec = self.records[key]
+            if device > self.device_budget and rec.device_arrays is not None and host <= self.host_budget:
+                rec.device_arrays = None                       # drop the HBM copy, keep the host arrays
+            else:
+                self._drop(key)
+            host, device = totals()
+
+    def _drop(self, key) -> None:
+        rec = self.records.pop(key)
+        if any(other is rec for other in self.records.values()):
+            return                                             # still reachable under another loader's key
+        for a in (rec.t, rec.u, rec.y):
+            self.by_id.pop(id(a), None)
+
+    def clear(self) -> None:
+        self.mats.clear()
+        self.records.clear()
+        self.by_id.clear()
+        self.file_facts.clear()
+        for k in self.stats:
+            self.stats[k] = 0
+
+
+STORE = RecordStore()

@@ -4,6 +4,8 @@ from __future__ import annotations
 import ctypes as C
 from typing import Optional
 
+import warnings
+
 import numpy as np
 import torch
 
@@ -31,12 +33,22 @@ def ptr(t: Optional[torch.Tensor]) -> C.c_void_p:
     return C.c_void_p(t.data_ptr())
 
 
+def from_numpy(a: np.ndarray) -> torch.Tensor:
+    """torch.from_numpy that accepts read-only arrays quietly (the tensors made here are only ever read:
+    they are the source of a host->device copy)."""
+    if a.flags.writeable:
+        return torch.from_numpy(a)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", UserWarning)
+        return torch.from_numpy(a)
+
+
 def to_device(a, dev: torch.device, dtype=F64) -> torch.Tensor:
     """Host array (NumPy or CPU torch, pinned or not) or device tensor -> contiguous device tensor."""
     if isinstance(a, torch.Tensor):
         t = a
     else:
-        t = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64 if dtype == F64 else None))
+        t = from_numpy(np.ascontiguousarray(a, dtype=np.float64 if dtype == F64 else None))
     if t.dtype != dtype:
         t = t.to(dtype)
     if not t.is_cuda:
@@ -59,7 +71,7 @@ def host_f64(a) -> torch.Tensor:
     """Host array -> contiguous float64 CPU tensor sharing its memory when possible (pinned stays pinned)."""
     if isinstance(a, torch.Tensor):
         return a.to(F64).contiguous()
-    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64))
+    return from_numpy(np.ascontiguousarray(a, dtype=np.float64))
 
 
 def stream_edges(n: int, n_chunks: int) -> list:

@@ -42,6 +42,19 @@ def _extract_tyu_from_mat_data(data: dict):
         return None, None, None
 
 
+def _validation_record(mat_file):
+    """(T, y, u) of the validation file through the record store: the same vectors (and HBM copies) that
+    ``fir_validation.load_mat_time_series`` hands out, so FRF, paper-mode FIR and Wave.mat validation of one
+    file share one parse and one upload (the reference parses it three times: data_loader.py:170,
+    fir_fitting.py:267, fir_validation.py:163)."""
+    from src.fir_model.fir_validation import load_mat_time_series
+    try:
+        ts = load_mat_time_series(mat_file)
+    except ValueError:
+        return None, None, None
+    return ts["t"], ts["y"], ts["u"]
+
+
 def plot_gp_fir_results_fixed(t, y, y_pred, u, rmse, fit_percent, r2, output_dir: Path,
                               prefix: str = "gp_fir_fixed", save_eps: bool = True):
     """Output-vs-predicted and error figures; plotting is outside the hot path (needs matplotlib)."""
@@ -100,7 +113,7 @@ def gp_to_fir_direct_pipeline(
         _, Ts = _load_timebase_from_mat(Path(mat_file))
         print(f"  Ts = {Ts:.6f} s (from MAT file)")
         results["Ts"] = float(Ts)
-        T, y, u = _extract_tyu_from_mat_data(loadmat(mat_file))
+        T, y, u = _validation_record(mat_file)
         if T is not None and y is not None and u is not None:
             print("  [STRICT MODE] No detrend - evaluating full frequency range including DC")
             metrics, y_pred = _fir.fir_validate(u, y, g, detrend=False, want_pred=True)

@@ -11,7 +11,9 @@ from pathlib import Path
 from typing import Callable, Optional, Tuple
 
 import numpy as np
-from scipy.io import loadmat
+from scipy.io import loadmat  # noqa: F401  (kept: part of the reference module's namespace)
+
+from b200id import records as _records
 
 from b200id import fir as _fir
 
@@ -66,8 +68,12 @@ def idft_to_fir_coeffs_two_sided(X: np.ndarray, N: int) -> Tuple[np.ndarray, np.
 
 
 def _load_timebase_from_mat(mat_file: Path) -> Tuple[np.ndarray, float]:
-    """(t, median Ts) from 't' / 'time' or the first row / column of a 3xN / Nx3 array (reference :144-189)."""
-    data = loadmat(mat_file)
+    """(t, median Ts) from 't' / 'time' or the first row / column of a 3xN / Nx3 array (reference :144-189).
+    Parsed and reduced once per file (b200id/records.py); t is read-only."""
+    return _records.STORE.file_fact(mat_file, "timebase", _timebase_of)
+
+
+def _timebase_of(data: dict) -> Tuple[np.ndarray, float]:
     t = None
     for key in ("t", "time"):
         if key in data:
@@ -85,6 +91,7 @@ def _load_timebase_from_mat(mat_file: Path) -> Tuple[np.ndarray, float]:
     dt = np.median(np.diff(t))
     if dt <= 0 or not np.isfinite(dt):
         raise ValueError("Invalid time vector; cannot compute Ts.")
+    t.setflags(write=False)
     return t, float(dt)
 
 

@@ -14,12 +14,19 @@ import numpy as np
 from scipy.io import loadmat
 
 from b200id import fir as _fir
+from b200id import records as _records
 
 
 def load_mat_time_series(mat_path) -> Dict[str, np.ndarray]:
-    """{'t', 'y', 'u'} from a 3xN / Nx3 [t, y, u] array or named variables (reference :30-86)."""
+    """{'t', 'y', 'u'} from a 3xN / Nx3 [t, y, u] array or named variables (reference :30-86).  Parsed once
+    per file; the arrays are the record store's read-only vectors (b200id/records.py)."""
     mat_path = Path(mat_path)
-    data = loadmat(mat_path)
+    rec = _records.STORE.record(mat_path, "time_series", lambda data: _extract_time_series(data, mat_path))
+    return {"t": rec.t, "y": rec.y, "u": rec.u}
+
+
+def _extract_time_series(data: dict, mat_path):
+    """(t, u, y) -- store order -- by the reference's rule: first 3xN / Nx3 array, else named variables."""
     T = y = u = None
     for key, val in data.items():
         if key.startswith("__") or not isinstance(val, np.ndarray):
@@ -37,7 +44,7 @@ def load_mat_time_series(mat_path) -> Dict[str, np.ndarray]:
             pass
     if T is None or y is None or u is None:
         raise ValueError(f"Could not extract [t, y, u] from {mat_path}. Expected named variables or a 3xN / Nx3 matrix.")
-    return {"t": T, "y": y, "u": u}
+    return T, u, y
 
 
 def compute_time_domain_metrics(y_true: np.ndarray, y_pred: np.ndarray, fir_length: int) -> Dict[str, float]:

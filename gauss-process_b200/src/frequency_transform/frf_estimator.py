@@ -20,6 +20,7 @@ import numpy as np
 from scipy.io import loadmat, savemat
 
 from b200id import frf as _frf
+from b200id import records as _records
 
 
 # ------------------------------------------------------------------ files
@@ -68,8 +69,16 @@ def _split_matrix(arr):
 
 def load_time_u_y(mat_path: Path, y_col: int = 0) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
     """(t, u, y) from a .mat file: named t/u/y (y column ``y_col``), else a [t, y, u] matrix, ``output``
-    preferred (reference :70-134)."""
-    data = loadmat(mat_path)
+    preferred (reference :70-134).
+
+    The file is parsed once per (path, mtime, size) and the arrays handed out are the record store's
+    read-only FP64 vectors (b200id/records.py): passing them on to ``synchronous_coefficients_trapz`` /
+    the FIR validation lets those run on the copy already resident in HBM."""
+    rec = _records.STORE.record(mat_path, ("time_u_y", int(y_col)), lambda data: _extract_time_u_y(data, mat_path, y_col))
+    return rec.t, rec.u, rec.y
+
+
+def _extract_time_u_y(data: dict, mat_path, y_col: int):
     t, u, y_raw = _as_vector(data.get("t")), _as_vector(data.get("u")), data.get("y")
     if t is not None and u is not None and y_raw is not None:
         ya = np.asarray(y_raw)
@@ -131,11 +140,18 @@ def matlab_freq_grid(n_points: int, f_low_log10: float, f_up_log10: float) -> Tu
 
 
 def describe_timebase(t: np.ndarray) -> Tuple[float, float, bool]:
-    """(median dt, span, strictly increasing?) (reference :186-191)."""
+    """(median dt, span, strictly increasing?) (reference :186-191); remembered for stored records."""
     if t.size <= 1:
         return float("nan"), 0.0, True
+    rec = _records.STORE.lookup(t)
+    if rec is not None and "timebase" in rec.facts:
+        return rec.facts["timebase"]
     d = np.diff(t)
-    return float(np.median(d)), float(t[-1] - t[0]), bool(np.all(d > 0))
+    out = (float(np.median(d)), float(t[-1] - t[0]), bool(np.all(d > 0)))
+    if rec is not None and rec.role_of(t) == "t":
+        rec.facts["timebase"] = out
+        rec.facts["monotone"] = out[2]
+    return out
 
 
 def synchronous_coefficients_trapz(t, x, w, drop_seconds: float = 0.0, subtract_mean: bool = True) -> np.ndarray:

@@ -14,6 +14,7 @@ from typing import List, Optional
 import numpy as np
 import pandas as pd
 
+from b200id import records as _records
 from src.frequency_transform import frf_estimator as _est
 from src.frequency_transform.frf_estimator import (  # noqa: F401  -- names the reference re-exports from here
     resolve_mat_files, load_time_u_y, try_load_frequency_from_mat, matlab_freq_grid, describe_timebase,
@@ -81,6 +82,14 @@ def _windowed(t, u, y, drop_seconds, time_duration):
     return t[inside], u[inside], y[inside], 0.0
 
 
+def _increasing(t: np.ndarray) -> bool:
+    """Strictly increasing time stamps?  Remembered per file for records that come from the store."""
+    rec = _records.STORE.lookup(t)
+    if rec is not None and rec.role_of(t) == "t":
+        return rec.monotone()
+    return describe_timebase(t)[2]
+
+
 def _estimate_frf(paths, nd, f_low, f_up, drop_seconds, time_duration, y_col, subtract_mean):
     """GPU FRF of a list of .mat records (reference :120-157): window, monotone order, fused u/y
     demodulation per record, cross-power average, sort by omega."""
@@ -88,7 +97,7 @@ def _estimate_frf(paths, nd, f_low, f_up, drop_seconds, time_duration, y_col, su
     coeffs = []
     for path in paths:
         t, u, y, drop = _windowed(*load_time_u_y(path, y_col=y_col), drop_seconds, time_duration)
-        if not describe_timebase(t)[2]:
+        if not _increasing(t):
             by_time = np.argsort(t)
             t, u, y = t[by_time], u[by_time], y[by_time]
         coeffs.append(synchronous_coefficients_trapz_pair(t, u, y, omega, drop, subtract_mean))

@@ -50,15 +50,22 @@ def gram(kernel_id: int, theta, X1, X2=None) -> np.ndarray:
 
 
 def batch_eval_device(kernel_id: int, kernel_ids_d: Optional[torch.Tensor], theta_d: torch.Tensor,
-                      X_d: torch.Tensor, y_d: torch.Tensor, noise: float, metric: int = METRIC_NLL,
+                      X_d: torch.Tensor, y_d: torch.Tensor, noise, metric: int = METRIC_NLL,
                       Xv_d: Optional[torch.Tensor] = None, yv_d: Optional[torch.Tensor] = None,
                       y_mean: float = 0.0, y_scale: float = 1.0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """metric[C] (device) for theta_d [C, 3]; one CTA per candidate."""
+    """metric[C] (device) for theta_d [C, 3]; one CTA per candidate.  ``noise`` = one float for all
+    candidates, or a device tensor [C] with one noise variance per candidate."""
     dev = theta_d.device
     c, n = theta_d.shape[0], X_d.numel()
     out = empty(c, dev) if out is None else out
     nv = 0 if Xv_d is None else Xv_d.numel()
     ws = Workspace.get("gp", _lib.load().b200id_gp_batch_workspace_bytes(c, n), dev)
+    if isinstance(noise, torch.Tensor):
+        assert noise.numel() == c and noise.dtype == F64
+        _lib.call("b200id_gp_batch_eval_noise", C.c_int(kernel_id), ptr(kernel_ids_d), ptr(theta_d), ptr(noise), C.c_int64(c),
+                  ptr(X_d), ptr(y_d), C.c_int(n), C.c_int(metric), ptr(Xv_d), ptr(yv_d), C.c_int(nv),
+                  C.c_double(y_mean), C.c_double(y_scale), ptr(out), ptr(ws), C.c_size_t(ws.numel()), stream_ptr())
+        return out
     _lib.call("b200id_gp_batch_eval", C.c_int(kernel_id), ptr(kernel_ids_d), ptr(theta_d), C.c_int64(c), ptr(X_d),
               ptr(y_d), C.c_int(n), C.c_double(noise), C.c_int(metric), ptr(Xv_d), ptr(yv_d), C.c_int(nv),
               C.c_double(y_mean), C.c_double(y_scale), ptr(out), ptr(ws), C.c_size_t(ws.numel()), stream_ptr())
@@ -76,16 +83,23 @@ def first_strict_min_device(metric_d: torch.Tensor):
     return best, idx
 
 
-def batch_eval(kernel, thetas, X, y, noise: float, Xv=None, yv=None, y_mean: Optional[float] = None,
+def batch_eval(kernel, thetas, X, y, noise, Xv=None, yv=None, y_mean: Optional[float] = None,
                y_scale: Optional[float] = None, kernel_ids: Optional[Sequence[int]] = None) -> np.ndarray:
-    """Candidate metrics on the host: NLL, or validation RMSE when (Xv, yv) are given."""
+    """Candidate metrics on the host: NLL, or validation RMSE when (Xv, yv) are given.  ``noise`` is a
+    scalar, or one value per candidate."""
     dev = require_cuda()
     kid = KERNEL_IDS[kernel][0] if isinstance(kernel, str) else int(kernel)
     th = to_device(_theta_block(thetas), dev)
     ids = None if kernel_ids is None else torch.as_tensor(np.asarray(kernel_ids, dtype=np.int32), device=dev)
     use_val = Xv is not None and yv is not None
+    if np.ndim(noise) == 0:
+        noise_arg = float(noise)
+    else:
+        noise_arg = to_device(np.ascontiguousarray(noise, dtype=np.float64).ravel(), dev)
+        if noise_arg.numel() != th.shape[0]:
+            raise ValueError(f"batch_eval: {noise_arg.numel()} noise values for {th.shape[0]} candidates")
     m = batch_eval_device(
-        kid, ids, th, to_device(_flat(X), dev), to_device(_flat(y), dev), float(noise),
+        kid, ids, th, to_device(_flat(X), dev), to_device(_flat(y), dev), noise_arg,
         METRIC_VAL_RMSE if use_val else METRIC_NLL,
         to_device(_flat(Xv), dev) if use_val else None, to_device(_flat(yv), dev) if use_val else None,
         0.0 if y_mean is None else float(y_mean), 1.0 if y_scale is None else float(y_scale))

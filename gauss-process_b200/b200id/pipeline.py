@@ -260,9 +260,6 @@ def _probe_paths(probes):
     """FRF path (uniform fast path or general) of several records with ONE device->host read.
 
     probes: list of (t_d, span, t0 or None, w_max)."""
-    import ctypes as C
-    from . import _lib
-    from .runtime import ptr, stream_ptr
     outs, metas = [], []
     for t_d, span, t0, w_max in probes:
         n = t_d.numel()
@@ -271,10 +268,7 @@ def _probe_paths(probes):
             continue
         t0 = float(t_d[0].item()) if t0 is None else float(t0)
         dt = span / (n - 1)
-        out = empty(1, t_d.device)
-        ws, _ = bfrf._ws(1, t_d.device)
-        _lib.call("b200id_frf_uniformity", ptr(t_d), C.c_int64(n), C.c_double(t0), C.c_double(dt), ptr(out), ptr(ws),
-                  C.c_size_t(ws.numel()), stream_ptr())
+        out = bfrf.uniformity_device_async(t_d, t0, dt)
         outs.append(out)
         metas.append((t0, dt, w_max, len(outs) - 1))
     vals = torch.cat(outs).cpu().tolist() if outs else []

@@ -29,7 +29,8 @@ __global__ void __launch_bounds__(GP_THREADS)
 gp_batch_kernel(int kernel_id, const int* __restrict__ kernel_ids, const double* __restrict__ theta,
                 const double* __restrict__ X, const double* __restrict__ y, int n, double noise,
                 int metric, const double* __restrict__ Xv, const double* __restrict__ yv, int nv,
-                double y_mean, double y_scale, double* __restrict__ metric_out) {
+                double y_mean, double y_scale, double* __restrict__ metric_out,
+                const double* __restrict__ noise_v /*per-candidate diagonal term, or NULL*/) {
     extern __shared__ double sm[];
     const int ld = gp_ld(n);
     double* A = sm;                              // [n][ld]
@@ -42,6 +43,7 @@ gp_batch_kernel(int kernel_id, const int* __restrict__ kernel_ids, const double*
     const int tid = threadIdx.x;
     const int kid = kernel_ids ? kernel_ids[cand] : kernel_id;
     const KernelParams kp = make_kernel_params(kid, theta + cand * B200ID_MAX_PARAMS);
+    if (noise_v) noise = noise_v[cand];
 
     if (tid == 0) status = 0;
     for (int i = tid; i < n; i += GP_THREADS) xs[i] = X[i];
@@ -281,7 +283,7 @@ int b200id_gp_fit_tiled_launch(int kernel_id, const double* theta, const double*
 int b200id_gp_batch_tiled_launch(int kernel_id, const int* kernel_ids, const double* theta, int64_t n_candidates,
                                  const double* X, const double* y, int n, double noise, int metric,
                                  const double* Xv, const double* yv, int nv, double y_mean, double y_scale,
-                                 double* metric_out, cudaStream_t st);
+                                 double* metric_out, const double* noise_v, cudaStream_t st);
 
 // gp_large.cu: global-memory path for n > 160 (blocked Cholesky)
 size_t b200id_gp_large_workspace_bytes(int n, int nv);
@@ -290,7 +292,7 @@ int b200id_gp_fit_large(int kernel_id, const double* theta, const double* X, con
 int b200id_gp_batch_eval_large(int kernel_id, const int* kernel_ids_host_or_null, const double* theta, int64_t n_candidates,
                                const double* X, const double* y, int n, double noise, int metric, const double* Xv,
                                const double* yv, int nv, double y_mean, double y_scale, double* metric_out,
-                               void* ws, size_t ws_bytes, cudaStream_t st);
+                               const double* noise_v, void* ws, size_t ws_bytes, cudaStream_t st);
 constexpr int GP_LARGE_NMAX = 8192;
 constexpr int GP_LARGE_NV_CAP = 8192;
 
@@ -327,10 +329,10 @@ extern "C" size_t b200id_gp_batch_workspace_bytes(int64_t n_candidates, int n) {
     return 256;     // the shared-memory paths need no global scratch
 }
 
-extern "C" int b200id_gp_batch_eval(int kernel_id, const int* kernel_ids, const double* theta, int64_t n_candidates,
-                                    const double* X, const double* y, int n, double noise, int metric,
-                                    const double* Xv, const double* yv, int nv, double y_mean, double y_scale,
-                                    double* metric_out, void* ws, size_t ws_bytes, void* stream) {
+static int gp_batch_eval_impl(int kernel_id, const int* kernel_ids, const double* theta, int64_t n_candidates,
+                              const double* X, const double* y, int n, double noise, const double* noise_v, int metric,
+                              const double* Xv, const double* yv, int nv, double y_mean, double y_scale,
+                              double* metric_out, void* ws, size_t ws_bytes, void* stream) {
     B200ID_REQUIRE(theta && X && y && metric_out, B200ID_E_ARG, "gp_batch_eval: null pointer");
     B200ID_REQUIRE(n_candidates > 0 && n > 0, B200ID_E_ARG, "gp_batch_eval: empty problem");
     B200ID_REQUIRE(kernel_ids || (kernel_id >= 0 && kernel_id < B200ID_K_COUNT), B200ID_E_ARG, "gp_batch_eval: unknown kernel id %d", kernel_id);
@@ -340,19 +342,36 @@ extern "C" int b200id_gp_batch_eval(int kernel_id, const int* kernel_ids, const 
         B200ID_REQUIRE(n <= GP_LARGE_NMAX && nv <= GP_LARGE_NV_CAP, B200ID_E_UNSUPPORTED, "gp_batch_eval: n=%d / nv=%d beyond the large-n limits", n, nv);
         B200ID_REQUIRE(ws, B200ID_E_ARG, "gp_batch_eval: the large-n path needs a workspace");
         return b200id_gp_batch_eval_large(kernel_id, kernel_ids, theta, n_candidates, X, y, n, noise, metric, Xv, yv, nv,
-                                          y_mean, y_scale, metric_out, ws, ws_bytes, (cudaStream_t)stream);
+                                          y_mean, y_scale, metric_out, noise_v, ws, ws_bytes, (cudaStream_t)stream);
     }
     B200ID_REQUIRE(n_candidates < (1LL << 31), B200ID_E_UNSUPPORTED, "gp_batch_eval: too many candidates");
     if (n <= 127 && !force_generic_gp_path())
         return b200id_gp_batch_tiled_launch(kernel_id, kernel_ids, theta, n_candidates, X, y, n, noise, metric, Xv, yv, nv,
-                                            y_mean, y_scale, metric_out, (cudaStream_t)stream);
+                                            y_mean, y_scale, metric_out, noise_v, (cudaStream_t)stream);
     const size_t smem = gp_smem_bytes(n);
     int rc = set_smem_attr((const void*)gp_batch_kernel, smem);
     if (rc) return rc;
     gp_batch_kernel<<<(unsigned)n_candidates, GP_THREADS, smem, (cudaStream_t)stream>>>(
-        kernel_id, kernel_ids, theta, X, y, n, noise, metric, Xv, yv, nv, y_mean, y_scale, metric_out);
+        kernel_id, kernel_ids, theta, X, y, n, noise, metric, Xv, yv, nv, y_mean, y_scale, metric_out, noise_v);
     B200ID_LAUNCH_CHECK("gp_batch_kernel");
     return B200ID_OK;
+}
+
+extern "C" int b200id_gp_batch_eval(int kernel_id, const int* kernel_ids, const double* theta, int64_t n_candidates,
+                                    const double* X, const double* y, int n, double noise, int metric,
+                                    const double* Xv, const double* yv, int nv, double y_mean, double y_scale,
+                                    double* metric_out, void* ws, size_t ws_bytes, void* stream) {
+    return gp_batch_eval_impl(kernel_id, kernel_ids, theta, n_candidates, X, y, n, noise, nullptr, metric, Xv, yv, nv,
+                              y_mean, y_scale, metric_out, ws, ws_bytes, stream);
+}
+
+extern "C" int b200id_gp_batch_eval_noise(int kernel_id, const int* kernel_ids, const double* theta, const double* noise,
+                                          int64_t n_candidates, const double* X, const double* y, int n, int metric,
+                                          const double* Xv, const double* yv, int nv, double y_mean, double y_scale,
+                                          double* metric_out, void* ws, size_t ws_bytes, void* stream) {
+    B200ID_REQUIRE(noise, B200ID_E_ARG, "gp_batch_eval_noise: null noise vector");
+    return gp_batch_eval_impl(kernel_id, kernel_ids, theta, n_candidates, X, y, n, 0.0, noise, metric, Xv, yv, nv,
+                              y_mean, y_scale, metric_out, ws, ws_bytes, stream);
 }
 
 extern "C" int b200id_first_strict_min(const double* metric, int64_t n_candidates, double* best_out, int64_t* idx_out,

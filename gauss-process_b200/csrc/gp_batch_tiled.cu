@@ -102,7 +102,8 @@ gp_batch_tiled_kernel(int kernel_id, const int* __restrict__ kernel_ids, const d
                       const double* __restrict__ X, const double* __restrict__ y, int n, double noise,
                       int metric, const double* __restrict__ Xv, const double* __restrict__ yv, int nv,
                       double y_mean, double y_scale, double* __restrict__ metric_out,
-                      double* __restrict__ fit_alpha, double* __restrict__ fit_L, int* __restrict__ fit_info) {
+                      double* __restrict__ fit_alpha, double* __restrict__ fit_L, int* __restrict__ fit_info,
+                      const double* __restrict__ noise_v /*per-candidate diagonal term, or NULL*/) {
     extern __shared__ __align__(16) double sm[];
     const int R = gt_rows(n), nblk = gt_nblk(n);
     double* Lb = sm;                                   // block-column storage
@@ -126,6 +127,7 @@ gp_batch_tiled_kernel(int kernel_id, const int* __restrict__ kernel_ids, const d
     __syncthreads();
 
     // ---- fill: K + noise*I (rows < n), y (row n), zeros (padding rows), block column by block column
+    if (noise_v) noise = noise_v[cand];
     B200ID_DISPATCH_KERNEL(kid, gt_fill, kp, xs, y, n, noise, R, nblk, Lb)
     GT_TICK(0);
     __syncthreads();
@@ -356,13 +358,13 @@ using namespace b200id;
 int b200id_gp_batch_tiled_launch(int kernel_id, const int* kernel_ids, const double* theta, int64_t n_candidates,
                                  const double* X, const double* y, int n, double noise, int metric,
                                  const double* Xv, const double* yv, int nv, double y_mean, double y_scale,
-                                 double* metric_out, cudaStream_t st) {
+                                 double* metric_out, const double* noise_v, cudaStream_t st) {
     const size_t smem = gt_smem_bytes(n);
     int rc = check_cuda(cudaFuncSetAttribute(gp_batch_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute(gp tiled)");
     if (rc) return rc;
     gp_batch_tiled_kernel<<<(unsigned)n_candidates, GT_THREADS, smem, st>>>(kernel_id, kernel_ids, theta, X, y, n, noise, metric,
                                                                            Xv, yv, nv, y_mean, y_scale, metric_out,
-                                                                           nullptr, nullptr, nullptr);
+                                                                           nullptr, nullptr, nullptr, noise_v);
     B200ID_LAUNCH_CHECK("gp_batch_tiled_kernel");
     return B200ID_OK;
 }
@@ -384,7 +386,7 @@ int b200id_gp_fit_tiled_launch(int kernel_id, const double* theta, const double*
     int rc = check_cuda(cudaFuncSetAttribute(gp_batch_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute(gp tiled)");
     if (rc) return rc;
     gp_batch_tiled_kernel<<<1, GT_THREADS, smem, st>>>(kernel_id, nullptr, theta, X, y, n, diag_add, GT_METRIC_FIT,
-                                                      nullptr, nullptr, 0, 0.0, 1.0, nullptr, alpha_out, L_out, info_out);
+                                                      nullptr, nullptr, 0, 0.0, 1.0, nullptr, alpha_out, L_out, info_out, nullptr);
     B200ID_LAUNCH_CHECK("gp_batch_tiled_kernel(fit)");
     return B200ID_OK;
 }

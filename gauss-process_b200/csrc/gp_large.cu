@@ -29,8 +29,9 @@ __device__ __forceinline__ void gl_gram_rows(const KernelParams& kp, const doubl
     }
 }
 __global__ void gl_gram_kernel(int kernel_id, const double* __restrict__ theta, const double* __restrict__ X, int n,
-                               double diag_add, double* __restrict__ A) {
+                               double diag_add, const double* __restrict__ diag_add_dev, double* __restrict__ A) {
     const KernelParams kp = make_kernel_params(kernel_id, theta);
+    if (diag_add_dev) diag_add = diag_add_dev[0];
     B200ID_DISPATCH_KERNEL(kernel_id, gl_gram_rows, kp, X, n, diag_add, A)
 }
 
@@ -225,9 +226,9 @@ static LargeWs carve(void* ws, int n, int nv) {
 }
 
 static int large_factor(int kernel_id, const double* theta, const double* X, int n, double diag_add, const LargeWs& w,
-                        int* info, cudaStream_t st) {
+                        int* info, cudaStream_t st, const double* diag_add_dev = nullptr) {
     int grid = sm_count() * 8;
-    gl_gram_kernel<<<grid, 256, 0, st>>>(kernel_id, theta, X, n, diag_add, w.A);
+    gl_gram_kernel<<<grid, 256, 0, st>>>(kernel_id, theta, X, n, diag_add, diag_add_dev, w.A);
     B200ID_LAUNCH_CHECK("gl_gram_kernel");
     return b200id_chol_blocked(w.A, n, n, info, w.chol_ws, w.chol_bytes, st);
 }
@@ -265,7 +266,7 @@ extern "C" int b200id_gp_predict(int kernel_id, const double* theta, const doubl
 int b200id_gp_batch_eval_large(int kernel_id, const int* kernel_ids_host_or_null, const double* theta, int64_t n_candidates,
                                const double* X, const double* y, int n, double noise, int metric, const double* Xv,
                                const double* yv, int nv, double y_mean, double y_scale, double* metric_out,
-                               void* ws, size_t ws_bytes, cudaStream_t st) {
+                               const double* noise_v, void* ws, size_t ws_bytes, cudaStream_t st) {
     B200ID_REQUIRE(kernel_ids_host_or_null == nullptr, B200ID_E_UNSUPPORTED, "gp_batch_eval(large n): per-candidate kernel ids are not supported");
     const size_t need = b200id_gp_large_workspace_bytes(n, nv) + 256;
     B200ID_REQUIRE(ws_bytes >= need, B200ID_E_WORKSPACE, "gp_batch_eval(large n): workspace %zu < %zu", ws_bytes, need);
@@ -274,7 +275,7 @@ int b200id_gp_batch_eval_large(int kernel_id, const int* kernel_ids_host_or_null
     const bool val = metric == B200ID_METRIC_VAL_RMSE;
     for (int64_t c = 0; c < n_candidates; ++c) {
         const double* th = theta + c * B200ID_MAX_PARAMS;
-        int rc = large_factor(kernel_id, th, X, n, noise, w, info, st);
+        int rc = large_factor(kernel_id, th, X, n, noise, w, info, st, noise_v ? noise_v + c : nullptr);
         if (rc) return rc;
         // alpha lives in `work` (in place) when the validation metric needs it
         gl_solve_kernel<<<1, GL_THREADS, 0, st>>>(w.A, n, y, info, val ? w.work : nullptr, w.terms, w.work);

@@ -76,15 +76,27 @@ class GaussianProcessRegressor:
     def _optimize_hyperparameters(self, n_restarts: int):
         """L-BFGS-B on the negative log marginal likelihood with random restarts (reference :102-155).
 
-        SciPy stays the host driver (finite-difference gradients, same bounds, same restart rule and
-        np.random stream); every NLL it asks for is one device evaluation."""
+        SciPy stays the host driver (its own forward-difference gradients, same bounds, same restart rule and
+        np.random stream); every NLL it asks for is a device evaluation.  The p + 1 forward-difference points
+        of one gradient are independent, so they go to the device as ONE batched launch with a per-candidate
+        noise variance (``b200id_gp_batch_eval_noise``) through SciPy's ``workers`` map hook; a SciPy without
+        that hook evaluates them one by one, as the reference does."""
         kid = self.kernel.kernel_id
+
+        def nll_many(points):
+            pts = np.asarray(points, dtype=np.float64).reshape(len(points), -1)
+            return _gp.batch_eval(kid, pts[:, :-1], self.X_train, self.y_train, np.exp(pts[:, -1]))
 
         def nll(params):
             self.kernel.set_params(params[:-1])
             self.noise_variance = np.exp(params[-1])
-            return float(_gp.batch_eval(kid, params[:-1], self.X_train, self.y_train, self.noise_variance)[0])
+            return float(nll_many([params])[0])
 
+        def batched_map(_fun, points):
+            points = list(points)
+            return [float(v) for v in nll_many(points)] if points else []
+
+        options = {"workers": batched_map} if _LBFGSB_TAKES_WORKERS else {}
         bounds = self.kernel.bounds + [LOG_NOISE_BOUNDS]
         best_x, best_f = None, np.inf
         for restart in range(n_restarts):
@@ -98,8 +110,21 @@ class GaussianProcessRegressor:
             start[-1] = np.log(self.noise_variance)
             if restart == 0:
                 start[:-1] = self.kernel.get_params()
-            res = minimize(nll, start, bounds=bounds, method="L-BFGS-B")
+            res = minimize(nll, start, bounds=bounds, method="L-BFGS-B", options=options)
             if res.fun < best_f:
                 best_f, best_x = res.fun, res.x
         self.kernel.set_params(best_x[:-1])
         self.noise_variance = np.exp(best_x[-1])
+
+
+def _lbfgsb_takes_workers() -> bool:
+    """Does this SciPy's L-BFGS-B forward a ``workers`` map to its finite differences?  (SciPy >= 1.16.)"""
+    try:
+        import inspect
+        from scipy.optimize import _lbfgsb_py
+        return "workers" in inspect.signature(_lbfgsb_py._minimize_lbfgsb).parameters
+    except Exception:
+        return False
+
+
+_LBFGSB_TAKES_WORKERS = _lbfgsb_takes_workers()

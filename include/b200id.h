@@ -130,6 +130,13 @@ int b200id_gp_batch_eval(int kernel_id, const int* kernel_ids, const double* the
                          const double* X, const double* y, int n, double noise, int metric,
                          const double* Xv, const double* yv, int nv, double y_mean, double y_scale,
                          double* metric_out, void* ws, size_t ws_bytes, void* stream);
+/* Same, with one noise variance PER CANDIDATE (noise [C], device): the finite-difference points of the
+ * L-BFGS-B hyperparameter optimisation perturb log(noise) as well, gpr_fitting.py:104-123,130,147 -- the
+ * value and all forward-difference points of one gradient are one launch. */
+int b200id_gp_batch_eval_noise(int kernel_id, const int* kernel_ids, const double* theta, const double* noise,
+                               int64_t n_candidates, const double* X, const double* y, int n, int metric,
+                               const double* Xv, const double* yv, int nv, double y_mean, double y_scale,
+                               double* metric_out, void* ws, size_t ws_bytes, void* stream);
 
 /* First strict minimum of metric[0..C) scanning in index order, NaNs skipped (grid_search.py:186-196).
  * best_out[0] = metric (+inf if none), idx_out[0] = index (-1 if none). */

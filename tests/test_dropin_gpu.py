@@ -107,6 +107,29 @@ def test_gpr_lbfgs_path(golden):
     record("dropin.gpr.lbfgs.nll", {"ours": nll, "ref": ref, "theta": gp.kernel.get_params().tolist(),
                                      "theta_ref": g["lbfgs_theta_matern52"].tolist()})
     assert nll <= ref + 1e-3 * abs(ref) + 1e-3
+    # the forward-difference points of each gradient go to the device as one batch (SciPy's `workers` hook);
+    # evaluating them one by one, as the reference does, walks the same path with several times the launches
+    import src.gpr.gpr_fitting as gf
+    from b200id import _lib
+    if gf._LBFGSB_TAKES_WORKERS:
+        def run(batched):
+            gf._LBFGSB_TAKES_WORKERS = batched
+            np.random.seed(42)
+            m = GaussianProcessRegressor(kernel=create_kernel("matern52"), noise_variance=1e-6)
+            before = _lib.launch_count
+            m.fit(g["X"], g["yr"], optimize=True, n_restarts=2)
+            return m, _lib.launch_count - before
+        try:
+            mb, launches_b = run(True)
+            ms, launches_s = run(False)
+        finally:
+            gf._LBFGSB_TAKES_WORKERS = True
+        fb = float(bgp.batch_eval("matern52", mb.kernel.get_params(), g["X"], g["yr"], mb.noise_variance)[0])
+        fs = float(bgp.batch_eval("matern52", ms.kernel.get_params(), g["X"], g["yr"], ms.noise_variance)[0])
+        record("dropin.gpr.lbfgs.batched_fd", {"launches_batched": launches_b, "launches_sequential": launches_s,
+                                                "nll_batched": fb, "nll_sequential": fs})
+        assert abs(fb - fs) <= 1e-6 * abs(fs) + 1e-6
+        assert launches_b < 0.7 * launches_s
 
 
 def test_fir_pipeline_and_validation(tmp_path, golden):

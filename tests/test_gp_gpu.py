@@ -387,3 +387,24 @@ def test_gpr_mirror_lazy_kinv_and_std(gp, golden):
     mean_o, std_o = ogp.predict("matern52", theta, X, alpha_o, Kinv_o, Xq, return_std=True)
     assert rel_max(mean, mean_o) < 100 * cond * 2.2e-16
     assert np.max(np.abs(std - std_o)) < 1e-6          # sqrt of a difference of O(1) terms at cond*eps
+
+
+@pytest.mark.parametrize("n,name", [(50, "matern52"), (100, "dc"), (140, "rbf"), (200, "matern32")])
+def test_per_candidate_noise_matches_scalar_calls(gp, n, name):
+    """b200id_gp_batch_eval_noise (one noise variance per candidate) on the tiled, generic and large-n paths:
+    each entry equals the scalar-noise evaluation of that candidate, and the oracle's NLL."""
+    rng = np.random.default_rng(n)
+    X = np.linspace(-1.7, 1.6, n)
+    y = np.sin(2.0 * X) + 0.1 * rng.standard_normal(n)
+    cands = ogp.grid_candidates(name, 200)[:6]
+    noises = np.array([1e-6, 1e-2, 3e-4, 1e-10, 5e-3, 1e-1])
+    got = gp.batch_eval(name, cands, X, y, noises)
+    for k in range(len(cands)):
+        one = gp.batch_eval(name, cands[k], X, y, float(noises[k]))[0]
+        ref = ogp.candidate_metric(name, cands[k], X.reshape(-1, 1), y, float(noises[k]))
+        assert (np.isnan(got[k]) and np.isnan(one)) or abs(got[k] - one) <= 1e-12 * abs(one), (k, got[k], one)
+        if np.isfinite(ref) and ref < 1e9 and got[k] < 1e9:
+            cond = np.linalg.cond(ogp.gram(name, cands[k], X.reshape(-1, 1)) + noises[k] * np.eye(n))
+            assert abs(got[k] - ref) <= max(TOL, 100 * cond * 2.2e-16) * abs(ref), (k, got[k], ref)
+    with pytest.raises(ValueError, match="noise values"):
+        gp.batch_eval(name, cands, X, y, noises[:3])

@@ -29,6 +29,7 @@ SIGNATURES = {
     "b200id_frf_project": (I, [P, P, P, L, L, L, P, I, P, D, P, P, Z, P]),
     "b200id_frf_uniformity": (I, [P, L, L, L, D, D, P, P, Z, P]),
     "b200id_frf_project_uniform": (I, [P, P, P, L, L, L, P, I, P, D, D, D, P, P, Z, P]),
+    "b200id_dft_bins": (I, [P, P, L, L, L, P, I, L, I, P, P, D, P, P, P, Z, P]),
     "b200id_frf_finalize": (I, [P, I, D, P, P, P]),
     "b200id_cross_power": (I, [P, P, I, I, D, P, P]),
     "b200id_gp_gram": (I, [I, P, P, I, P, I, P, P]),
@@ -66,7 +67,7 @@ _lib = None
 
 # kernels launched per successful entry-point call (bench.py reports the sum as gpu_launches)
 LAUNCHES_PER_CALL = {
-    "b200id_frf_moments": 2, "b200id_frf_project": 2, "b200id_frf_project_uniform": 3, "b200id_frf_uniformity": 2, "b200id_frf_finalize": 1, "b200id_cross_power": 1,
+    "b200id_frf_moments": 2, "b200id_frf_project": 2, "b200id_frf_project_uniform": 3, "b200id_frf_uniformity": 2, "b200id_frf_finalize": 1, "b200id_cross_power": 1, "b200id_dft_bins": 2,
     "b200id_gp_gram": 1, "b200id_gp_batch_eval": 1, "b200id_gp_batch_eval_noise": 1, "b200id_first_strict_min": 1, "b200id_gp_fit": 1,
     "b200id_gp_fit_pinv": 1, "b200id_gp_predict": 1, "b200id_idft_hermitian": 1, "b200id_fir_eval": 3,
     "b200id_fp64_peak_probe": 1,

@@ -475,6 +475,113 @@ __global__ void cross_power_kernel(const double* __restrict__ U, const double* _
     }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Selected DFT bins of a windowed, mean-removed record -- the Fourier estimator
+// (reference src/frequency_transform/fourier_estimator.py:120-223).  The reference takes a full n-point
+// FFT of u and of y and then np.interp's Y/U onto a coarse linear grid (transform.py:160-181), i.e. it
+// only ever looks at the two FFT bins either side of each of the N_d grid frequencies.  Those <= 2 N_d + 2
+// bins are evaluated directly, with the same (sample x bin) tiling as the FRF projection:
+//     S_c[k] = sum_j a_j cos(2 pi j k / n_fft),  S_s[k] = sum_j a_j sin(2 pi j k / n_fft),
+//     a_j = win_j (x_j - mean_x)                                  (fourier_estimator.py:147-155)
+// so that X[k] = S_c - i S_s.  The phase 2 pi (j k mod n_fft) / n_fft is reduced exactly in integers at the
+// start of every chain and advanced by a rotation (re-seeded every tile); 8 FP64 ops per sample-bin.
+// window_mode: 0 = none, 1 = periodic Hann 0.5 - 0.5 cos(2 pi j / n) (scipy get_window('hann', n)),
+// 2 = caller-provided window_vals[n].  j counts from index 0 of the resident arrays.
+__device__ __forceinline__ void dft_phase(int64_t j, int64_t k, int64_t n_fft, double& s, double& c) {
+    const int64_t r = (int64_t)(((unsigned __int128)(uint64_t)j * (uint64_t)k) % (unsigned __int128)(uint64_t)n_fft);
+    sincospi(2.0 * ((double)r / (double)n_fft), &s, &c);
+}
+
+template <bool HAS_Y>
+__global__ void __launch_bounds__(FRF_THREADS, FRF_CTAS_PER_SM)
+dft_bins_kernel(const double* __restrict__ u, const double* __restrict__ y, int64_t n, int64_t own_begin,
+                int64_t own_end, const int64_t* __restrict__ bins, int nb_total, int64_t n_fft, int window_mode,
+                const double* __restrict__ window_vals, const double* __restrict__ sums, double inv_count,
+                int tile, int n_tiles, double* __restrict__ cta_partial) {
+    extern __shared__ __align__(16) double smem[];
+    double2* ab = reinterpret_cast<double2*>(smem);                 // [tile] (win (u - mean), win (y - mean))
+    const int tid = threadIdx.x;
+    const int bin0 = blockIdx.y * FRF_THREADS;
+    const int nb = min(nb_total - bin0, FRF_THREADS);
+    const int R = FRF_THREADS / nb;
+    const int b = tid % nb, r = tid / nb;
+    const bool active = r < R;
+    const int64_t k = bins[bin0 + b];
+    const double mean_u = sums ? sums[0] * inv_count : 0.0;
+    const double mean_y = (HAS_Y && sums) ? sums[1] * inv_count : 0.0;
+    const int stride = R * FRFU_CHAINS;
+    double sd, cd;                                                  // rotation by `stride` samples
+    dft_phase(stride, k, n_fft, sd, cd);
+    double uc[FRFU_CHAINS] = {0.0, 0.0}, us[FRFU_CHAINS] = {0.0, 0.0}, yc[FRFU_CHAINS] = {0.0, 0.0}, ys[FRFU_CHAINS] = {0.0, 0.0};
+
+    for (int tl = blockIdx.x; tl < n_tiles; tl += gridDim.x) {
+        const int64_t i0 = own_begin + (int64_t)tl * tile;
+        const int cnt = (int)min((int64_t)tile, own_end - i0);
+        __syncthreads();
+        for (int j = tid; j < cnt; j += FRF_THREADS) {
+            const int64_t i = i0 + j;
+            double win = 1.0;
+            if (window_mode == 1) win = 0.5 - 0.5 * cospi(2.0 * ((double)i / (double)n));
+            else if (window_mode == 2) win = __ldg(window_vals + i);
+            ab[j] = make_double2(win * (__ldg(u + i) - mean_u), HAS_Y ? win * (__ldg(y + i) - mean_y) : 0.0);
+        }
+        __syncthreads();
+        if (active) {
+            double cs[FRFU_CHAINS], sn[FRFU_CHAINS];
+#pragma unroll
+            for (int q = 0; q < FRFU_CHAINS; ++q) dft_phase(i0 + r + R * q, k, n_fft, sn[q], cs[q]);
+            int j = r;
+            for (; j + R * (FRFU_CHAINS - 1) < cnt; j += stride) {
+#pragma unroll
+                for (int q = 0; q < FRFU_CHAINS; ++q) {
+                    const double2 a = ab[j + R * q];
+                    uc[q] = fma(a.x, cs[q], uc[q]); us[q] = fma(a.x, sn[q], us[q]);
+                    if (HAS_Y) { yc[q] = fma(a.y, cs[q], yc[q]); ys[q] = fma(a.y, sn[q], ys[q]); }
+                    const double cn = fma(cs[q], cd, -(sn[q] * sd));
+                    sn[q] = fma(sn[q], cd, cs[q] * sd);
+                    cs[q] = cn;
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < FRFU_CHAINS; ++q) {
+                if (j + R * q < cnt) {
+                    const double2 a = ab[j + R * q];
+                    uc[q] = fma(a.x, cs[q], uc[q]); us[q] = fma(a.x, sn[q], us[q]);
+                    if (HAS_Y) { yc[q] = fma(a.y, cs[q], yc[q]); ys[q] = fma(a.y, sn[q], ys[q]); }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    double* red = smem;
+    red[0 * FRF_THREADS + tid] = uc[0] + uc[1];
+    red[1 * FRF_THREADS + tid] = us[0] + us[1];
+    red[2 * FRF_THREADS + tid] = HAS_Y ? yc[0] + yc[1] : 0.0;
+    red[3 * FRF_THREADS + tid] = HAS_Y ? ys[0] + ys[1] : 0.0;
+    __syncthreads();
+    if (tid < nb) {
+        double* out = cta_partial + (size_t)blockIdx.x * 4 * nb_total + bin0 + tid;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            double v = 0.0;
+            for (int rr = 0; rr < R; ++rr) v += red[c * FRF_THREADS + rr * nb + tid];
+            out[(size_t)c * nb_total] = v;
+        }
+    }
+}
+
+// sum of the window over [0, n) (fourier_estimator.py:153 `np.sum(win) / n`) for the analytic Hann window
+__global__ void __launch_bounds__(MOM_THREADS)
+hann_sum_kernel(int64_t n, int64_t chunk, double* __restrict__ cta_partial) {
+    __shared__ double scratch[MOM_THREADS / 32];
+    const int64_t lo = (int64_t)blockIdx.x * chunk, hi = min(lo + chunk, n);
+    double acc = 0.0;
+    for (int64_t i = lo + threadIdx.x; i < hi; i += MOM_THREADS) acc += 0.5 - 0.5 * cospi(2.0 * ((double)i / (double)n));
+    acc = block_sum(acc, scratch);
+    if (threadIdx.x == 0) { cta_partial[2 * blockIdx.x] = acc; cta_partial[2 * blockIdx.x + 1] = 0.0; }
+}
+
 constexpr size_t FRF_SMEM_BYTES = (size_t)(3 * FRF_TILE_MAX + 2) * sizeof(double);
 constexpr size_t FRFU_SMEM_BYTES = (size_t)(4 * FRF_TILE_MAX) * sizeof(double);
 
@@ -539,6 +646,51 @@ extern "C" int b200id_frf_project(const double* t, const double* u, const double
     const int len = 4 * nd;
     frf_fold_kernel<<<(len + 31) / 32, FOLD_WARPS * 32, 0, st>>>(part, p.grid_x, len, partial_out);
     B200ID_LAUNCH_CHECK("frf_fold_kernel");
+    return B200ID_OK;
+}
+
+extern "C" int b200id_dft_bins(const double* u, const double* y, int64_t n, int64_t own_begin, int64_t own_end,
+                               const int64_t* bins, int nb, int64_t n_fft, int window_mode, const double* window_vals,
+                               const double* sums, double inv_count, double* partial_out, double* window_sum_out,
+                               void* ws, size_t ws_bytes, void* stream) {
+    B200ID_REQUIRE(u && bins && partial_out && ws, B200ID_E_ARG, "dft_bins: null pointer");
+    B200ID_REQUIRE(n >= 1 && nb > 0 && n_fft >= 1, B200ID_E_ARG, "dft_bins: need n >= 1, nb > 0, n_fft >= 1");
+    B200ID_REQUIRE(own_begin >= 0 && own_end <= n && own_begin < own_end, B200ID_E_ARG,
+                   "dft_bins: bad owned range [%lld,%lld) of %lld", (long long)own_begin, (long long)own_end, (long long)n);
+    B200ID_REQUIRE(window_mode >= 0 && window_mode <= 2 && (window_mode != 2 || window_vals), B200ID_E_ARG, "dft_bins: bad window");
+    cudaStream_t st = (cudaStream_t)stream;
+    const FrfPlan p = frf_plan(own_end - own_begin, nb);
+    const size_t need = (size_t)p.grid_x * 4 * nb * sizeof(double);
+    B200ID_REQUIRE(ws_bytes >= need, B200ID_E_WORKSPACE, "dft_bins: workspace %zu < %zu", ws_bytes, need);
+    double* part = (double*)ws;
+    const size_t smem = (size_t)(4 * FRF_THREADS > 2 * FRF_TILE_MAX ? 4 * FRF_THREADS : 2 * FRF_TILE_MAX) * sizeof(double);
+    int rc = check_cuda(cudaFuncSetAttribute(dft_bins_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr");
+    if (rc) return rc;
+    rc = check_cuda(cudaFuncSetAttribute(dft_bins_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr");
+    if (rc) return rc;
+    dim3 grid(p.grid_x, p.grid_y);
+    if (y)
+        dft_bins_kernel<true><<<grid, FRF_THREADS, smem, st>>>(u, y, n, own_begin, own_end, bins, nb, n_fft, window_mode, window_vals, sums, inv_count, p.tile, p.n_tiles, part);
+    else
+        dft_bins_kernel<false><<<grid, FRF_THREADS, smem, st>>>(u, nullptr, n, own_begin, own_end, bins, nb, n_fft, window_mode, window_vals, sums, inv_count, p.tile, p.n_tiles, part);
+    B200ID_LAUNCH_CHECK("dft_bins_kernel");
+    const int len = 4 * nb;
+    frf_fold_kernel<<<(len + 31) / 32, FOLD_WARPS * 32, 0, st>>>(part, p.grid_x, len, partial_out);
+    B200ID_LAUNCH_CHECK("frf_fold_kernel(dft)");
+    if (window_sum_out) {
+        // analytic Hann: the same per-sample expression the kernel applied; other windows: the caller sums its own
+        B200ID_REQUIRE(window_mode == 1, B200ID_E_ARG, "dft_bins: window_sum_out is only produced for the Hann window");
+        int g = sm_count() * 4;
+        int64_t chunk = (n + g - 1) / g;
+        chunk = (chunk + 255) / 256 * 256;
+        g = (int)((n + chunk - 1) / chunk);
+        double* wpart = part + (size_t)p.grid_x * 4 * nb;
+        B200ID_REQUIRE(ws_bytes >= need + (size_t)g * 2 * sizeof(double), B200ID_E_WORKSPACE, "dft_bins: workspace too small for the window sum");
+        hann_sum_kernel<<<g, MOM_THREADS, 0, st>>>(n, chunk, wpart);
+        B200ID_LAUNCH_CHECK("hann_sum_kernel");
+        frf_fold_kernel<<<1, FOLD_WARPS * 32, 0, st>>>(wpart, g, 2, window_sum_out);
+        B200ID_LAUNCH_CHECK("frf_fold_kernel(hann)");
+    }
     return B200ID_OK;
 }
 

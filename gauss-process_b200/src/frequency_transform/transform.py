@@ -3,8 +3,9 @@
 Drop-in for reference src/frequency_transform/transform.py (:45-193): same name, arguments, defaults,
 exceptions and the same six-column DataFrame.  For ``method='frf'`` every record is demodulated for u and y
 in ONE fused pass on the device and the records are combined by one cross-power average; the FFT estimator
-(``method='fourier'``) and the optional disk cache are host-side features outside the hot path (SURVEY.md
-section 2, rows 3-4) and are borrowed from a reference checkout when one is on ``src.__path__``.
+(``method='fourier'``) evaluates only the FFT bins its interpolation reads, also on the device (SURVEY.md
+section 8(f) rank 3); the optional disk cache is a host-side feature outside the hot path and is borrowed from a
+reference checkout when one is on ``src.__path__``.
 """
 from __future__ import annotations
 
@@ -106,21 +107,66 @@ def _estimate_frf(paths, nd, f_low, f_up, drop_seconds, time_duration, y_col, su
     return _build_dataframe(omega[rank], G[rank])
 
 
+def _load_time_data(data: dict, y_col: int):
+    """(t, u, y) by the Fourier estimator's own loader rule (reference fourier_estimator.py:32-77): named
+    t / u / y first, else the first 2-D array with three rows (or columns) read as [t, y, u]."""
+    t, u, y = data.get("t"), data.get("u"), data.get("y")
+    if t is None or u is None or y is None:
+        for key, value in data.items():
+            if key.startswith("__"):
+                continue
+            arr = np.asarray(value)
+            if arr.ndim == 2 and arr.shape[0] == 3:
+                t, y, u = arr[0], arr[1], arr[2]
+                break
+            if arr.ndim == 2 and arr.shape[1] == 3:
+                t, y, u = arr[:, 0], arr[:, 1], arr[:, 2]
+                break
+    t, u, y = np.asarray(t).squeeze(), np.asarray(u).squeeze(), np.asarray(y).squeeze()
+    if y.ndim == 2:
+        y = y[:, y_col]
+    if t.size != u.size or t.size != y.size:
+        raise ValueError(f"Inconsistent array sizes: t={t.size}, u={u.size}, y={y.size}")
+    return t.astype(float), u.astype(float), y.astype(float)
+
+
+def _fourier_window(t, u, y, drop_seconds, time_duration):
+    """Reference fourier_estimator.py:80-114: drop the transient, then keep ``t <= t[0] + duration`` of the rest."""
+    if drop_seconds > 0:
+        keep = t >= (t[0] + drop_seconds)
+        t, u, y = t[keep], u[keep], y[keep]
+    if time_duration is not None:
+        keep = t <= t[0] + time_duration
+        t, u, y = t[keep], u[keep], y[keep]
+    return t, u, y
+
+
 def _estimate_fourier(paths, nd, f_min, f_max, drop_seconds, time_duration, y_col, window):
-    try:
-        from src.frequency_transform import fourier_estimator as fe           # reference host module
-    except ImportError as exc:
-        raise NotImplementedError("method='fourier' is outside the b200id hot path (SURVEY.md section 2 row 3); "
-                                  "put a reference checkout on GP_REFERENCE_ROOT to use it") from exc
-    spectra, top = [], 0.0
+    """GPU form of the FFT-ratio estimator (reference :160-181, fourier_estimator.py:120-254): per record only
+    the FFT bins that the interpolation onto the linear grid reads are evaluated (b200id_dft_bins), then
+    Y / (U + 1e-10), np.interp of real and imaginary parts, complex mean over records."""
+    from b200id import fourier as _fou
+    from b200id.runtime import require_cuda
+    dev = require_cuda()
+    win = None if window == "none" else window
+    records, top = [], 0.0
     for path in paths:
-        t, u, y = fe.apply_time_window(*fe.load_time_data(path, y_col=y_col), drop_seconds, time_duration)
-        freq, G = fe.compute_transfer_function(t, u, y, window=None if window == "none" else window)
-        spectra.append((freq, G))
-        top = max(top, freq[-1])
-    grid = fe.linear_frequency_grid(f_min, top if f_max is None else min(f_max, top), nd)
-    resampled = [fe.interpolate_to_grid(freq, G, grid) for freq, G in spectra]
-    return _build_dataframe(2.0 * np.pi * grid, resampled[0] if len(resampled) == 1 else fe.average_multiple_estimates(resampled))
+        rec = _records.STORE.record(path, ("fourier_time_data", int(y_col)), lambda data: _load_time_data(data, y_col))
+        t, u, y = _fourier_window(rec.t, rec.u, rec.y, drop_seconds, time_duration)
+        whole = t is rec.t
+        dt = rec.facts.get("mean_dt") if whole else None
+        if dt is None:
+            dt = float(np.mean(np.diff(t)))
+            if whole:
+                rec.facts["mean_dt"] = dt
+        top = max(top, _fou.top_frequency(len(t), dt))
+        resident = _records.STORE.on_device(rec, dev)[1:] if (whole and _records.ENABLED) else None
+        records.append((t, u, y, dt, resident))
+    grid = np.linspace(f_min, min(f_max, top) if f_max is not None else top, nd)
+    per_record = [_fou.transfer_function_on_grid(t, u, y, grid, window=win, device_arrays=resident, dt=dt)
+                  for t, u, y, dt, resident in records]
+    G = per_record[0] if len(per_record) == 1 else np.mean(np.vstack(per_record), axis=0)
+    return _build_dataframe(2.0 * np.pi * grid, G)
 
 
 def _build_dataframe(omega: np.ndarray, G: np.ndarray) -> pd.DataFrame:

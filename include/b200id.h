@@ -104,6 +104,21 @@ int b200id_frf_project_uniform(const double* t, const double* u, const double* y
                                const double* sums /*[2] or NULL*/, double inv_count, double t0, double dt,
                                double* partial_out /*[4*nd]*/, void* ws, size_t ws_bytes, void* stream);
 
+/* Selected DFT bins of a windowed, mean-removed record: what the Fourier estimator needs of its two n-point
+ * FFTs (fourier_estimator.py:120-223 feeding np.interp at transform.py:160-181 -- only the FFT bins either
+ * side of each grid frequency are ever read).  For k = bins[b] (0 <= k < n_fft):
+ *   partial_out[0*nb+b] = sum_j a_j cos(2 pi j k / n_fft),  [1*nb+b] = sum_j a_j sin(...)   (a from u)
+ *   partial_out[2*nb+b],  [3*nb+b]                                                        (a from y)
+ * a_j = win_j (x_j - mean_x), mean from sums*inv_count (NULL -> 0), j over [own_begin, own_end) of the resident
+ * arrays; X[k] = (cos sum) - i (sin sum).  window_mode 0 none, 1 periodic Hann (scipy get_window('hann', n)),
+ * 2 window_vals[n].  window_sum_out [2] (Hann only, may be NULL) receives sum_j win_j in [0].
+ * Workspace: b200id_frf_workspace_bytes(nb). */
+int b200id_dft_bins(const double* u, const double* y /*may be NULL*/, int64_t n, int64_t own_begin, int64_t own_end,
+                    const int64_t* bins /*[nb] device*/, int nb, int64_t n_fft, int window_mode,
+                    const double* window_vals, const double* sums /*[2] or NULL*/, double inv_count,
+                    double* partial_out /*[4*nb]*/, double* window_sum_out /*[2] or NULL*/,
+                    void* ws, size_t ws_bytes, void* stream);
+
 /* U[k] = scale * (S_uc[k] - j S_us[k]), Y likewise; scale = 2/T. frf_estimator.py:225-231 */
 int b200id_frf_finalize(const double* partial /*[4*nd]*/, int nd, double scale,
                         double* U_out /*[2*nd]*/, double* Y_out /*[2*nd] or NULL*/, void* stream);

@@ -335,13 +335,43 @@ def golden_pipeline(out: Path):
     print("pipeline.npz", len(d), "arrays")
 
 
+# ------------------------------------------------------------------ Fourier estimator
+def golden_fourier(out: Path):
+    """method='fourier' (fourier_estimator.py + transform.py:160-181): per-stage vectors on an even- and an
+    odd-length record, and the file-level entry with two files, a window, a drop and a duration."""
+    from src.frequency_transform import fourier_estimator as R_fe
+    d = {"versions": VERSIONS}
+    for tag, n in (("even", 6000), ("odd", 4999)):
+        t, u, y = synth.make_record(n, 50, "multisine", seed=11)
+        # (records are regenerated in the tests from the same seeds: synth.make_record(n, 50, "multisine", seed=11))
+        for wname in (("hann", "none", "blackman") if tag == "even" else ("hann",)):
+            f, G = R_fe.compute_transfer_function(t, u, y, window=None if wname == "none" else wname)
+            d[f"G_{tag}_{wname}"] = G
+        d[f"f_{tag}"] = f
+        fu, U = R_fe.compute_fourier_transform(t, u, None, "hann")
+        d[f"U_{tag}_hann"] = U
+    t, u, y = synth.make_record(6000, 50, "multisine", seed=0)
+    t2, u2, y2 = synth.make_record(5555, 50, "multisine", seed=3)
+    with tempfile.TemporaryDirectory() as tmp:
+        p1 = synth.write_mat(Path(tmp) / "a.mat", t, u, y)
+        p2 = synth.write_mat(Path(tmp) / "b.mat", t2, u2, y2)
+        d["df_2files"] = quiet(R_estimate, [str(p1), str(p2)], method="fourier", nd=40, f_low=0.1, f_up=100.0, n_files=2).to_numpy()
+        d["df_window"] = quiet(R_estimate, [str(p1)], method="fourier", nd=25, f_low=0.5, f_up=60.0, time_duration=7.0,
+                               drop_seconds=1.0, n_files=1, window="none").to_numpy()
+        d["df_top"] = quiet(R_estimate, [str(p1)], method="fourier", nd=30, f_low=0.0, f_up=1e9, n_files=1).to_numpy()
+        d["df_blackman"] = quiet(R_estimate, [str(p2)], method="fourier", nd=17, f_low=1.0, f_up=33.0, n_files=1,
+                                 window="blackman").to_numpy()
+    np.savez_compressed(out / "fourier.npz", **d)
+    print("fourier.npz", {k: np.shape(v) for k, v in d.items()})
+
+
 def main():
     ap_ = argparse.ArgumentParser()
     ap_.add_argument("--out", default=str(ROOT / "tests" / "golden"))
     ap_.add_argument("--only", default="")
     a = ap_.parse_args()
     out = Path(a.out); out.mkdir(parents=True, exist_ok=True)
-    todo = {"frf": golden_frf, "gp": golden_gp, "fir": golden_fir, "pipeline": golden_pipeline}
+    todo = {"frf": golden_frf, "gp": golden_gp, "fir": golden_fir, "pipeline": golden_pipeline, "fourier": golden_fourier}
     for name, fn in todo.items():
         if a.only and name not in a.only.split(","):
             continue

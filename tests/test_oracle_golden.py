@@ -182,3 +182,30 @@ def test_paper_fir_and_validation(golden):
     assert np.array_equal([m["rmse"], m["fit_percent"], m["r2"], m["transient_skip"]], g["pipe_interp_metrics"])
     m, _ = ofir.fir_validate(g["u"], g["y"], taps[:64], detrend=True)
     assert np.array_equal([m["rmse"], m["fit_percent"], m["r2"], m["transient_skip"]], g["validate_detrend_metrics"])
+
+
+# ------------------------------------------------------------------ Fourier estimator
+def test_fourier_oracle_bit_exact(golden):
+    from oracle import fourier as ofou
+    import sys
+    from pathlib import Path
+    sys.path.insert(0, str(Path(__file__).resolve().parent.parent / "gauss-process_b200" / "b200id"))
+    import synth
+    g = golden("fourier")
+    for tag, n in (("even", 6000), ("odd", 4999)):
+        t, u, y = synth.make_record(n, 50, "multisine", seed=11)
+        for wname in (("hann", "none", "blackman") if tag == "even" else ("hann",)):
+            f, G = ofou.transfer_function(t, u, y, None if wname == "none" else wname)
+            assert np.array_equal(f, g[f"f_{tag}"]) and np.array_equal(G, g[f"G_{tag}_{wname}"]), (tag, wname)
+        assert np.array_equal(ofou.spectrum(t, u, "hann")[1], g[f"U_{tag}_hann"])
+    r1 = synth.make_record(6000, 50, "multisine", seed=0)
+    r2 = synth.make_record(5555, 50, "multisine", seed=3)
+
+    def table(grid, G):
+        w = 2.0 * np.pi * grid
+        return np.c_[w, w / (2.0 * np.pi), G.real, G.imag, np.abs(G), np.angle(G)]
+
+    assert np.array_equal(table(*ofou.estimate([r1, r2], 40, 0.1, 100.0)), g["df_2files"])
+    assert np.array_equal(table(*ofou.estimate([r1], 25, 0.5, 60.0, drop_seconds=1.0, time_duration=7.0, window="none")), g["df_window"])
+    assert np.array_equal(table(*ofou.estimate([r1], 30, 0.0, 1e9)), g["df_top"])
+    assert np.array_equal(table(*ofou.estimate([r2], 17, 1.0, 33.0, window="blackman")), g["df_blackman"])

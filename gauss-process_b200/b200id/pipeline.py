@@ -292,34 +292,36 @@ def _async_to_host(t: torch.Tensor):
     return host, ev
 
 
-def _device_pick(cs: "CandidateSet", pend: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
-    """(theta [3] on the device, global index, metric) of the selected candidate WITHOUT a host round trip.
+def _device_pick(cs: "CandidateSet", pends: Sequence[torch.Tensor]) -> List[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]]:
+    """[(theta [3] on the device, global index, metric)] of the selected candidate of each search in ``pends``
+    WITHOUT a host round trip.
 
-    pend = [best metric, local index] on the device.  With several ranks the (metric, global index) pairs are
-    all-gathered and the first strict minimum in global scan order is taken on the device (ties -> smallest
-    global index, NaN / empty shards skipped), reproducing grid_search.py:186-196."""
-    dev = pend.device
-    best, lidx = pend[0], pend[1].to(torch.int64)
+    pends[k] = [best metric, local index] on the device.  With several ranks the (metric, global index) pairs
+    of ALL searches travel in one all-gather and the first strict minimum in global scan order is taken on the
+    device (ties -> smallest global index, NaN / empty shards skipped), reproducing grid_search.py:186-196."""
+    k = len(pends)
+    pend = torch.stack(list(pends))                                   # [k, 2]
+    best, lidx = pend[:, 0], pend[:, 1].to(torch.int64)
     if cs.global_index is None:
         gidx = lidx
     else:
+        import torch.distributed as dist
         gmap = cs.global_index_dev
         gidx = torch.where(lidx >= 0, gmap[lidx.clamp(min=0)], torch.full_like(lidx, -1))
-        import torch.distributed as dist
         ws = bdist.world()[1]
-        mine = torch.stack([best, gidx.to(F64)])
-        tab = torch.empty(ws * 2, dtype=F64, device=dev)
+        mine = torch.stack([best, gidx.to(F64)], dim=1).reshape(-1).contiguous()     # [k*2]
+        tab = torch.empty(ws * 2 * k, dtype=F64, device=pend.device)
         dist.all_gather_into_tensor(tab, mine)
-        tab = tab.view(ws, 2)
-        m, g = tab[:, 0], tab[:, 1]
+        tab = tab.view(ws, k, 2)
+        m, g = tab[:, :, 0], tab[:, :, 1]
         valid = (g >= 0) & (m == m)
         m = torch.where(valid, m, torch.full_like(m, float("inf")))
-        best = m.min()
+        best = m.min(dim=0).values                                     # [k]
         g = torch.where((m == best) & valid & (best < float("inf")), g, torch.full_like(g, float("inf")))
-        gsel = g.min()
+        gsel = g.min(dim=0).values
         gidx = torch.where(torch.isfinite(gsel), gsel, torch.full_like(gsel, -1.0)).to(torch.int64)
-    theta = cs.full_theta_dev[gidx.clamp(min=0)]
-    return theta.contiguous(), gidx, best
+    theta = cs.full_theta_dev[gidx.clamp(min=0)]                       # [k, 3]
+    return [(theta[j].contiguous(), gidx[j], best[j]) for j in range(k)]
 
 
 def identify_device(train: Sequence[Tuple[torch.Tensor, torch.Tensor, torch.Tensor, float]],
@@ -353,19 +355,37 @@ def identify_device(train: Sequence[Tuple[torch.Tensor, torch.Tensor, torch.Tens
     if want_val_frf:
         probes.append((val[0], val[3], val[5] if len(val) > 5 else None, gi.wv_max))
     paths = _probe_paths(probes)
-    # ---- FRF: per-record coefficients, cross-power numerator / denominator, one all-reduce
+    # ---- FRF: per-record coefficients -> cross-power numerator / denominator of the training records and, when
+    # the search metric needs it, of the validation record(s); under torch.distributed every rank contributes
+    # its records and ONE all-reduce carries both sets (3 N_d + 3 N_v doubles)
     num = torch.zeros(nd, dtype=torch.complex128, device=dev)
     den = torch.zeros(nd, dtype=F64, device=dev)
     for rec, path in zip(train, paths):
         U, Y = bfrf.record_coefficients_device(rec[0], rec[1], rec[2], w_d, rec[3], path=path)
         num += Y * U.conj()
         den += U.abs() ** 2
+    use_val_metric = candidates is not None and use_validation_metric and val is not None
+    num_v = den_v = None
+    if use_val_metric:
+        if val_frf is None:
+            Uv, Yv = bfrf.record_coefficients_device(val[0], val[1], val[2], gi.wv_d, val[3], path=paths[-1])
+        else:
+            Uv, Yv = val_frf
+        num_v, den_v = Yv * Uv.conj(), Uv.abs() ** 2
     if bdist.world()[1] > 1:
-        packed = torch.cat([torch.view_as_real(num).reshape(-1), den])
+        parts = [torch.view_as_real(num).reshape(-1), den]
+        if use_val_metric:
+            parts += [torch.view_as_real(num_v).reshape(-1), den_v]
+        packed = torch.cat(parts)
         bdist.allreduce_sum_(packed)
         num = torch.view_as_complex(packed[:2 * nd].view(nd, 2).contiguous())
-        den = packed[2 * nd:]
-    G = torch.where(den > 1e-15, num / den, torch.full_like(num, complex(float("nan"), float("nan"))))
+        den = packed[2 * nd:3 * nd]
+        if use_val_metric:
+            nv = den_v.numel()
+            num_v = torch.view_as_complex(packed[3 * nd:3 * nd + 2 * nv].view(nv, 2).contiguous())
+            den_v = packed[3 * nd + 2 * nv:]
+    nan_c = complex(float("nan"), float("nan"))
+    G = torch.where(den > 1e-15, num / den, torch.full_like(num, nan_c))
     # ---- StandardScaler statistics of Re G, Im G: computed on the device, copied asynchronously
     ri = torch.view_as_real(G)
     mean2 = ri.mean(dim=0)
@@ -374,17 +394,12 @@ def identify_device(train: Sequence[Tuple[torch.Tensor, torch.Tensor, torch.Tens
     stats_host, stats_ev = _async_to_host(torch.cat([mean2, sd2]))
     yr = ((G.real - mean2[0]) / sd2[0]).contiguous()
     yi = ((G.imag - mean2[1]) / sd2[1]).contiguous()
-    # ---- validation FRF (150 bins) is enqueued BEFORE the host waits for the statistics
     Xv_d = yv_r = yv_i = None
-    if candidates is not None and use_validation_metric and val is not None:
-        if val_frf is None:
-            Uv, Yv = bfrf.record_coefficients_device(val[0], val[1], val[2], gi.wv_d, val[3], path=paths[-1])
-        else:
-            Uv, Yv = val_frf
-        Gv = bfrf.cross_power_device(Uv, Yv)
+    if use_val_metric:
+        Gv = torch.where(den_v > 1e-15, num_v / den_v, torch.full_like(num_v, nan_c))   # frf_estimator.py:239-252
         Xv_d = gi.Xv_d
         yv_r, yv_i = Gv.real.contiguous(), Gv.imag.contiguous()
-    stats_ev.synchronize()                                  # GPU keeps working on the validation FRF meanwhile
+    stats_ev.synchronize()
     st = stats_host.tolist()
     sr, si = Standardizer(st[0], st[2]), Standardizer(st[1], st[3])
     # ---- model selection (grid_search.py:48-203): Re and Im searches on two streams, winners stay on the device
@@ -400,8 +415,7 @@ def identify_device(train: Sequence[Tuple[torch.Tensor, torch.Tensor, torch.Tens
         with torch.cuda.stream(side):
             pend_i = select_candidates_async(candidates, X_d, yi, noise, Xv_d, yv_i, si)
         main.wait_stream(side)
-        th_r_d, gidx_r, best_r = _device_pick(candidates, pend_r)
-        th_i_d, gidx_i, best_i = _device_pick(candidates, pend_i)
+        (th_r_d, gidx_r, best_r), (th_i_d, gidx_i, best_i) = _device_pick(candidates, [pend_r, pend_i])
         sel = torch.stack([gidx_r.to(F64), best_r, gidx_i.to(F64), best_i])
     else:
         th = bgp._theta_block(np.asarray(theta0, dtype=np.float64))[0]

@@ -121,3 +121,49 @@ def test_two_rank_multi_argmin_gather():
     for p in procs:
         p.join(120)
     assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
+
+
+def _worker_device_pick(rank, world, port, q):
+    """pipeline._device_pick (the pick bench.py's N>1 step uses: both searches in ONE all-gather, winner's
+    hyperparameters taken from the full list without a host round trip) against the sequential scan."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    bdist.init_from_env(backend="gloo")
+    from b200id import pipeline as P
+    rng = np.random.default_rng(3)
+    C = 203
+    full = np.c_[rng.uniform(0.1, 5, C), rng.uniform(0.1, 5, C), np.zeros(C)]
+    mine = bdist.shard_round_robin(C, rank, world)
+    cs = P.CandidateSet(kernel="matern52", theta_host=full[mine], theta=torch.from_numpy(full[mine]), kernel_ids=None,
+                        global_index=mine, full_theta=full, full_theta_dev=torch.from_numpy(full),
+                        global_index_dev=torch.from_numpy(mine))
+    for case in range(5):
+        a = rng.integers(0, 7, C).astype(np.float64); b = rng.integers(0, 7, C).astype(np.float64)
+        a[rng.integers(0, C, 30)] = np.nan
+        if case == 3:
+            b[:] = np.nan                                      # no finite candidate anywhere: index -1
+        if case == 4:
+            a[:] = 1e10                                        # every candidate failed: global index 0 wins
+        pends = []
+        for metrics in (a, b):
+            li, lb = ogp.first_strict_min(metrics[mine])
+            pends.append(torch.tensor([lb if li >= 0 else float("inf"), float(li)], dtype=torch.float64))
+        picks = P._device_pick(cs, pends)
+        for (theta, gidx, best), metrics in zip(picks, (a, b)):
+            ei, eb = ogp.first_strict_min(metrics)
+            assert int(gidx) == ei, (case, int(gidx), ei)
+            if ei >= 0:
+                assert float(best) == eb and np.array_equal(theta.numpy(), full[ei])
+    q.put(rank)
+    dist.destroy_process_group()
+
+
+def test_two_rank_device_pick_both_searches_one_gather():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_device_pick, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]

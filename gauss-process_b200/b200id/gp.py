@@ -72,6 +72,41 @@ def batch_eval_device(kernel_id: int, kernel_ids_d: Optional[torch.Tensor], thet
     return out
 
 
+def batch_eval_pair_device(kernel_id: int, kernel_ids_d: Optional[torch.Tensor], theta_d: torch.Tensor,
+                           X_d: torch.Tensor, y_a: torch.Tensor, y_b: torch.Tensor, noise: float, metric: int = METRIC_NLL,
+                           Xv_d: Optional[torch.Tensor] = None, yv_a: Optional[torch.Tensor] = None,
+                           yv_b: Optional[torch.Tensor] = None, scale_a=(0.0, 1.0), scale_b=(0.0, 1.0)):
+    """(metric_a[C], metric_b[C]) for two targets on the same inputs / candidates / noise: ONE factorisation per
+    candidate serves both right-hand sides (b200id_gp_batch_eval_pair).  scale_* = (y_mean, y_scale)."""
+    dev = theta_d.device
+    c, n = theta_d.shape[0], X_d.numel()
+    out = empty(2 * c, dev)
+    nv = 0 if Xv_d is None else Xv_d.numel()
+    ws = Workspace.get("gp", _lib.load().b200id_gp_batch_workspace_bytes(c, n), dev)
+    _lib.call("b200id_gp_batch_eval_pair", C.c_int(kernel_id), ptr(kernel_ids_d), ptr(theta_d), C.c_int64(c), ptr(X_d),
+              ptr(y_a), ptr(y_b), C.c_int(n), C.c_double(noise), C.c_int(metric), ptr(Xv_d), ptr(yv_a), ptr(yv_b), C.c_int(nv),
+              C.c_double(scale_a[0]), C.c_double(scale_a[1]), C.c_double(scale_b[0]), C.c_double(scale_b[1]),
+              ptr(out[:c]), ptr(out[c:]), ptr(ws), C.c_size_t(ws.numel()), stream_ptr())
+    return out[:c], out[c:]
+
+
+def batch_eval_pair(kernel, thetas, X, y_a, y_b, noise: float, Xv=None, yv_a=None, yv_b=None,
+                    scale_a=(0.0, 1.0), scale_b=(0.0, 1.0), kernel_ids: Optional[Sequence[int]] = None):
+    """Host form of :func:`batch_eval_pair_device`: NumPy in, (metric_a, metric_b) NumPy out."""
+    dev = require_cuda()
+    kid = KERNEL_IDS[kernel][0] if isinstance(kernel, str) else int(kernel)
+    th = to_device(_theta_block(thetas), dev)
+    ids = None if kernel_ids is None else torch.as_tensor(np.asarray(kernel_ids, dtype=np.int32), device=dev)
+    use_val = Xv is not None and yv_a is not None and yv_b is not None
+    d = lambda a: to_device(_flat(a), dev)
+    ma, mb = batch_eval_pair_device(kid, ids, th, d(X), d(y_a), d(y_b), float(noise),
+                                    METRIC_VAL_RMSE if use_val else METRIC_NLL,
+                                    d(Xv) if use_val else None, d(yv_a) if use_val else None, d(yv_b) if use_val else None,
+                                    scale_a, scale_b)
+    both = torch.cat([ma, mb]).cpu().numpy()
+    return both[:len(both) // 2], both[len(both) // 2:]
+
+
 def first_strict_min_device(metric_d: torch.Tensor):
     """(best[1], idx[1]) device tensors: first strict minimum in index order, NaNs skipped."""
     dev = metric_d.device

@@ -408,13 +408,8 @@ def identify_device(train: Sequence[Tuple[torch.Tensor, torch.Tensor, torch.Tens
     infos = torch.zeros(2, dtype=torch.int32, device=dev)
     sel = None
     if candidates is not None:
-        main = torch.cuda.current_stream()
-        side = _side_stream(dev)
-        side.wait_stream(main)
-        pend_r = select_candidates_async(candidates, X_d, yr, noise, Xv_d, yv_r, sr)
-        with torch.cuda.stream(side):
-            pend_i = select_candidates_async(candidates, X_d, yi, noise, Xv_d, yv_i, si)
-        main.wait_stream(side)
+        # the two searches share inputs, candidates and noise: one factorisation per candidate serves both
+        pend_r, pend_i = select_candidates_pair_async(candidates, X_d, yr, yi, noise, Xv_d, yv_r, yv_i, sr, si)
         (th_r_d, gidx_r, best_r), (th_i_d, gidx_i, best_i) = _device_pick(candidates, [pend_r, pend_i])
         sel = torch.stack([gidx_r.to(F64), best_r, gidx_i.to(F64), best_i])
     else:
@@ -518,6 +513,23 @@ def select_candidates_async(cs: CandidateSet, X_d, y_d, noise: float, Xv_d=None,
                               scaler.mean if (use_val and scaler) else 0.0, scaler.scale if (use_val and scaler) else 1.0)
     best, idx = bgp.first_strict_min_device(m)
     return torch.stack([best[0], idx[0].to(F64)])
+
+
+def select_candidates_pair_async(cs: CandidateSet, X_d, y_a, y_b, noise: float, Xv_d=None, yv_a=None, yv_b=None,
+                                 scaler_a: Optional[Standardizer] = None, scaler_b: Optional[Standardizer] = None):
+    """Two searches over the same candidate list (the Re and Im targets) from ONE batched launch that factorises
+    each candidate once; returns the two device [2] tensors (best metric, local index as double)."""
+    kid = bgp.KERNEL_IDS[cs.kernel][0] if cs.kernel is not None else 0
+    use_val = Xv_d is not None
+    sa = (scaler_a.mean, scaler_a.scale) if (use_val and scaler_a) else (0.0, 1.0)
+    sb = (scaler_b.mean, scaler_b.scale) if (use_val and scaler_b) else (0.0, 1.0)
+    ma, mb = bgp.batch_eval_pair_device(kid, cs.kernel_ids, cs.theta, X_d, y_a, y_b, noise,
+                                        bgp.METRIC_VAL_RMSE if use_val else bgp.METRIC_NLL, Xv_d, yv_a, yv_b, sa, sb)
+    out = []
+    for m in (ma, mb):
+        best, idx = bgp.first_strict_min_device(m)
+        out.append(torch.stack([best[0], idx[0].to(F64)]))
+    return out[0], out[1]
 
 
 def _finish_selection(cs: CandidateSet, pair_host: torch.Tensor, dev) -> Tuple[int, float]:

@@ -283,7 +283,10 @@ int b200id_gp_fit_tiled_launch(int kernel_id, const double* theta, const double*
 int b200id_gp_batch_tiled_launch(int kernel_id, const int* kernel_ids, const double* theta, int64_t n_candidates,
                                  const double* X, const double* y, int n, double noise, int metric,
                                  const double* Xv, const double* yv, int nv, double y_mean, double y_scale,
-                                 double* metric_out, const double* noise_v, cudaStream_t st);
+                                 double* metric_out, const double* noise_v, cudaStream_t st,
+                                 const double* y_b = nullptr, const double* yv_b = nullptr, double y_mean_b = 0.0,
+                                 double y_scale_b = 1.0, double* metric_out_b = nullptr);
+constexpr int GT_PAIR_NMAX = 126;       // n + 2 rows must fit the 128-row warp map of the tiled kernel
 
 // gp_large.cu: global-memory path for n > 160 (blocked Cholesky)
 size_t b200id_gp_large_workspace_bytes(int n, int nv);
@@ -372,6 +375,32 @@ extern "C" int b200id_gp_batch_eval_noise(int kernel_id, const int* kernel_ids, 
     B200ID_REQUIRE(noise, B200ID_E_ARG, "gp_batch_eval_noise: null noise vector");
     return gp_batch_eval_impl(kernel_id, kernel_ids, theta, n_candidates, X, y, n, 0.0, noise, metric, Xv, yv, nv,
                               y_mean, y_scale, metric_out, ws, ws_bytes, stream);
+}
+
+extern "C" int b200id_gp_batch_eval_pair(int kernel_id, const int* kernel_ids, const double* theta, int64_t n_candidates,
+                                         const double* X, const double* y_a, const double* y_b, int n, double noise, int metric,
+                                         const double* Xv, const double* yv_a, const double* yv_b, int nv,
+                                         double y_mean_a, double y_scale_a, double y_mean_b, double y_scale_b,
+                                         double* metric_out_a, double* metric_out_b, void* ws, size_t ws_bytes, void* stream) {
+    B200ID_REQUIRE(y_b && metric_out_b, B200ID_E_ARG, "gp_batch_eval_pair: null second target");
+    const bool val = metric == B200ID_METRIC_VAL_RMSE;
+    B200ID_REQUIRE(!val || yv_b, B200ID_E_ARG, "gp_batch_eval_pair: validation metric needs yv_b");
+    if (n > GT_PAIR_NMAX || force_generic_gp_path()) {
+        // no shared factorisation on the other paths: two plain evaluations
+        int rc = gp_batch_eval_impl(kernel_id, kernel_ids, theta, n_candidates, X, y_a, n, noise, nullptr, metric, Xv, yv_a, nv,
+                                    y_mean_a, y_scale_a, metric_out_a, ws, ws_bytes, stream);
+        if (rc) return rc;
+        return gp_batch_eval_impl(kernel_id, kernel_ids, theta, n_candidates, X, y_b, n, noise, nullptr, metric, Xv, yv_b, nv,
+                                  y_mean_b, y_scale_b, metric_out_b, ws, ws_bytes, stream);
+    }
+    B200ID_REQUIRE(theta && X && y_a && metric_out_a, B200ID_E_ARG, "gp_batch_eval_pair: null pointer");
+    B200ID_REQUIRE(n_candidates > 0 && n_candidates < (1LL << 31) && n > 0, B200ID_E_ARG, "gp_batch_eval_pair: bad problem size");
+    B200ID_REQUIRE(kernel_ids || (kernel_id >= 0 && kernel_id < B200ID_K_COUNT), B200ID_E_ARG, "gp_batch_eval_pair: unknown kernel id %d", kernel_id);
+    B200ID_REQUIRE(metric == B200ID_METRIC_NLL || metric == B200ID_METRIC_VAL_RMSE, B200ID_E_ARG, "gp_batch_eval_pair: unknown metric %d", metric);
+    B200ID_REQUIRE(!val || (Xv && yv_a && nv > 0), B200ID_E_ARG, "gp_batch_eval_pair: validation metric needs Xv, yv");
+    return b200id_gp_batch_tiled_launch(kernel_id, kernel_ids, theta, n_candidates, X, y_a, n, noise, metric, Xv, yv_a, nv,
+                                        y_mean_a, y_scale_a, metric_out_a, nullptr, (cudaStream_t)stream,
+                                        y_b, yv_b, y_mean_b, y_scale_b, metric_out_b);
 }
 
 extern "C" int b200id_first_strict_min(const double* metric, int64_t n_candidates, double* best_out, int64_t* idx_out,

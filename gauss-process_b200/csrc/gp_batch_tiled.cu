@@ -48,14 +48,25 @@ struct TiledLayout {
     int nblk;                           // number of block columns
 };
 
-__host__ __device__ inline int gt_rows(int n) { return (n + 1 + 3) & ~3; }
+// rows = n matrix rows + one row per right-hand side (y; in pair mode also the second target), rounded up to 4
+__host__ __device__ inline int gt_rows(int n, int nrhs = 1) { return (n + nrhs + 3) & ~3; }
 __host__ __device__ inline int gt_nblk(int n) { return (n + GT_NB - 1) / GT_NB; }
 // offset (in doubles) of block column J: sum_{q<J} 16 * (R - 16 q)
 __host__ __device__ inline int gt_off(int R, int J) { return GT_NB * (J * R - GT_NB * J * (J - 1) / 2); }
-static inline size_t gt_smem_bytes(int n) {
-    const int R = gt_rows(n), nb = gt_nblk(n);
-    return ((size_t)gt_off(R, nb) + 3 * (size_t)(n + 4) + 16) * sizeof(double);
+static inline size_t gt_smem_bytes(int n, int nrhs = 1) {
+    const int R = gt_rows(n, nrhs), nb = gt_nblk(n);
+    return ((size_t)gt_off(R, nb) + (size_t)(2 + nrhs) * (size_t)(n + 4) + 16) * sizeof(double);
 }
+
+// Second regression target sharing the candidate's factorisation (pair mode): the Re and Im searches of the
+// pipeline use the same inputs, candidates and noise, so K + noise I and its Cholesky factor are common and only
+// the right-hand side differs.  All-null when unused.
+struct GtSecond {
+    const double* y;            // [n] second target (NULL -> single-target mode)
+    const double* yv;           // [nv] its validation values (VAL_RMSE)
+    double y_mean, y_scale;
+    double* metric_out;         // [C]
+};
 
 // Gram fill of the block-column storage, kernel id fixed at compile time.  Thread (c = tid / 8, r8 = tid % 8)
 // walks rows r8, r8 + 8, ... of column c of each block column: no integer division, 8 consecutive rows per
@@ -63,7 +74,7 @@ static inline size_t gt_smem_bytes(int n) {
 template <int ID>
 __device__ __forceinline__ void gt_fill(const KernelParams& kp, const double* __restrict__ xs,
                                         const double* __restrict__ y, int n, double noise, int R, int nblk,
-                                        double* __restrict__ Lb) {
+                                        double* __restrict__ Lb, const double* __restrict__ y2) {
     const int c = threadIdx.x >> 3, r8 = threadIdx.x & 7;
     for (int J = 0; J < nblk; ++J) {
         const int ld = R - GT_NB * J;
@@ -71,6 +82,7 @@ __device__ __forceinline__ void gt_fill(const KernelParams& kp, const double* __
         const int j = GT_NB * J + c;
         const double xj = j < n ? xs[j] : 0.0;
         const double yj = j < n ? y[j] : 0.0;
+        const double y2j = (y2 && j < n) ? y2[j] : 0.0;
         for (int r = r8; r < ld; r += 8) {
             const int i = GT_NB * J + r;
             double v = 0.0;
@@ -81,6 +93,8 @@ __device__ __forceinline__ void gt_fill(const KernelParams& kp, const double* __
                     if (i == j) v = B200ID_ADD(v, noise);
                 } else if (i == n) {
                     v = yj;
+                } else if (i == n + 1) {
+                    v = y2j;                                  // zero in single-target mode (padding row)
                 }
             }
             col[r] = v;
@@ -97,20 +111,38 @@ __device__ __forceinline__ void gt_predict_point(const KernelParams& kp, double 
     *out = pred;
 }
 
+// same for two coefficient vectors at once: the covariance entries are evaluated once
+template <int ID>
+__device__ __forceinline__ void gt_predict_point2(const KernelParams& kp, double xv, const double* __restrict__ xs,
+                                                  const double* __restrict__ alpha, const double* __restrict__ alpha2,
+                                                  int n, double* out, double* out2) {
+    double pred = 0.0, pred2 = 0.0;
+    for (int j = 0; j < n; ++j) {
+        const double kv = kernel_entry_t<ID>(kp, xv, xs[j]);
+        pred = fma(kv, alpha[j], pred);
+        pred2 = fma(kv, alpha2[j], pred2);
+    }
+    *out = pred;
+    *out2 = pred2;
+}
+
 __global__ void __launch_bounds__(GT_THREADS)
 gp_batch_tiled_kernel(int kernel_id, const int* __restrict__ kernel_ids, const double* __restrict__ theta,
                       const double* __restrict__ X, const double* __restrict__ y, int n, double noise,
                       int metric, const double* __restrict__ Xv, const double* __restrict__ yv, int nv,
                       double y_mean, double y_scale, double* __restrict__ metric_out,
                       double* __restrict__ fit_alpha, double* __restrict__ fit_L, int* __restrict__ fit_info,
-                      const double* __restrict__ noise_v /*per-candidate diagonal term, or NULL*/) {
+                      const double* __restrict__ noise_v /*per-candidate diagonal term, or NULL*/,
+                      const GtSecond sec) {
     extern __shared__ __align__(16) double sm[];
-    const int R = gt_rows(n), nblk = gt_nblk(n);
+    const int nrhs = sec.y ? 2 : 1;
+    const int R = gt_rows(n, nrhs), nblk = gt_nblk(n);
     double* Lb = sm;                                   // block-column storage
     double* xs = Lb + gt_off(R, nblk);                 // [n]  inputs
     double* idg = xs + (n + 4);                        // [n]  reciprocal diagonal of L
     double* zz = idg + (n + 4);                        // [n]  z, then alpha
-    double* scratch = zz + (n + 4);                    // [8]
+    double* scratch = zz + (n + 4);                    // [16]
+    double* zz2 = scratch + 16;                        // [n]  second target's z / alpha (pair mode only)
     __shared__ int status;
 
     const int64_t cand = blockIdx.x;
@@ -128,7 +160,7 @@ gp_batch_tiled_kernel(int kernel_id, const int* __restrict__ kernel_ids, const d
 
     // ---- fill: K + noise*I (rows < n), y (row n), zeros (padding rows), block column by block column
     if (noise_v) noise = noise_v[cand];
-    B200ID_DISPATCH_KERNEL(kid, gt_fill, kp, xs, y, n, noise, R, nblk, Lb)
+    B200ID_DISPATCH_KERNEL(kid, gt_fill, kp, xs, y, n, noise, R, nblk, Lb, sec.y)
     GT_TICK(0);
     __syncthreads();
     GT_TICK(1);
@@ -250,7 +282,10 @@ gp_batch_tiled_kernel(int kernel_id, const int* __restrict__ kernel_ids, const d
         if (status != 0) {
             if (tid == 0) {
                 if (metric == GT_METRIC_FIT) fit_info[0] = status;
-                else metric_out[cand] = B200ID_FAIL_METRIC;
+                else {
+                    metric_out[cand] = B200ID_FAIL_METRIC;
+                    if (sec.y) sec.metric_out[cand] = B200ID_FAIL_METRIC;
+                }
             }
             return;
         }
@@ -259,7 +294,7 @@ gp_batch_tiled_kernel(int kernel_id, const int* __restrict__ kernel_ids, const d
             // rows start right after the ncols diagonal rows: in a partial last block the y row (offset n - 16J)
             // sits inside the 16-row range of the block
             const int r = ncols + tid;                  // row offset inside the block column
-            if (r < ldJ && GT_NB * J + r <= n) {
+            if (r < ldJ && GT_NB * J + r < n + nrhs) {
                 double x[GT_NB];
 #pragma unroll
                 for (int c = 0; c < GT_NB; ++c) x[c] = (c < ncols) ? colJ[c * ldJ + r] : 0.0;
@@ -292,18 +327,31 @@ gp_batch_tiled_kernel(int kernel_id, const int* __restrict__ kernel_ids, const d
 
     if (metric == B200ID_METRIC_NLL) {
         // 0.5 y.alpha + sum log L_ii + 0.5 n log(2 pi), with y.alpha = z.z        grid_search.py:128-130
-        double part = 0.0;
+        double part = 0.0, part2 = 0.0;
         for (int j = tid; j < n; j += GT_THREADS) {
             const double zj = Lat(n, j);
-            part += 0.5 * zj * zj + log(Lat(j, j));
+            const double lg = log(Lat(j, j));
+            part += 0.5 * zj * zj + lg;
+            if (sec.y) {
+                const double z2 = Lat(n + 1, j);
+                part2 += 0.5 * z2 * z2 + lg;
+            }
         }
         const double tot = block_sum(part, scratch);
         if (tid == 0) metric_out[cand] = tot + 0.5 * (double)n * 1.8378770664093453;
+        if (sec.y) {
+            __syncthreads();
+            const double tot2 = block_sum(part2, scratch);
+            if (tid == 0) sec.metric_out[cand] = tot2 + 0.5 * (double)n * 1.8378770664093453;
+        }
         return;
     }
 
     // ---- validation RMSE: alpha = L^-T z by blocked back substitution, then K(Xv, X) alpha
-    for (int j = tid; j < n; j += GT_THREADS) zz[j] = Lat(n, j);
+    for (int j = tid; j < n; j += GT_THREADS) {
+        zz[j] = Lat(n, j);
+        if (sec.y) zz2[j] = Lat(n + 1, j);
+    }
     __syncthreads();
     for (int J = nblk - 1; J >= 0; --J) {
         const int ncols = min(GT_NB, n - GT_NB * J);
@@ -312,18 +360,28 @@ gp_batch_tiled_kernel(int kernel_id, const int* __restrict__ kernel_ids, const d
             for (int k = ncols - 1; k >= 0; --k) {
                 const int gk = GT_NB * J + k;
                 const double ak = zz[gk] * idg[gk];
+                const double ak2 = sec.y ? zz2[gk] * idg[gk] : 0.0;
                 __syncwarp();
-                if (lane == 0) zz[gk] = ak;
-                if (lane < k) zz[GT_NB * J + lane] = fma(-Lat(gk, GT_NB * J + lane), ak, zz[GT_NB * J + lane]);
+                if (lane == 0) { zz[gk] = ak; if (sec.y) zz2[gk] = ak2; }
+                if (lane < k) {
+                    const double lkj = Lat(gk, GT_NB * J + lane);
+                    zz[GT_NB * J + lane] = fma(-lkj, ak, zz[GT_NB * J + lane]);
+                    if (sec.y) zz2[GT_NB * J + lane] = fma(-lkj, ak2, zz2[GT_NB * J + lane]);
+                }
                 __syncwarp();
             }
         }
         __syncthreads();
         // z[j] -= sum_{k in block J} L[k][j] alpha_k for j < 16 J
         for (int j = tid; j < GT_NB * J; j += GT_THREADS) {
-            double s = zz[j];
-            for (int k = 0; k < ncols; ++k) s = fma(-Lat(GT_NB * J + k, j), zz[GT_NB * J + k], s);
+            double s = zz[j], s2 = sec.y ? zz2[j] : 0.0;
+            for (int k = 0; k < ncols; ++k) {
+                const double lkj = Lat(GT_NB * J + k, j);
+                s = fma(-lkj, zz[GT_NB * J + k], s);
+                if (sec.y) s2 = fma(-lkj, zz2[GT_NB * J + k], s2);
+            }
             zz[j] = s;
+            if (sec.y) zz2[j] = s2;
         }
         __syncthreads();
     }
@@ -337,17 +395,29 @@ gp_batch_tiled_kernel(int kernel_id, const int* __restrict__ kernel_ids, const d
         if (tid == 0) fit_info[0] = 0;
         return;
     }
-    double se = 0.0;
+    double se = 0.0, se2 = 0.0;
     for (int v = tid; v < nv; v += GT_THREADS) {
         const double xv = Xv[v];
-        double pred = 0.0;
-        B200ID_DISPATCH_KERNEL(kid, gt_predict_point, kp, xv, xs, zz, n, &pred)
+        double pred = 0.0, pred2 = 0.0;
+        if (sec.y) {
+            B200ID_DISPATCH_KERNEL(kid, gt_predict_point2, kp, xv, xs, zz, zz2, n, &pred, &pred2)
+            pred2 = pred2 * sec.y_scale + sec.y_mean;
+            const double e2 = sec.yv[v] - pred2;
+            se2 = fma(e2, e2, se2);
+        } else {
+            B200ID_DISPATCH_KERNEL(kid, gt_predict_point, kp, xv, xs, zz, n, &pred)
+        }
         pred = pred * y_scale + y_mean;
         const double e = yv[v] - pred;
         se = fma(e, e, se);
     }
     const double tot = block_sum(se, scratch);
     if (tid == 0) metric_out[cand] = sqrt(tot / (double)nv);
+    if (sec.y) {
+        __syncthreads();
+        const double tot2 = block_sum(se2, scratch);
+        if (tid == 0) sec.metric_out[cand] = sqrt(tot2 / (double)nv);
+    }
 }
 
 }  // namespace b200id
@@ -358,13 +428,16 @@ using namespace b200id;
 int b200id_gp_batch_tiled_launch(int kernel_id, const int* kernel_ids, const double* theta, int64_t n_candidates,
                                  const double* X, const double* y, int n, double noise, int metric,
                                  const double* Xv, const double* yv, int nv, double y_mean, double y_scale,
-                                 double* metric_out, const double* noise_v, cudaStream_t st) {
-    const size_t smem = gt_smem_bytes(n);
+                                 double* metric_out, const double* noise_v, cudaStream_t st,
+                                 const double* y_b, const double* yv_b, double y_mean_b, double y_scale_b,
+                                 double* metric_out_b) {
+    const GtSecond sec{y_b, yv_b, y_mean_b, y_scale_b, metric_out_b};
+    const size_t smem = gt_smem_bytes(n, y_b ? 2 : 1);
     int rc = check_cuda(cudaFuncSetAttribute(gp_batch_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute(gp tiled)");
     if (rc) return rc;
     gp_batch_tiled_kernel<<<(unsigned)n_candidates, GT_THREADS, smem, st>>>(kernel_id, kernel_ids, theta, X, y, n, noise, metric,
                                                                            Xv, yv, nv, y_mean, y_scale, metric_out,
-                                                                           nullptr, nullptr, nullptr, noise_v);
+                                                                           nullptr, nullptr, nullptr, noise_v, sec);
     B200ID_LAUNCH_CHECK("gp_batch_tiled_kernel");
     return B200ID_OK;
 }
@@ -386,7 +459,7 @@ int b200id_gp_fit_tiled_launch(int kernel_id, const double* theta, const double*
     int rc = check_cuda(cudaFuncSetAttribute(gp_batch_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute(gp tiled)");
     if (rc) return rc;
     gp_batch_tiled_kernel<<<1, GT_THREADS, smem, st>>>(kernel_id, nullptr, theta, X, y, n, diag_add, GT_METRIC_FIT,
-                                                      nullptr, nullptr, 0, 0.0, 1.0, nullptr, alpha_out, L_out, info_out, nullptr);
+                                                      nullptr, nullptr, 0, 0.0, 1.0, nullptr, alpha_out, L_out, info_out, nullptr, GtSecond{nullptr, nullptr, 0.0, 1.0, nullptr});
     B200ID_LAUNCH_CHECK("gp_batch_tiled_kernel(fit)");
     return B200ID_OK;
 }

@@ -145,6 +145,15 @@ int b200id_gp_batch_eval(int kernel_id, const int* kernel_ids, const double* the
                          const double* X, const double* y, int n, double noise, int metric,
                          const double* Xv, const double* yv, int nv, double y_mean, double y_scale,
                          double* metric_out, void* ws, size_t ws_bytes, void* stream);
+/* Two regression targets on the same inputs, candidates and noise (the Re and Im searches of the pipeline,
+ * gp_pipeline.py:125-156): K + noise I and its Cholesky factor are common, only the right-hand side differs, so
+ * one factorisation per candidate serves both (n <= 126; larger n runs the two evaluations one after the other).
+ * Outputs metric_out_a [C], metric_out_b [C]; a failed factorisation gives 1e10 in both. */
+int b200id_gp_batch_eval_pair(int kernel_id, const int* kernel_ids, const double* theta, int64_t n_candidates,
+                              const double* X, const double* y_a, const double* y_b, int n, double noise, int metric,
+                              const double* Xv, const double* yv_a, const double* yv_b, int nv,
+                              double y_mean_a, double y_scale_a, double y_mean_b, double y_scale_b,
+                              double* metric_out_a, double* metric_out_b, void* ws, size_t ws_bytes, void* stream);
 /* Same, with one noise variance PER CANDIDATE (noise [C], device): the finite-difference points of the
  * L-BFGS-B hyperparameter optimisation perturb log(noise) as well, gpr_fitting.py:104-123,130,147 -- the
  * value and all forward-difference points of one gradient are one launch. */

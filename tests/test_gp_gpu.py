@@ -408,3 +408,32 @@ def test_per_candidate_noise_matches_scalar_calls(gp, n, name):
             assert abs(got[k] - ref) <= max(TOL, 100 * cond * 2.2e-16) * abs(ref), (k, got[k], ref)
     with pytest.raises(ValueError, match="noise values"):
         gp.batch_eval(name, cands, X, y, noises[:3])
+
+
+@pytest.mark.parametrize("n,name,mode", [(100, "matern52", "val"), (99, "rbf", "nll"), (126, "dc", "val"), (17, "ss2", "nll"),
+                                         (127, "matern32", "val"), (140, "matern52", "nll")])
+def test_pair_evaluation_shares_one_factorisation(gp, n, name, mode):
+    """b200id_gp_batch_eval_pair: two targets (Re / Im of G) on the same inputs, candidates and noise from one
+    factorisation per candidate = two separate evaluations, including failed (1e10) and NaN candidates;
+    n = 127 and 140 take the two-evaluation fallback behind the same entry point."""
+    rng = np.random.default_rng(n)
+    X = np.linspace(-1.7, 1.6, n)
+    ya = np.sin(2.0 * X) + 0.1 * rng.standard_normal(n)
+    yb = np.cos(3.0 * X) * 0.5 + 0.05 * rng.standard_normal(n)
+    cands = ogp.grid_candidates(name, 300)
+    noise = 1e-6 if name != "ss2" else 0.0          # ss2 at noise 0 exercises the failure / NaN categories
+    kw_a, kw_b, kw = {}, {}, {}
+    if mode == "val":
+        Xv = np.linspace(-1.5, 1.5, 41)
+        yva, yvb = 0.7 * np.sin(2.0 * Xv) + 0.2, 1.3 * np.cos(3.0 * Xv) - 0.1
+        kw_a = dict(Xv=Xv, yv=yva, y_mean=0.2, y_scale=0.7)
+        kw_b = dict(Xv=Xv, yv=yvb, y_mean=-0.1, y_scale=1.3)
+        kw = dict(Xv=Xv, yv_a=yva, yv_b=yvb, scale_a=(0.2, 0.7), scale_b=(-0.1, 1.3))
+    ma, mb = gp.batch_eval_pair(name, cands, X, ya, yb, noise, **kw)
+    ra = gp.batch_eval(name, cands, X, ya, noise, **kw_a)
+    rb = gp.batch_eval(name, cands, X, yb, noise, **kw_b)
+    for got, ref, tag in ((ma, ra, "a"), (mb, rb, "b")):
+        assert np.array_equal(np.isnan(got), np.isnan(ref)), tag
+        assert np.array_equal(got >= 1e10, ref >= 1e10), tag
+        np.testing.assert_allclose(got, ref, rtol=1e-12, atol=0, equal_nan=True, err_msg=tag)
+    assert ogp.first_strict_min(ma) == ogp.first_strict_min(ra) and ogp.first_strict_min(mb) == ogp.first_strict_min(rb)

@@ -513,7 +513,7 @@ dft_bins_kernel(const double* __restrict__ u, const double* __restrict__ y, int6
     const int stride = R * FRFU_CHAINS;
     double sd, cd;                                                  // rotation by `stride` samples
     dft_phase(stride, k, n_fft, sd, cd);
-    double uc[FRFU_CHAINS] = {0.0, 0.0}, us[FRFU_CHAINS] = {0.0, 0.0}, yc[FRFU_CHAINS] = {0.0, 0.0}, ys[FRFU_CHAINS] = {0.0, 0.0};
+    double uc[FRFU_CHAINS] = {}, us[FRFU_CHAINS] = {}, yc[FRFU_CHAINS] = {}, ys[FRFU_CHAINS] = {};
 
     for (int tl = blockIdx.x; tl < n_tiles; tl += gridDim.x) {
         const int64_t i0 = own_begin + (int64_t)tl * tile;
@@ -555,10 +555,13 @@ dft_bins_kernel(const double* __restrict__ u, const double* __restrict__ y, int6
     }
     __syncthreads();
     double* red = smem;
-    red[0 * FRF_THREADS + tid] = uc[0] + uc[1];
-    red[1 * FRF_THREADS + tid] = us[0] + us[1];
-    red[2 * FRF_THREADS + tid] = HAS_Y ? yc[0] + yc[1] : 0.0;
-    red[3 * FRF_THREADS + tid] = HAS_Y ? ys[0] + ys[1] : 0.0;
+    double tu = 0.0, tus = 0.0, ty = 0.0, tys = 0.0;
+#pragma unroll
+    for (int q = 0; q < FRFU_CHAINS; ++q) { tu += uc[q]; tus += us[q]; ty += yc[q]; tys += ys[q]; }
+    red[0 * FRF_THREADS + tid] = tu;
+    red[1 * FRF_THREADS + tid] = tus;
+    red[2 * FRF_THREADS + tid] = HAS_Y ? ty : 0.0;
+    red[3 * FRF_THREADS + tid] = HAS_Y ? tys : 0.0;
     __syncthreads();
     if (tid < nb) {
         double* out = cta_partial + (size_t)blockIdx.x * 4 * nb_total + bin0 + tid;

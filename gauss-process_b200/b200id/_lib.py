@@ -29,6 +29,8 @@ SIGNATURES = {
     "b200id_frf_project": (I, [P, P, P, L, L, L, P, I, P, D, P, P, Z, P]),
     "b200id_frf_uniformity": (I, [P, L, L, L, D, D, P, P, Z, P]),
     "b200id_frf_project_uniform": (I, [P, P, P, L, L, L, P, I, P, D, D, D, P, P, Z, P]),
+    "b200id_cross_power_sums": (I, [P, P, I, I, I, P, P]),
+    "b200id_gp_targets": (I, [P, I, D, P, P, P, P, P]),
     "b200id_dft_bins": (I, [P, P, L, L, L, P, I, L, I, P, P, D, P, P, P, Z, P]),
     "b200id_frf_finalize": (I, [P, I, D, P, P, P]),
     "b200id_cross_power": (I, [P, P, I, I, D, P, P]),
@@ -40,6 +42,7 @@ SIGNATURES = {
     "b200id_first_strict_min": (I, [P, L, P, P, P, Z, P]),
     "b200id_gp_fit_workspace_bytes": (Z, [I]),
     "b200id_gp_fit": (I, [I, P, P, P, I, D, P, P, P, P, Z, P]),
+    "b200id_gp_fit_batch": (I, [I, P, P, P, I, I, D, P, P, P, Z, P]),
     "b200id_gp_fit_pinv": (I, [I, P, P, P, I, D, D, P, P, P, Z, P]),
     "b200id_gp_predict": (I, [I, P, P, I, P, P, P, I, P, P, P]),
     "b200id_chol_blocked_workspace_bytes": (Z, [I]),

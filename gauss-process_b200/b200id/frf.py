@@ -121,6 +121,28 @@ def cross_power_device(U: torch.Tensor, Y: torch.Tensor, eps: float = 1e-15) -> 
     return torch.view_as_complex(G.view(nd, 2))
 
 
+def cross_power_sums_device(U: torch.Tensor, Y: torch.Tensor, out: torch.Tensor, accumulate: bool = False) -> torch.Tensor:
+    """out [3*nd] (+)= {Re sum Y conj(U), Im sum Y conj(U), sum |U|^2} over the records in U, Y ([nd] or [R, nd])."""
+    U2 = U.reshape(-1, U.shape[-1]).contiguous()
+    Y2 = Y.reshape(-1, Y.shape[-1]).contiguous()
+    R, nd = U2.shape
+    _lib.call("b200id_cross_power_sums", ptr(torch.view_as_real(U2)), ptr(torch.view_as_real(Y2)), C.c_int(R), C.c_int(nd),
+              C.c_int(1 if accumulate else 0), ptr(out), stream_ptr())
+    return out
+
+
+def gp_targets_device(sums: torch.Tensor, nd: int, standardise: bool, eps: float = 1e-15):
+    """(G [nd] complex, stats [4] or None, y_re [nd], y_im [nd]) from cross-power sums [3*nd]: G = num / den; with
+    ``standardise`` the StandardScaler statistics {mean Re, mean Im, std Re, std Im} and the standardised real /
+    imaginary targets, else the raw real / imaginary parts as two contiguous vectors."""
+    dev = sums.device
+    G = empty(2 * nd, dev)
+    stats = empty(4, dev) if standardise else None
+    y_re, y_im = empty(nd, dev), empty(nd, dev)
+    _lib.call("b200id_gp_targets", ptr(sums), C.c_int(nd), C.c_double(eps), ptr(G), ptr(stats), ptr(y_re), ptr(y_im), stream_ptr())
+    return torch.view_as_complex(G.view(nd, 2)), stats, y_re, y_im
+
+
 def record_coefficients_device(t_d, u_d, y_d, w_d, span: float, subtract_mean: bool = True,
                                t0: Optional[float] = None, w_max: Optional[float] = None, path=None):
     """(U, Y) of one resident record.  ``span`` = t[-1] - t[0] (the caller knows it on the host).

@@ -209,6 +209,22 @@ def fit(kernel_id: int, theta, X, y, diag_add: float, want_kinv: bool = True):
     return out
 
 
+def fit_batch(kernel_id: int, thetas, X, ys, diag_add: float):
+    """(alpha [B, n], info [B]) of B fits sharing X, the kernel family and the diagonal term, in one launch
+    (b200id_gp_fit_batch; n <= 127 or n > 160).  info[b] > 0 = failing pivot of problem b (use :func:`fit`)."""
+    dev = require_cuda()
+    th = to_device(_theta_block(thetas), dev)
+    yy = to_device(np.ascontiguousarray(np.asarray(ys, dtype=np.float64)).reshape(th.shape[0], -1), dev)
+    x = to_device(_flat(X), dev)
+    b, n = yy.shape
+    alpha = empty(b * n, dev)
+    info = torch.zeros(b, dtype=torch.int32, device=dev)
+    ws = Workspace.get("gpfit", b * _lib.load().b200id_gp_fit_workspace_bytes(n), dev)
+    _lib.call("b200id_gp_fit_batch", C.c_int(kernel_id), ptr(th), ptr(x), ptr(yy), C.c_int(n), C.c_int(b), C.c_double(diag_add),
+              ptr(alpha), ptr(info), ptr(ws), C.c_size_t(ws.numel()), stream_ptr())
+    return alpha.view(b, n).cpu().numpy(), info.cpu().numpy()
+
+
 def search_and_fit(kernel_id: int, start_theta, candidates, X, y, noise: float, fit_diag_add: float,
                    Xv=None, yv=None, y_mean: Optional[float] = None, y_scale: Optional[float] = None):
     """Whole grid search of one target in ONE host<->device round trip.

@@ -358,47 +358,28 @@ def identify_device(train: Sequence[Tuple[torch.Tensor, torch.Tensor, torch.Tens
     # ---- FRF: per-record coefficients -> cross-power numerator / denominator of the training records and, when
     # the search metric needs it, of the validation record(s); under torch.distributed every rank contributes
     # its records and ONE all-reduce carries both sets (3 N_d + 3 N_v doubles)
-    num = torch.zeros(nd, dtype=torch.complex128, device=dev)
-    den = torch.zeros(nd, dtype=F64, device=dev)
-    for rec, path in zip(train, paths):
-        U, Y = bfrf.record_coefficients_device(rec[0], rec[1], rec[2], w_d, rec[3], path=path)
-        num += Y * U.conj()
-        den += U.abs() ** 2
     use_val_metric = candidates is not None and use_validation_metric and val is not None
-    num_v = den_v = None
+    nv = gi.wv_d.numel() if use_val_metric else 0
+    sums_all = empty(3 * nd + 3 * nv, dev)                  # {Re num, Im num, den} of the train set, then of the validation set
+    for r, (rec, path) in enumerate(zip(train, paths)):
+        U, Y = bfrf.record_coefficients_device(rec[0], rec[1], rec[2], w_d, rec[3], path=path)
+        bfrf.cross_power_sums_device(U, Y, sums_all[:3 * nd], accumulate=r > 0)
     if use_val_metric:
         if val_frf is None:
             Uv, Yv = bfrf.record_coefficients_device(val[0], val[1], val[2], gi.wv_d, val[3], path=paths[-1])
         else:
             Uv, Yv = val_frf
-        num_v, den_v = Yv * Uv.conj(), Uv.abs() ** 2
-    if bdist.world()[1] > 1:
-        parts = [torch.view_as_real(num).reshape(-1), den]
-        if use_val_metric:
-            parts += [torch.view_as_real(num_v).reshape(-1), den_v]
-        packed = torch.cat(parts)
-        bdist.allreduce_sum_(packed)
-        num = torch.view_as_complex(packed[:2 * nd].view(nd, 2).contiguous())
-        den = packed[2 * nd:3 * nd]
-        if use_val_metric:
-            nv = den_v.numel()
-            num_v = torch.view_as_complex(packed[3 * nd:3 * nd + 2 * nv].view(nv, 2).contiguous())
-            den_v = packed[3 * nd + 2 * nv:]
-    nan_c = complex(float("nan"), float("nan"))
-    G = torch.where(den > 1e-15, num / den, torch.full_like(num, nan_c))
-    # ---- StandardScaler statistics of Re G, Im G: computed on the device, copied asynchronously
-    ri = torch.view_as_real(G)
-    mean2 = ri.mean(dim=0)
-    sd2 = torch.sqrt(((ri - mean2) ** 2).mean(dim=0))
-    sd2 = torch.where(sd2 == 0.0, torch.ones_like(sd2), sd2)
-    stats_host, stats_ev = _async_to_host(torch.cat([mean2, sd2]))
-    yr = ((G.real - mean2[0]) / sd2[0]).contiguous()
-    yi = ((G.imag - mean2[1]) / sd2[1]).contiguous()
+        bfrf.cross_power_sums_device(Uv, Yv, sums_all[3 * nd:])
+    bdist.allreduce_sum_(sums_all)
+    # ---- G, StandardScaler statistics of Re G / Im G and the standardised targets: one kernel; the statistics
+    # travel to the host asynchronously
+    G, stats_d, yr, yi = bfrf.gp_targets_device(sums_all[:3 * nd], nd, standardise=True)
+    mean2, sd2 = stats_d[0:2], stats_d[2:4]
+    stats_host, stats_ev = _async_to_host(stats_d)
     Xv_d = yv_r = yv_i = None
     if use_val_metric:
-        Gv = torch.where(den_v > 1e-15, num_v / den_v, torch.full_like(num_v, nan_c))   # frf_estimator.py:239-252
+        _, _, yv_r, yv_i = bfrf.gp_targets_device(sums_all[3 * nd:], nv, standardise=False)   # frf_estimator.py:239-252
         Xv_d = gi.Xv_d
-        yv_r, yv_i = Gv.real.contiguous(), Gv.imag.contiguous()
     stats_ev.synchronize()
     st = stats_host.tolist()
     sr, si = Standardizer(st[0], st[2]), Standardizer(st[1], st[3])
@@ -418,13 +399,23 @@ def identify_device(train: Sequence[Tuple[torch.Tensor, torch.Tensor, torch.Tens
     # ---- final fits (gpr_fitting.py:73-83); status flags are read at the end
     nbytes = _lib.load().b200id_gp_fit_workspace_bytes(n)
     alphas = []
-    for k, (th_d, y_d) in enumerate(((th_r_d, yr), (th_i_d, yi))):
-        alpha = empty(n, dev)
-        ws = Workspace.get(f"gpfit{k}", nbytes, dev)
-        kinv = empty(n * n, dev) if n > 127 else None
-        _lib.call("b200id_gp_fit", C.c_int(kid), ptr(th_d), ptr(X_d), ptr(y_d), C.c_int(n), C.c_double(diag), ptr(alpha),
-                  ptr(kinv), ptr(infos[k:k + 1]), ptr(ws), C.c_size_t(ws.numel()), stream_ptr())
-        alphas.append((alpha, kinv))
+    if n <= 127:
+        # both fits in one launch (one CTA each); K_inv is not needed for the posterior mean
+        th2 = torch.stack([th_r_d.reshape(-1)[:3], th_i_d.reshape(-1)[:3]]).contiguous()
+        y2 = torch.stack([yr, yi]).contiguous()
+        al2 = empty(2 * n, dev)
+        ws = Workspace.get("gpfit0", 2 * nbytes, dev)
+        _lib.call("b200id_gp_fit_batch", C.c_int(kid), ptr(th2), ptr(X_d), ptr(y2), C.c_int(n), C.c_int(2), C.c_double(diag),
+                  ptr(al2), ptr(infos), ptr(ws), C.c_size_t(ws.numel()), stream_ptr())
+        alphas = [(al2[:n], None), (al2[n:], None)]
+    else:
+        for k, (th_d, y_d) in enumerate(((th_r_d, yr), (th_i_d, yi))):
+            alpha = empty(n, dev)
+            ws = Workspace.get(f"gpfit{k}", nbytes, dev)
+            kinv = empty(n * n, dev) if n <= bgp.SMEM_NMAX else None
+            _lib.call("b200id_gp_fit", C.c_int(kid), ptr(th_d), ptr(X_d), ptr(y_d), C.c_int(n), C.c_double(diag), ptr(alpha),
+                      ptr(kinv), ptr(infos[k:k + 1]), ptr(ws), C.c_size_t(ws.numel()), stream_ptr())
+            alphas.append((alpha, kinv))
 
     def tail(al_r, al_i):
         # paper-mode FIR: 1000-point uniform omega grid -> GP mean -> Hermitian IDFT -> taps -> validation

@@ -476,6 +476,72 @@ __global__ void cross_power_kernel(const double* __restrict__ U, const double* _
 }
 
 
+// Cross-power sums of R records (frf_estimator.py:245-247): out = { Re sum Y conj(U), Im sum Y conj(U), sum |U|^2 }
+// as three rows of nd doubles -- the form that is all-reduced when the records are spread over ranks.
+__global__ void cross_power_sums_kernel(const double* __restrict__ U, const double* __restrict__ Y,
+                                        int n_records, int nd, int accumulate, double* __restrict__ out) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nd) return;
+    double nr = 0.0, ni = 0.0, den = 0.0;
+    for (int r = 0; r < n_records; ++r) {
+        const double ur = U[2 * ((size_t)r * nd + k)], ui = U[2 * ((size_t)r * nd + k) + 1];
+        const double yr = Y[2 * ((size_t)r * nd + k)], yi = Y[2 * ((size_t)r * nd + k) + 1];
+        nr += yr * ur + yi * ui;
+        ni += yi * ur - yr * ui;
+        const double a = hypot(ur, ui);       // np.abs(U) ** 2
+        den += a * a;
+    }
+    if (accumulate) { nr += out[k]; ni += out[nd + k]; den += out[2 * nd + k]; }
+    out[k] = nr; out[nd + k] = ni; out[2 * nd + k] = den;
+}
+
+// G = num / den (NaN + NaN j where den <= eps, frf_estimator.py:248-251) and, when y_re / y_im are given, the two
+// regression targets the pipeline builds from it: StandardScaler statistics (mean, population std, std 0 -> 1) of
+// Re G and Im G and the standardised vectors (gp_pipeline.py:130-132).  One CTA.
+constexpr int TARGETS_THREADS = 256;
+__global__ void __launch_bounds__(TARGETS_THREADS)
+gp_targets_kernel(const double* __restrict__ sums, int nd, double eps, double* __restrict__ G,
+                  double* __restrict__ stats, double* __restrict__ y_re, double* __restrict__ y_im) {
+    __shared__ double scratch[TARGETS_THREADS / 32];
+    const int tid = threadIdx.x;
+    double sr = 0.0, si = 0.0;
+    for (int k = tid; k < nd; k += TARGETS_THREADS) {
+        const double den = sums[2 * nd + k];
+        double gr, gi;
+        if (den > eps) { gr = sums[k] / den; gi = sums[nd + k] / den; }
+        else { gr = nan(""); gi = nan(""); }
+        G[2 * k] = gr; G[2 * k + 1] = gi;
+        sr += gr; si += gi;
+        if (!stats && y_re) { y_re[k] = gr; y_im[k] = gi; }      // planar copy of the raw parts
+    }
+    if (!stats) return;
+    __shared__ double bc[4];
+    // block_sum leaves the total in warp 0 only: publish the four reductions through shared memory
+    const double t_r = block_sum(sr, scratch), t_i = block_sum(si, scratch);
+    if (tid == 0) { bc[0] = t_r / (double)nd; bc[1] = t_i / (double)nd; }
+    __syncthreads();
+    const double mr = bc[0], mi = bc[1];
+    double vr = 0.0, vi = 0.0;
+    for (int k = tid; k < nd; k += TARGETS_THREADS) {       // own writes only: no barrier needed before the re-read
+        const double dr = G[2 * k] - mr, di = G[2 * k + 1] - mi;
+        vr = fma(dr, dr, vr); vi = fma(di, di, vi);
+    }
+    const double q_r = block_sum(vr, scratch), q_i = block_sum(vi, scratch);
+    if (tid == 0) { bc[2] = sqrt(q_r / (double)nd); bc[3] = sqrt(q_i / (double)nd); }
+    __syncthreads();
+    double sdr = bc[2], sdi = bc[3];
+    if (sdr == 0.0) sdr = 1.0;
+    if (sdi == 0.0) sdi = 1.0;
+    if (tid == 0) { stats[0] = mr; stats[1] = mi; stats[2] = sdr; stats[3] = sdi; }
+    if (y_re && y_im) {
+        for (int k = tid; k < nd; k += TARGETS_THREADS) {
+            y_re[k] = (G[2 * k] - mr) / sdr;
+            y_im[k] = (G[2 * k + 1] - mi) / sdi;
+        }
+    }
+}
+
+
 // ------------------------------------------------------------------------------------------
 // Selected DFT bins of a windowed, mean-removed record -- the Fourier estimator
 // (reference src/frequency_transform/fourier_estimator.py:120-223).  The reference takes a full n-point
@@ -764,6 +830,23 @@ extern "C" int b200id_cross_power(const double* U, const double* Y, int n_record
     B200ID_REQUIRE(U && Y && G_out && n_records > 0 && nd > 0, B200ID_E_ARG, "cross_power: bad argument");
     cross_power_kernel<<<(nd + 127) / 128, 128, 0, (cudaStream_t)stream>>>(U, Y, n_records, nd, eps, G_out);
     B200ID_LAUNCH_CHECK("cross_power_kernel");
+    return B200ID_OK;
+}
+
+extern "C" int b200id_cross_power_sums(const double* U, const double* Y, int n_records, int nd, int accumulate,
+                                       double* sums_out, void* stream) {
+    B200ID_REQUIRE(U && Y && sums_out && n_records > 0 && nd > 0, B200ID_E_ARG, "cross_power_sums: bad argument");
+    cross_power_sums_kernel<<<(nd + 127) / 128, 128, 0, (cudaStream_t)stream>>>(U, Y, n_records, nd, accumulate, sums_out);
+    B200ID_LAUNCH_CHECK("cross_power_sums_kernel");
+    return B200ID_OK;
+}
+
+extern "C" int b200id_gp_targets(const double* sums, int nd, double eps, double* G_out, double* stats_out,
+                                 double* y_re_out, double* y_im_out, void* stream) {
+    B200ID_REQUIRE(sums && G_out && nd > 0, B200ID_E_ARG, "gp_targets: bad argument");
+    B200ID_REQUIRE((y_re_out == nullptr) == (y_im_out == nullptr), B200ID_E_ARG, "gp_targets: y_re / y_im come together");
+    gp_targets_kernel<<<1, TARGETS_THREADS, 0, (cudaStream_t)stream>>>(sums, nd, eps, G_out, stats_out, y_re_out, y_im_out);
+    B200ID_LAUNCH_CHECK("gp_targets_kernel");
     return B200ID_OK;
 }
 

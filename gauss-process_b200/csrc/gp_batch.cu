@@ -279,7 +279,8 @@ using namespace b200id;
 
 // gp_batch_tiled.cu: blocked register-tiled path for n <= 127
 int b200id_gp_fit_tiled_launch(int kernel_id, const double* theta, const double* X, const double* y, int n,
-                               double diag_add, double* alpha_out, double* L_out, int* info_out, cudaStream_t st);
+                               double diag_add, double* alpha_out, double* L_out, int* info_out, cudaStream_t st,
+                               int n_problems = 1);
 int b200id_gp_batch_tiled_launch(int kernel_id, const int* kernel_ids, const double* theta, int64_t n_candidates,
                                  const double* X, const double* y, int n, double noise, int metric,
                                  const double* Xv, const double* yv, int nv, double y_mean, double y_scale,
@@ -447,6 +448,30 @@ extern "C" int b200id_gp_fit(int kernel_id, const double* theta, const double* X
     if (rc) return rc;
     gp_fit_kernel<<<1, GP_THREADS, smem, st>>>(kernel_id, theta, X, y, n, diag_add, alpha_out, (double*)ws, Kinv_out, info_out);
     B200ID_LAUNCH_CHECK("gp_fit_kernel");
+    return B200ID_OK;
+}
+
+// Several final fits that share X and the kernel family (the Re and Im models of one identification) as ONE
+// launch: theta [B][B200ID_MAX_PARAMS], y [B][n] -> alpha [B][n], info [B]; K_inv is not produced (the
+// posterior mean needs only alpha).  n <= 127 runs one CTA per problem; other sizes fit one after the other.
+extern "C" int b200id_gp_fit_batch(int kernel_id, const double* theta, const double* X, const double* y, int n,
+                                   int n_problems, double diag_add, double* alpha_out, int* info_out,
+                                   void* ws, size_t ws_bytes, void* stream) {
+    B200ID_REQUIRE(theta && X && y && alpha_out && info_out && ws, B200ID_E_ARG, "gp_fit_batch: null pointer");
+    B200ID_REQUIRE(kernel_id >= 0 && kernel_id < B200ID_K_COUNT, B200ID_E_ARG, "gp_fit_batch: unknown kernel id %d", kernel_id);
+    B200ID_REQUIRE(n > 0 && n_problems > 0 && n_problems <= 64, B200ID_E_ARG, "gp_fit_batch: bad sizes n=%d B=%d", n, n_problems);
+    if (n <= 127 && !force_generic_gp_path()) {
+        B200ID_REQUIRE(ws_bytes >= (size_t)n_problems * n * n * sizeof(double), B200ID_E_WORKSPACE,
+                       "gp_fit_batch: workspace %zu < %zu", ws_bytes, (size_t)n_problems * n * n * sizeof(double));
+        return b200id_gp_fit_tiled_launch(kernel_id, theta, X, y, n, diag_add, alpha_out, (double*)ws, info_out,
+                                          (cudaStream_t)stream, n_problems);
+    }
+    B200ID_REQUIRE(n > GP_NMAX_SMEM, B200ID_E_UNSUPPORTED, "gp_fit_batch: 128 <= n <= 160 needs K_inv storage; use b200id_gp_fit");
+    for (int b = 0; b < n_problems; ++b) {
+        int rc = b200id_gp_fit(kernel_id, theta + (size_t)b * B200ID_MAX_PARAMS, X, y + (size_t)b * n, n, diag_add,
+                               alpha_out + (size_t)b * n, nullptr, info_out + b, ws, ws_bytes, stream);
+        if (rc) return rc;
+    }
     return B200ID_OK;
 }
 

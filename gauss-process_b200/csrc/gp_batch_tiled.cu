@@ -160,6 +160,13 @@ gp_batch_tiled_kernel(int kernel_id, const int* __restrict__ kernel_ids, const d
 
     // ---- fill: K + noise*I (rows < n), y (row n), zeros (padding rows), block column by block column
     if (noise_v) noise = noise_v[cand];
+    if (metric == GT_METRIC_FIT) {
+        // fit mode: CTA b factorises problem b of a small batch (theta[b], y[b]) -> alpha[b], L[b], info[b]
+        y += cand * n;
+        fit_alpha += cand * n;
+        fit_L += cand * (int64_t)n * n;
+        fit_info += cand;
+    }
     B200ID_DISPATCH_KERNEL(kid, gt_fill, kp, xs, y, n, noise, R, nblk, Lb, sec.y)
     GT_TICK(0);
     __syncthreads();
@@ -452,14 +459,16 @@ extern "C" int b200id_debug_gt_profile(unsigned long long* out16_host, int reset
 }
 #endif
 
-// Final fit through the same blocked kernel (one CTA): alpha, dense L (row-major lower) and info.
+// Final fits through the same blocked kernel, one CTA per problem: theta [B][3], y [B][n] -> alpha [B][n],
+// dense L [B][n*n] (row-major lower) and info [B].
 int b200id_gp_fit_tiled_launch(int kernel_id, const double* theta, const double* X, const double* y, int n,
-                               double diag_add, double* alpha_out, double* L_out, int* info_out, cudaStream_t st) {
+                               double diag_add, double* alpha_out, double* L_out, int* info_out, cudaStream_t st,
+                               int n_problems) {
     const size_t smem = gt_smem_bytes(n);
     int rc = check_cuda(cudaFuncSetAttribute(gp_batch_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute(gp tiled)");
     if (rc) return rc;
-    gp_batch_tiled_kernel<<<1, GT_THREADS, smem, st>>>(kernel_id, nullptr, theta, X, y, n, diag_add, GT_METRIC_FIT,
-                                                      nullptr, nullptr, 0, 0.0, 1.0, nullptr, alpha_out, L_out, info_out, nullptr, GtSecond{nullptr, nullptr, 0.0, 1.0, nullptr});
+    gp_batch_tiled_kernel<<<n_problems, GT_THREADS, smem, st>>>(kernel_id, nullptr, theta, X, y, n, diag_add, GT_METRIC_FIT,
+                                                               nullptr, nullptr, 0, 0.0, 1.0, nullptr, alpha_out, L_out, info_out, nullptr, GtSecond{nullptr, nullptr, 0.0, 1.0, nullptr});
     B200ID_LAUNCH_CHECK("gp_batch_tiled_kernel(fit)");
     return B200ID_OK;
 }

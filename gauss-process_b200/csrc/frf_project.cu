@@ -791,12 +791,77 @@ constexpr size_t FRFU_SMEM_BYTES = (size_t)(4 * FRF_TILE_MAX) * sizeof(double);
 
 }  // namespace b200id
 
+#include "frf_mma.cuh"
+
 using namespace b200id;
+
+#include <stdlib.h>
+
+// bytes of the per-CTA partial area + the moments area (the layout every FRF entry point shares); the tables of the
+// matrix-product path follow it
+static size_t frf_partial_area_bytes(int nd) {
+    const size_t ctas = (size_t)sm_count() * FRF_CTAS_PER_SM + 8;
+    return align_up(ctas * 4 * (size_t)nd * sizeof(double), 256) + align_up((size_t)sm_count() * 4 * 2 * sizeof(double), 256) + 256;
+}
+
+static bool frf_mma_enabled() {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("B200ID_FRF_MMA");
+        on = (e && e[0] == '1') ? 1 : 0;                      // opt-in (experimental)
+    }
+    return on == 1;
+}
+
+// Matrix-product path of b200id_frf_project_uniform (two signals, nd <= FM_NDMAX).  Returns 1 when the shape does
+// not fit (caller falls back to the recurrence kernels), 0 on success, < 0 on error.
+static int frf_project_mma_launch(const double* t, const double* u, const double* y, int64_t n, int64_t own_begin,
+                                  int64_t own_end, const double* w, int nd, const double* sums, double inv_count,
+                                  double t0, double dt, double* partial_out, void* ws, size_t ws_bytes, cudaStream_t st) {
+    if (nd > FM_NDMAX) return 1;
+    const size_t tables_off = frf_partial_area_bytes(nd);
+    if (ws_bytes < tables_off + fm_tables_bytes()) return 1;
+    const int ndp = (nd + 3) / 4 * 4;
+    int dev = 0, smem_max = 0;
+    int rc = check_cuda(cudaGetDevice(&dev), "cudaGetDevice");
+    if (rc) return rc;
+    rc = check_cuda(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev), "smem attribute");
+    if (rc) return rc;
+    int nblk = 64;
+    if (fm_smem_bytes(ndp, nblk) > (size_t)smem_max) nblk = 32;
+    const size_t smem = fm_smem_bytes(ndp, nblk);
+    if (smem > (size_t)smem_max) return 1;
+    const int64_t n_own = own_end - own_begin;
+    const int ts = nblk * FM_BLK;
+    const int64_t n_tiles64 = (n_own + ts - 1) / ts;
+    if (n_tiles64 > 0x7fffffff) return 1;
+    const int n_tiles = (int)n_tiles64;
+    const int grid = n_tiles < sm_count() ? n_tiles : sm_count();
+    double* part = (double*)ws;
+    FmTables T = fm_tables_at((char*)ws + tables_off);
+
+    const double t_first = t0 + (double)own_begin * dt, t_last = t0 + (double)(own_end - 1) * dt;
+    frf_mma_setup_kernel<<<(FM_NDMAX * FM_BLK + 255) / 256, 256, 0, st>>>(w, nd, ndp, t0, dt, t_first, t_last, T);
+    B200ID_LAUNCH_CHECK("frf_mma_setup_kernel");
+    if (nblk == 64) {
+        rc = check_cuda(cudaFuncSetAttribute(frf_project_mma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr");
+        if (rc) return rc;
+        frf_project_mma_kernel<64><<<grid, FM_THREADS, smem, st>>>(t, u, y, n, own_begin, own_end, nd, ndp, sums, inv_count, t0, dt, n_tiles, T, part);
+    } else {
+        rc = check_cuda(cudaFuncSetAttribute(frf_project_mma_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr");
+        if (rc) return rc;
+        frf_project_mma_kernel<32><<<grid, FM_THREADS, smem, st>>>(t, u, y, n, own_begin, own_end, nd, ndp, sums, inv_count, t0, dt, n_tiles, T, part);
+    }
+    B200ID_LAUNCH_CHECK("frf_project_mma_kernel");
+    const int len = 4 * nd;
+    frf_fold_kernel<<<(len + 31) / 32, FOLD_WARPS * 32, 0, st>>>(part, grid, len, partial_out);
+    B200ID_LAUNCH_CHECK("frf_fold_kernel");
+    return B200ID_OK;
+}
 
 extern "C" size_t b200id_frf_workspace_bytes(int nd) {
     if (nd <= 0) return 0;
-    const size_t ctas = (size_t)sm_count() * FRF_CTAS_PER_SM + 8;
-    return align_up(ctas * 4 * (size_t)nd * sizeof(double), 256) + align_up((size_t)sm_count() * 4 * 2 * sizeof(double), 256) + 256;
+    return frf_partial_area_bytes(nd) + fm_tables_bytes();
 }
 
 extern "C" int b200id_frf_moments(const double* u, const double* y, int64_t n, int64_t own_begin,
@@ -931,6 +996,10 @@ extern "C" int b200id_frf_project_uniform(const double* t, const double* u, cons
     B200ID_REQUIRE(ws_bytes >= need, B200ID_E_WORKSPACE, "frf_project_uniform: workspace %zu < %zu", ws_bytes, need);
     double* part = (double*)ws;
     int rc = 0;
+    if (y && frf_mma_enabled()) {
+        rc = frf_project_mma_launch(t, u, y, n, own_begin, own_end, w, nd, sums, inv_count, t0, dt, partial_out, ws, ws_bytes, st);
+        if (rc <= 0) return rc;                     // done (0) or failed (< 0); 1 = shape not covered, use the recurrence kernels
+    }
     const void* fns[4] = {(const void*)frf_project_uniform_kernel<true, true>, (const void*)frf_project_uniform_kernel<true, false>,
                           (const void*)frf_project_uniform_kernel<false, true>, (const void*)frf_project_uniform_kernel<false, false>};
     for (int k = 0; k < 4; ++k) {

@@ -84,6 +84,19 @@ def project_uniform_device(t_d, u_d, y_d, w_d, t0: float, dt: float, own=None, s
     return out
 
 
+def project_uniform_mma_device(t_d, u_d, y_d, w_d, t0: float, dt: float, own=None, sums=None, inv_count: float = 0.0):
+    """Same partial sums through the experimental matrix-product evaluation (b200id_frf_project_uniform_mma)."""
+    dev = t_d.device
+    n, nd = t_d.numel(), w_d.numel()
+    own = (0, n) if own is None else own
+    out = empty(4 * nd, dev)
+    ws, _ = _ws(nd, dev)
+    _lib.call("b200id_frf_project_uniform_mma", ptr(t_d), ptr(u_d), ptr(y_d), C.c_int64(n), C.c_int64(own[0]),
+              C.c_int64(own[1]), ptr(w_d), C.c_int(nd), ptr(sums), C.c_double(inv_count), C.c_double(t0),
+              C.c_double(dt), ptr(out), ptr(ws), C.c_size_t(ws.numel()), stream_ptr())
+    return out
+
+
 def choose_path(t_d: torch.Tensor, span: float, w_max: float, t0: Optional[float] = None):
     """('uniform', t0, dt) when the record's time stamps sit on an arithmetic progression up to FP64
     rounding (then the fast kernel reproduces the reference's per-sample phase rounding to first order),

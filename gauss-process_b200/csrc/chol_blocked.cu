@@ -47,70 +47,119 @@ __device__ __forceinline__ void stage_tile_kmajor(const double* __restrict__ M, 
     }
 }
 
-// (1) diagonal block: factorise in shared memory, write L back, write L^-1 (row-major [c][p], lower).
+// (1) diagonal block: factorise in shared memory, write L back.
+// This kernel is the serial link of the factorisation (one CTA, n / 64 times), so it is written for latency:
+// right-looking with ONE barrier per column -- the scaled column goes to the unused upper triangle, so nobody
+// overwrites what the trailing update of the same step still reads; each thread forms l_i = a_ik * (1/d) itself (the
+// same product the scaled column holds: potf2's SCAL + SYR arithmetic).
 __global__ void __launch_bounds__(CB_THREADS)
-cholb_diag_kernel(double* __restrict__ A, int lda, int n, int k0, double* __restrict__ Linv, int* __restrict__ info) {
-    __shared__ double D[CB_NB * (CB_NB + 1)];      // column-major, ld = 65
-    __shared__ int status;
+cholb_diag_kernel(double* __restrict__ A, int lda, int n, int k0, int* __restrict__ info) {
+    constexpr int ld = CB_NB + 1;
+    // Lower triangle, column-major D[j * ld + i] (i >= j): the working copy; once column j is final its scaled copy
+    // L[i][j] goes to the UPPER triangle at D[i * ld + j] (i > j) and the pivot root to dg[j], so the trailing update of
+    // the same step still reads the unscaled column.
+    __shared__ double D[CB_NB * ld];
+    __shared__ double dg[CB_NB];
     if (info[0] != 0) return;                       // an earlier block already failed
     const int nb = min(CB_NB, n - k0);
-    const int ld = CB_NB + 1;
     const int tid = threadIdx.x;
-    if (tid == 0) status = 0;
+#ifdef CB_PROFILE
+    long long tk0 = clock64(), tk1, tk2;
+#endif
     for (int e = tid; e < nb * nb; e += CB_THREADS) {
         const int i = e / nb, j = e - i * nb;
         if (i >= j) D[j * ld + i] = A[(size_t)(k0 + i) * lda + k0 + j];
     }
     __syncthreads();
-    chol_smem(D, nb, ld, 0, &status);
-    if (status != 0) {
-        if (tid == 0) info[0] = k0 + status;
-        return;
+#ifdef CB_PROFILE
+    tk1 = clock64();
+#endif
+    // thread (ty, tx) of a 16 x 16 grid owns rows i = ty (mod 16) and columns j = tx (mod 16): no index division in the
+    // loop that runs once per pivot
+    const int ty = tid >> 4, tx = tid & 15;
+    for (int k = 0; k < nb; ++k) {
+        const double* colk = D + k * ld;
+        const double piv = colk[k];
+        // pivot <= 0 or +inf -> failure, NaN goes on: the rule of chol_smem (gp_linalg.cuh); every thread reads the
+        // same value, so the branch is uniform
+        if (piv <= 0.0 || piv == INFINITY) {
+            if (tid == 0) info[0] = k0 + k + 1;
+            return;
+        }
+        // sqrt(piv) and its reciprocal from one rsqrt + Newton steps (both within 1 ulp), as the batched kernel does:
+        // the n pivots are the critical path, an IEEE sqrt followed by an IEEE division is ~300 cycles each
+        double inv = rsqrt(piv);
+        double d = piv * inv;
+        d = fma(0.5 * inv, fma(-d, d, piv), d);
+        inv = fma(inv, fma(-d, inv, 1.0), inv);
+        if (tid == 0) dg[k] = d;
+        for (int i = k + 1 + tid; i < nb; i += CB_THREADS) D[i * ld + k] = colk[i] * inv;
+        double lj[4];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int j = tx + 16 * b;
+            lj[b] = (j > k && j < nb) ? colk[j] * inv : 0.0;
+        }
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const int i = ty + 16 * a;
+            if (i > k && i < nb) {
+                const double li = colk[i] * inv;
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const int j = tx + 16 * b;
+                    if (j > k && j <= i) D[j * ld + i] = fma(-li, lj[b], D[j * ld + i]);
+                }
+            }
+        }
+        __syncthreads();
     }
+#ifdef CB_PROFILE
+    tk2 = clock64();
+#endif
     for (int e = tid; e < nb * nb; e += CB_THREADS) {
         const int i = e / nb, j = e - i * nb;
-        if (i >= j) A[(size_t)(k0 + i) * lda + k0 + j] = D[j * ld + i];
-    }
-    // L^-1 column c by forward substitution (thread c), stored Linv[i*CB_NB + c] = (L^-1)[i][c]
-    for (int c = tid; c < CB_NB; c += CB_THREADS) {
-        for (int i = 0; i < CB_NB; ++i) {
-            double v = 0.0;
-            if (c < nb && i < nb && i >= c) {
-                double s = (i == c) ? 1.0 : 0.0;
-                for (int p = c; p < i; ++p) s = fma(-D[p * ld + i], Linv[p * CB_NB + c], s);
-                v = s / D[i * ld + i];
-            }
-            Linv[i * CB_NB + c] = v;
-        }
+        if (i >= j) A[(size_t)(k0 + i) * lda + k0 + j] = (i == j) ? dg[i] : D[i * ld + j];
     }
 }
 
-// (2) panel: rows [k0+64, n) of block column k0:  P[r][c] = sum_{p<=c} A[r][k0+p] * Linv[c][p]
+// (2) panel: rows [k0+64, n) of block column k0:  P L_kk^T = A, by forward substitution over the 64 columns (the
+// backward-stable TRSM; a product with an explicit L_kk^-1 loses cond(L_kk) eps).  A CTA owns 64 rows; four threads
+// share a row and split each dot product, so a column step is <= 16 FMAs, two shuffles and a __syncwarp -- the rows
+// of a warp never touch each other's data, no block barrier inside the loop.
+constexpr int CB_LDP = CB_NB + 1;
 __global__ void __launch_bounds__(CB_THREADS)
-cholb_panel_kernel(double* __restrict__ A, int lda, int n, int k0, const double* __restrict__ Linv,
-                   const int* __restrict__ info) {
+cholb_panel_kernel(double* __restrict__ A, int lda, int n, int k0, const int* __restrict__ info) {
     extern __shared__ __align__(16) double cb_sm[];
-    double* As = cb_sm;
-    double* Bs = cb_sm + CB_NB * CB_LDT;
+    double* Ps = cb_sm;                              // [64][65] rows of the panel tile
+    double* Ls = cb_sm + CB_NB * CB_LDP;             // [64][65] L_kk, Ls[c][p] = L[c][p], p <= c
+    __shared__ double idg[CB_NB];
     if (info[0] != 0) return;
+    const int tid = threadIdx.x;
     const int r0 = k0 + CB_NB + blockIdx.x * CB_NB;
-    stage_tile_kmajor(A, lda, r0, n, k0, As);
-    // Bs[p][c] = Linv[c][p]
-    for (int e = threadIdx.x; e < CB_NB * CB_NB; e += CB_THREADS) {
-        const int c = e / CB_NB, p = e - c * CB_NB;
-        Bs[p * CB_LDT + c] = Linv[c * CB_NB + p];
+    for (int e = tid; e < CB_NB * CB_NB; e += CB_THREADS) {
+        const int r = e >> 6, c = e & 63;
+        Ps[r * CB_LDP + c] = (r0 + r < n) ? A[(size_t)(r0 + r) * lda + k0 + c] : 0.0;
+        Ls[r * CB_LDP + c] = (c <= r) ? A[(size_t)(k0 + r) * lda + k0 + c] : 0.0;
     }
     __syncthreads();
-    const int ty = threadIdx.x / 16, tx = threadIdx.x % 16;
-    double acc[4][4] = {};
-    tile_mm(As, Bs, CB_NB, ty, tx, acc);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int r = r0 + 4 * ty + i;
-        if (r < n) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) A[(size_t)r * lda + k0 + 4 * tx + j] = acc[i][j];
-        }
+    if (tid < CB_NB) idg[tid] = 1.0 / Ls[tid * CB_LDP + tid];
+    __syncthreads();
+    const int r = tid >> 2, q = tid & 3;
+    double* prow = Ps + r * CB_LDP;
+    for (int c = 0; c < CB_NB; ++c) {
+        const double* lrow = Ls + c * CB_LDP;
+        double sacc = 0.0;
+        for (int p = q; p < c; p += 4) sacc = fma(prow[p], lrow[p], sacc);
+        sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
+        sacc += __shfl_xor_sync(0xffffffffu, sacc, 2);
+        if (q == 0) prow[c] = (prow[c] - sacc) * idg[c];
+        __syncwarp();
+    }
+    __syncthreads();
+    for (int e = tid; e < CB_NB * CB_NB; e += CB_THREADS) {
+        const int rr = e >> 6, c = e & 63;
+        if (r0 + rr < n) A[(size_t)(r0 + rr) * lda + k0 + c] = Ps[rr * CB_LDP + c];
     }
 }
 
@@ -163,18 +212,19 @@ extern "C" int b200id_chol_blocked(double* A, int n, int lda, int* info_out, voi
     cudaStream_t st = (cudaStream_t)stream;
     int rc = check_cuda(cudaMemsetAsync(info_out, 0, sizeof(int), st), "cudaMemsetAsync(info)");
     if (rc) return rc;
-    double* Linv = (double*)ws;
+    (void)ws;                                        // kept in the signature: earlier versions staged L_kk^-1 here
+    const size_t smem_panel = 2 * (size_t)CB_NB * CB_LDP * sizeof(double);
     const size_t smem = 2 * (size_t)CB_NB * CB_LDT * sizeof(double);
-    rc = check_cuda(cudaFuncSetAttribute(cholb_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute(panel)");
+    rc = check_cuda(cudaFuncSetAttribute(cholb_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_panel), "cudaFuncSetAttribute(panel)");
     if (rc) return rc;
     rc = check_cuda(cudaFuncSetAttribute(cholb_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute(syrk)");
     if (rc) return rc;
     for (int k0 = 0; k0 < n; k0 += CB_NB) {
-        cholb_diag_kernel<<<1, CB_THREADS, 0, st>>>(A, lda, n, k0, Linv, info_out);
+        cholb_diag_kernel<<<1, CB_THREADS, 0, st>>>(A, lda, n, k0, info_out);
         const int m = n - (k0 + CB_NB);
         if (m <= 0) break;
         const int tiles = (m + CB_NB - 1) / CB_NB;
-        cholb_panel_kernel<<<tiles, CB_THREADS, smem, st>>>(A, lda, n, k0, Linv, info_out);
+        cholb_panel_kernel<<<tiles, CB_THREADS, smem_panel, st>>>(A, lda, n, k0, info_out);
         cholb_syrk_kernel<<<tiles * (tiles + 1) / 2, CB_THREADS, smem, st>>>(A, lda, n, k0, info_out);
     }
     B200ID_LAUNCH_CHECK("chol_blocked kernels");

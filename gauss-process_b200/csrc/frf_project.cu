@@ -1035,6 +1035,21 @@ extern "C" int b200id_frf_project_uniform(const double* t, const double* u, cons
     return B200ID_OK;
 }
 
+extern "C" int b200id_frf_project_uniform_mma(const double* t, const double* u, const double* y, int64_t n,
+                                              int64_t own_begin, int64_t own_end, const double* w, int nd,
+                                              const double* sums, double inv_count, double t0, double dt,
+                                              double* partial_out, void* ws, size_t ws_bytes, void* stream) {
+    B200ID_REQUIRE(t && u && w && partial_out && ws, B200ID_E_ARG, "frf_project_uniform_mma: null pointer");
+    B200ID_REQUIRE(n >= 2 && nd > 0 && dt > 0.0, B200ID_E_ARG, "frf_project_uniform_mma: need n >= 2, nd > 0, dt > 0");
+    B200ID_REQUIRE(own_begin >= 0 && own_end <= n && own_begin < own_end, B200ID_E_ARG,
+                   "frf_project_uniform_mma: bad owned range [%lld,%lld) of %lld", (long long)own_begin, (long long)own_end, (long long)n);
+    B200ID_REQUIRE(y != nullptr, B200ID_E_UNSUPPORTED, "frf_project_uniform_mma: needs both signals");
+    const int rc = frf_project_mma_launch(t, u, y, n, own_begin, own_end, w, nd, sums, inv_count, t0, dt, partial_out, ws, ws_bytes,
+                                          (cudaStream_t)stream);
+    B200ID_REQUIRE(rc != 1, B200ID_E_UNSUPPORTED, "frf_project_uniform_mma: shape not covered (nd=%d, workspace %zu)", nd, ws_bytes);
+    return rc;
+}
+
 extern "C" int b200id_frf_finalize(const double* partial, int nd, double scale, double* U_out,
                                    double* Y_out, void* stream) {
     B200ID_REQUIRE(partial && U_out && nd > 0, B200ID_E_ARG, "frf_finalize: bad argument");

@@ -262,30 +262,79 @@ int b200id_gp_fit_large(int kernel_id, const double* theta, const double* X, con
 extern "C" int b200id_gp_predict(int kernel_id, const double* theta, const double* X, int n, const double* alpha,
                                  const double* Kinv, const double* Xs, int m, double* mean_out, double* std_out, void* stream);
 
-// candidate metrics for n > 160: candidates are factorised one after another (one to a few per GPU)
+// candidate metrics for n > 160.  One factorisation is a chain of ~100 short, mutually dependent launches (n / 64
+// block columns x diag / panel / update), i.e. latency bound; candidates are independent, so up to GL_LANES of them
+// run side by side on internal streams, each with its own workspace slice, forked from and joined back into the
+// caller's stream with events (no host synchronisation; capturable).  Lanes are created once per process.
+constexpr int GL_LANES = 8;
+static cudaStream_t g_lane[GL_LANES];
+static cudaEvent_t g_lane_done[GL_LANES], g_fork;
+static int g_lanes_dev = -1;
+static int ensure_lanes() {
+    int dev = 0;
+    int rc = check_cuda(cudaGetDevice(&dev), "cudaGetDevice");
+    if (rc) return rc;
+    if (g_lanes_dev == dev) return B200ID_OK;
+    B200ID_REQUIRE(g_lanes_dev < 0, B200ID_E_UNSUPPORTED, "gp_batch_eval(large n): lanes belong to device %d, called on %d", g_lanes_dev, dev);
+    for (int s = 0; s < GL_LANES; ++s) {
+        rc = check_cuda(cudaStreamCreateWithFlags(&g_lane[s], cudaStreamNonBlocking), "cudaStreamCreate(lane)");
+        if (rc) return rc;
+        rc = check_cuda(cudaEventCreateWithFlags(&g_lane_done[s], cudaEventDisableTiming), "cudaEventCreate(lane)");
+        if (rc) return rc;
+    }
+    rc = check_cuda(cudaEventCreateWithFlags(&g_fork, cudaEventDisableTiming), "cudaEventCreate(fork)");
+    if (rc) return rc;
+    g_lanes_dev = dev;
+    return B200ID_OK;
+}
+
 int b200id_gp_batch_eval_large(int kernel_id, const int* kernel_ids_host_or_null, const double* theta, int64_t n_candidates,
                                const double* X, const double* y, int n, double noise, int metric, const double* Xv,
                                const double* yv, int nv, double y_mean, double y_scale, double* metric_out,
                                const double* noise_v, void* ws, size_t ws_bytes, cudaStream_t st) {
     B200ID_REQUIRE(kernel_ids_host_or_null == nullptr, B200ID_E_UNSUPPORTED, "gp_batch_eval(large n): per-candidate kernel ids are not supported");
-    const size_t need = b200id_gp_large_workspace_bytes(n, nv) + 256;
-    B200ID_REQUIRE(ws_bytes >= need, B200ID_E_WORKSPACE, "gp_batch_eval(large n): workspace %zu < %zu", ws_bytes, need);
-    const LargeWs w = carve(ws, n, nv);
-    int* info = (int*)((char*)w.chol_ws + w.chol_bytes);
+    const size_t slice = align_up(b200id_gp_large_workspace_bytes(n, nv) + 256, 256);
+    B200ID_REQUIRE(ws_bytes >= slice, B200ID_E_WORKSPACE, "gp_batch_eval(large n): workspace %zu < %zu", ws_bytes, slice);
+    int lanes = (int)(ws_bytes / slice);
+    if (lanes > GL_LANES) lanes = GL_LANES;
+    if ((int64_t)lanes > n_candidates) lanes = (int)n_candidates;
     const bool val = metric == B200ID_METRIC_VAL_RMSE;
-    for (int64_t c = 0; c < n_candidates; ++c) {
-        const double* th = theta + c * B200ID_MAX_PARAMS;
-        int rc = large_factor(kernel_id, th, X, n, noise, w, info, st, noise_v ? noise_v + c : nullptr);
+    int rc = B200ID_OK;
+    if (lanes > 1) {
+        rc = ensure_lanes();
         if (rc) return rc;
-        // alpha lives in `work` (in place) when the validation metric needs it
-        gl_solve_kernel<<<1, GL_THREADS, 0, st>>>(w.A, n, y, info, val ? w.work : nullptr, w.terms, w.work);
-        B200ID_LAUNCH_CHECK("gl_solve_kernel");
-        if (val) {
-            rc = b200id_gp_predict(kernel_id, th, X, n, w.work, nullptr, Xv, nv, w.pred, nullptr, (void*)st);
+        rc = check_cuda(cudaEventRecord(g_fork, st), "cudaEventRecord(fork)");
+        if (rc) return rc;
+        for (int s = 0; s < lanes; ++s) {
+            rc = check_cuda(cudaStreamWaitEvent(g_lane[s], g_fork, 0), "cudaStreamWaitEvent(fork)");
             if (rc) return rc;
         }
-        gl_metric_kernel<<<1, 256, 0, st>>>(metric, n, info, w.terms, w.pred, yv, nv, y_mean, y_scale, metric_out + c);
+    }
+    for (int64_t c = 0; c < n_candidates; ++c) {
+        const int s = (int)(c % lanes);
+        cudaStream_t ls = lanes > 1 ? g_lane[s] : st;
+        const LargeWs w = carve((char*)ws + (size_t)s * slice, n, nv);
+        int* info = (int*)((char*)w.chol_ws + w.chol_bytes);
+        const double* th = theta + c * B200ID_MAX_PARAMS;
+        rc = large_factor(kernel_id, th, X, n, noise, w, info, ls, noise_v ? noise_v + c : nullptr);
+        if (rc) return rc;
+        // alpha lives in `work` (in place) when the validation metric needs it
+        gl_solve_kernel<<<1, GL_THREADS, 0, ls>>>(w.A, n, y, info, val ? w.work : nullptr, w.terms, w.work);
+        B200ID_LAUNCH_CHECK("gl_solve_kernel");
+        if (val) {
+            rc = b200id_gp_predict(kernel_id, th, X, n, w.work, nullptr, Xv, nv, w.pred, nullptr, (void*)ls);
+            if (rc) return rc;
+        }
+        gl_metric_kernel<<<1, 256, 0, ls>>>(metric, n, info, w.terms, w.pred, yv, nv, y_mean, y_scale, metric_out + c);
         B200ID_LAUNCH_CHECK("gl_metric_kernel");
+    }
+    if (lanes > 1) {
+        for (int s = 0; s < lanes; ++s) {
+            rc = check_cuda(cudaEventRecord(g_lane_done[s], g_lane[s]), "cudaEventRecord(lane)");
+            if (rc) return rc;
+            rc = check_cuda(cudaStreamWaitEvent(st, g_lane_done[s], 0), "cudaStreamWaitEvent(join)");
+            if (rc) return rc;
+        }
     }
     return B200ID_OK;
 }

@@ -104,6 +104,17 @@ int b200id_frf_project_uniform(const double* t, const double* u, const double* y
                                const double* sums /*[2] or NULL*/, double inv_count, double t0, double dt,
                                double* partial_out /*[4*nd]*/, void* ws, size_t ws_bytes, void* stream);
 
+/* EXPERIMENTAL alternative evaluation of b200id_frf_project_uniform (same arguments, same outputs, same
+ * reference lines frf_estimator.py:226-231): the exact-phase part as a blocked FP64 matrix product on
+ * mma.sync.m8n8k4.f64 and the reference's per-sample phase rounding as a fixed-point / FP32 correction
+ * (csrc/frf_mma.cuh).  Needs y != NULL and nd <= 160, else B200ID_E_UNSUPPORTED.  Parity-tested against the
+ * recurrence kernels; currently slower than them, so b200id_frf_project_uniform only takes
+ * this route when the environment has B200ID_FRF_MMA=1. */
+int b200id_frf_project_uniform_mma(const double* t, const double* u, const double* y, int64_t n,
+                                   int64_t own_begin, int64_t own_end, const double* w, int nd,
+                                   const double* sums /*[2] or NULL*/, double inv_count, double t0, double dt,
+                                   double* partial_out /*[4*nd]*/, void* ws, size_t ws_bytes, void* stream);
+
 /* Selected DFT bins of a windowed, mean-removed record: what the Fourier estimator needs of its two n-point
  * FFTs (fourier_estimator.py:120-223 feeding np.interp at transform.py:160-181 -- only the FFT bins either
  * side of each grid frequency are ever read).  For k = bins[b] (0 <= k < n_fft):

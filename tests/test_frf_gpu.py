@@ -321,3 +321,39 @@ def test_cross_power_sums_and_gp_targets(frf, nd, R):
     sums[:] = torch.cat([torch.full((nd,), 2.0), torch.full((nd,), -3.0), torch.ones(nd)]).to(dev)
     _, stats, y_re, _ = frf.gp_targets_device(sums, nd, standardise=True)
     assert stats.cpu().tolist() == [2.0, -3.0, 1.0, 1.0] and float(y_re.abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("n,nd,kind,t_shift", [(200_000, 100, "multisine", 0.0), (300_001, 150, "square", 0.0),
+                                               (100_000, 50, "multisine", 1.9e6), (65_537, 150, "square", 123.4567),
+                                               (4_097, 7, "multisine", 0.0), (70_000, 160, "square", -33.3)])
+def test_matrix_product_path_matches_recurrence_and_oracle(frf, n, nd, kind, t_shift):
+    """The experimental block-phasor evaluation (FP64 mma.sync main term + fixed-point rounding correction,
+    b200id_frf_project_uniform_mma) against the recurrence kernels and the oracle: weak bins of the square-wave
+    record, phases ~1e9 rad, ragged tiles, nd not a multiple of 4, the largest supported nd, negative times."""
+    from b200id import synth
+    from b200id.runtime import require_cuda, to_device
+    dev = require_cuda()
+    t, u, y = synth.make_record(n, min(nd, 100), kind, seed=5)
+    t = t + t_shift
+    _, w = ofrf.freq_grid(nd)
+    span = float(t[-1] - t[0])
+    t_d, u_d, y_d, w_d = (to_device(a, dev) for a in (t, u, y, w))
+    t0, dt = float(t[0]), span / (n - 1)
+    sums = frf.moments_device(u_d, y_d, (0, n))
+    a = frf.project_uniform_mma_device(t_d, u_d, y_d, w_d, t0, dt, (0, n), sums, 1.0 / n)
+    b = frf.project_uniform_device(t_d, u_d, y_d, w_d, t0, dt, (0, n), sums, 1.0 / n)
+    Ua, Ya = (x.cpu().numpy() for x in frf.finalize_device(a, nd, 2.0 / span))
+    Ub, Yb = (x.cpu().numpy() for x in frf.finalize_device(b, nd, 2.0 / span))
+    e_r = record(f"frf.mma.{kind}.n{n}.nd{nd}.shift{t_shift:g}.vs_recurrence", max(rel_each(Ua, Ub), rel_each(Ya, Yb)))
+    Ur, Yr = ofrf.demod_trapz(t, u, w, threads=8), ofrf.demod_trapz(t, y, w, threads=8)
+    e_o = record(f"frf.mma.{kind}.n{n}.nd{nd}.shift{t_shift:g}.vs_oracle", max(rel_each(Ua, Ur), rel_each(Ya, Yr)))
+    assert e_r < TOL and e_o < TOL
+    # owned sub-ranges add up (the streamed upload and the time-segment shards use them)
+    cut = n // 3 + 5
+    a1 = frf.project_uniform_mma_device(t_d, u_d, y_d, w_d, t0, dt, (0, cut), sums, 1.0 / n)
+    a2 = frf.project_uniform_mma_device(t_d, u_d, y_d, w_d, t0, dt, (cut, n), sums, 1.0 / n)
+    scale = float(a.abs().max())
+    assert record(f"frf.mma.{kind}.n{n}.segments", float((a1 + a2 - a).abs().max()) / scale) < 1e-12
+    again = frf.project_uniform_mma_device(t_d, u_d, y_d, w_d, t0, dt, (0, n), sums, 1.0 / n)
+    import torch
+    assert torch.equal(again, a), "the matrix-product path must be deterministic run to run"

@@ -41,9 +41,20 @@ __device__ __forceinline__ void tile_mm(const double* __restrict__ As, const dou
 // Rows >= r_end are zero filled.
 __device__ __forceinline__ void stage_tile_kmajor(const double* __restrict__ M, int ld, int r0, int r_end, int c0,
                                                   double* __restrict__ T) {
-    for (int e = threadIdx.x; e < CB_NB * CB_NB; e += CB_THREADS) {
-        const int r = e / CB_NB, k = e - r * CB_NB;
-        T[k * CB_LDT + r] = (r0 + r < r_end) ? M[(size_t)(r0 + r) * ld + c0 + k] : 0.0;
+    // all 16 global loads of a thread are issued before the first shared-memory store, so their latencies overlap
+    constexpr int PER = CB_NB * CB_NB / CB_THREADS;
+    double v[PER];
+#pragma unroll
+    for (int it = 0; it < PER; ++it) {
+        const int e = threadIdx.x + it * CB_THREADS;
+        const int r = e >> 6, k = e & 63;
+        v[it] = (r0 + r < r_end) ? __ldg(M + (size_t)(r0 + r) * ld + c0 + k) : 0.0;
+    }
+#pragma unroll
+    for (int it = 0; it < PER; ++it) {
+        const int e = threadIdx.x + it * CB_THREADS;
+        const int r = e >> 6, k = e & 63;
+        T[k * CB_LDT + r] = v[it];
     }
 }
 
@@ -66,9 +77,21 @@ cholb_diag_kernel(double* __restrict__ A, int lda, int n, int k0, int* __restric
 #ifdef CB_PROFILE
     long long tk0 = clock64(), tk1, tk2;
 #endif
-    for (int e = tid; e < nb * nb; e += CB_THREADS) {
-        const int i = e / nb, j = e - i * nb;
-        if (i >= j) D[j * ld + i] = A[(size_t)(k0 + i) * lda + k0 + j];
+    {
+        constexpr int PER = CB_NB * CB_NB / CB_THREADS;
+        double v[PER];
+#pragma unroll
+        for (int it = 0; it < PER; ++it) {
+            const int e = tid + it * CB_THREADS;
+            const int i = e >> 6, j = e & 63;
+            v[it] = (i < nb && j <= i) ? A[(size_t)(k0 + i) * lda + k0 + j] : 0.0;
+        }
+#pragma unroll
+        for (int it = 0; it < PER; ++it) {
+            const int e = tid + it * CB_THREADS;
+            const int i = e >> 6, j = e & 63;
+            if (i < nb && j <= i) D[j * ld + i] = v[it];
+        }
     }
     __syncthreads();
 #ifdef CB_PROFILE
@@ -77,7 +100,13 @@ cholb_diag_kernel(double* __restrict__ A, int lda, int n, int k0, int* __restric
     // thread (ty, tx) of a 16 x 16 grid owns rows i = ty (mod 16) and columns j = tx (mod 16): no index division in the
     // loop that runs once per pivot
     const int ty = tid >> 4, tx = tid & 15;
+#ifdef CB_PROFILE
+    long long c_piv = 0, c_upd = 0, c_bar = 0;
+#endif
     for (int k = 0; k < nb; ++k) {
+#ifdef CB_PROFILE
+        const long long q0 = clock64();
+#endif
         const double* colk = D + k * ld;
         const double piv = colk[k];
         // pivot <= 0 or +inf -> failure, NaN goes on: the rule of chol_smem (gp_linalg.cuh); every thread reads the
@@ -86,36 +115,68 @@ cholb_diag_kernel(double* __restrict__ A, int lda, int n, int k0, int* __restric
             if (tid == 0) info[0] = k0 + k + 1;
             return;
         }
-        // sqrt(piv) and its reciprocal from one rsqrt + Newton steps (both within 1 ulp), as the batched kernel does:
-        // the n pivots are the critical path, an IEEE sqrt followed by an IEEE division is ~300 cycles each
-        double inv = rsqrt(piv);
-        double d = piv * inv;
-        d = fma(0.5 * inv, fma(-d, d, piv), d);
-        inv = fma(inv, fma(-d, inv, 1.0), inv);
-        if (tid == 0) dg[k] = d;
-        for (int i = k + 1 + tid; i < nb; i += CB_THREADS) D[i * ld + k] = colk[i] * inv;
-        double lj[4];
+        // 1 / sqrt(piv): hardware approximation (2^-22) + two Newton steps -- the shortest dependent chain that reaches
+        // 1 ulp; the root itself (only stored) is taken off the critical path
+        double inv;
+        asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(inv) : "d"(piv));
+        inv = fma(0.5 * inv, fma(-piv * inv, inv, 1.0), inv);
+        inv = fma(0.5 * inv, fma(-piv * inv, inv, 1.0), inv);
+        if (tid == 0) {
+            double d = piv * inv;
+            d = fma(0.5 * inv, fma(-d, d, piv), d);
+            dg[k] = d;
+        }
+#ifdef CB_PROFILE
+        const long long q1 = clock64() + (long long)(inv == 123.456);
+#endif
+        // loads first, then the FMAs, then the stores: a shared-memory store keeps the compiler from moving later loads
+        // of the same array above it, which would serialise the 16 element updates of a thread
+        double lj[4], li[4], dv[4][4];
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
             const int j = tx + 16 * b;
-            lj[b] = (j > k && j < nb) ? colk[j] * inv : 0.0;
+            lj[b] = (j > k && j < nb) ? colk[j] : 0.0;
         }
 #pragma unroll
         for (int a = 0; a < 4; ++a) {
             const int i = ty + 16 * a;
-            if (i > k && i < nb) {
-                const double li = colk[i] * inv;
+            li[a] = (i > k && i < nb) ? colk[i] : 0.0;
 #pragma unroll
-                for (int b = 0; b < 4; ++b) {
-                    const int j = tx + 16 * b;
-                    if (j > k && j <= i) D[j * ld + i] = fma(-li, lj[b], D[j * ld + i]);
-                }
+            for (int b = 0; b < 4; ++b) {
+                const int j = tx + 16 * b;
+                dv[a][b] = (i > k && i < nb && j > k && j <= i) ? D[j * ld + i] : 0.0;
             }
         }
+        const double lnew = (k + 1 + tid < nb) ? colk[k + 1 + tid] * inv : 0.0;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) lj[b] *= inv;
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            li[a] *= inv;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) dv[a][b] = fma(-li[a], lj[b], dv[a][b]);
+        }
+        if (k + 1 + tid < nb) D[(k + 1 + tid) * ld + k] = lnew;
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const int i = ty + 16 * a;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const int j = tx + 16 * b;
+                if (i > k && i < nb && j > k && j <= i) D[j * ld + i] = dv[a][b];
+            }
+        }
+#ifdef CB_PROFILE
+        const long long q2 = clock64();
+#endif
         __syncthreads();
+#ifdef CB_PROFILE
+        c_piv += q1 - q0; c_upd += q2 - q1; c_bar += clock64() - q2;
+#endif
     }
 #ifdef CB_PROFILE
     tk2 = clock64();
+    if (tid == 0 && k0 == 64) printf("diag cycles: load %lld factor %lld (pivot %lld update %lld barrier %lld)\n", tk1 - tk0, tk2 - tk1, c_piv, c_upd, c_bar);
 #endif
     for (int e = tid; e < nb * nb; e += CB_THREADS) {
         const int i = e / nb, j = e - i * nb;
@@ -137,26 +198,62 @@ cholb_panel_kernel(double* __restrict__ A, int lda, int n, int k0, const int* __
     if (info[0] != 0) return;
     const int tid = threadIdx.x;
     const int r0 = k0 + CB_NB + blockIdx.x * CB_NB;
-    for (int e = tid; e < CB_NB * CB_NB; e += CB_THREADS) {
-        const int r = e >> 6, c = e & 63;
-        Ps[r * CB_LDP + c] = (r0 + r < n) ? A[(size_t)(r0 + r) * lda + k0 + c] : 0.0;
-        Ls[r * CB_LDP + c] = (c <= r) ? A[(size_t)(k0 + r) * lda + k0 + c] : 0.0;
+#ifdef CB_PROFILE
+    const long long pk0 = clock64();
+#endif
+    {
+        constexpr int PER = CB_NB * CB_NB / CB_THREADS;
+        double vp[PER], vl[PER];
+#pragma unroll
+        for (int it = 0; it < PER; ++it) {
+            const int e = tid + it * CB_THREADS;
+            const int r = e >> 6, c = e & 63;
+            vp[it] = (r0 + r < n) ? A[(size_t)(r0 + r) * lda + k0 + c] : 0.0;
+            vl[it] = (c <= r) ? A[(size_t)(k0 + r) * lda + k0 + c] : 0.0;
+        }
+#pragma unroll
+        for (int it = 0; it < PER; ++it) {
+            const int e = tid + it * CB_THREADS;
+            const int r = e >> 6, c = e & 63;
+            Ps[r * CB_LDP + c] = vp[it];
+            Ls[r * CB_LDP + c] = vl[it];
+        }
     }
     __syncthreads();
     if (tid < CB_NB) idg[tid] = 1.0 / Ls[tid * CB_LDP + tid];
     __syncthreads();
+#ifdef CB_PROFILE
+    const long long pk1 = clock64();
+#endif
+    // thread (r, q) keeps P[r][q], P[r][q + 4], ... in registers (column loop fully unrolled, so the indices are
+    // static); L_kk rows are read-only broadcast loads that never wait for a store
     const int r = tid >> 2, q = tid & 3;
-    double* prow = Ps + r * CB_LDP;
+    double pr[CB_NB / 4];
+#pragma unroll
+    for (int m = 0; m < CB_NB / 4; ++m) pr[m] = Ps[r * CB_LDP + 4 * m + q];
+#pragma unroll
     for (int c = 0; c < CB_NB; ++c) {
-        const double* lrow = Ls + c * CB_LDP;
-        double sacc = 0.0;
-        for (int p = q; p < c; p += 4) sacc = fma(prow[p], lrow[p], sacc);
+        const double* lrow = Ls + c * CB_LDP + q;
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+        for (int m = 0; m < CB_NB / 4; ++m) {
+            if (4 * m < c) {                         // compile-time bound on m; the lane's own column p = 4 m + q must be < c
+                const double lv = (4 * m + q < c) ? lrow[4 * m] : 0.0;
+                if (m & 1) s1 = fma(pr[m], lv, s1);
+                else s0 = fma(pr[m], lv, s0);
+            }
+        }
+        double sacc = s0 + s1;
         sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
         sacc += __shfl_xor_sync(0xffffffffu, sacc, 2);
-        if (q == 0) prow[c] = (prow[c] - sacc) * idg[c];
-        __syncwarp();
+        if (q == (c & 3)) pr[c >> 2] = (pr[c >> 2] - sacc) * idg[c];
     }
+#pragma unroll
+    for (int m = 0; m < CB_NB / 4; ++m) Ps[r * CB_LDP + 4 * m + q] = pr[m];
     __syncthreads();
+#ifdef CB_PROFILE
+    if (tid == 0 && k0 == 64 && blockIdx.x == 0) printf("panel cycles: load %lld solve %lld\n", pk1 - pk0, clock64() - pk1);
+#endif
     for (int e = tid; e < CB_NB * CB_NB; e += CB_THREADS) {
         const int rr = e >> 6, c = e & 63;
         if (r0 + rr < n) A[(size_t)(r0 + rr) * lda + k0 + c] = Ps[rr * CB_LDP + c];
@@ -184,14 +281,23 @@ cholb_syrk_kernel(double* __restrict__ A, int lda, int n, int k0, const int* __r
     const int ty = threadIdx.x / 16, tx = threadIdx.x % 16;
     double acc[4][4] = {};
     tile_mm(As, Bs, CB_NB, ty, tx, acc);
+    double cv[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int r = r0 + 4 * ty + i;
-        if (r >= n) continue;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int c = c0 + 4 * tx + j;
-            if (c <= r) A[(size_t)r * lda + c] -= acc[i][j];
+            cv[i][j] = (r < n && c <= r) ? A[(size_t)r * lda + c] : 0.0;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int r = r0 + 4 * ty + i;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int c = c0 + 4 * tx + j;
+            if (r < n && c <= r) A[(size_t)r * lda + c] = cv[i][j] - acc[i][j];
         }
     }
 }

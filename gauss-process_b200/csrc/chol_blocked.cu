@@ -4,12 +4,14 @@
 // too large for one CTA's shared memory.  Right-looking blocked algorithm on the row-major lower
 // triangle in global memory (32 MB at n = 2048, i.e. L2 resident on B200):
 //   for each 64-wide block column k:
-//     (1) diag : one CTA factorises the 64x64 diagonal block in shared memory and inverts L_kk
-//     (2) panel: P = A[k+64:, k:k+64] L_kk^-T          -- 64x64x64 FP64 tile products
-//     (3) syrk : A[i,j] -= P_i P_j^T for tiles i >= j  -- 64x64x64 FP64 tile products
-// Steps (2) and (3) share one register-tiled micro-kernel: 256 threads, each a 4x4 block of the
-// 64x64 output tile, operands staged k-major in shared memory so that a thread's 4 rows / 4 columns
-// are one 32-byte vector load and the FP64 pipe (16 DFMA per 8 loaded doubles) is the bound.
+//     (1) diag : one CTA factorises the 64x64 diagonal block in shared memory (fused into step (3) of the block
+//                column before, except for the first)
+//     (2) panel: P L_kk^T = A[k+64:, k:k+64] by substitution, the row held in registers
+//     (3) syrk : A[i,j] -= P_i P_j^T for tiles i >= j  -- 64x64x64 FP64 tile products, 256 threads, each a 4x4 block
+//                of the output tile, operands staged k-major in shared memory (one 32-byte vector load per 4 rows /
+//                4 columns, 16 DFMA per 8 loaded doubles)
+// One factorisation is a chain of 2 n / 64 dependent launches, i.e. latency bound at n = 2048 (1.9 ms where the flops
+// alone would take 0.1 ms); throughput comes from running several candidates side by side (gp_large.cu).
 #include "common.cuh"
 #include "gp_linalg.cuh"
 
@@ -63,57 +65,26 @@ __device__ __forceinline__ void stage_tile_kmajor(const double* __restrict__ M, 
 // right-looking with ONE barrier per column -- the scaled column goes to the unused upper triangle, so nobody
 // overwrites what the trailing update of the same step still reads; each thread forms l_i = a_ik * (1/d) itself (the
 // same product the scaled column holds: potf2's SCAL + SYR arithmetic).
-__global__ void __launch_bounds__(CB_THREADS)
-cholb_diag_kernel(double* __restrict__ A, int lda, int n, int k0, int* __restrict__ info) {
-    constexpr int ld = CB_NB + 1;
-    // Lower triangle, column-major D[j * ld + i] (i >= j): the working copy; once column j is final its scaled copy
-    // L[i][j] goes to the UPPER triangle at D[i * ld + j] (i > j) and the pivot root to dg[j], so the trailing update of
-    // the same step still reads the unscaled column.
-    __shared__ double D[CB_NB * ld];
-    __shared__ double dg[CB_NB];
-    if (info[0] != 0) return;                       // an earlier block already failed
-    const int nb = min(CB_NB, n - k0);
+constexpr int CB_LDD = CB_NB + 1;
+// Factorises the nb x nb block held in D (lower triangle, column-major D[j * CB_LDD + i]) and writes L to
+// A[k0 + i][k0 + j].  Once column j is final its scaled copy L[i][j] goes to the UPPER triangle at D[i * CB_LDD + j]
+// (i > j) and the pivot root to dg[j], so the trailing update of the same step still reads the unscaled column.
+// All CB_THREADS threads call; D must be complete (caller synchronised).  Returns false on a failed pivot.
+__device__ __forceinline__ bool cholb_factor_block(double* __restrict__ D, double* __restrict__ dg, int nb,
+                                                   double* __restrict__ A, int lda, int k0, int* __restrict__ info) {
+    constexpr int ld = CB_LDD;
     const int tid = threadIdx.x;
-#ifdef CB_PROFILE
-    long long tk0 = clock64(), tk1, tk2;
-#endif
-    {
-        constexpr int PER = CB_NB * CB_NB / CB_THREADS;
-        double v[PER];
-#pragma unroll
-        for (int it = 0; it < PER; ++it) {
-            const int e = tid + it * CB_THREADS;
-            const int i = e >> 6, j = e & 63;
-            v[it] = (i < nb && j <= i) ? A[(size_t)(k0 + i) * lda + k0 + j] : 0.0;
-        }
-#pragma unroll
-        for (int it = 0; it < PER; ++it) {
-            const int e = tid + it * CB_THREADS;
-            const int i = e >> 6, j = e & 63;
-            if (i < nb && j <= i) D[j * ld + i] = v[it];
-        }
-    }
-    __syncthreads();
-#ifdef CB_PROFILE
-    tk1 = clock64();
-#endif
     // thread (ty, tx) of a 16 x 16 grid owns rows i = ty (mod 16) and columns j = tx (mod 16): no index division in the
     // loop that runs once per pivot
     const int ty = tid >> 4, tx = tid & 15;
-#ifdef CB_PROFILE
-    long long c_piv = 0, c_upd = 0, c_bar = 0;
-#endif
     for (int k = 0; k < nb; ++k) {
-#ifdef CB_PROFILE
-        const long long q0 = clock64();
-#endif
         const double* colk = D + k * ld;
         const double piv = colk[k];
         // pivot <= 0 or +inf -> failure, NaN goes on: the rule of chol_smem (gp_linalg.cuh); every thread reads the
         // same value, so the branch is uniform
         if (piv <= 0.0 || piv == INFINITY) {
             if (tid == 0) info[0] = k0 + k + 1;
-            return;
+            return false;
         }
         // 1 / sqrt(piv): hardware approximation (2^-22) + two Newton steps -- the shortest dependent chain that reaches
         // 1 ulp; the root itself (only stored) is taken off the critical path
@@ -126,9 +97,6 @@ cholb_diag_kernel(double* __restrict__ A, int lda, int n, int k0, int* __restric
             d = fma(0.5 * inv, fma(-d, d, piv), d);
             dg[k] = d;
         }
-#ifdef CB_PROFILE
-        const long long q1 = clock64() + (long long)(inv == 123.456);
-#endif
         // loads first, then the FMAs, then the stores: a shared-memory store keeps the compiler from moving later loads
         // of the same array above it, which would serialise the 16 element updates of a thread
         double lj[4], li[4], dv[4][4];
@@ -166,22 +134,40 @@ cholb_diag_kernel(double* __restrict__ A, int lda, int n, int k0, int* __restric
                 if (i > k && i < nb && j > k && j <= i) D[j * ld + i] = dv[a][b];
             }
         }
-#ifdef CB_PROFILE
-        const long long q2 = clock64();
-#endif
         __syncthreads();
-#ifdef CB_PROFILE
-        c_piv += q1 - q0; c_upd += q2 - q1; c_bar += clock64() - q2;
-#endif
     }
-#ifdef CB_PROFILE
-    tk2 = clock64();
-    if (tid == 0 && k0 == 64) printf("diag cycles: load %lld factor %lld (pivot %lld update %lld barrier %lld)\n", tk1 - tk0, tk2 - tk1, c_piv, c_upd, c_bar);
-#endif
-    for (int e = tid; e < nb * nb; e += CB_THREADS) {
-        const int i = e / nb, j = e - i * nb;
-        if (i >= j) A[(size_t)(k0 + i) * lda + k0 + j] = (i == j) ? dg[i] : D[i * ld + j];
+    for (int e = tid; e < CB_NB * CB_NB; e += CB_THREADS) {
+        const int i = e >> 6, j = e & 63;
+        if (i < nb && j <= i) A[(size_t)(k0 + i) * lda + k0 + j] = (i == j) ? dg[i] : D[i * ld + j];
     }
+    return true;
+}
+
+__global__ void __launch_bounds__(CB_THREADS)
+cholb_diag_kernel(double* __restrict__ A, int lda, int n, int k0, int* __restrict__ info) {
+    __shared__ double D[CB_NB * CB_LDD];
+    __shared__ double dg[CB_NB];
+    if (info[0] != 0) return;                       // an earlier block already failed
+    const int nb = min(CB_NB, n - k0);
+    const int tid = threadIdx.x;
+    {
+        constexpr int PER = CB_NB * CB_NB / CB_THREADS;
+        double v[PER];
+#pragma unroll
+        for (int it = 0; it < PER; ++it) {
+            const int e = tid + it * CB_THREADS;
+            const int i = e >> 6, j = e & 63;
+            v[it] = (i < nb && j <= i) ? A[(size_t)(k0 + i) * lda + k0 + j] : 0.0;
+        }
+#pragma unroll
+        for (int it = 0; it < PER; ++it) {
+            const int e = tid + it * CB_THREADS;
+            const int i = e >> 6, j = e & 63;
+            if (i < nb && j <= i) D[j * CB_LDD + i] = v[it];
+        }
+    }
+    __syncthreads();
+    cholb_factor_block(D, dg, nb, A, lda, k0, info);
 }
 
 // (2) panel: rows [k0+64, n) of block column k0:  P L_kk^T = A, by forward substitution over the 64 columns (the
@@ -198,9 +184,6 @@ cholb_panel_kernel(double* __restrict__ A, int lda, int n, int k0, const int* __
     if (info[0] != 0) return;
     const int tid = threadIdx.x;
     const int r0 = k0 + CB_NB + blockIdx.x * CB_NB;
-#ifdef CB_PROFILE
-    const long long pk0 = clock64();
-#endif
     {
         constexpr int PER = CB_NB * CB_NB / CB_THREADS;
         double vp[PER], vl[PER];
@@ -222,9 +205,6 @@ cholb_panel_kernel(double* __restrict__ A, int lda, int n, int k0, const int* __
     __syncthreads();
     if (tid < CB_NB) idg[tid] = 1.0 / Ls[tid * CB_LDP + tid];
     __syncthreads();
-#ifdef CB_PROFILE
-    const long long pk1 = clock64();
-#endif
     // thread (r, q) keeps P[r][q], P[r][q + 4], ... in registers (column loop fully unrolled, so the indices are
     // static); L_kk rows are read-only broadcast loads that never wait for a store
     const int r = tid >> 2, q = tid & 3;
@@ -251,9 +231,6 @@ cholb_panel_kernel(double* __restrict__ A, int lda, int n, int k0, const int* __
 #pragma unroll
     for (int m = 0; m < CB_NB / 4; ++m) Ps[r * CB_LDP + 4 * m + q] = pr[m];
     __syncthreads();
-#ifdef CB_PROFILE
-    if (tid == 0 && k0 == 64 && blockIdx.x == 0) printf("panel cycles: load %lld solve %lld\n", pk1 - pk0, clock64() - pk1);
-#endif
     for (int e = tid; e < CB_NB * CB_NB; e += CB_THREADS) {
         const int rr = e >> 6, c = e & 63;
         if (r0 + rr < n) A[(size_t)(r0 + rr) * lda + k0 + c] = Ps[rr * CB_LDP + c];
@@ -262,7 +239,7 @@ cholb_panel_kernel(double* __restrict__ A, int lda, int n, int k0, const int* __
 
 // (3) trailing update over lower-triangle tiles (ti >= tj) of the matrix starting at s = k0 + 64
 __global__ void __launch_bounds__(CB_THREADS)
-cholb_syrk_kernel(double* __restrict__ A, int lda, int n, int k0, const int* __restrict__ info) {
+cholb_syrk_kernel(double* __restrict__ A, int lda, int n, int k0, int* __restrict__ info) {
     extern __shared__ __align__(16) double cb_sm[];
     double* As = cb_sm;
     double* Bs = cb_sm + CB_NB * CB_LDT;
@@ -290,6 +267,26 @@ cholb_syrk_kernel(double* __restrict__ A, int lda, int n, int k0, const int* __r
             const int c = c0 + 4 * tx + j;
             cv[i][j] = (r < n && c <= r) ? A[(size_t)r * lda + c] : 0.0;
         }
+    }
+    if (lin == 0) {
+        // tile (0, 0) of the trailing matrix is the NEXT diagonal block: factorise it here instead of in a launch of
+        // its own (the other CTAs of this launch do not depend on it, the next launch sees it finished) -- one link
+        // less in the chain of dependent launches per block column
+        __syncthreads();                             // everybody is done with the staged operands
+        double* D = cb_sm;                           // reuses the operand tiles: 64 x 65 doubles + 64
+        double* dg = cb_sm + CB_NB * CB_LDD;
+        const int nb = min(CB_NB, n - s);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int ii = 4 * ty + i, jj = 4 * tx + j;
+                if (ii < nb && jj <= ii) D[jj * CB_LDD + ii] = cv[i][j] - acc[i][j];
+            }
+        }
+        __syncthreads();
+        cholb_factor_block(D, dg, nb, A, lda, s, info);
+        return;
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -325,8 +322,10 @@ extern "C" int b200id_chol_blocked(double* A, int n, int lda, int* info_out, voi
     if (rc) return rc;
     rc = check_cuda(cudaFuncSetAttribute(cholb_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute(syrk)");
     if (rc) return rc;
+    // the first diagonal block has a launch of its own; every later one is factorised by the update kernel of the
+    // block column before it (CTA of tile (0, 0))
+    cholb_diag_kernel<<<1, CB_THREADS, 0, st>>>(A, lda, n, 0, info_out);
     for (int k0 = 0; k0 < n; k0 += CB_NB) {
-        cholb_diag_kernel<<<1, CB_THREADS, 0, st>>>(A, lda, n, k0, info_out);
         const int m = n - (k0 + CB_NB);
         if (m <= 0) break;
         const int tiles = (m + CB_NB - 1) / CB_NB;

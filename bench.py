@@ -286,6 +286,14 @@ def main():
     e2e_dir = ROOT / "gpurun_out" / f"bench_e2e_rank{rank}"
 
     def step_e2e():
+        # ONE public call on host buffers (b200id.pipeline.identify_host, the array-level counterpart of the
+        # reference's run_gp_pipeline): each record crosses the link once, uploads queued back to back and
+        # overlapped with the projections, the FIR pass reads the resident validation record; the taps and the
+        # metrics come back to the host.
+        r = P.identify_host([tuple(host[0])], tuple(host[1]), a.nd, KERNEL, NOISE, cands, n_taps=N_TAPS)
+        return r.fir, r.taps.cpu().numpy(), r
+
+    def step_e2e_calls():
         with contextlib.redirect_stdout(io.StringIO()):
             (t, u, y), (tv, uv, yv) = host
             U, Y = synchronous_coefficients_trapz_pair(t, u, y, omega_h)
@@ -349,10 +357,16 @@ def main():
     ms_inst, _, log, _ = timed(step_resident, a.steps, 1, with_events=True)
     stage_ms = {k: sum(s.elapsed_time(e) for s, e in v) / a.steps for k, v in (log or {}).items()}
     # ---- e2e timing: host pinned buffers in, result out
-    ms_e2e, (metrics_e, taps_e), _, _ = timed(step_e2e, a.steps, a.warmup)
-    # per step: train (t,u,y) + validation (t,u,y) for the two FRFs + validation (u,y) again for the FIR pass
-    h2d = 8 * a.n * (3 + 3 + 2) + 8 * (a.nd + VAL_ND) * 2 + 2 * 900 * 3 * 8 + 2 * 8 * (a.nd * 2 + VAL_ND * 2) + 8 * (N_TAPS + 1000 * 2)
-    d2h = 16 * 2 * (a.nd + VAL_ND) * 2 + 2 * (900 * 8 + 16) + 2 * 8 * (a.nd + a.nd * a.nd) + 2 * 1000 * 8 + N_TAPS * 8 + 4 * 8
+    ms_e2e, (metrics_e, taps_e, res_e), _, _ = timed(step_e2e, a.steps, a.warmup)
+    # per step: train (t,u,y) + validation (t,u,y), each once; back: StandardScaler statistics (4), the final pack
+    # (status 2, theta 6, selection 4, FIR sums 4, time-base verdicts 2) and the taps
+    h2d = 8 * a.n * (3 + 3)
+    d2h = 8 * (4 + 2 + 6 + 4 + 4 + 2) + 8 * N_TAPS
+    # the same work as the reference's call sequence (drop-in surface, one synchronous call per stage, NumPy in
+    # and out of every call): the validation record goes up twice (FRF, then FIR) and nothing overlaps across calls
+    ms_calls, (metrics_c, taps_c), _, _ = timed(step_e2e_calls, a.steps, a.warmup)
+    h2d_calls = 8 * a.n * (3 + 3 + 2) + 8 * (a.nd + VAL_ND) * 2 + 2 * 900 * 3 * 8 + 2 * 8 * (a.nd * 2 + VAL_ND * 2) + 8 * (N_TAPS + 1000 * 2)
+    d2h_calls = 16 * 2 * (a.nd + VAL_ND) * 2 + 2 * (900 * 8 + 16) + 2 * 8 * (a.nd + a.nd * a.nd) + 2 * 1000 * 8 + N_TAPS * 8 + 4 * 8
 
     total_samples = a.n * world
     value = total_samples / (ms_step * 1e-3)
@@ -438,10 +452,15 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "config": workload_config(a, world),
-        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "call": "b200id.pipeline.identify_host (host NumPy records in pinned memory -> taps, metrics, theta on the host)"},
+        "e2e_call_by_call": {"value": total_samples / (ms_calls * 1e-3), "unit": UNIT, "ms_per_step": ms_calls,
+                             "h2d_bytes_per_step": h2d_calls, "d2h_bytes_per_step": d2h_calls,
+                             "call": "src.frequency_transform / src.gpr / src.fir_model drop-in functions, one synchronous call per stage"},
         "gpu_launches": launches, "clocks": clk, "roofline": roofline, "cpu_baseline": cpu, "stages": stages,
         "result": {"theta_real": res.theta_real.tolist(), "theta_imag": res.theta_imag.tolist(), "fir_rmse": res.fir.get("rmse"),
-                   "e2e_fir_rmse": metrics_e.get("rmse")},
+                   "e2e_fir_rmse": metrics_e.get("rmse"), "e2e_theta_real": res_e.theta_real.tolist(),
+                   "e2e_theta_imag": res_e.theta_imag.tolist(), "e2e_call_by_call_fir_rmse": metrics_c.get("rmse")},
         "device": {"sm_count": sm, "cc": f"{major}.{minor}"},
     }
     print(json.dumps(line), flush=True)

@@ -181,90 +181,124 @@ STREAM_HEAD_SAMPLES = 4096       # host-side look at the time base before any of
 _STREAM = os.environ.get("B200ID_FRF_STREAM", "1") != "0"
 
 
+class StreamedRecord:
+    """One HOST-resident record on its way to the device, the projection overlapped with the copy.
+
+    The signals u, y go up first (the mean needs all of them); the time stamps follow in ``n_chunks`` pieces
+    on the copy stream and each piece is projected as soon as it has landed, so only the last piece's kernel
+    is exposed after the copy.  The path is guessed from the first few thousand time stamps on the host; a
+    'uniform' guess is verified on the device over the whole record once it is resident
+    (:meth:`uniformity_async`), and the caller re-projects with the general kernel in the rare case that a
+    later part is off the grid (:meth:`reproject_general`).
+
+    Two phases so that several records can share the link back to back: :meth:`enqueue_copies` (copy stream,
+    returns at once) for every record first, then :meth:`project` (current stream) for each.
+    """
+
+    def __init__(self, t_h, u_h, y_h, w_d, span: float, subtract_mean: bool = True, w_max: Optional[float] = None,
+                 n_chunks: int = STREAM_CHUNKS, trace: Optional[list] = None):
+        self.dev = dev = w_d.device
+        self.th, self.uh = host_f64(t_h), host_f64(u_h)
+        self.yh = None if y_h is None else host_f64(y_h)
+        self.w_d, self.span, self.subtract_mean, self.trace = w_d, float(span), subtract_mean, trace
+        n = self.th.numel()
+        self.n, self.nd = n, w_d.numel()
+        self.edges = stream_edges(n, n_chunks)
+        self.n_chunks = len(self.edges) - 1
+        self.t_d, self.u_d = empty(n, dev), empty(n, dev)
+        self.y_d = None if self.yh is None else empty(n, dev)
+        timing = trace is not None
+        self.landed = [torch.cuda.Event(enable_timing=timing) for _ in range(self.n_chunks)]
+        self.signals_up = torch.cuda.Event(enable_timing=timing)
+        self.sums = None
+        self.t0, self.dt = float(self.th[0]), self.span / (n - 1)
+        self.w_max = float(w_d.max().item()) if w_max is None else float(w_max)
+        # Path guess from the head of the record on the host (no device round trip); the device check over the
+        # whole record is what decides whether the guess stands.
+        self.kind = "general"
+        if _FORCE_PATH == "uniform":
+            self.kind = "uniform"
+        elif _FORCE_PATH != "general" and n >= 3 and self.dt > 0.0:
+            head = self.th[:min(n, STREAM_HEAD_SAMPLES)].numpy()
+            grid = self.t0 + np.arange(head.size, dtype=np.float64) * self.dt
+            if float(np.max(np.abs(head - grid))) * self.w_max < UNIFORM_PHASE_TOL:
+                self.kind = "uniform"
+
+    def _mark(self, label, stream=None):
+        if self.trace is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record(torch.cuda.current_stream() if stream is None else stream)
+            self.trace.append((label, ev))
+
+    def enqueue_copies(self) -> None:
+        main, side = torch.cuda.current_stream(), side_stream(self.dev)
+        side.wait_stream(main)        # the fresh buffers may still be in use by earlier work on this stream
+        self._mark("start")
+        if self.trace is not None:
+            self.trace.append(("signals_up", self.signals_up))
+            self.trace.extend((f"t_landed[{k}]", self.landed[k]) for k in range(self.n_chunks))
+        e = self.edges
+        with torch.cuda.stream(side):
+            self.u_d.copy_(self.uh, non_blocking=True)
+            if self.y_d is not None:
+                self.y_d.copy_(self.yh, non_blocking=True)
+            self.signals_up.record(side)
+            for k in range(self.n_chunks):
+                self.t_d[e[k]:e[k + 1]].copy_(self.th[e[k]:e[k + 1]], non_blocking=True)
+                self.landed[k].record(side)
+
+    def project(self) -> torch.Tensor:
+        """Partial sums [4*nd] of the whole record, enqueued on the current stream piece by piece."""
+        main = torch.cuda.current_stream()
+        n, e = self.n, self.edges
+        main.wait_event(self.signals_up)
+        self.sums = moments_device(self.u_d, self.y_d, (0, n)) if self.subtract_mean else None
+        self._mark("moments_done")
+        part = None
+        for k in range(self.n_chunks):
+            main.wait_event(self.landed[k])
+            # a sample's trapezoid weight needs its right neighbour: piece k owns up to its last-but-one sample
+            own = (e[k] - (1 if k > 0 else 0), e[k + 1] - 1 if k + 1 < self.n_chunks else n)
+            if self.kind == "uniform":
+                pk = project_uniform_device(self.t_d, self.u_d, self.y_d, self.w_d, self.t0, self.dt, own, self.sums, 1.0 / n)
+            else:
+                pk = project_device(self.t_d, self.u_d, self.y_d, self.w_d, own, self.sums, 1.0 / n)
+            part = pk if part is None else part.add_(pk)
+            self._mark(f"projected[{k}]")
+        return part
+
+    def needs_check(self) -> bool:
+        return self.kind == "uniform" and _FORCE_PATH != "uniform"
+
+    def uniformity_async(self) -> torch.Tensor:
+        """max |t_i - (t0 + i dt)| of the resident record as a 1-element device tensor (after :meth:`project`)."""
+        return uniformity_device_async(self.t_d, self.t0, self.dt)
+
+    def guess_holds(self, dmax: float) -> bool:
+        return dmax * self.w_max < UNIFORM_PHASE_TOL
+
+    def reproject_general(self) -> torch.Tensor:
+        self.kind = "general"
+        return project_device(self.t_d, self.u_d, self.y_d, self.w_d, (0, self.n), self.sums, 1.0 / self.n)
+
+    def finalize(self, part: torch.Tensor):
+        return finalize_device(part, self.nd, 2.0 / self.span, want_y=self.y_d is not None)
+
+
 def record_coefficients_streamed(t_h, u_h, y_h, w_d, span: float, subtract_mean: bool = True,
                                  w_max: Optional[float] = None, n_chunks: int = STREAM_CHUNKS, trace: Optional[list] = None,
                                  keep: Optional[dict] = None):
-    """(U, Y) of one HOST-resident record, with the projection overlapped with the host->device copy.
-
-    The signals u, y go up first (the mean needs all of them); the time stamps follow in ``n_chunks`` pieces
-    on a copy stream and each piece is projected as soon as it has landed, so only the last piece's kernel is
-    exposed after the copy.  The path is guessed from the first few thousand time stamps on the host; a
-    'uniform' guess is verified on the device over the whole record once it is resident, and the record is
-    re-projected with the general kernel in the rare case that a later part is off the grid.  Same sums as
-    :func:`record_coefficients_device` up to the order of the final additions.
-    """
-    dev = w_d.device
-    th, uh = host_f64(t_h), host_f64(u_h)
-    yh = None if y_h is None else host_f64(y_h)
-    n, nd = th.numel(), w_d.numel()
-    edges = stream_edges(n, n_chunks)
-    n_chunks = len(edges) - 1
-    main, side = torch.cuda.current_stream(), side_stream(dev)
-    t_d, u_d = empty(n, dev), empty(n, dev)
-    y_d = None if yh is None else empty(n, dev)
-    side.wait_stream(main)            # the fresh buffers may still be in use by earlier work on this stream
-    landed = [torch.cuda.Event(enable_timing=trace is not None) for _ in range(n_chunks)]
-    signals_up = torch.cuda.Event(enable_timing=trace is not None)
-
-    def mark(label, stream=None):
-        if trace is not None:
-            ev = torch.cuda.Event(enable_timing=True)
-            ev.record(main if stream is None else stream)
-            trace.append((label, ev))
-
-    mark("start")
-    if trace is not None:
-        trace.append(("signals_up", signals_up))
-        trace.extend((f"t_landed[{k}]", landed[k]) for k in range(n_chunks))
-
-    def send(k):
-        with torch.cuda.stream(side):
-            t_d[edges[k]:edges[k + 1]].copy_(th[edges[k]:edges[k + 1]], non_blocking=True)
-            landed[k].record(side)
-
-    with torch.cuda.stream(side):
-        u_d.copy_(uh, non_blocking=True)
-        if y_d is not None:
-            y_d.copy_(yh, non_blocking=True)
-        signals_up.record(side)
-    for k in range(min(2, n_chunks)):
-        send(k)
-    main.wait_event(signals_up)
-    sums = moments_device(u_d, y_d, (0, n)) if subtract_mean else None
-    mark("moments_done")
-
-    t0, dt = float(th[0]), span / (n - 1)
-    w_max = float(w_d.max().item()) if w_max is None else w_max
-    # Path guess from the head of the record on the host (no device round trip); the device check over the
-    # whole record below is what decides whether the guess stands.
-    kind = "general"
-    if _FORCE_PATH == "uniform":
-        kind = "uniform"
-    elif _FORCE_PATH != "general" and n >= 3 and dt > 0.0:
-        head = th[:min(n, STREAM_HEAD_SAMPLES)].numpy()
-        grid = t0 + np.arange(head.size, dtype=np.float64) * dt
-        if float(np.max(np.abs(head - grid))) * w_max < UNIFORM_PHASE_TOL:
-            kind = "uniform"
-
-    part = None
-    for k in range(n_chunks):
-        if k + 2 < n_chunks:
-            send(k + 2)
-        main.wait_event(landed[k])
-        # a sample's trapezoid weight needs its right neighbour: piece k owns up to its last-but-one sample
-        own = (edges[k] - (1 if k > 0 else 0), edges[k + 1] - 1 if k + 1 < n_chunks else n)
-        if kind == "uniform":
-            pk = project_uniform_device(t_d, u_d, y_d, w_d, t0, dt, own, sums, 1.0 / n)
-        else:
-            pk = project_device(t_d, u_d, y_d, w_d, own, sums, 1.0 / n)
-        part = pk if part is None else part.add_(pk)
-        mark(f"projected[{k}]")
-    if kind == "uniform" and _FORCE_PATH != "uniform":
-        if not (uniformity_device(t_d, t0, dt) * w_max < UNIFORM_PHASE_TOL):
-            part = project_device(t_d, u_d, y_d, w_d, (0, n), sums, 1.0 / n)
+    """(U, Y) of one HOST-resident record, with the projection overlapped with the host->device copy
+    (:class:`StreamedRecord`).  Same sums as :func:`record_coefficients_device` up to the order of the final
+    additions."""
+    sr = StreamedRecord(t_h, u_h, y_h, w_d, span, subtract_mean, w_max, n_chunks, trace)
+    sr.enqueue_copies()
+    part = sr.project()
+    if sr.needs_check() and not sr.guess_holds(float(sr.uniformity_async().item())):
+        part = sr.reproject_general()
     if keep is not None:
-        keep["device_arrays"] = (t_d, u_d, y_d)      # every copy has been waited for on this stream
-    return finalize_device(part, nd, 2.0 / span, want_y=y_d is not None)
+        keep["device_arrays"] = (sr.t_d, sr.u_d, sr.y_d)      # every copy has been waited for on this stream
+    return sr.finalize(part)
 
 
 def _coefficients(t, u, y, w_d, span, subtract_mean, w_max):

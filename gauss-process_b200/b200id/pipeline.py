@@ -197,6 +197,11 @@ def fit_device(kernel: str, theta, X_d: torch.Tensor, y_d: torch.Tensor, noise: 
     return FittedGP(kernel, np.asarray(theta, dtype=np.float64), alpha, Kinv, X_d, used_pinv)
 
 
+class TimebaseGuessFailed(RuntimeError):
+    """A streamed record was projected with the uniform-timebase kernel on the strength of its first few
+    thousand time stamps and the check over the whole record says otherwise (identify_host redoes the pass)."""
+
+
 @dataclass
 class IdentifyResult:
     omega: np.ndarray
@@ -329,7 +334,9 @@ def identify_device(train: Sequence[Tuple[torch.Tensor, torch.Tensor, torch.Tens
                     nd: int, kernel: str = "matern52", noise: float = 1e-6,
                     candidates: Optional[CandidateSet] = None, theta0: Optional[Sequence[float]] = None,
                     use_validation_metric: bool = True, n_taps: int = PAPER_TAPS,
-                    val_frf: Optional[Tuple[torch.Tensor, torch.Tensor]] = None) -> IdentifyResult:
+                    val_frf: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
+                    train_frf: Optional[Sequence[Tuple[torch.Tensor, torch.Tensor]]] = None,
+                    frf_checks: Optional[Sequence[torch.Tensor]] = None) -> IdentifyResult:
     """One pass of the hot path with every array resident on the device.
 
     train: list of records (t, u, y, span[, t0]) -- span = t[-1] - t[0], t0 = t[0]; several records are
@@ -337,6 +344,11 @@ def identify_device(train: Sequence[Tuple[torch.Tensor, torch.Tensor, torch.Tens
     and the per-bin numerator/denominator are all-reduced.  val: the validation record
     (t, u, y, span[, y0[, t0]]) -- FIR validation, and the 150-bin validation FRF when
     use_validation_metric.  candidates: grid (None -> no search, theta0 is used as is).
+
+    train_frf / val_frf: per-record coefficients (U, Y) already enqueued on this stream (identify_host projects
+    each record while it is still being uploaded); the records themselves are then only read by the FIR pass.
+    frf_checks: 1-element device tensors that must be 0 for those coefficients to stand (time-base guess of a
+    streamed record); they ride in the final host read and a non-zero one raises TimebaseGuessFailed.
 
     The host only blocks twice: once for the timebase probes, once at the end.  Everything in between is
     enqueued ahead of the GPU (the selected hyperparameters, the fit status and the all-gathered argmin stay
@@ -351,18 +363,21 @@ def identify_device(train: Sequence[Tuple[torch.Tensor, torch.Tensor, torch.Tens
     n = X_d.numel()
     want_val_frf = candidates is not None and use_validation_metric and val is not None and val_frf is None
     # ---- timebase probes of every record: one host read
-    probes = [(r[0], r[3], r[4] if len(r) > 4 else None, gi.w_max) for r in train]
+    probes = [(r[0], r[3], r[4] if len(r) > 4 else None, gi.w_max) for r in train] if train_frf is None else []
     if want_val_frf:
         probes.append((val[0], val[3], val[5] if len(val) > 5 else None, gi.wv_max))
-    paths = _probe_paths(probes)
+    paths = _probe_paths(probes) if probes else []
     # ---- FRF: per-record coefficients -> cross-power numerator / denominator of the training records and, when
     # the search metric needs it, of the validation record(s); under torch.distributed every rank contributes
     # its records and ONE all-reduce carries both sets (3 N_d + 3 N_v doubles)
     use_val_metric = candidates is not None and use_validation_metric and val is not None
     nv = gi.wv_d.numel() if use_val_metric else 0
     sums_all = empty(3 * nd + 3 * nv, dev)                  # {Re num, Im num, den} of the train set, then of the validation set
-    for r, (rec, path) in enumerate(zip(train, paths)):
-        U, Y = bfrf.record_coefficients_device(rec[0], rec[1], rec[2], w_d, rec[3], path=path)
+    for r, rec in enumerate(train):
+        if train_frf is None:
+            U, Y = bfrf.record_coefficients_device(rec[0], rec[1], rec[2], w_d, rec[3], path=paths[r])
+        else:
+            U, Y = train_frf[r]
         bfrf.cross_power_sums_device(U, Y, sums_all[:3 * nd], accumulate=r > 0)
     if use_val_metric:
         if val_frf is None:
@@ -443,7 +458,11 @@ def identify_device(train: Sequence[Tuple[torch.Tensor, torch.Tensor, torch.Tens
         pack.append(sel)
     if sums is not None:
         pack.append(sums)
+    if frf_checks:
+        pack.append(torch.cat([c.reshape(1) for c in frf_checks]))
     host = torch.cat(pack).cpu().tolist()
+    if frf_checks and any(v != 0.0 for v in host[-len(frf_checks):]):
+        raise TimebaseGuessFailed()
     flags = (int(host[0]), int(host[1]))
     nparams = bgp.KERNEL_IDS[kernel][1]
     th_r, th_i = np.array(host[2:2 + nparams]), np.array(host[5:5 + nparams])
@@ -480,6 +499,60 @@ def identify_device(train: Sequence[Tuple[torch.Tensor, torch.Tensor, torch.Tens
     if host_sums is not None:
         res.fir = bfir.metrics_from_sums(host_sums, min(10, taps.numel() // 10))
     return res
+
+
+def identify_host(train: Sequence[Tuple[np.ndarray, np.ndarray, np.ndarray]],
+                  val: Optional[Tuple[np.ndarray, np.ndarray, np.ndarray]],
+                  nd: int, kernel: str = "matern52", noise: float = 1e-6,
+                  candidates: Optional[CandidateSet] = None, theta0: Optional[Sequence[float]] = None,
+                  use_validation_metric: bool = True, n_taps: int = PAPER_TAPS,
+                  n_chunks: int = bfrf.STREAM_CHUNKS) -> IdentifyResult:
+    """The same pass as :func:`identify_device` for records that live in HOST memory (NumPy arrays or CPU
+    tensors, ideally pinned): what run_gp_pipeline does for .mat files (gp_pipeline.py:60-247), for arrays.
+
+    Every record crosses the link exactly once per call: all uploads are queued on the copy stream up front
+    (validation record first, its 150-bin projection is the longer one to hide), each record is projected
+    piece by piece as its time stamps land, and the FIR validation reads the validation record's resident
+    copy -- so the link never idles between stages and only the last piece's projection, the GP stage and the
+    FIR pass are exposed after the final byte.  The uniform-timebase guess of each record (host look at its
+    first 4096 stamps) is verified on the device over the whole resident record; the verdicts come back with
+    the final host read, and a failed guess reruns the pass through :func:`identify_device` on the resident
+    copies (general kernel).
+    """
+    dev = require_cuda()
+    gi = GridInputs.get(nd, dev)
+    use_val_metric = candidates is not None and use_validation_metric and val is not None
+    span = lambda t: float(t[-1]) - float(t[0])
+    val_sr = None
+    if val is not None:
+        # the validation grid is only projected when the search metric needs it; the upload serves the FIR pass
+        val_sr = bfrf.StreamedRecord(val[0], val[1], val[2], gi.wv_d, span(val[0]), True, gi.wv_max,
+                                     n_chunks if use_val_metric else 1)
+    train_sr = [bfrf.StreamedRecord(t, u, y, gi.w_d, span(t), True, gi.w_max, n_chunks) for (t, u, y) in train]
+    order = ([val_sr] if val_sr is not None else []) + train_sr
+    for sr in order:
+        sr.enqueue_copies()
+    checks, coeffs = [], {}
+    for sr in order:
+        if sr is val_sr and not use_val_metric:
+            torch.cuda.current_stream().wait_event(sr.landed[-1])
+            continue
+        part = sr.project()
+        if sr.needs_check():
+            dmax = sr.uniformity_async()
+            checks.append((dmax * sr.w_max >= bfrf.UNIFORM_PHASE_TOL).to(F64))
+        coeffs[id(sr)] = sr.finalize(part)
+    train_d = [(sr.t_d, sr.u_d, sr.y_d, sr.span, sr.t0) for sr in train_sr]
+    val_d = None
+    if val_sr is not None:
+        skip = min(10, min(n_taps, 2 * PAPER_ND - 1) // 10)
+        val_d = (val_sr.t_d, val_sr.u_d, val_sr.y_d, val_sr.span, float(val_sr.yh[skip]), val_sr.t0)
+    try:
+        return identify_device(train_d, val_d, nd, kernel, noise, candidates, theta0, use_validation_metric, n_taps,
+                               val_frf=coeffs.get(id(val_sr)) if use_val_metric else None,
+                               train_frf=[coeffs[id(sr)] for sr in train_sr], frf_checks=checks)
+    except TimebaseGuessFailed:
+        return identify_device(train_d, val_d, nd, kernel, noise, candidates, theta0, use_validation_metric, n_taps)
 
 
 _SIDE_STREAMS: Dict[int, "torch.cuda.Stream"] = {}

@@ -34,7 +34,7 @@ struct FrfPlan {
     int grid_y;      // bin groups of <= FRF_THREADS bins
 };
 
-static FrfPlan frf_plan(int64_t n_own, int nd) {
+static FrfPlan frf_plan(int64_t n_own, int nd, int tile_max = FRF_TILE_MAX) {
     FrfPlan p;
     p.grid_y = (nd + FRF_THREADS - 1) / FRF_THREADS;
     const int resident = sm_count() * FRF_CTAS_PER_SM;
@@ -42,7 +42,7 @@ static FrfPlan frf_plan(int64_t n_own, int nd) {
     int64_t tile = (n_own + want_x - 1) / want_x;
     tile = (tile + 63) / 64 * 64;
     if (tile < 64) tile = 64;
-    if (tile > FRF_TILE_MAX) tile = FRF_TILE_MAX;
+    if (tile > tile_max) tile = tile_max;
     p.tile = (int)tile;
     const int64_t nt = (n_own + tile - 1) / tile;
     p.n_tiles = (int)nt;
@@ -586,6 +586,161 @@ frf_project_uniform3_kernel(const double* __restrict__ t, const double* __restri
     }
 }
 
+// Goertzel form, two bins per thread (same thread / stripe / tile mapping and the same per-tile re-seeding as
+// frf_project_uniform3_kernel; ill-conditioned bins again go to frf_project_uniform_kernel<., false>).
+// To first order in eps  sum_i a_i exp(-j (theta_i + eps_i)) = sum_i (a_i - j a_i eps_i) exp(-j theta_i),  theta on an
+// exact arithmetic progression along a chain, so both sums are Goertzel recurrences on the ACCUMULATOR
+//     s[m] = x_m + 2 cos(D) s[m-1] - s[m-2],    sum_l x_l exp(-j theta_l) = exp(-j theta_last) (s[M-1] - exp(-j D) s[M-2])
+// and no basis value is ever formed:
+//   * main term  x = a        : FP64, one DADD + one DFMA per signal
+//   * rounding term x = a eps : |eps| < 2.5e-6 and the term only has to be good to ~1e-3 of itself (it is <= 1e-7 of a
+//     bin's value), so it runs in FP32 with the two signals packed in f32x2 registers (FMUL2, FADD2, FFMA2); an FP32
+//     rounding error injected at any step reaches the result with unit gain, so the term is good to
+//     ~2^-24 sqrt(M) / |sin D| of itself
+//   * e_i = w t_i - fl(w t_i) is still exact (DMUL + DFMA); it is narrowed to FP32 and w delta_i joins it there.
+// FP64-pipe instructions per sample-bin: 2 (e) + 1 (narrowing) + 4 (two Goertzel steps) = 7 of which only 3 read three
+// distinct registers, against 11 / 9 in the three-term kernel.  Accumulators live in shared memory (touched once per
+// tile), which keeps the loop under the 64-register cap.
+constexpr int FRFG_TILE_MAX = 1536;
+constexpr size_t FRFG_SMEM_BYTES = (size_t)FRFG_TILE_MAX * (16 + 8 + 16) + (size_t)8 * FRF_THREADS * sizeof(double);
+
+template <bool HAS_Y>
+__global__ void __launch_bounds__(FRF_THREADS, FRF_CTAS_PER_SM)
+frf_project_uniform_g_kernel(const double* __restrict__ t, const double* __restrict__ u,
+                             const double* __restrict__ y, int64_t n, int64_t own_begin, int64_t own_end,
+                             const double* __restrict__ w, int nd, const double* __restrict__ sums,
+                             double inv_count, double t0, double dt, int tile, int n_tiles,
+                             double* __restrict__ cta_partial) {
+    extern __shared__ __align__(16) double smem[];
+    double2* ab = reinterpret_cast<double2*>(smem);                 // [tile] (w_i (u_i - mean), w_i (y_i - mean))
+    float4* f4 = reinterpret_cast<float4*>(ab + FRFG_TILE_MAX);      // [tile] (delta_i, a_u, a_y, -) in FP32
+    double* tt = reinterpret_cast<double*>(f4 + FRFG_TILE_MAX);      // [tile] t_i
+    double* acc = tt + FRFG_TILE_MAX;                                // [8][FRF_THREADS] running sums of this thread
+    __shared__ int s_good[FRF_THREADS];
+
+    const int tid = threadIdx.x;
+    const int bin0 = blockIdx.y * FRF_THREADS;
+    const int nb_all = min(nd - bin0, FRF_THREADS);
+    const int nb2 = (nb_all + 1) / 2;
+    const int R = FRF_THREADS / nb2;                                 // = frfu_three_step(nb_all)
+    s_good[tid] = ((tid < nb_all) && frfu_bin_is_good(w[bin0 + tid], R, dt)) ? 1 : 0;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[c * FRF_THREADS + tid] = 0.0;
+    __syncthreads();
+    const int b2 = tid % nb2, r = tid / nb2;
+    const bool active = r < R;
+    const int binA = b2, binB = b2 + nb2;
+    const double wA = w[bin0 + binA];
+    const double wB = w[bin0 + (binB < nb_all ? binB : binA)];     // odd group: the last pair's second bin is a dummy
+    const double mean_u = sums ? sums[0] * inv_count : 0.0;
+    const double mean_y = (HAS_Y && sums) ? sums[1] * inv_count : 0.0;
+    double sdA, cdA, sdB, cdB;                                       // chain step D = w R dt
+    {
+        DD step; const double kk = (double)R;
+        step.hi = kk * dt; step.lo = fma(kk, dt, -step.hi);
+        sincos_dd(wA, step, sdA, cdA);
+        sincos_dd(wB, step, sdB, cdB);
+    }
+    const double KA = 2.0 * cdA, KB = 2.0 * cdB;
+    const float wAf = (float)wA, wBf = (float)wB;
+    const float2 KAf = make_float2((float)KA, (float)KA), KBf = make_float2((float)KB, (float)KB);
+
+    for (int tl = blockIdx.x; tl < n_tiles; tl += gridDim.x) {
+        const int64_t i0 = own_begin + (int64_t)tl * tile;
+        const int cnt = (int)min((int64_t)tile, own_end - i0);
+        __syncthreads();
+        for (int j = tid; j < cnt; j += FRF_THREADS) {
+            const int64_t i = i0 + j;
+            const double ti = __ldg(t + i);
+            const double tm = __ldg(t + (i > 0 ? i - 1 : 0)), tp = __ldg(t + (i < n - 1 ? i + 1 : n - 1));
+            const double wt = 0.5 * (tp - tm);
+            const double k = (double)i;
+            const double ph = k * dt, pl = fma(k, dt, -ph);
+            const double d = ti - t0, bb = d - ti;
+            const double derr = (ti - (d - bb)) + (-t0 - bb);
+            const double au = wt * (__ldg(u + i) - mean_u), ay = HAS_Y ? wt * (__ldg(y + i) - mean_y) : 0.0;
+            tt[j] = ti;
+            ab[j] = make_double2(au, ay);
+            f4[j] = make_float4((float)(((d - ph) - pl) + derr), (float)au, (float)ay, 0.0f);
+        }
+        __syncthreads();
+        if (active && r < cnt) {
+            double uA1 = 0.0, uA2 = 0.0, yA1 = 0.0, yA2 = 0.0, uB1 = 0.0, uB2 = 0.0, yB1 = 0.0, yB2 = 0.0;
+            float2 qA1 = make_float2(0.f, 0.f), qA2 = qA1, qB1 = qA1, qB2 = qA1;
+// one Goertzel step of one bin: (U1, Y1, Q1) hold s[m-1], (U2, Y2, Q2) hold s[m-2] and receive s[m]
+#define FRFG_BIN(wk, wkf, K, Kf, U1, U2, Y1, Y2, Q1, Q2)                                             \
+    {                                                                                                \
+        const double p = (wk) * tv;                                                                  \
+        const float ef = (float)fma((wk), tv, -p);                                                   \
+        const float epsf = fmaf((wkf), fv.x, -ef);                                                   \
+        U2 = fma((K), U1, abv.x - U2);                                                               \
+        if (HAS_Y) Y2 = fma((K), Y1, abv.y - Y2);                                                    \
+        const float2 xe = __fmul2_rn(make_float2(fv.y, fv.z), make_float2(epsf, epsf));              \
+        Q2 = __ffma2_rn((Kf), Q1, __fadd2_rn(xe, make_float2(-Q2.x, -Q2.y)));                        \
+    }
+            int j = r;
+            for (; j + R < cnt; j += 2 * R) {
+                {
+                    const double tv = tt[j]; const double2 abv = ab[j]; const float4 fv = f4[j];
+                    FRFG_BIN(wA, wAf, KA, KAf, uA1, uA2, yA1, yA2, qA1, qA2)
+                    FRFG_BIN(wB, wBf, KB, KBf, uB1, uB2, yB1, yB2, qB1, qB2)
+                }
+                {
+                    const double tv = tt[j + R]; const double2 abv = ab[j + R]; const float4 fv = f4[j + R];
+                    FRFG_BIN(wA, wAf, KA, KAf, uA2, uA1, yA2, yA1, qA2, qA1)
+                    FRFG_BIN(wB, wBf, KB, KBf, uB2, uB1, yB2, yB1, qB2, qB1)
+                }
+            }
+            if (j < cnt) {                                                   // odd sample count: one more step, roles end swapped
+                const double tv = tt[j]; const double2 abv = ab[j]; const float4 fv = f4[j];
+                FRFG_BIN(wA, wAf, KA, KAf, uA1, uA2, yA1, yA2, qA1, qA2)
+                FRFG_BIN(wB, wBf, KB, KBf, uB1, uB2, yB1, yB2, qB1, qB2)
+                double sw; float2 sq;
+                sw = uA1; uA1 = uA2; uA2 = sw; sw = yA1; yA1 = yA2; yA2 = sw; sq = qA1; qA1 = qA2; qA2 = sq;
+                sw = uB1; uB1 = uB2; uB2 = sw; sw = yB1; yB1 = yB2; yB2 = sw; sq = qB1; qB1 = qB2; qB2 = sq;
+                j += R;
+            }
+#undef FRFG_BIN
+            // (.1) = s[M-1], (.2) = s[M-2]; last sample of the chain is j - R
+            const DD x = dd_time(t0, (double)(i0 + (j - R)), dt);
+// Z = (s1 - e^{-jD} s2)_main - j (s1 - e^{-jD} s2)_rounding;  sums += e^{-j theta_last} Z  as (cos part, sin part)
+#define FRFG_FOLD1(cd, sd, S1, S2, Q1c, Q2c, slotc, slots)                                            \
+    {                                                                                                \
+        const double q1 = (double)(Q1c), q2 = (double)(Q2c);                                         \
+        const double mr = fma(-(cd), S2, S1), mi = (sd) * S2;                                        \
+        const double er = fma(-(cd), q2, q1), ei = (sd) * q2;                                        \
+        const double zr = mr + ei, zi = mi - er;                                                     \
+        acc[(slotc) * FRF_THREADS + tid] += fma(cl, zr, sl * zi);                                    \
+        acc[(slots) * FRF_THREADS + tid] += fma(sl, zr, -(cl * zi));                                 \
+    }
+            {
+                double sl, cl;
+                sincos_dd(wA, x, sl, cl);
+                FRFG_FOLD1(cdA, sdA, uA1, uA2, qA1.x, qA2.x, 0, 1)
+                if (HAS_Y) FRFG_FOLD1(cdA, sdA, yA1, yA2, qA1.y, qA2.y, 2, 3)
+            }
+            {
+                double sl, cl;
+                sincos_dd(wB, x, sl, cl);
+                FRFG_FOLD1(cdB, sdB, uB1, uB2, qB1.x, qB2.x, 4, 5)
+                if (HAS_Y) FRFG_FOLD1(cdB, sdB, yB1, yB2, qB1.y, qB2.y, 6, 7)
+            }
+#undef FRFG_FOLD1
+        }
+    }
+    __syncthreads();
+    if (tid < nb_all && s_good[tid] != 0) {
+        const int slot = tid < nb2 ? 0 : 4, base = tid < nb2 ? tid : tid - nb2;
+        double* out = cta_partial + (size_t)blockIdx.x * 4 * nd + bin0 + tid;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            double v = 0.0;
+            for (int rr = 0; rr < R; ++rr) v += acc[(slot + c) * FRF_THREADS + rr * nb2 + base];
+            out[(size_t)c * nd] = v;
+        }
+    }
+}
+
 __global__ void cross_power_kernel(const double* __restrict__ U, const double* __restrict__ Y,
                                    int n_records, int nd, double eps, double* __restrict__ G) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -813,6 +968,23 @@ static bool frf_mma_enabled() {
     return on == 1;
 }
 
+#ifndef FRF_GOERTZEL_DEFAULT
+#define FRF_GOERTZEL_DEFAULT 0
+#endif
+static int g_frf_goertzel = -1;
+static bool frf_goertzel_enabled() {
+    if (g_frf_goertzel < 0) {
+        const char* e = getenv("B200ID_FRF_GOERTZEL");
+        g_frf_goertzel = e ? (e[0] == '1' ? 1 : 0) : FRF_GOERTZEL_DEFAULT;
+    }
+    return g_frf_goertzel == 1;
+}
+extern "C" int b200id_frf_select_recurrence(int which) {
+    const int prev = frf_goertzel_enabled() ? 1 : 0;
+    g_frf_goertzel = which < 0 ? -1 : (which ? 1 : 0);
+    return prev;
+}
+
 // Matrix-product path of b200id_frf_project_uniform (two signals, nd <= FM_NDMAX).  Returns 1 when the shape does
 // not fit (caller falls back to the recurrence kernels), 0 on success, < 0 on error.
 static int frf_project_mma_launch(const double* t, const double* u, const double* y, int64_t n, int64_t own_begin,
@@ -1005,6 +1177,28 @@ extern "C" int b200id_frf_project_uniform(const double* t, const double* u, cons
     for (int k = 0; k < 4; ++k) {
         rc = check_cuda(cudaFuncSetAttribute(fns[k], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FRFU_SMEM_BYTES), "smem attr");
         if (rc) return rc;
+    }
+    if (frf_goertzel_enabled()) {
+        // Goertzel form: own tile size (its per-thread accumulators live in shared memory next to the tile)
+        const FrfPlan pg = frf_plan(own_end - own_begin, nd, FRFG_TILE_MAX);
+        B200ID_REQUIRE(ws_bytes >= (size_t)pg.grid_x * 4 * nd * sizeof(double), B200ID_E_WORKSPACE, "frf_project_uniform: workspace too small");
+        rc = check_cuda(cudaFuncSetAttribute(frf_project_uniform_g_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FRFG_SMEM_BYTES), "smem attr");
+        if (rc) return rc;
+        rc = check_cuda(cudaFuncSetAttribute(frf_project_uniform_g_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FRFG_SMEM_BYTES), "smem attr");
+        if (rc) return rc;
+        dim3 gg(pg.grid_x, pg.grid_y);
+        if (y) {
+            frf_project_uniform_g_kernel<true><<<gg, FRF_THREADS, FRFG_SMEM_BYTES, st>>>(t, u, y, n, own_begin, own_end, w, nd, sums, inv_count, t0, dt, pg.tile, pg.n_tiles, part);
+            frf_project_uniform_kernel<true, false><<<gg, FRF_THREADS, FRFU_SMEM_BYTES, st>>>(t, u, y, n, own_begin, own_end, w, nd, sums, inv_count, t0, dt, pg.tile, pg.n_tiles, part);
+        } else {
+            frf_project_uniform_g_kernel<false><<<gg, FRF_THREADS, FRFG_SMEM_BYTES, st>>>(t, u, nullptr, n, own_begin, own_end, w, nd, sums, inv_count, t0, dt, pg.tile, pg.n_tiles, part);
+            frf_project_uniform_kernel<false, false><<<gg, FRF_THREADS, FRFU_SMEM_BYTES, st>>>(t, u, nullptr, n, own_begin, own_end, w, nd, sums, inv_count, t0, dt, pg.tile, pg.n_tiles, part);
+        }
+        B200ID_LAUNCH_CHECK("frf_project_uniform_g_kernel");
+        const int glen = 4 * nd;
+        frf_fold_kernel<<<(glen + 31) / 32, FOLD_WARPS * 32, 0, st>>>(part, pg.grid_x, glen, partial_out);
+        B200ID_LAUNCH_CHECK("frf_fold_kernel");
+        return B200ID_OK;
     }
     dim3 grid(p.grid_x, p.grid_y);
 #if FRFU_THREE_PAIRS

@@ -104,6 +104,13 @@ int b200id_frf_project_uniform(const double* t, const double* u, const double* y
                                const double* sums /*[2] or NULL*/, double inv_count, double t0, double dt,
                                double* partial_out /*[4*nd]*/, void* ws, size_t ws_bytes, void* stream);
 
+/* Which recurrence b200id_frf_project_uniform runs for the well-conditioned bins: 0 = three-term recurrence on
+ * the basis values (frf_project_uniform3_kernel), 1 = Goertzel recurrence on the accumulators with the rounding
+ * term in packed FP32 (frf_project_uniform_g_kernel), -1 = back to the default (environment B200ID_FRF_GOERTZEL,
+ * else the build's default).  Process-wide, not stream-ordered: meant for tests and for timing one form against
+ * the other.  Returns the previous setting. */
+int b200id_frf_select_recurrence(int which);
+
 /* EXPERIMENTAL alternative evaluation of b200id_frf_project_uniform (same arguments, same outputs, same
  * reference lines frf_estimator.py:226-231): the exact-phase part as a blocked FP64 matrix product on
  * mma.sync.m8n8k4.f64 and the reference's per-sample phase rounding as a fixed-point / FP32 correction

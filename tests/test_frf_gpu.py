@@ -357,3 +357,49 @@ def test_matrix_product_path_matches_recurrence_and_oracle(frf, n, nd, kind, t_s
     again = frf.project_uniform_mma_device(t_d, u_d, y_d, w_d, t0, dt, (0, n), sums, 1.0 / n)
     import torch
     assert torch.equal(again, a), "the matrix-product path must be deterministic run to run"
+
+
+@pytest.mark.parametrize("n,nd,kind,t_shift", [(200_000, 100, "multisine", 0.0), (300_001, 150, "square", 0.0),
+                                               (100_000, 50, "multisine", 1.9e6), (65_537, 150, "square", 123.4567),
+                                               (4_097, 7, "multisine", 0.0), (70_000, 160, "square", -33.3),
+                                               (1_000_003, 100, "square", 0.0), (50_000, 601, "multisine", 0.0)])
+def test_goertzel_form_matches_three_term_and_oracle(frf, n, nd, kind, t_shift):
+    """The Goertzel form of the uniform path (recurrence on the accumulators, rounding term in packed FP32,
+    frf_project_uniform_g_kernel) against the three-term kernel and the oracle, on the records that stress the
+    rounding term: weak bins of the square-wave record, phases ~1e9 rad, ragged tiles, odd bin counts, more than
+    one bin group, negative times."""
+    import ctypes as C
+    import torch
+    from b200id import _lib, synth
+    from b200id.runtime import require_cuda, to_device
+    dev = require_cuda()
+    t, u, y = synth.make_record(n, min(nd, 100), kind, seed=5)
+    t = t + t_shift
+    _, w = ofrf.freq_grid(nd)
+    span = float(t[-1] - t[0])
+    t_d, u_d, y_d, w_d = (to_device(a, dev) for a in (t, u, y, w))
+    t0, dt = float(t[0]), span / (n - 1)
+    sums = frf.moments_device(u_d, y_d, (0, n))
+    lib = _lib.load()
+    prev = lib.b200id_frf_select_recurrence(C.c_int(1))
+    try:
+        a = frf.project_uniform_device(t_d, u_d, y_d, w_d, t0, dt, (0, n), sums, 1.0 / n)
+        cut = n // 3 + 5
+        a1 = frf.project_uniform_device(t_d, u_d, y_d, w_d, t0, dt, (0, cut), sums, 1.0 / n)
+        a2 = frf.project_uniform_device(t_d, u_d, y_d, w_d, t0, dt, (cut, n), sums, 1.0 / n)
+        again = frf.project_uniform_device(t_d, u_d, y_d, w_d, t0, dt, (0, n), sums, 1.0 / n)
+        only_u = frf.project_uniform_device(t_d, u_d, None, w_d, t0, dt, (0, n), sums, 1.0 / n)
+        lib.b200id_frf_select_recurrence(C.c_int(0))
+        b = frf.project_uniform_device(t_d, u_d, y_d, w_d, t0, dt, (0, n), sums, 1.0 / n)
+    finally:
+        lib.b200id_frf_select_recurrence(C.c_int(prev))
+    Ua, Ya = (x.cpu().numpy() for x in frf.finalize_device(a, nd, 2.0 / span))
+    Ub, Yb = (x.cpu().numpy() for x in frf.finalize_device(b, nd, 2.0 / span))
+    e_r = record(f"frf.goertzel.{kind}.n{n}.nd{nd}.shift{t_shift:g}.vs_three_term", max(rel_each(Ua, Ub), rel_each(Ya, Yb)))
+    Ur, Yr = ofrf.demod_trapz(t, u, w, threads=8), ofrf.demod_trapz(t, y, w, threads=8)
+    e_o = record(f"frf.goertzel.{kind}.n{n}.nd{nd}.shift{t_shift:g}.vs_oracle", max(rel_each(Ua, Ur), rel_each(Ya, Yr)))
+    assert e_r < TOL and e_o < TOL
+    scale = float(a.abs().max())
+    assert record(f"frf.goertzel.{kind}.n{n}.segments", float((a1 + a2 - a).abs().max()) / scale) < 1e-12
+    assert torch.equal(again, a), "deterministic run to run"
+    assert torch.equal(only_u[:2 * nd], a[:2 * nd]), "u sums do not depend on whether y rides along"

@@ -57,3 +57,61 @@ def test_identify_device_validation_metric_against_oracle(kernel, n, nd):
     tol = max(1e-6, 100.0 * cond * 2.2e-16)
     record(f"pipeline.{kernel}.cond", cond)
     assert e_taps < tol and abs(res.fir["rmse"] - m["rmse"]) <= tol * m["rmse"]
+
+
+def _host_vs_device(t, u, y, tv, uv, yv, nd, kernel="matern52", n_chunks=6):
+    import torch
+    from b200id import pipeline as P
+    from b200id.runtime import require_cuda, to_device
+    dev = require_cuda()
+    skip = min(10, 1024 // 10)
+    train = [(to_device(t, dev), to_device(u, dev), to_device(y, dev), float(t[-1] - t[0]), float(t[0]))]
+    val = (to_device(tv, dev), to_device(uv, dev), to_device(yv, dev), float(tv[-1] - tv[0]), float(yv[skip]), float(tv[0]))
+    cands = P.CandidateSet.build(kernel, P.grid_candidates(kernel), dev)
+    ref = P.identify_device(train, val, nd, kernel, 1e-6, cands, use_validation_metric=True)
+    got = P.identify_host([(t, u, y)], (tv, uv, yv), nd, kernel, 1e-6, cands, use_validation_metric=True, n_chunks=n_chunks)
+    torch.cuda.synchronize()
+    return ref, got
+
+
+@pytest.mark.parametrize("n,pinned", [(1 << 21, True), (50_001, False)])
+def test_identify_host_matches_identify_device(n, pinned):
+    """One call on HOST records (each uploaded once, projected piece by piece while it lands, FIR pass on the
+    resident copy) gives what the device-resident pass gives: same selection, FRF / taps / metrics to the order
+    of the final additions."""
+    import torch
+    from b200id import synth
+    nd = 40
+    t, u, y = synth.make_record(n, nd, "multisine", seed=11)
+    tv, uv, yv = synth.make_record(n, nd, "square", seed=12)
+    if pinned:
+        keep = [torch.from_numpy(a).pin_memory() for a in (t, u, y, tv, uv, yv)]
+        t, u, y, tv, uv, yv = [k.numpy() for k in keep]
+    ref, got = _host_vs_device(t, u, y, tv, uv, yv, nd)
+    assert np.array_equal(ref.theta_real, got.theta_real) and np.array_equal(ref.theta_imag, got.theta_imag)
+    Gr, Gg = ref.G.cpu().numpy(), got.G.cpu().numpy()
+    assert record(f"identify_host.frf.{n}", float(np.max(np.abs(Gg - Gr) / np.abs(Gr)))) < 1e-11
+    tr, tg = ref.taps.cpu().numpy(), got.taps.cpu().numpy()
+    assert record(f"identify_host.taps.{n}", float(np.max(np.abs(tg - tr)) / np.max(np.abs(tr)))) < 1e-8
+    assert abs(got.fir["rmse"] - ref.fir["rmse"]) <= 1e-8 * ref.fir["rmse"]
+    assert abs(got.metric_real - ref.metric_real) <= 1e-8 * abs(ref.metric_real)
+
+
+def test_identify_host_recovers_from_a_wrong_timebase_guess():
+    """The head of the record sits on the grid, a later stretch does not: the uniform-kernel guess made on the
+    host is overturned by the device check over the whole record and the pass is redone with the general kernel,
+    i.e. the result is the device-resident pass's (which probes the whole record first)."""
+    from b200id import synth
+    n, nd = 300_000, 30
+    t, u, y = synth.make_record(n, nd, "multisine", seed=21)
+    tv, uv, yv = synth.make_record(n, nd, "square", seed=22)
+    t = t.copy()
+    rng = np.random.default_rng(5)
+    t[n // 2: n // 2 + 5000] += rng.uniform(0.0, 2e-4, 5000)        # w_max * delta ~ 0.25 rad, still monotone
+    assert np.all(np.diff(t) > 0)
+    ref, got = _host_vs_device(t, u, y, tv, uv, yv, nd)
+    Gr, Gg = ref.G.cpu().numpy(), got.G.cpu().numpy()
+    assert float(np.max(np.abs(Gg - Gr) / np.abs(Gr))) < 1e-12
+    assert np.array_equal(ref.theta_real, got.theta_real) and np.array_equal(ref.theta_imag, got.theta_imag)
+    w, G = ofrf.estimate_frf([(t, u, y)], nd)
+    assert float(np.max(np.abs(Gg - G) / np.abs(G))) < 1e-9

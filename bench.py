@@ -42,8 +42,8 @@ NOISE = 1e-6
 N_TAPS = 1024
 VAL_ND = 150
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures
-# (profiles/r01_ncu_full_*.txt), 10^7-sample record: FRF reads t,u,y once (240 MB), FIR reads u,y (160 MB)
-NCU_TRAFFIC_BYTES = {"frf_project_uniform3_kernel": 245.2e6, "frf_project_uniform_kernel": 245.2e6, "frf_project_kernel": 245.3e6, "fir_eval_kernel": 167.3e6,
+# (profiles/r01_ncu_*.txt), 10^7-sample record: FRF reads t,u,y once (240 MB), FIR reads u,y (160 MB)
+NCU_TRAFFIC_BYTES = {"frf_project_uniform_g_kernel": 245.9e6, "fir_fft16_kernel": 167.5e6, "frf_project_uniform3_kernel": 245.2e6, "frf_project_uniform_kernel": 245.2e6, "frf_project_kernel": 245.3e6, "fir_eval_kernel": 167.3e6,
                      "fir_fft_kernel": 163.6e6, "gp_batch_tiled_kernel": 0.33e6}
 FRF_BYTES_PER_SAMPLE = 24        # t, u, y FP64 read once
 FIR_BYTES_PER_SAMPLE = 16        # u, y FP64 read once, y_pred not materialised
@@ -397,19 +397,21 @@ def main():
 
     # ---- roofline of the dominant kernel (largest share of the step among the instrumented calls)
     frf_ms = stage_ms.get("b200id_frf_project", 0.0) + stage_ms.get("b200id_frf_project_uniform", 0.0)
-    frf_kernel = "frf_project_uniform3_kernel" if stage_ms.get("b200id_frf_project_uniform", 0.0) > stage_ms.get("b200id_frf_project", 0.0) else "frf_project_kernel"
+    frf_uniform_kernel = "frf_project_uniform3_kernel" if os.environ.get("B200ID_FRF_GOERTZEL", "1") == "0" else "frf_project_uniform_g_kernel"
+    fir_kernel = "fir_fft_kernel" if os.environ.get("B200ID_FIR_RADIX4", "0") == "1" else "fir_fft16_kernel"
+    frf_kernel = frf_uniform_kernel if stage_ms.get("b200id_frf_project_uniform", 0.0) > stage_ms.get("b200id_frf_project", 0.0) else "frf_project_kernel"
     fir_ms = stage_ms.get("b200id_fir_eval", 0.0)
     # Re and Im searches share one factorisation per candidate (b200id_gp_batch_eval_pair); the candidate count and
     # the algorithmic flops below stay those of the reference's 2 x 900 separate evaluations
     gp_ms = stage_ms.get("b200id_gp_batch_eval", 0.0) + stage_ms.get("b200id_gp_batch_eval_pair", 0.0)
-    dominant = max(((frf_kernel, frf_ms), ("fir_fft_kernel", fir_ms), ("gp_batch_tiled_kernel", gp_ms)), key=lambda kv: kv[1])[0]
+    dominant = max(((frf_kernel, frf_ms), (fir_kernel, fir_ms), ("gp_batch_tiled_kernel", gp_ms)), key=lambda kv: kv[1])[0]
     frf_bytes = FRF_BYTES_PER_SAMPLE * a.n * 2            # two launches per step: train (nd bins) + validation (150 bins)
     frf_flops = 8.0 * a.n * (a.nd + VAL_ND)               # 2 signals x (cos, sin) x FMA, both launches
     fir_bytes = FIR_BYTES_PER_SAMPLE * a.n
     fir_flops = 2.0 * N_TAPS * a.n
     gp_flops = 1800 / world * (a.nd ** 3 / 3.0 + 2.0 * a.nd ** 2)
     fp64_peak = max(fp64.values()) if fp64 else None
-    if dominant == "fir_fft_kernel":
+    if dominant == fir_kernel:
         ach = fir_bytes / (fir_ms * 1e-3) / 1e9
     else:
         ach = frf_bytes / (frf_ms * 1e-3) / 1e9 if frf_ms > 0 else 0.0
@@ -418,8 +420,9 @@ def main():
         "kernel": dominant, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
         "traffic": NCU_TRAFFIC_BYTES.get(dominant), "peak_source": peak_src,
         "launches_per_step": 2 if dominant.startswith("frf") else 1,
-        "note": "FP64-issue bound by construction: the reference rounds the phase per sample, so each sample-bin costs 11 "
-                "(uniform timebase) or 24 (general) FP64 ops where 4 are algorithmic; see the fp64 block and DESIGN.md",
+        "note": "FP64-issue bound by construction: the reference rounds the phase per sample, so each sample-bin costs 7 "
+                "FP64-pipe instructions (uniform timebase, Goertzel form) or 24 (general) where 4 are algorithmic; see the "
+                "fp64 block and DESIGN.md",
         "fp64": {
             "peak_tflops_measured": fp64_peak, **fp64,
             "frf_algorithmic_tflops": frf_flops / (frf_ms * 1e-3) / 1e12 if frf_ms > 0 else None,

@@ -30,6 +30,7 @@ SIGNATURES = {
     "b200id_frf_uniformity": (I, [P, L, L, L, D, D, P, P, Z, P]),
     "b200id_frf_project_uniform": (I, [P, P, P, L, L, L, P, I, P, D, D, D, P, P, Z, P]),
     "b200id_frf_select_recurrence": (I, [I]),
+    "b200id_fir_select_fft": (I, [I]),
     "b200id_frf_project_uniform_mma": (I, [P, P, P, L, L, L, P, I, P, D, D, D, P, P, Z, P]),
     "b200id_cross_power_sums": (I, [P, P, I, I, I, P, P]),
     "b200id_gp_targets": (I, [P, I, D, P, P, P, P, P]),

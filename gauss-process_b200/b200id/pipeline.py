@@ -345,7 +345,8 @@ def identify_device(train: Sequence[Tuple[torch.Tensor, torch.Tensor, torch.Tens
     (t, u, y, span[, y0[, t0]]) -- FIR validation, and the 150-bin validation FRF when
     use_validation_metric.  candidates: grid (None -> no search, theta0 is used as is).
 
-    train_frf / val_frf: per-record coefficients (U, Y) already enqueued on this stream (identify_host projects
+    train_frf / val_frf: per-record coefficients (U, Y) already enqueued on this stream; val_frf may also be a
+    callable returning them, which is then invoked AFTER the training targets are on their way to the host (identify_host projects
     each record while it is still being uploaded); the records themselves are then only read by the FIR pass.
     frf_checks: 1-element device tensors that must be 0 for those coefficients to stand (time-base guess of a
     streamed record); they ride in the final host read and a non-zero one raises TimebaseGuessFailed.
@@ -379,19 +380,33 @@ def identify_device(train: Sequence[Tuple[torch.Tensor, torch.Tensor, torch.Tens
         else:
             U, Y = train_frf[r]
         bfrf.cross_power_sums_device(U, Y, sums_all[:3 * nd], accumulate=r > 0)
-    if use_val_metric:
+    lazy_val = use_val_metric and callable(val_frf)
+
+    def val_sums():
         if val_frf is None:
             Uv, Yv = bfrf.record_coefficients_device(val[0], val[1], val[2], gi.wv_d, val[3], path=paths[-1])
         else:
-            Uv, Yv = val_frf
+            Uv, Yv = val_frf() if lazy_val else val_frf
         bfrf.cross_power_sums_device(Uv, Yv, sums_all[3 * nd:])
-    bdist.allreduce_sum_(sums_all)
+
+    if lazy_val:
+        bdist.allreduce_sum_(sums_all[:3 * nd])
+    else:
+        if use_val_metric:
+            val_sums()
+        bdist.allreduce_sum_(sums_all)
     # ---- G, StandardScaler statistics of Re G / Im G and the standardised targets: one kernel; the statistics
     # travel to the host asynchronously
     G, stats_d, yr, yi = bfrf.gp_targets_device(sums_all[:3 * nd], nd, standardise=True)
     mean2, sd2 = stats_d[0:2], stats_d[2:4]
     stats_host, stats_ev = _async_to_host(stats_d)
     Xv_d = yv_r = yv_i = None
+    if lazy_val:
+        # the validation coefficients are enqueued only now: the statistics' copy above completes as soon as the
+        # training records are done, so the host wait below ends while the validation record is still arriving
+        # and everything after it is queued ahead of the GPU
+        val_sums()
+        bdist.allreduce_sum_(sums_all[3 * nd:])
     if use_val_metric:
         _, _, yv_r, yv_i = bfrf.gp_targets_device(sums_all[3 * nd:], nv, standardise=False)   # frf_estimator.py:239-252
         Xv_d = gi.Xv_d
@@ -511,10 +526,11 @@ def identify_host(train: Sequence[Tuple[np.ndarray, np.ndarray, np.ndarray]],
     tensors, ideally pinned): what run_gp_pipeline does for .mat files (gp_pipeline.py:60-247), for arrays.
 
     Every record crosses the link exactly once per call: all uploads are queued on the copy stream up front
-    (validation record first, its 150-bin projection is the longer one to hide), each record is projected
-    piece by piece as its time stamps land, and the FIR validation reads the validation record's resident
-    copy -- so the link never idles between stages and only the last piece's projection, the GP stage and the
-    FIR pass are exposed after the final byte.  The uniform-timebase guess of each record (host look at its
+    (training records first, so that their targets' statistics -- the one mid-pass host read -- are back while
+    the validation record is still arriving), each record is projected piece by piece as its time stamps land,
+    and the FIR validation reads the validation record's resident copy -- so the link never idles between
+    stages, the host has everything queued before the last byte lands, and only the last piece's projection,
+    the GP stage and the FIR pass are exposed after it.  The uniform-timebase guess of each record (host look at its
     first 4096 stamps) is verified on the device over the whole resident record; the verdicts come back with
     the final host read, and a failed guess reruns the pass through :func:`identify_device` on the resident
     copies (general kernel).
@@ -529,19 +545,20 @@ def identify_host(train: Sequence[Tuple[np.ndarray, np.ndarray, np.ndarray]],
         val_sr = bfrf.StreamedRecord(val[0], val[1], val[2], gi.wv_d, span(val[0]), True, gi.wv_max,
                                      n_chunks if use_val_metric else 1)
     train_sr = [bfrf.StreamedRecord(t, u, y, gi.w_d, span(t), True, gi.w_max, n_chunks) for (t, u, y) in train]
-    order = ([val_sr] if val_sr is not None else []) + train_sr
+    order = train_sr + ([val_sr] if val_sr is not None else [])
     for sr in order:
         sr.enqueue_copies()
-    checks, coeffs = [], {}
-    for sr in order:
-        if sr is val_sr and not use_val_metric:
-            torch.cuda.current_stream().wait_event(sr.landed[-1])
-            continue
+    checks = []
+
+    def coefficients(sr):
         part = sr.project()
         if sr.needs_check():
-            dmax = sr.uniformity_async()
-            checks.append((dmax * sr.w_max >= bfrf.UNIFORM_PHASE_TOL).to(F64))
-        coeffs[id(sr)] = sr.finalize(part)
+            checks.append((sr.uniformity_async() * sr.w_max >= bfrf.UNIFORM_PHASE_TOL).to(F64))
+        return sr.finalize(part)
+
+    train_frf = [coefficients(sr) for sr in train_sr]
+    if val_sr is not None and not use_val_metric:
+        torch.cuda.current_stream().wait_event(val_sr.landed[-1])
     train_d = [(sr.t_d, sr.u_d, sr.y_d, sr.span, sr.t0) for sr in train_sr]
     val_d = None
     if val_sr is not None:
@@ -549,8 +566,8 @@ def identify_host(train: Sequence[Tuple[np.ndarray, np.ndarray, np.ndarray]],
         val_d = (val_sr.t_d, val_sr.u_d, val_sr.y_d, val_sr.span, float(val_sr.yh[skip]), val_sr.t0)
     try:
         return identify_device(train_d, val_d, nd, kernel, noise, candidates, theta0, use_validation_metric, n_taps,
-                               val_frf=coeffs.get(id(val_sr)) if use_val_metric else None,
-                               train_frf=[coeffs[id(sr)] for sr in train_sr], frf_checks=checks)
+                               val_frf=(lambda: coefficients(val_sr)) if use_val_metric else None,
+                               train_frf=train_frf, frf_checks=checks)
     except TimebaseGuessFailed:
         return identify_device(train_d, val_d, nd, kernel, noise, candidates, theta0, use_validation_metric, n_taps)
 

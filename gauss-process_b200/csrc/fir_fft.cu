@@ -210,6 +210,274 @@ fir_fft_kernel(const double* __restrict__ u, const double* __restrict__ y, int64
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Radix-16 organisation of the same transform: every pass keeps 16 elements of a thread in registers and runs TWO
+// of the radix-4 stages above on them (identical butterflies in identical order, so the values are the ones the
+// radix-4 kernel produces), which cuts the shared-memory round trips per unit from 11 to 4 and the barriers from
+// 13 to 5:
+//   A  : global -> registers, stages L = 4096, 1024            -> shared (natural order, padded)
+//   B  : stages L = 256, 64                                     -> shared, TRANSPOSED (element 16 g + e at e * 257 + g)
+//   C  : stages L = 16, 4, product with the tap spectrum, inverse stages L = 4, 16 (in place, transposed layout:
+//        a thread's 16 consecutive elements are 16 rows of pitch 257, so a warp reads consecutive addresses)
+//   B' : inverse stages L = 64, 256                             -> shared (natural order)
+//   A' : inverse stages L = 1024, 4096 -> registers -> error sums / y_pred straight from registers
+constexpr int FF_TPITCH = 257;
+
+__device__ __forceinline__ void bf4_dif(cplx& v0, cplx& v1, cplx& v2, cplx& v3, const cplx w1) {
+    const cplx w2 = cmul(w1, w1), w3 = cmul(w2, w1);
+    const cplx b0 = cadd(v0, v2), b1 = csub(v0, v2), b2 = cadd(v1, v3), b3 = mul_mj(csub(v1, v3));
+    v0 = cadd(b0, b2); v1 = cmul(cadd(b1, b3), w1); v2 = cmul(csub(b0, b2), w2); v3 = cmul(csub(b1, b3), w3);
+}
+__device__ __forceinline__ void bf4_dif_last(cplx& v0, cplx& v1, cplx& v2, cplx& v3) {
+    const cplx b0 = cadd(v0, v2), b1 = csub(v0, v2), b2 = cadd(v1, v3), b3 = mul_mj(csub(v1, v3));
+    v0 = cadd(b0, b2); v1 = cadd(b1, b3); v2 = csub(b0, b2); v3 = csub(b1, b3);
+}
+__device__ __forceinline__ void bf4_dit(cplx& v0, cplx& v1, cplx& v2, cplx& v3, const cplx w1) {
+    const cplx w2 = cmul(w1, w1), w3 = cmul(w2, w1);
+    const cplx c0 = v0, c1 = cmulc(v1, w1), c2 = cmulc(v2, w2), c3 = cmulc(v3, w3);
+    const cplx e0 = cadd(c0, c2), e1 = csub(c0, c2), e2 = cadd(c1, c3), e3 = mul_pj(csub(c1, c3));
+    v0 = cadd(e0, e2); v1 = cadd(e1, e3); v2 = csub(e0, e2); v3 = csub(e1, e3);
+}
+__device__ __forceinline__ void bf4_dit_first(cplx& v0, cplx& v1, cplx& v2, cplx& v3) {
+    const cplx e0 = cadd(v0, v2), e1 = csub(v0, v2), e2 = cadd(v1, v3), e3 = mul_pj(csub(v1, v3));
+    v0 = cadd(e0, e2); v1 = cadd(e1, e3); v2 = csub(e0, e2); v3 = csub(e1, e3);
+}
+__device__ __forceinline__ cplx ldtw(const double2* tw, int k) { const double2 t = tw[k]; return {t.x, t.y}; }
+
+// tap spectrum by the same radix-16 passes (forward half only): identical values to fir_fft_taps_kernel, a third of
+// its barriers -- this single-CTA launch sits serially in front of the main kernel
+__global__ void __launch_bounds__(FF_THREADS)
+fir_fft16_taps_kernel(const double* __restrict__ g, int n_taps, double2* __restrict__ Grev) {
+    extern __shared__ __align__(16) double2 ff_sm[];
+    double2* x = ff_sm;
+    double2* tw = ff_sm + FF_DATA_ELEMS;
+    const int tid = threadIdx.x;
+    const int gB = tid >> 4, jB = tid & 15;
+    cplx v[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int m = a * 1024 + b * 256 + tid;
+            v[a][b] = {m < n_taps ? __ldg(g + m) : 0.0, 0.0};
+        }
+    ff_make_twiddles(tw);
+    __syncthreads();
+#pragma unroll
+    for (int b = 0; b < 4; ++b) bf4_dif(v[0][b], v[1][b], v[2][b], v[3][b], ldtw(tw, b * 256 + tid));
+    {
+        const cplx w = ldtw(tw, 4 * tid);
+#pragma unroll
+        for (int a = 0; a < 4; ++a) bf4_dif(v[a][0], v[a][1], v[a][2], v[a][3], w);
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) sts(x, a * 1024 + b * 256 + tid, v[a][b]);
+    __syncthreads();
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) v[a][b] = lds(x, gB * 256 + a * 64 + b * 16 + jB);
+#pragma unroll
+    for (int b = 0; b < 4; ++b) bf4_dif(v[0][b], v[1][b], v[2][b], v[3][b], ldtw(tw, (b * 16 + jB) * 16));
+    {
+        const cplx w = ldtw(tw, jB * 64);
+#pragma unroll
+        for (int a = 0; a < 4; ++a) bf4_dif(v[a][0], v[a][1], v[a][2], v[a][3], w);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) x[jB * FF_TPITCH + 16 * gB + 4 * a + b] = make_double2(v[a][b].x, v[a][b].y);
+    __syncthreads();
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) { const double2 t = x[(4 * a + b) * FF_TPITCH + tid]; v[a][b] = {t.x, t.y}; }
+#pragma unroll
+    for (int b = 0; b < 4; ++b) bf4_dif(v[0][b], v[1][b], v[2][b], v[3][b], ldtw(tw, b * 256));
+    const double inv_n = 1.0 / (double)FF_N;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        bf4_dif_last(v[a][0], v[a][1], v[a][2], v[a][3]);
+#pragma unroll
+        for (int b = 0; b < 4; ++b) Grev[16 * tid + 4 * a + b] = make_double2(v[a][b].x * inv_n, v[a][b].y * inv_n);
+    }
+}
+
+__global__ void __launch_bounds__(FF_THREADS, FF_CTAS_PER_SM)
+fir_fft16_kernel(const double* __restrict__ u, const double* __restrict__ y, int64_t n, int64_t lead, int n_taps,
+                 const double2* __restrict__ Grev, int64_t skip, double y0, int64_t n_units,
+                 double* __restrict__ y_pred, double* __restrict__ cta_sums) {
+    extern __shared__ __align__(16) double2 ff_sm[];
+    double2* x = ff_sm;
+    double2* tw = ff_sm + FF_DATA_ELEMS;
+    __shared__ double scratch[FF_THREADS / 32];
+    const int tid = threadIdx.x;
+    const int hist = n_taps - 1;
+    const int V = FF_N - hist;                       // valid outputs per block
+    ff_make_twiddles(tw);
+    double se = 0.0, sy = 0.0, st = 0.0, cnt = 0.0;
+    const int gB = tid >> 4, jB = tid & 15;          // pass B / B': group of 256, offset inside the group's 16-blocks
+    cplx v[4][4];
+
+    for (int64_t unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+        const int64_t oA = unit * 2 * (int64_t)V, oB = oA + V;       // first output of blocks A and B
+        // ---- pass A: element a*1024 + b*256 + tid of z = uA + j uB straight from global memory.  Index windows as
+        // ints relative to the block start, so that every load is base pointer + immediate offset
+        const int64_t sA = oA - hist, sB = oB - hist;
+        const int loA = (int)max((int64_t)0, min((int64_t)FF_N, -lead - sA)), hiA = (int)max((int64_t)0, min((int64_t)FF_N, n - sA));
+        const int loB = (int)max((int64_t)0, min((int64_t)FF_N, -lead - sB)), hiB = (int)max((int64_t)0, min((int64_t)FF_N, n - sB));
+        const int skA = (int)max((int64_t)hist, min((int64_t)FF_N, skip - sA)), skB = (int)max((int64_t)hist, min((int64_t)FF_N, skip - sB));
+        {
+            const double* pa = u + sA + tid;
+            const double* pb = u + sB + tid;
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const int m = a * 1024 + b * 256 + tid;
+                    v[a][b].x = (m >= loA && m < hiA) ? __ldg(pa + (a * 1024 + b * 256)) : 0.0;
+                    v[a][b].y = (m >= loB && m < hiB) ? __ldg(pb + (a * 1024 + b * 256)) : 0.0;
+                }
+        }
+        __syncthreads();                                             // twiddles ready / previous unit's pass A' has read x
+#pragma unroll
+        for (int b = 0; b < 4; ++b) bf4_dif(v[0][b], v[1][b], v[2][b], v[3][b], ldtw(tw, b * 256 + tid));
+        {
+            const cplx w = ldtw(tw, 4 * tid);
+#pragma unroll
+            for (int a = 0; a < 4; ++a) bf4_dif(v[a][0], v[a][1], v[a][2], v[a][3], w);
+        }
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) sts(x, a * 1024 + b * 256 + tid, v[a][b]);
+        __syncthreads();
+        // ---- pass B: element g*256 + a*64 + b*16 + j
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) v[a][b] = lds(x, gB * 256 + a * 64 + b * 16 + jB);
+#pragma unroll
+        for (int b = 0; b < 4; ++b) bf4_dif(v[0][b], v[1][b], v[2][b], v[3][b], ldtw(tw, (b * 16 + jB) * 16));
+        {
+            const cplx w = ldtw(tw, jB * 64);
+#pragma unroll
+            for (int a = 0; a < 4; ++a) bf4_dif(v[a][0], v[a][1], v[a][2], v[a][3], w);
+        }
+        __syncthreads();                                             // every thread has read its pass-B inputs
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) x[jB * FF_TPITCH + 16 * gB + 4 * a + b] = make_double2(v[a][b].x, v[a][b].y);
+        __syncthreads();
+        // ---- pass C: elements 16 tid + 4a + b (transposed layout), spectrum product in the middle
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) { const double2 t = x[(4 * a + b) * FF_TPITCH + tid]; v[a][b] = {t.x, t.y}; }
+#pragma unroll
+        for (int b = 0; b < 4; ++b) bf4_dif(v[0][b], v[1][b], v[2][b], v[3][b], ldtw(tw, b * 256));
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            bf4_dif_last(v[a][0], v[a][1], v[a][2], v[a][3]);
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const double2 g = __ldg(Grev + 16 * tid + 4 * a + b);
+                v[a][b] = cmul(v[a][b], {g.x, g.y});
+            }
+            bf4_dit_first(v[a][0], v[a][1], v[a][2], v[a][3]);
+        }
+#pragma unroll
+        for (int b = 0; b < 4; ++b) bf4_dit(v[0][b], v[1][b], v[2][b], v[3][b], ldtw(tw, b * 256));
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) x[(4 * a + b) * FF_TPITCH + tid] = make_double2(v[a][b].x, v[a][b].y);
+        __syncthreads();
+        // ---- pass B': inverse stages L = 64 (over b), 256 (over a)
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) { const double2 t = x[jB * FF_TPITCH + 16 * gB + 4 * a + b]; v[a][b] = {t.x, t.y}; }
+        {
+            const cplx w = ldtw(tw, jB * 64);
+#pragma unroll
+            for (int a = 0; a < 4; ++a) bf4_dit(v[a][0], v[a][1], v[a][2], v[a][3], w);
+        }
+#pragma unroll
+        for (int b = 0; b < 4; ++b) bf4_dit(v[0][b], v[1][b], v[2][b], v[3][b], ldtw(tw, (b * 16 + jB) * 16));
+        __syncthreads();                                             // every thread has read its pass-B' inputs
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) sts(x, gB * 256 + a * 64 + b * 16 + jB, v[a][b]);
+        __syncthreads();
+        // ---- pass A': inverse stages L = 1024 (over b), 4096 (over a); results stay in registers
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) v[a][b] = lds(x, a * 1024 + b * 256 + tid);
+        {
+            const cplx w = ldtw(tw, 4 * tid);
+#pragma unroll
+            for (int a = 0; a < 4; ++a) bf4_dit(v[a][0], v[a][1], v[a][2], v[a][3], w);
+        }
+#pragma unroll
+        for (int b = 0; b < 4; ++b) bf4_dit(v[0][b], v[1][b], v[2][b], v[3][b], ldtw(tw, b * 256 + tid));
+        // ---- epilogue: m = a*1024 + b*256 + tid; valid part m in [hist, N) -> outputs sA + m (real part), sB + m
+        // (imaginary part); the sums take m >= skA / skB (>= hist, and past the transient skip)
+        {
+            const double* qa = y + sA + tid;
+            const double* qb = y + sB + tid;
+            double* ra = y_pred + sA + tid;
+            double* rb = y_pred + sB + tid;
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                double ya[4], yb[4];
+                if (y) {
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        const int m = a * 1024 + b * 256 + tid;
+                        ya[b] = (m >= skA && m < hiA) ? __ldg(qa + (a * 1024 + b * 256)) : 0.0;
+                        yb[b] = (m >= skB && m < hiB) ? __ldg(qb + (a * 1024 + b * 256)) : 0.0;
+                    }
+                }
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const int m = a * 1024 + b * 256 + tid;
+                    if (y_pred) {
+                        if (m >= hist && m < hiA) ra[a * 1024 + b * 256] = v[a][b].x;
+                        if (m >= hist && m < hiB) rb[a * 1024 + b * 256] = v[a][b].y;
+                    }
+                    if (y) {
+                        if (m >= skA && m < hiA) {
+                            const double yi = ya[b], e = yi - v[a][b].x, d0 = yi - y0;
+                            se = fma(e, e, se); sy = fma(yi, yi, sy); st = fma(d0, d0, st); cnt += 1.0;
+                        }
+                        if (m >= skB && m < hiB) {
+                            const double yi = yb[b], e = yi - v[a][b].y, d0 = yi - y0;
+                            se = fma(e, e, se); sy = fma(yi, yi, sy); st = fma(d0, d0, st); cnt += 1.0;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    se = block_sum(se, scratch);
+    sy = block_sum(sy, scratch);
+    st = block_sum(st, scratch);
+    cnt = block_sum(cnt, scratch);
+    if (tid == 0) {
+        double* o = cta_sums + 4 * (size_t)blockIdx.x;
+        o[0] = se; o[1] = sy; o[2] = st; o[3] = cnt;
+    }
+}
+
 constexpr size_t FF_SMEM_BYTES = (size_t)(FF_DATA_ELEMS + FF_N / 4) * sizeof(double2);
 
 }  // namespace b200id
@@ -221,6 +489,15 @@ size_t b200id_fir_fft_workspace_bytes() {
 }
 bool b200id_fir_fft_applicable(int64_t n, int n_taps) {
     return n_taps >= 128 && n_taps <= FF_MAX_TAPS && n >= 32768;
+}
+
+// organisation of the overlap-save transform: 0 = radix-16 passes (default), 1 = radix-4 passes; -1 = not yet read
+// from the environment (B200ID_FIR_RADIX4=1)
+static int g_fir_radix4 = -1;
+extern "C" int b200id_fir_select_fft(int radix4) {
+    const int prev = g_fir_radix4 == 1 ? 1 : 0;
+    g_fir_radix4 = radix4 < 0 ? -1 : (radix4 ? 1 : 0);
+    return prev;
 }
 
 // fir_fold_kernel lives in fir_conv.cu
@@ -236,14 +513,29 @@ int b200id_fir_eval_fft(const double* u, const double* y, int64_t n, int64_t lea
     if (rc) return rc;
     rc = check_cuda(cudaFuncSetAttribute(fir_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FF_SMEM_BYTES), "cudaFuncSetAttribute(fir fft)");
     if (rc) return rc;
-    fir_fft_taps_kernel<<<1, FF_THREADS, FF_SMEM_BYTES, st>>>(g, n_taps, Grev);
-    B200ID_LAUNCH_CHECK("fir_fft_taps_kernel");
+    if (g_fir_radix4 < 0) { const char* e = getenv("B200ID_FIR_RADIX4"); g_fir_radix4 = (e && e[0] == '1') ? 1 : 0; }
+    if (g_fir_radix4) {
+        fir_fft_taps_kernel<<<1, FF_THREADS, FF_SMEM_BYTES, st>>>(g, n_taps, Grev);
+        B200ID_LAUNCH_CHECK("fir_fft_taps_kernel");
+    } else {
+        rc = check_cuda(cudaFuncSetAttribute(fir_fft16_taps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FF_SMEM_BYTES), "cudaFuncSetAttribute(fir fft16 taps)");
+        if (rc) return rc;
+        fir_fft16_taps_kernel<<<1, FF_THREADS, FF_SMEM_BYTES, st>>>(g, n_taps, Grev);
+        B200ID_LAUNCH_CHECK("fir_fft16_taps_kernel");
+    }
     const int V = FF_N - (n_taps - 1);
     const int64_t n_units = (n + 2 * (int64_t)V - 1) / (2 * (int64_t)V);
     int grid = sm_count() * FF_CTAS_PER_SM;
     if (n_units < grid) grid = (int)n_units;
-    fir_fft_kernel<<<grid, FF_THREADS, FF_SMEM_BYTES, st>>>(u, y, n, lead, n_taps, Grev, skip, y0, n_units, y_pred_out, cta_sums);
-    B200ID_LAUNCH_CHECK("fir_fft_kernel");
+    if (g_fir_radix4) {
+        fir_fft_kernel<<<grid, FF_THREADS, FF_SMEM_BYTES, st>>>(u, y, n, lead, n_taps, Grev, skip, y0, n_units, y_pred_out, cta_sums);
+        B200ID_LAUNCH_CHECK("fir_fft_kernel");
+    } else {
+        rc = check_cuda(cudaFuncSetAttribute(fir_fft16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FF_SMEM_BYTES), "cudaFuncSetAttribute(fir fft16)");
+        if (rc) return rc;
+        fir_fft16_kernel<<<grid, FF_THREADS, FF_SMEM_BYTES, st>>>(u, y, n, lead, n_taps, Grev, skip, y0, n_units, y_pred_out, cta_sums);
+        B200ID_LAUNCH_CHECK("fir_fft16_kernel");
+    }
     fir_fold_kernel<<<1, 256, 0, st>>>(cta_sums, grid, sums_out);
     B200ID_LAUNCH_CHECK("fir_fold_kernel");
     return B200ID_OK;

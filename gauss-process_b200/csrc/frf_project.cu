@@ -613,7 +613,7 @@ frf_project_uniform_g_kernel(const double* __restrict__ t, const double* __restr
                              double* __restrict__ cta_partial) {
     extern __shared__ __align__(16) double smem[];
     double2* ab = reinterpret_cast<double2*>(smem);                 // [tile] (w_i (u_i - mean), w_i (y_i - mean))
-    float4* f4 = reinterpret_cast<float4*>(ab + FRFG_TILE_MAX);      // [tile] (delta_i, a_u, a_y, -) in FP32
+    float4* f4 = reinterpret_cast<float4*>(ab + FRFG_TILE_MAX);      // [tile] (a_u, a_y, delta_i, -) in FP32: (a_u, a_y) is an aligned f32x2 pair
     double* tt = reinterpret_cast<double*>(f4 + FRFG_TILE_MAX);      // [tile] t_i
     double* acc = tt + FRFG_TILE_MAX;                                // [8][FRF_THREADS] running sums of this thread
     __shared__ int s_good[FRF_THREADS];
@@ -661,7 +661,7 @@ frf_project_uniform_g_kernel(const double* __restrict__ t, const double* __restr
             const double au = wt * (__ldg(u + i) - mean_u), ay = HAS_Y ? wt * (__ldg(y + i) - mean_y) : 0.0;
             tt[j] = ti;
             ab[j] = make_double2(au, ay);
-            f4[j] = make_float4((float)(((d - ph) - pl) + derr), (float)au, (float)ay, 0.0f);
+            f4[j] = make_float4((float)au, (float)ay, (float)(((d - ph) - pl) + derr), 0.0f);
         }
         __syncthreads();
         if (active && r < cnt) {
@@ -672,10 +672,10 @@ frf_project_uniform_g_kernel(const double* __restrict__ t, const double* __restr
     {                                                                                                \
         const double p = (wk) * tv;                                                                  \
         const float ef = (float)fma((wk), tv, -p);                                                   \
-        const float epsf = fmaf((wkf), fv.x, -ef);                                                   \
+        const float epsf = fmaf((wkf), fv.z, -ef);                                                   \
         U2 = fma((K), U1, abv.x - U2);                                                               \
         if (HAS_Y) Y2 = fma((K), Y1, abv.y - Y2);                                                    \
-        const float2 xe = __fmul2_rn(make_float2(fv.y, fv.z), make_float2(epsf, epsf));              \
+        const float2 xe = __fmul2_rn(make_float2(fv.x, fv.y), make_float2(epsf, epsf));              \
         Q2 = __ffma2_rn((Kf), Q1, __fadd2_rn(xe, make_float2(-Q2.x, -Q2.y)));                        \
     }
             int j = r;
@@ -969,7 +969,7 @@ static bool frf_mma_enabled() {
 }
 
 #ifndef FRF_GOERTZEL_DEFAULT
-#define FRF_GOERTZEL_DEFAULT 0
+#define FRF_GOERTZEL_DEFAULT 1
 #endif
 static int g_frf_goertzel = -1;
 static bool frf_goertzel_enabled() {

@@ -237,6 +237,12 @@ int b200id_chol_blocked(double* A, int n, int lda, int* info_out, void* ws, size
  * extension of G_pos (M = 2 nd - 1, X[0] = Re G[0]).  fir_helpers.py:75-137. */
 int b200id_idft_hermitian(const double* G_pos /*[2*nd]*/, int nd, double* h_out, int n_taps, void* stream);
 
+/* Organisation of b200id_fir_eval's overlap-save transform: 0 = radix-16 passes (fir_fft16_kernel, default),
+ * 1 = radix-4 passes (fir_fft_kernel; same butterflies in the same order, hence the same values), -1 = back to the
+ * default (environment B200ID_FIR_RADIX4).  Process-wide, for tests and timing comparisons.  Returns the previous
+ * setting. */
+int b200id_fir_select_fft(int radix4);
+
 /* Causal FIR y_pred[i] = sum_{j<n_taps, j<=i+lead} g[j] u[i-j] over OWNED outputs [own_begin, own_end)
  * of a resident slice (u has `lead` samples of history before index 0 of y: u points at the slice start,
  * u[-lead..-1] must be readable when lead > 0), fused with the error sums over i >= skip_global:

@@ -131,3 +131,35 @@ def test_public_validate_streams_large_host_records(fir, monkeypatch):
     assert rel_max(ps, pb) < 1e-13
     for k in ("rmse", "fit_percent", "r2"):
         assert abs(ms[k] - mb[k]) <= 1e-12 * max(1.0, abs(mb[k])), k
+
+
+@pytest.mark.parametrize("n,taps,lead", [(100_003, 1024, 0), (65_536, 128, 0), (70_001, 2048, 0), (250_000, 1024, 1023),
+                                         (40_000, 777, 300)])
+def test_radix16_passes_reproduce_radix4_passes(fir, n, taps, lead):
+    """The radix-16 organisation of the overlap-save transform (fir_fft16_kernel: two radix-4 stages per pass in
+    registers) runs the radix-4 kernel's butterflies in the same order, so the predictions are the radix-4
+    kernel's bit for bit -- ragged last unit, shortest / longest tap counts, history before the slice."""
+    import ctypes as C
+    import torch
+    from b200id import _lib
+    from b200id.runtime import require_cuda, to_device
+    dev = require_cuda()
+    rng = np.random.default_rng(n + taps)
+    u_full, y_full, g = rng.standard_normal(n + lead), rng.standard_normal(n + lead), rng.standard_normal(taps) * 0.02
+    u_d, y_d, g_d = to_device(u_full, dev), to_device(y_full, dev), to_device(g, dev)
+    skip, y0 = 10, float(y_full[lead + 10])
+    lib = _lib.load()
+    out = {}
+    prev = lib.b200id_fir_select_fft(C.c_int(0))
+    try:
+        for radix4 in (0, 1):
+            lib.b200id_fir_select_fft(C.c_int(radix4))
+            sums, pred = fir.fir_eval_device(u_d[lead:], y_d[lead:], g_d, skip, y0, want_pred=True, lead=lead)
+            torch.cuda.synchronize()
+            out[radix4] = (sums.cpu().numpy(), pred.cpu().numpy())
+    finally:
+        lib.b200id_fir_select_fft(C.c_int(-1 if prev == 0 else prev))
+    assert np.array_equal(out[0][1], out[1][1])                      # predictions: bit for bit
+    np.testing.assert_allclose(out[0][0], out[1][0], rtol=1e-13)     # sums: other thread -> element map, other addition order
+    ref = np.convolve(u_full, g)[lead:lead + n]
+    assert record(f"fir.fft16.n{n}.taps{taps}.lead{lead}", float(np.max(np.abs(out[0][1] - ref)) / np.max(np.abs(ref)))) < 1e-12

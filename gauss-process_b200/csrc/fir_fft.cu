@@ -332,6 +332,16 @@ fir_fft16_kernel(const double* __restrict__ u, const double* __restrict__ y, int
         const int loB = (int)max((int64_t)0, min((int64_t)FF_N, -lead - sB)), hiB = (int)max((int64_t)0, min((int64_t)FF_N, n - sB));
         const int skA = (int)max((int64_t)hist, min((int64_t)FF_N, skip - sA)), skB = (int)max((int64_t)hist, min((int64_t)FF_N, skip - sB));
         {
+            // L2 prefetch, one 128-byte line per thread and step: this unit's measured outputs (read in the epilogue)
+            // and the NEXT unit's input window [sA', sA' + 2V + hist), so that neither is a DRAM round trip when the
+            // 16 warps of an SM get to it
+            const int64_t nA = sA + (int64_t)gridDim.x * 2 * V;
+            for (int ln = tid; ln * 16 < 2 * V + hist + 16; ln += FF_THREADS) {
+                const int64_t iu = nA + (int64_t)ln * 16;
+                if (iu >= -lead && iu < n) asm volatile("prefetch.global.L2 [%0];" ::"l"(u + iu));
+                const int64_t iy = oA + (int64_t)ln * 16;
+                if (y && iy < n && ln * 16 < 2 * V + 16) asm volatile("prefetch.global.L2 [%0];" ::"l"(y + iy));
+            }
             const double* pa = u + sA + tid;
             const double* pb = u + sB + tid;
 #pragma unroll

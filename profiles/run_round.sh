@@ -1,9 +1,10 @@
 #!/bin/bash
-# One GPU call: parity tests of the changed kernels, then the hot kernels once plain and once under ncu --set full.
+# One GPU call: the full GPU suite, the default bench line, then the launch list of a short bench run under ncu.
 mkdir -p gpurun_out
-python -m pytest tests/test_frf_gpu.py tests/test_fir_gpu.py tests/test_pipeline_gpu.py -m gpu -q 2>&1 | tail -8 > gpurun_out/pytest_gpu_part.log
-cat gpurun_out/pytest_gpu_part.log
-python profiles/run_kernels.py --cands 2048 > gpurun_out/run_kernels.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:'frf_project_uniform_g_kernel|fir_fft16_kernel' -c 4 \
-    -o gpurun_out/prof_r1g -f python profiles/run_kernels.py --cands 2048 > gpurun_out/ncu_run.log 2>&1
-cat gpurun_out/run_kernels.log; tail -5 gpurun_out/ncu_run.log
+python -m pytest tests -m gpu -q 2>&1 | tail -12 > gpurun_out/pytest_gpu.log
+cat gpurun_out/pytest_gpu.log
+python bench.py > gpurun_out/bench.log 2> gpurun_out/bench.err
+python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/bench_plain.log 2>&1 &&
+ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/launches.csv \
+    python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
+tail -c 300 gpurun_out/bench.err gpurun_out/ncu_bench.log

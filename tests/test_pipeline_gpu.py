@@ -115,3 +115,32 @@ def test_identify_host_recovers_from_a_wrong_timebase_guess():
     assert np.array_equal(ref.theta_real, got.theta_real) and np.array_equal(ref.theta_imag, got.theta_imag)
     w, G = ofrf.estimate_frf([(t, u, y)], nd)
     assert float(np.max(np.abs(Gg - G) / np.abs(G))) < 1e-9
+
+
+def test_identify_host_two_training_records_and_no_search():
+    """Cross-power average over two host records (transform.py:124-150) and the no-search branch (fixed theta,
+    validation record used by the FIR pass only, i.e. uploaded but not projected)."""
+    import torch
+    from b200id import pipeline as P, synth
+    from b200id.runtime import require_cuda, to_device
+    dev = require_cuda()
+    n, nd = 120_000, 30
+    recs = [synth.make_record(n, nd, "multisine", seed=s) for s in (31, 32)]
+    tv, uv, yv = synth.make_record(n, nd, "square", seed=33)
+    skip = min(10, 1024 // 10)
+    train_d = [(to_device(t, dev), to_device(u, dev), to_device(y, dev), float(t[-1] - t[0]), float(t[0])) for t, u, y in recs]
+    val_d = (to_device(tv, dev), to_device(uv, dev), to_device(yv, dev), float(tv[-1] - tv[0]), float(yv[skip]), float(tv[0]))
+    cands = P.CandidateSet.build("matern52", P.grid_candidates("matern52"), dev)
+    for kwargs in ({"candidates": cands}, {"candidates": None, "theta0": [0.7, 1.3]}):
+        ref = P.identify_device(train_d, val_d, nd, "matern52", 1e-6, **kwargs)
+        got = P.identify_host(recs, (tv, uv, yv), nd, "matern52", 1e-6, **kwargs)
+        torch.cuda.synchronize()
+        Gr, Gg = ref.G.cpu().numpy(), got.G.cpu().numpy()
+        assert float(np.max(np.abs(Gg - Gr) / np.abs(Gr))) < 1e-11
+        assert np.array_equal(ref.theta_real, got.theta_real) and np.array_equal(ref.theta_imag, got.theta_imag)
+        assert abs(got.fir["rmse"] - ref.fir["rmse"]) <= 1e-8 * ref.fir["rmse"]
+    # no validation record at all: FRF -> fit -> taps only
+    got = P.identify_host(recs, None, nd, "matern52", 1e-6, candidates=None, theta0=[0.7, 1.3])
+    ref = P.identify_device(train_d, None, nd, "matern52", 1e-6, candidates=None, theta0=[0.7, 1.3])
+    tr, tg = ref.taps.cpu().numpy(), got.taps.cpu().numpy()
+    assert float(np.max(np.abs(tg - tr)) / np.max(np.abs(tr))) < 1e-8 and got.fir == {}

@@ -10,6 +10,9 @@
 //     (3) syrk : A[i,j] -= P_i P_j^T for tiles i >= j  -- 64x64x64 FP64 tile products, 256 threads, each a 4x4 block
 //                of the output tile, operands staged k-major in shared memory (one 32-byte vector load per 4 rows /
 //                4 columns, 16 DFMA per 8 loaded doubles)
+// Extra rows (n_rows > n, the right-hand sides of the GP solve stored as rows n.. of the same array) ride along: the
+// panel step turns them into z^T = (L^-1 y)^T block column by block column and the trailing update keeps them current,
+// so the forward substitution of the solve costs no launch of its own (cholb_factor_rows; gp_large.cu).
 // One factorisation is a chain of 2 n / 64 dependent launches, i.e. latency bound at n = 2048 (1.9 ms where the flops
 // alone would take 0.1 ms); throughput comes from running several candidates side by side (gp_large.cu).
 #include "common.cuh"
@@ -144,9 +147,11 @@ __device__ __forceinline__ bool cholb_factor_block(double* __restrict__ D, doubl
 }
 
 __global__ void __launch_bounds__(CB_THREADS)
-cholb_diag_kernel(double* __restrict__ A, int lda, int n, int k0, int* __restrict__ info) {
+cholb_diag_kernel(double* __restrict__ A, int lda, int n, int k0, int* __restrict__ info, size_t a_stride, size_t info_stride) {
     __shared__ double D[CB_NB * CB_LDD];
     __shared__ double dg[CB_NB];
+    A += blockIdx.z * a_stride;                      // blockIdx.z = matrix of a batch advancing in lockstep
+    info += blockIdx.z * info_stride;
     if (info[0] != 0) return;                       // an earlier block already failed
     const int nb = min(CB_NB, n - k0);
     const int tid = threadIdx.x;
@@ -176,14 +181,20 @@ cholb_diag_kernel(double* __restrict__ A, int lda, int n, int k0, int* __restric
 // of a warp never touch each other's data, no block barrier inside the loop.
 constexpr int CB_LDP = CB_NB + 1;
 __global__ void __launch_bounds__(CB_THREADS)
-cholb_panel_kernel(double* __restrict__ A, int lda, int n, int k0, const int* __restrict__ info) {
+cholb_panel_kernel(double* __restrict__ A, int lda, int n, int n_rows, int k0, const int* __restrict__ info,
+                   size_t a_stride, size_t info_stride) {
     extern __shared__ __align__(16) double cb_sm[];
     double* Ps = cb_sm;                              // [64][65] rows of the panel tile
     double* Ls = cb_sm + CB_NB * CB_LDP;             // [64][65] L_kk, Ls[c][p] = L[c][p], p <= c
     __shared__ double idg[CB_NB];
+    A += blockIdx.z * a_stride;
+    info += blockIdx.z * info_stride;
     if (info[0] != 0) return;
     const int tid = threadIdx.x;
-    const int r0 = k0 + CB_NB + blockIdx.x * CB_NB;
+    // nb < 64 only for the last block column, which has a panel only when extra rows ride along: L_kk is then
+    // completed by an identity block and the columns past n are neither read nor written
+    const int nb = min(CB_NB, n - k0);
+    const int r0 = k0 + nb + blockIdx.x * CB_NB;
     {
         constexpr int PER = CB_NB * CB_NB / CB_THREADS;
         double vp[PER], vl[PER];
@@ -191,8 +202,8 @@ cholb_panel_kernel(double* __restrict__ A, int lda, int n, int k0, const int* __
         for (int it = 0; it < PER; ++it) {
             const int e = tid + it * CB_THREADS;
             const int r = e >> 6, c = e & 63;
-            vp[it] = (r0 + r < n) ? A[(size_t)(r0 + r) * lda + k0 + c] : 0.0;
-            vl[it] = (c <= r) ? A[(size_t)(k0 + r) * lda + k0 + c] : 0.0;
+            vp[it] = (r0 + r < n_rows && c < nb) ? A[(size_t)(r0 + r) * lda + k0 + c] : 0.0;
+            vl[it] = (r < nb) ? ((c <= r) ? A[(size_t)(k0 + r) * lda + k0 + c] : 0.0) : (c == r ? 1.0 : 0.0);
         }
 #pragma unroll
         for (int it = 0; it < PER; ++it) {
@@ -233,16 +244,19 @@ cholb_panel_kernel(double* __restrict__ A, int lda, int n, int k0, const int* __
     __syncthreads();
     for (int e = tid; e < CB_NB * CB_NB; e += CB_THREADS) {
         const int rr = e >> 6, c = e & 63;
-        if (r0 + rr < n) A[(size_t)(r0 + rr) * lda + k0 + c] = Ps[rr * CB_LDP + c];
+        if (r0 + rr < n_rows && c < nb) A[(size_t)(r0 + rr) * lda + k0 + c] = Ps[rr * CB_LDP + c];
     }
 }
 
 // (3) trailing update over lower-triangle tiles (ti >= tj) of the matrix starting at s = k0 + 64
 __global__ void __launch_bounds__(CB_THREADS)
-cholb_syrk_kernel(double* __restrict__ A, int lda, int n, int k0, int* __restrict__ info) {
+cholb_syrk_kernel(double* __restrict__ A, int lda, int n, int n_rows, int k0, int* __restrict__ info,
+                  size_t a_stride, size_t info_stride) {
     extern __shared__ __align__(16) double cb_sm[];
     double* As = cb_sm;
     double* Bs = cb_sm + CB_NB * CB_LDT;
+    A += blockIdx.z * a_stride;
+    info += blockIdx.z * info_stride;
     if (info[0] != 0) return;
     // linear tile index -> (ti, tj), ti >= tj
     const int lin = blockIdx.x;
@@ -252,7 +266,7 @@ cholb_syrk_kernel(double* __restrict__ A, int lda, int n, int k0, int* __restric
     const int tj = lin - ti * (ti + 1) / 2;
     const int s = k0 + CB_NB;
     const int r0 = s + ti * CB_NB, c0 = s + tj * CB_NB;
-    stage_tile_kmajor(A, lda, r0, n, k0, As);
+    stage_tile_kmajor(A, lda, r0, n_rows, k0, As);
     stage_tile_kmajor(A, lda, c0, n, k0, Bs);
     __syncthreads();
     const int ty = threadIdx.x / 16, tx = threadIdx.x % 16;
@@ -265,7 +279,7 @@ cholb_syrk_kernel(double* __restrict__ A, int lda, int n, int k0, int* __restric
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int c = c0 + 4 * tx + j;
-            cv[i][j] = (r < n && c <= r) ? A[(size_t)r * lda + c] : 0.0;
+            cv[i][j] = (r < n_rows && c <= r && c < n) ? A[(size_t)r * lda + c] : 0.0;
         }
     }
     if (lin == 0) {
@@ -284,6 +298,16 @@ cholb_syrk_kernel(double* __restrict__ A, int lda, int n, int k0, int* __restric
                 if (ii < nb && jj <= ii) D[jj * CB_LDD + ii] = cv[i][j] - acc[i][j];
             }
         }
+        // rows of this tile below the diagonal block exist only as extra rows (nb < 64): plain update
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int r = r0 + 4 * ty + i;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int c = c0 + 4 * tx + j;
+                if (4 * ty + i >= nb && r < n_rows && c < n) A[(size_t)r * lda + c] = cv[i][j] - acc[i][j];
+            }
+        }
         __syncthreads();
         cholb_factor_block(D, dg, nb, A, lda, s, info);
         return;
@@ -294,7 +318,7 @@ cholb_syrk_kernel(double* __restrict__ A, int lda, int n, int k0, int* __restric
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int c = c0 + 4 * tx + j;
-            if (r < n && c <= r) A[(size_t)r * lda + c] = cv[i][j] - acc[i][j];
+            if (r < n_rows && c <= r && c < n) A[(size_t)r * lda + c] = cv[i][j] - acc[i][j];
         }
     }
 }
@@ -308,14 +332,17 @@ extern "C" size_t b200id_chol_blocked_workspace_bytes(int n) {
     return align_up((size_t)CB_NB * CB_NB * sizeof(double), 256);
 }
 
-extern "C" int b200id_chol_blocked(double* A, int n, int lda, int* info_out, void* ws, size_t ws_bytes, void* stream) {
-    B200ID_REQUIRE(A && info_out && ws, B200ID_E_ARG, "chol_blocked: null pointer");
-    B200ID_REQUIRE(n > 0 && lda >= n, B200ID_E_ARG, "chol_blocked: bad sizes n=%d lda=%d", n, lda);
-    B200ID_REQUIRE(ws_bytes >= (size_t)CB_NB * CB_NB * sizeof(double), B200ID_E_WORKSPACE, "chol_blocked: workspace too small");
-    cudaStream_t st = (cudaStream_t)stream;
-    int rc = check_cuda(cudaMemsetAsync(info_out, 0, sizeof(int), st), "cudaMemsetAsync(info)");
-    if (rc) return rc;
-    (void)ws;                                        // kept in the signature: earlier versions staged L_kk^-1 here
+// Factorise the n x n lower triangle of row-major A (ld = lda) and carry rows [n, n_rows) along (see the header).
+// batch > 1: `batch` matrices a_stride doubles apart (status words info_stride ints apart) advance in LOCKSTEP, one
+// launch per step for all of them (blockIdx.z): the chain of dependent launches is paid once per batch, not once per
+// matrix, and every launch brings batch times the CTAs.
+int cholb_factor_rows(double* A, int n, int n_rows, int lda, int* info_out, cudaStream_t st, int batch, size_t a_stride,
+                      size_t info_stride) {
+    int rc = B200ID_OK;
+    for (int z = 0; z < batch; ++z) {
+        rc = check_cuda(cudaMemsetAsync(info_out + (size_t)z * info_stride, 0, sizeof(int), st), "cudaMemsetAsync(info)");
+        if (rc) return rc;
+    }
     const size_t smem_panel = 2 * (size_t)CB_NB * CB_LDP * sizeof(double);
     const size_t smem = 2 * (size_t)CB_NB * CB_LDT * sizeof(double);
     rc = check_cuda(cudaFuncSetAttribute(cholb_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_panel), "cudaFuncSetAttribute(panel)");
@@ -324,14 +351,25 @@ extern "C" int b200id_chol_blocked(double* A, int n, int lda, int* info_out, voi
     if (rc) return rc;
     // the first diagonal block has a launch of its own; every later one is factorised by the update kernel of the
     // block column before it (CTA of tile (0, 0))
-    cholb_diag_kernel<<<1, CB_THREADS, 0, st>>>(A, lda, n, 0, info_out);
+    cholb_diag_kernel<<<dim3(1, 1, batch), CB_THREADS, 0, st>>>(A, lda, n, 0, info_out, a_stride, info_stride);
     for (int k0 = 0; k0 < n; k0 += CB_NB) {
-        const int m = n - (k0 + CB_NB);
-        if (m <= 0) break;
-        const int tiles = (m + CB_NB - 1) / CB_NB;
-        cholb_panel_kernel<<<tiles, CB_THREADS, smem_panel, st>>>(A, lda, n, k0, info_out);
-        cholb_syrk_kernel<<<tiles * (tiles + 1) / 2, CB_THREADS, smem, st>>>(A, lda, n, k0, info_out);
+        const int nb = n - k0 < CB_NB ? n - k0 : CB_NB;
+        const int below = n_rows - (k0 + nb);                // rows under this diagonal block (incl. extra rows)
+        if (below <= 0) break;
+        cholb_panel_kernel<<<dim3((below + CB_NB - 1) / CB_NB, 1, batch), CB_THREADS, smem_panel, st>>>(A, lda, n, n_rows, k0, info_out, a_stride, info_stride);
+        if (n - (k0 + CB_NB) > 0) {                           // trailing columns left
+            const int tiles = (n_rows - (k0 + CB_NB) + CB_NB - 1) / CB_NB;
+            cholb_syrk_kernel<<<dim3(tiles * (tiles + 1) / 2, 1, batch), CB_THREADS, smem, st>>>(A, lda, n, n_rows, k0, info_out, a_stride, info_stride);
+        }
     }
     B200ID_LAUNCH_CHECK("chol_blocked kernels");
     return B200ID_OK;
+}
+
+extern "C" int b200id_chol_blocked(double* A, int n, int lda, int* info_out, void* ws, size_t ws_bytes, void* stream) {
+    B200ID_REQUIRE(A && info_out && ws, B200ID_E_ARG, "chol_blocked: null pointer");
+    B200ID_REQUIRE(n > 0 && lda >= n, B200ID_E_ARG, "chol_blocked: bad sizes n=%d lda=%d", n, lda);
+    B200ID_REQUIRE(ws_bytes >= (size_t)CB_NB * CB_NB * sizeof(double), B200ID_E_WORKSPACE, "chol_blocked: workspace too small");
+    (void)ws;                                        // kept in the signature: earlier versions staged L_kk^-1 here
+    return cholb_factor_rows(A, n, n, lda, info_out, (cudaStream_t)stream, 1, 0, 0);
 }

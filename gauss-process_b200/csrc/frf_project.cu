@@ -601,7 +601,14 @@ frf_project_uniform3_kernel(const double* __restrict__ t, const double* __restri
 // FP64-pipe instructions per sample-bin: 2 (e) + 1 (narrowing) + 4 (two Goertzel steps) = 7 of which only 3 read three
 // distinct registers, against 11 / 9 in the three-term kernel.  Accumulators live in shared memory (touched once per
 // tile), which keeps the loop under the 64-register cap.
-constexpr int FRFG_TILE_MAX = 1536;
+#ifndef FRFG_TILE
+#define FRFG_TILE 1536
+#endif
+#ifndef FRFG_UNROLL
+#define FRFG_UNROLL 1
+#endif
+constexpr int FRFG_TILE_MAX = FRFG_TILE;
+constexpr int FRFG_UNROLL_N = FRFG_UNROLL;
 constexpr size_t FRFG_SMEM_BYTES = (size_t)FRFG_TILE_MAX * (16 + 8 + 16) + (size_t)8 * FRF_THREADS * sizeof(double);
 
 template <bool HAS_Y>
@@ -679,6 +686,7 @@ frf_project_uniform_g_kernel(const double* __restrict__ t, const double* __restr
         Q2 = __ffma2_rn((Kf), Q1, __fadd2_rn(xe, make_float2(-Q2.x, -Q2.y)));                        \
     }
             int j = r;
+#pragma unroll FRFG_UNROLL_N
             for (; j + R < cnt; j += 2 * R) {
                 {
                     const double tv = tt[j]; const double2 abv = ab[j]; const float4 fv = f4[j];

@@ -328,9 +328,9 @@ extern "C" int b200id_gp_gram(int kernel_id, const double* theta, const double* 
 }
 
 extern "C" size_t b200id_gp_batch_workspace_bytes(int64_t n_candidates, int n) {
-    // large n: one slice per concurrently factorised candidate (up to 8 lanes, see b200id_gp_batch_eval_large)
+    // large n: one slice per concurrently factorised candidate (up to 16 lanes, see b200id_gp_batch_eval_large)
     if (n > GP_NMAX_SMEM) {
-        const size_t lanes = (size_t)(n_candidates < 1 ? 1 : (n_candidates > 8 ? 8 : n_candidates));
+        const size_t lanes = (size_t)(n_candidates < 1 ? 1 : (n_candidates > 16 ? 16 : n_candidates));
         return lanes * (b200id_gp_large_workspace_bytes(n, GP_LARGE_NV_CAP) + 512);
     }
     return 256;     // the shared-memory paths need no global scratch

@@ -9,6 +9,9 @@
 
 extern "C" size_t b200id_chol_blocked_workspace_bytes(int n);
 extern "C" int b200id_chol_blocked(double* A, int n, int lda, int* info_out, void* ws, size_t ws_bytes, void* stream);
+// chol_blocked.cu: same factorisation with rows [n, n_rows) of A carried along (right-hand sides as extra rows)
+int cholb_factor_rows(double* A, int n, int n_rows, int lda, int* info_out, cudaStream_t st, int batch, size_t a_stride,
+                      size_t info_stride);
 
 namespace b200id {
 
@@ -28,26 +31,41 @@ __device__ __forceinline__ void gl_gram_rows(const KernelParams& kp, const doubl
         A[e] = v;
     }
 }
+// blockIdx.z = candidate of a lockstep batch: theta [z][B200ID_MAX_PARAMS], diag_add_dev [z], arrays a_stride apart
 __global__ void gl_gram_kernel(int kernel_id, const double* __restrict__ theta, const double* __restrict__ X, int n,
-                               double diag_add, const double* __restrict__ diag_add_dev, double* __restrict__ A) {
-    const KernelParams kp = make_kernel_params(kernel_id, theta);
-    if (diag_add_dev) diag_add = diag_add_dev[0];
+                               double diag_add, const double* __restrict__ diag_add_dev, double* __restrict__ A,
+                               const double* __restrict__ y, size_t a_stride) {
+    const KernelParams kp = make_kernel_params(kernel_id, theta + (size_t)blockIdx.z * B200ID_MAX_PARAMS);
+    if (diag_add_dev) diag_add = diag_add_dev[blockIdx.z];
+    A += blockIdx.z * a_stride;
+    // row n of the array: the right-hand side, which the factorisation turns into z = L^-1 y on the way
+    if (y)
+        for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) A[(size_t)n * n + j] = y[j];
     B200ID_DISPATCH_KERNEL(kernel_id, gl_gram_rows, kp, X, n, diag_add, A)
 }
 
 // z = L^-1 r then (optionally) alpha = L^-T z, single CTA, blocks of 64.  L row-major lower, ld = n.
 // out_z / out_alpha may alias r.  nll_terms_out[0] = sum log L_ii, [1] = z.z
+// have_z != 0: rhs already IS z (it rode along the factorisation as row n of the array), the forward sweep is skipped.
 __global__ void __launch_bounds__(GL_THREADS)
 gl_solve_kernel(const double* __restrict__ L, int n, const double* __restrict__ rhs, const int* __restrict__ info,
-                double* __restrict__ alpha_out, double* __restrict__ nll_terms_out, double* __restrict__ work /*[n]*/) {
+                double* __restrict__ alpha_out, double* __restrict__ nll_terms_out, double* __restrict__ work /*[n]*/,
+                int have_z, size_t lane_stride /*doubles between the candidates of a batch (blockIdx.x); 0 = single*/) {
     __shared__ double xb[GL_BLK];
     __shared__ double red[GL_THREADS / 32];
+    {
+        const size_t off = blockIdx.x * lane_stride;
+        L += off; rhs += off; work += off;
+        info += 2 * off;                                            // ints: same byte offset
+        if (alpha_out) alpha_out += off;
+        if (nll_terms_out) nll_terms_out += off;
+    }
     if (info[0] != 0) return;
     const int tid = threadIdx.x, lane = tid & 31;
     for (int i = tid; i < n; i += GL_THREADS) work[i] = rhs[i];
     __syncthreads();
     // ---- forward: L z = r
-    for (int kb = 0; kb < n; kb += GL_BLK) {
+    for (int kb = have_z ? n : 0; kb < n; kb += GL_BLK) {
         const int nb = min(GL_BLK, n - kb);
         if (tid < 32) {
             for (int c = 0; c < nb; ++c) {
@@ -105,8 +123,12 @@ gl_solve_kernel(const double* __restrict__ L, int n, const double* __restrict__ 
 // metric from the solve: NLL, or (with pred = K* alpha already formed) validation RMSE
 __global__ void gl_metric_kernel(int metric, int n, const int* __restrict__ info, const double* __restrict__ nll_terms,
                                  const double* __restrict__ pred, const double* __restrict__ yv, int nv,
-                                 double y_mean, double y_scale, double* __restrict__ out) {
+                                 double y_mean, double y_scale, double* __restrict__ out, size_t lane_stride) {
     __shared__ double red[8];
+    {
+        const size_t off = blockIdx.x * lane_stride;               // candidate of a batch; out is dense
+        info += 2 * off; nll_terms += off; pred += off; out += blockIdx.x;
+    }
     if (info[0] != 0) {
         if (threadIdx.x == 0) out[0] = B200ID_FAIL_METRIC;
         return;
@@ -201,9 +223,9 @@ gl_kinv_tiles_kernel(const double* __restrict__ T, int n, const int* __restrict_
 
 using namespace b200id;
 
-// workspace layout: A [n*n] | work [n] | nll_terms [2] | pred [nv] | chol ws
+// workspace layout: A [(n+1)*n] (row n = right-hand side) | work [n] | nll_terms [2] | pred [nv] | chol ws
 size_t b200id_gp_large_workspace_bytes(int n, int nv) {
-    return align_up((size_t)n * n * sizeof(double), 256) + align_up((size_t)(n + 2 + (nv > 0 ? nv : 0) + 8) * sizeof(double), 256)
+    return align_up((size_t)(n + 1) * n * sizeof(double), 256) + align_up((size_t)(n + 2 + (nv > 0 ? nv : 0) + 8) * sizeof(double), 256)
            + b200id_chol_blocked_workspace_bytes(n) + 256;
 }
 
@@ -215,7 +237,7 @@ struct LargeWs {
 static LargeWs carve(void* ws, int n, int nv) {
     LargeWs w;
     char* p = (char*)ws;
-    w.A = (double*)p; p += align_up((size_t)n * n * sizeof(double), 256);
+    w.A = (double*)p; p += align_up((size_t)(n + 1) * n * sizeof(double), 256);
     w.work = (double*)p;
     w.terms = w.work + n;
     w.pred = w.terms + 2;
@@ -225,12 +247,16 @@ static LargeWs carve(void* ws, int n, int nv) {
     return w;
 }
 
-static int large_factor(int kernel_id, const double* theta, const double* X, int n, double diag_add, const LargeWs& w,
-                        int* info, cudaStream_t st, const double* diag_add_dev = nullptr) {
-    int grid = sm_count() * 8;
-    gl_gram_kernel<<<grid, 256, 0, st>>>(kernel_id, theta, X, n, diag_add, diag_add_dev, w.A);
+// Gram + factorisation of `batch` candidates in lockstep (theta [batch][3], arrays lane_bytes apart); with y the
+// right-hand side rides along as row n and comes back as z = L^-1 y (A + n*n)
+static int large_factor(int kernel_id, const double* theta, const double* X, const double* y, int n, double diag_add,
+                        const LargeWs& w, int* info, cudaStream_t st, const double* diag_add_dev = nullptr, int batch = 1,
+                        size_t lane_bytes = 0) {
+    int gx = sm_count() * 8 / batch;
+    if (gx < sm_count()) gx = sm_count();
+    gl_gram_kernel<<<dim3(gx, 1, batch), 256, 0, st>>>(kernel_id, theta, X, n, diag_add, diag_add_dev, w.A, y, lane_bytes / sizeof(double));
     B200ID_LAUNCH_CHECK("gl_gram_kernel");
-    return b200id_chol_blocked(w.A, n, n, info, w.chol_ws, w.chol_bytes, st);
+    return cholb_factor_rows(w.A, n, y ? n + 1 : n, n, info, st, batch, lane_bytes / sizeof(double), lane_bytes / sizeof(int));
 }
 
 // final fit for n > 160: alpha, optional K_inv; ws from b200id_gp_large_workspace_bytes(n, 0) (+ n*n for K_inv scratch)
@@ -240,9 +266,9 @@ int b200id_gp_fit_large(int kernel_id, const double* theta, const double* X, con
     const size_t need = base + (Kinv_out ? align_up((size_t)n * n * sizeof(double), 256) : 0);
     B200ID_REQUIRE(ws_bytes >= need, B200ID_E_WORKSPACE, "gp_fit(large): workspace %zu < %zu", ws_bytes, need);
     const LargeWs w = carve(ws, n, 0);
-    int rc = large_factor(kernel_id, theta, X, n, diag_add, w, info_out, st);
+    int rc = large_factor(kernel_id, theta, X, y, n, diag_add, w, info_out, st);
     if (rc) return rc;
-    gl_solve_kernel<<<1, GL_THREADS, 0, st>>>(w.A, n, y, info_out, alpha_out, w.terms, w.work);
+    gl_solve_kernel<<<1, GL_THREADS, 0, st>>>(w.A, n, w.A + (size_t)n * n, info_out, alpha_out, w.terms, w.work, 1, 0);
     B200ID_LAUNCH_CHECK("gl_solve_kernel");
     if (Kinv_out) {
         double* T = (double*)((char*)ws + base);
@@ -262,31 +288,12 @@ int b200id_gp_fit_large(int kernel_id, const double* theta, const double* X, con
 extern "C" int b200id_gp_predict(int kernel_id, const double* theta, const double* X, int n, const double* alpha,
                                  const double* Kinv, const double* Xs, int m, double* mean_out, double* std_out, void* stream);
 
-// candidate metrics for n > 160.  One factorisation is a chain of ~100 short, mutually dependent launches (n / 64
-// block columns x diag / panel / update), i.e. latency bound; candidates are independent, so up to GL_LANES of them
-// run side by side on internal streams, each with its own workspace slice, forked from and joined back into the
-// caller's stream with events (no host synchronisation; capturable).  Lanes are created once per process.
-constexpr int GL_LANES = 8;
-static cudaStream_t g_lane[GL_LANES];
-static cudaEvent_t g_lane_done[GL_LANES], g_fork;
-static int g_lanes_dev = -1;
-static int ensure_lanes() {
-    int dev = 0;
-    int rc = check_cuda(cudaGetDevice(&dev), "cudaGetDevice");
-    if (rc) return rc;
-    if (g_lanes_dev == dev) return B200ID_OK;
-    B200ID_REQUIRE(g_lanes_dev < 0, B200ID_E_UNSUPPORTED, "gp_batch_eval(large n): lanes belong to device %d, called on %d", g_lanes_dev, dev);
-    for (int s = 0; s < GL_LANES; ++s) {
-        rc = check_cuda(cudaStreamCreateWithFlags(&g_lane[s], cudaStreamNonBlocking), "cudaStreamCreate(lane)");
-        if (rc) return rc;
-        rc = check_cuda(cudaEventCreateWithFlags(&g_lane_done[s], cudaEventDisableTiming), "cudaEventCreate(lane)");
-        if (rc) return rc;
-    }
-    rc = check_cuda(cudaEventCreateWithFlags(&g_fork, cudaEventDisableTiming), "cudaEventCreate(fork)");
-    if (rc) return rc;
-    g_lanes_dev = dev;
-    return B200ID_OK;
-}
+// candidate metrics for n > 160.  One factorisation is a chain of ~2 n / 64 short, mutually dependent launches, i.e.
+// latency bound; candidates are independent, so up to GL_BATCH of them advance in LOCKSTEP: every launch of the chain
+// carries all of them (blockIdx.z), each with its own workspace slice.  The chain's latency is paid once per batch,
+// every launch brings GL_BATCH times the CTAs, and the host issues the ~70 launches once per batch (no internal
+// streams, no host synchronisation; capturable).
+constexpr int GL_BATCH = 16;
 
 int b200id_gp_batch_eval_large(int kernel_id, const int* kernel_ids_host_or_null, const double* theta, int64_t n_candidates,
                                const double* X, const double* y, int n, double noise, int metric, const double* Xv,
@@ -296,45 +303,29 @@ int b200id_gp_batch_eval_large(int kernel_id, const int* kernel_ids_host_or_null
     const size_t slice = align_up(b200id_gp_large_workspace_bytes(n, nv) + 256, 256);
     B200ID_REQUIRE(ws_bytes >= slice, B200ID_E_WORKSPACE, "gp_batch_eval(large n): workspace %zu < %zu", ws_bytes, slice);
     int lanes = (int)(ws_bytes / slice);
-    if (lanes > GL_LANES) lanes = GL_LANES;
-    if ((int64_t)lanes > n_candidates) lanes = (int)n_candidates;
+    if (lanes > GL_BATCH) lanes = GL_BATCH;
     const bool val = metric == B200ID_METRIC_VAL_RMSE;
-    int rc = B200ID_OK;
-    if (lanes > 1) {
-        rc = ensure_lanes();
+    const LargeWs w = carve(ws, n, nv);                     // slice 0; slice z sits z * slice bytes further
+    int* info = (int*)((char*)w.chol_ws + w.chol_bytes);
+    const size_t lane_d = slice / sizeof(double);
+    for (int64_t c0 = 0; c0 < n_candidates; c0 += lanes) {
+        const int b = (int)((n_candidates - c0 < lanes) ? (n_candidates - c0) : lanes);
+        const double* th = theta + c0 * B200ID_MAX_PARAMS;
+        int rc = large_factor(kernel_id, th, X, y, n, noise, w, info, st, noise_v ? noise_v + c0 : nullptr, b, slice);
         if (rc) return rc;
-        rc = check_cuda(cudaEventRecord(g_fork, st), "cudaEventRecord(fork)");
-        if (rc) return rc;
-        for (int s = 0; s < lanes; ++s) {
-            rc = check_cuda(cudaStreamWaitEvent(g_lane[s], g_fork, 0), "cudaStreamWaitEvent(fork)");
-            if (rc) return rc;
-        }
-    }
-    for (int64_t c = 0; c < n_candidates; ++c) {
-        const int s = (int)(c % lanes);
-        cudaStream_t ls = lanes > 1 ? g_lane[s] : st;
-        const LargeWs w = carve((char*)ws + (size_t)s * slice, n, nv);
-        int* info = (int*)((char*)w.chol_ws + w.chol_bytes);
-        const double* th = theta + c * B200ID_MAX_PARAMS;
-        rc = large_factor(kernel_id, th, X, n, noise, w, info, ls, noise_v ? noise_v + c : nullptr);
-        if (rc) return rc;
-        // alpha lives in `work` (in place) when the validation metric needs it
-        gl_solve_kernel<<<1, GL_THREADS, 0, ls>>>(w.A, n, y, info, val ? w.work : nullptr, w.terms, w.work);
+        // z = L^-1 y came back as row n of each array: only the NLL pieces (and, for the validation metric, the
+        // backward sweep) are left; alpha lives in `work` (in place) when the validation metric needs it
+        gl_solve_kernel<<<b, GL_THREADS, 0, st>>>(w.A, n, w.A + (size_t)n * n, info, val ? w.work : nullptr, w.terms, w.work, 1, lane_d);
         B200ID_LAUNCH_CHECK("gl_solve_kernel");
         if (val) {
-            rc = b200id_gp_predict(kernel_id, th, X, n, w.work, nullptr, Xv, nv, w.pred, nullptr, (void*)ls);
-            if (rc) return rc;
+            for (int z = 0; z < b; ++z) {
+                rc = b200id_gp_predict(kernel_id, th + (size_t)z * B200ID_MAX_PARAMS, X, n, w.work + z * lane_d, nullptr, Xv, nv,
+                                       w.pred + z * lane_d, nullptr, (void*)st);
+                if (rc) return rc;
+            }
         }
-        gl_metric_kernel<<<1, 256, 0, ls>>>(metric, n, info, w.terms, w.pred, yv, nv, y_mean, y_scale, metric_out + c);
+        gl_metric_kernel<<<b, 256, 0, st>>>(metric, n, info, w.terms, w.pred, yv, nv, y_mean, y_scale, metric_out + c0, lane_d);
         B200ID_LAUNCH_CHECK("gl_metric_kernel");
-    }
-    if (lanes > 1) {
-        for (int s = 0; s < lanes; ++s) {
-            rc = check_cuda(cudaEventRecord(g_lane_done[s], g_lane[s]), "cudaEventRecord(lane)");
-            if (rc) return rc;
-            rc = check_cuda(cudaStreamWaitEvent(st, g_lane_done[s], 0), "cudaStreamWaitEvent(join)");
-            if (rc) return rc;
-        }
     }
     return B200ID_OK;
 }

@@ -300,6 +300,18 @@ def test_config4_large_n_fit_and_metrics(gp, n):
     got_val = gp.batch_eval(name, thetas, X, y, noise, Xv=Xv, yv=yv, y_mean=0.1, y_scale=1.3)
     _compare_metrics(got_nll, ref_nll, f"cfg4.nll.n{n}", cond)
     _compare_metrics(got_val, ref_val, f"cfg4.val.n{n}", cond)
+    # lockstep batches (gp_large.cu): up to 16 candidates share every launch of the factorisation chain; 35 candidates
+    # are three rounds (16 + 16 + 3), and a candidate's metric does not depend on its position or on its neighbours
+    from b200id.runtime import require_cuda, to_device
+    dev = require_cuda()
+    X_d, y_d = to_device(X.ravel(), dev), to_device(y, dev)
+    th3_d = to_device(gp._theta_block(thetas), dev)
+    runs = [gp.batch_eval_device(ogp.KERNELS[name][0], None, th3_d, X_d, y_d, noise).cpu().numpy() for _ in range(3)]
+    assert np.array_equal(runs[0], runs[1]) and np.array_equal(runs[0], runs[2])
+    _compare_metrics(runs[2], ref_nll, f"cfg4.nll.graph.n{n}", cond)
+    th35_d = to_device(gp._theta_block(np.tile(thetas, (12, 1))[:35]), dev)
+    many = [gp.batch_eval_device(ogp.KERNELS[name][0], None, th35_d, X_d, y_d, noise).cpu().numpy() for _ in range(2)]
+    assert np.array_equal(many[0], many[1]) and np.array_equal(many[0], np.tile(runs[0], 12)[:35])
     # failure convention on the large path: an indefinite Gram -> 1e10
     bad = gp.batch_eval("ss1", np.array([[1.0, 1.0]]), X, y, 0.0)
     assert bad[0] == 1e10

@@ -323,6 +323,124 @@ cholb_syrk_kernel(double* __restrict__ A, int lda, int n, int n_rows, int k0, in
     }
 }
 
+// (3') the same trailing update on the FP64 tensor pipe: mma.sync.m8n8k4.f64 (DMMA.8x8x4 in SASS), one warp
+// instruction = 256 FMAs.  FP64 MMA and FP64 FMA share one pipe on B200 (same 37 TFLOP/s peak), so
+// the gain is not a higher ceiling but reaching it: a DFMA reading three distinct registers holds the pipe for 3 cycles
+// instead of 2 and needs one issue slot per 32 FMAs, the register-tiled loop above runs at ~36 % of the peak; here the
+// 64 x 64 x 64 tile product is 128 DMMAs per warp fed by 6 conflict-free LDS.64 per 8 of them.
+// Operands are staged ROW-major (Ts[r][k], pitch 68 doubles): no transposition on the way in (coalesced global rows ->
+// consecutive shared-memory words), and the fragment of lane l -- row l / 4, k-column l % 4, for the A operand and for
+// the B operand alike, since the update is P_r P_c^T -- touches every bank exactly twice per 64-bit warp load.
+// Warp w owns rows [16 (w / 2), +16) x columns [32 (w % 2), +32) of the tile = 2 x 4 accumulator fragments; lane l
+// holds C[l / 4][2 (l % 4) .. +1] of each 8 x 8 fragment.
+constexpr int CB_LDR = CB_NB + 4;
+__device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void stage_tile_rowmajor(const double* __restrict__ M, int ld, int r0, int r_end, int c0,
+                                                    double* __restrict__ T) {
+    constexpr int PER = CB_NB * CB_NB / CB_THREADS;
+    double v[PER];
+#pragma unroll
+    for (int it = 0; it < PER; ++it) {
+        const int e = threadIdx.x + it * CB_THREADS;
+        const int r = e >> 6, k = e & 63;
+        v[it] = (r0 + r < r_end) ? __ldg(M + (size_t)(r0 + r) * ld + c0 + k) : 0.0;
+    }
+#pragma unroll
+    for (int it = 0; it < PER; ++it) {
+        const int e = threadIdx.x + it * CB_THREADS;
+        T[(e >> 6) * CB_LDR + (e & 63)] = v[it];
+    }
+}
+
+__global__ void __launch_bounds__(CB_THREADS, 3)
+cholb_syrk_mma_kernel(double* __restrict__ A, int lda, int n, int n_rows, int k0, int* __restrict__ info,
+                      size_t a_stride, size_t info_stride) {
+    extern __shared__ __align__(16) double cb_sm[];
+    double* As = cb_sm;
+    double* Bs = cb_sm + CB_NB * CB_LDR;
+    A += blockIdx.z * a_stride;
+    info += blockIdx.z * info_stride;
+    if (info[0] != 0) return;
+    const int lin = blockIdx.x;
+    int ti = (int)((sqrt(8.0 * lin + 1.0) - 1.0) * 0.5);
+    while ((ti + 1) * (ti + 2) / 2 <= lin) ++ti;
+    while (ti * (ti + 1) / 2 > lin) --ti;
+    const int tj = lin - ti * (ti + 1) / 2;
+    const int s = k0 + CB_NB;
+    const int r0 = s + ti * CB_NB, c0 = s + tj * CB_NB;
+    stage_tile_rowmajor(A, lda, r0, n_rows, k0, As);
+    stage_tile_rowmajor(A, lda, c0, n, k0, Bs);
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wy = warp >> 1, wx = warp & 1, fr = lane >> 2, fk = lane & 3;
+    double acc[2][4][2] = {};
+    const double* pa = As + (16 * wy + fr) * CB_LDR + fk;
+    const double* pb = Bs + (32 * wx + fr) * CB_LDR + fk;
+#pragma unroll 4
+    for (int kk = 0; kk < CB_NB; kk += 4) {
+        double a[2], b[4];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) a[i] = pa[8 * i * CB_LDR + kk];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) b[j] = pb[8 * j * CB_LDR + kk];
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+    }
+    // this lane's elements: tile row 16 wy + 8 i + fr, tile columns 32 wx + 8 j + 2 fk + {0, 1}
+    double cv[2][4][2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int r = r0 + 16 * wy + 8 * i + fr;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int c = c0 + 32 * wx + 8 * j + 2 * fk + q;
+                cv[i][j][q] = (r < n_rows && c <= r && c < n) ? A[(size_t)r * lda + c] : 0.0;
+            }
+    }
+    if (lin == 0) {
+        // tile (0, 0) of the trailing matrix is the NEXT diagonal block: factorise it here (see cholb_syrk_kernel)
+        __syncthreads();                             // everybody is done with the staged operands
+        double* D = cb_sm;
+        double* dg = cb_sm + CB_NB * CB_LDD;
+        const int nb = min(CB_NB, n - s);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int ii = 16 * wy + 8 * i + fr;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int jj = 32 * wx + 8 * j + 2 * fk + q;
+                    const double v = cv[i][j][q] - acc[i][j][q];
+                    if (ii < nb && jj <= ii) D[jj * CB_LDD + ii] = v;
+                    // rows of this tile below the diagonal block exist only as extra rows (nb < 64): plain update
+                    else if (ii >= nb && r0 + ii < n_rows && c0 + jj < n) A[(size_t)(r0 + ii) * lda + c0 + jj] = v;
+                }
+        }
+        __syncthreads();
+        cholb_factor_block(D, dg, nb, A, lda, s, info);
+        return;
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int r = r0 + 16 * wy + 8 * i + fr;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int c = c0 + 32 * wx + 8 * j + 2 * fk + q;
+                if (r < n_rows && c <= r && c < n) A[(size_t)r * lda + c] = cv[i][j][q] - acc[i][j][q];
+            }
+    }
+}
+
 }  // namespace b200id
 
 using namespace b200id;
@@ -344,7 +462,11 @@ int cholb_factor_rows(double* A, int n, int n_rows, int lda, int* info_out, cuda
         if (rc) return rc;
     }
     const size_t smem_panel = 2 * (size_t)CB_NB * CB_LDP * sizeof(double);
-    const size_t smem = 2 * (size_t)CB_NB * CB_LDT * sizeof(double);
+    static int use_mma = -1;                     // B200ID_CHOL_MMA=0: the register-tiled DFMA update (timing comparisons)
+    if (use_mma < 0) { const char* e = getenv("B200ID_CHOL_MMA"); use_mma = (e && e[0] == '0') ? 0 : 1; }
+    const size_t smem = 2 * (size_t)CB_NB * (use_mma ? CB_LDR : CB_LDT) * sizeof(double);
+    rc = check_cuda(cudaFuncSetAttribute(cholb_syrk_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute(syrk mma)");
+    if (rc) return rc;
     rc = check_cuda(cudaFuncSetAttribute(cholb_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_panel), "cudaFuncSetAttribute(panel)");
     if (rc) return rc;
     rc = check_cuda(cudaFuncSetAttribute(cholb_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute(syrk)");
@@ -359,7 +481,10 @@ int cholb_factor_rows(double* A, int n, int n_rows, int lda, int* info_out, cuda
         cholb_panel_kernel<<<dim3((below + CB_NB - 1) / CB_NB, 1, batch), CB_THREADS, smem_panel, st>>>(A, lda, n, n_rows, k0, info_out, a_stride, info_stride);
         if (n - (k0 + CB_NB) > 0) {                           // trailing columns left
             const int tiles = (n_rows - (k0 + CB_NB) + CB_NB - 1) / CB_NB;
-            cholb_syrk_kernel<<<dim3(tiles * (tiles + 1) / 2, 1, batch), CB_THREADS, smem, st>>>(A, lda, n, n_rows, k0, info_out, a_stride, info_stride);
+            if (use_mma)
+                cholb_syrk_mma_kernel<<<dim3(tiles * (tiles + 1) / 2, 1, batch), CB_THREADS, smem, st>>>(A, lda, n, n_rows, k0, info_out, a_stride, info_stride);
+            else
+                cholb_syrk_kernel<<<dim3(tiles * (tiles + 1) / 2, 1, batch), CB_THREADS, smem, st>>>(A, lda, n, n_rows, k0, info_out, a_stride, info_stride);
         }
     }
     B200ID_LAUNCH_CHECK("chol_blocked kernels");

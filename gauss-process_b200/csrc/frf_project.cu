@@ -602,10 +602,10 @@ frf_project_uniform3_kernel(const double* __restrict__ t, const double* __restri
 // distinct registers, against 11 / 9 in the three-term kernel.  Accumulators live in shared memory (touched once per
 // tile), which keeps the loop under the 64-register cap.
 #ifndef FRFG_TILE
-#define FRFG_TILE 1536
+#define FRFG_TILE 1792
 #endif
 #ifndef FRFG_UNROLL
-#define FRFG_UNROLL 1
+#define FRFG_UNROLL 2
 #endif
 constexpr int FRFG_TILE_MAX = FRFG_TILE;
 constexpr int FRFG_UNROLL_N = FRFG_UNROLL;

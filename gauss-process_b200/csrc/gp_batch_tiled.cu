@@ -83,36 +83,21 @@ __device__ __forceinline__ void gt_fill(const KernelParams& kp, const double* __
         const double xj = j < n ? xs[j] : 0.0;
         const double yj = j < n ? y[j] : 0.0;
         const double y2j = (y2 && j < n) ? y2[j] : 0.0;
-        // FOUR rows per step: an entry is one IEEE division and one exp, ~80 dependent FP64 instructions, and a thread
-        // walks ~40 entries -- evaluated one after the other that chain is a quarter of the kernel's run time.  The
-        // four evaluations of a step are independent (indices clamped into the matrix, results selected afterwards), so
-        // their latencies overlap.
-        for (int r = r8; r < ld; r += 32) {
-            double v[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int i = min(GT_NB * J + r + 8 * q, n - 1);
-                v[q] = 0.0;
-                if (j < n) {
+        for (int r = r8; r < ld; r += 8) {
+            const int i = GT_NB * J + r;
+            double v = 0.0;
+            if (j < n) {
+                if (i < n) {
                     // evaluate with the larger index first, as the lower triangle of kernel(X) is laid out
-                    const double xi = xs[i];
-                    const bool low = i >= j;
-                    v[q] = kernel_entry_t<ID>(kp, low ? xi : xj, low ? xj : xi);
+                    v = (i >= j) ? kernel_entry_t<ID>(kp, xs[i], xj) : kernel_entry_t<ID>(kp, xj, xs[i]);
+                    if (i == j) v = B200ID_ADD(v, noise);
+                } else if (i == n) {
+                    v = yj;
+                } else if (i == n + 1) {
+                    v = y2j;                                  // zero in single-target mode (padding row)
                 }
             }
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int rr = r + 8 * q, i = GT_NB * J + rr;
-                if (rr < ld) {
-                    double out = 0.0;
-                    if (j < n) {
-                        if (i < n) out = (i == j) ? B200ID_ADD(v[q], noise) : v[q];
-                        else if (i == n) out = yj;
-                        else if (i == n + 1) out = y2j;           // zero in single-target mode (padding row)
-                    }
-                    col[rr] = out;
-                }
-            }
+            col[r] = v;
         }
     }
 }

@@ -1,11 +1,10 @@
 #!/bin/bash
-# One GPU call: the full GPU suite, the default bench line, then the launch list of a short bench run under ncu.
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -q 2>&1 | tail -12 > gpurun_out/pytest_gpu.log
-cat gpurun_out/pytest_gpu.log
-python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; tail -3 gpurun_out/smoke.log
-python bench.py > gpurun_out/bench.log 2> gpurun_out/bench.err
-python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/bench_plain.log 2>&1 &&
-ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/launches.csv \
-    python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
-tail -c 300 gpurun_out/bench.err
+timeout 900 python -m pytest tests/test_gp_gpu.py tests/test_pipeline_gpu.py tests/test_dropin_gpu.py -m gpu -q 2>&1 | tail -4
+python profiles/run_kernels.py --cands 8192 --reps 3 2>&1 | grep gp_batch
+python bench.py --no-cpu-baseline > gpurun_out/bench_ilp.log 2> gpurun_out/bench_ilp.err; tail -c 300 gpurun_out/bench_ilp.err
+python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/bench_ilp.log').read().strip().splitlines()[-1])
+print('ms_step',round(d['ms_per_step'],3), {k:round(v,3) for k,v in d['stages']['ms_per_step_by_call'].items() if 'gp' in k})
+PY

@@ -609,7 +609,10 @@ frf_project_uniform3_kernel(const double* __restrict__ t, const double* __restri
 #endif
 constexpr int FRFG_TILE_MAX = FRFG_TILE;
 constexpr int FRFG_UNROLL_N = FRFG_UNROLL;
-constexpr size_t FRFG_SMEM_BYTES = (size_t)FRFG_TILE_MAX * (16 + 8 + 16) + (size_t)8 * FRF_THREADS * sizeof(double);
+#ifndef FRFG_SMEM_PAD
+#define FRFG_SMEM_PAD 0            // occupancy experiments: extra bytes that push the kernel to one CTA per SM
+#endif
+constexpr size_t FRFG_SMEM_BYTES = (size_t)FRFG_TILE_MAX * (16 + 8 + 16) + (size_t)8 * FRF_THREADS * sizeof(double) + FRFG_SMEM_PAD;
 
 template <bool HAS_Y>
 __global__ void __launch_bounds__(FRF_THREADS, FRF_CTAS_PER_SM)

@@ -1,10 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gp_gpu.py tests/test_pipeline_gpu.py tests/test_dropin_gpu.py -m gpu -q 2>&1 | tail -4
-python profiles/run_kernels.py --cands 8192 --reps 3 2>&1 | grep gp_batch
-python bench.py --no-cpu-baseline > gpurun_out/bench_ilp.log 2> gpurun_out/bench_ilp.err; tail -c 300 gpurun_out/bench_ilp.err
-python - <<'PY'
-import json
-d=json.loads(open('gpurun_out/bench_ilp.log').read().strip().splitlines()[-1])
-print('ms_step',round(d['ms_per_step'],3), {k:round(v,3) for k,v in d['stages']['ms_per_step_by_call'].items() if 'gp' in k})
-PY
+python profiles/run_cfg4_batch.py 2 > gpurun_out/cfg4_plain.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:'cholb_syrk_mma_kernel|cholb_panel_kernel' -c 4 \
+    -o gpurun_out/prof_r1_chol -f python profiles/run_cfg4_batch.py 2 > gpurun_out/ncu_chol.log 2>&1
+cat gpurun_out/cfg4_plain.log; tail -3 gpurun_out/ncu_chol.log

@@ -332,7 +332,9 @@ cholb_syrk_kernel(double* __restrict__ A, int lda, int n, int n_rows, int k0, in
 // consecutive shared-memory words), and the fragment of lane l -- row l / 4, k-column l % 4, for the A operand and for
 // the B operand alike, since the update is P_r P_c^T -- touches every bank exactly twice per 64-bit warp load.
 // Warp w owns rows [16 (w / 2), +16) x columns [32 (w % 2), +32) of the tile = 2 x 4 accumulator fragments; lane l
-// holds C[l / 4][2 (l % 4) .. +1] of each 8 x 8 fragment.
+// holds C[l / 4][2 (l % 4) .. +1] of each 8 x 8 fragment.  The C tile is fetched BEFORE the product so that its latency
+// hides under the DMMAs; that needs 128 registers, i.e. 2 CTAs per SM -- measured (16 candidates at n = 2048): late C,
+// 3 CTAs/SM 5.22 ms; early C, 3 CTAs/SM (spills) 5.77 ms; late C, 2 CTAs/SM 5.0 ms; early C, 2 CTAs/SM 4.7-4.9 ms.
 constexpr int CB_LDR = CB_NB + 4;
 __device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -355,7 +357,13 @@ __device__ __forceinline__ void stage_tile_rowmajor(const double* __restrict__ M
     }
 }
 
-__global__ void __launch_bounds__(CB_THREADS, 3)
+#ifndef CB_SYRK_CTAS
+#define CB_SYRK_CTAS 2
+#endif
+#ifndef CB_EARLY_C
+#define CB_EARLY_C 1            // 1: the C tile is loaded before the product instead of after it (more live registers)
+#endif
+__global__ void __launch_bounds__(CB_THREADS, CB_SYRK_CTAS)
 cholb_syrk_mma_kernel(double* __restrict__ A, int lda, int n, int n_rows, int k0, int* __restrict__ info,
                       size_t a_stride, size_t info_stride) {
     extern __shared__ __align__(16) double cb_sm[];
@@ -376,6 +384,22 @@ cholb_syrk_mma_kernel(double* __restrict__ A, int lda, int n, int n_rows, int k0
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int wy = warp >> 1, wx = warp & 1, fr = lane >> 2, fk = lane & 3;
+    // this lane's elements: tile row 16 wy + 8 i + fr, tile columns 32 wx + 8 j + 2 fk + {0, 1}
+    double cv[2][4][2];
+    auto load_c = [&]() {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int r = r0 + 16 * wy + 8 * i + fr;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int c = c0 + 32 * wx + 8 * j + 2 * fk + q;
+                    cv[i][j][q] = (r < n_rows && c <= r && c < n) ? A[(size_t)r * lda + c] : 0.0;
+                }
+        }
+    };
+    if (CB_EARLY_C) load_c();
     double acc[2][4][2] = {};
     const double* pa = As + (16 * wy + fr) * CB_LDR + fk;
     const double* pb = Bs + (32 * wx + fr) * CB_LDR + fk;
@@ -391,19 +415,7 @@ cholb_syrk_mma_kernel(double* __restrict__ A, int lda, int n, int n_rows, int k0
 #pragma unroll
             for (int j = 0; j < 4; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
     }
-    // this lane's elements: tile row 16 wy + 8 i + fr, tile columns 32 wx + 8 j + 2 fk + {0, 1}
-    double cv[2][4][2];
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        const int r = r0 + 16 * wy + 8 * i + fr;
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                const int c = c0 + 32 * wx + 8 * j + 2 * fk + q;
-                cv[i][j][q] = (r < n_rows && c <= r && c < n) ? A[(size_t)r * lda + c] : 0.0;
-            }
-    }
+    if (!CB_EARLY_C) load_c();
     if (lin == 0) {
         // tile (0, 0) of the trailing matrix is the NEXT diagonal block: factorise it here (see cholb_syrk_kernel)
         __syncthreads();                             // everybody is done with the staged operands

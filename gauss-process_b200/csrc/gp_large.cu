@@ -44,48 +44,27 @@ __global__ void gl_gram_kernel(int kernel_id, const double* __restrict__ theta, 
     B200ID_DISPATCH_KERNEL(kernel_id, gl_gram_rows, kp, X, n, diag_add, A)
 }
 
-// z = L^-1 r then (optionally) alpha = L^-T z, single CTA, blocks of 64.  L row-major lower, ld = n.
-// out_z / out_alpha may alias r.  nll_terms_out[0] = sum log L_ii, [1] = z.z
-// have_z != 0: rhs already IS z (it rode along the factorisation as row n of the array), the forward sweep is skipped.
+// What is left of the solve after the factorisation: z = L^-1 y rode along as row n of the array (chol_blocked.cu), so
+// this kernel forms the NLL pieces nll_terms_out[0] = sum log L_ii, [1] = z.z and, when alpha_out is given, the backward
+// sweep alpha = L^-T z.  Single CTA per candidate (blockIdx.x, arrays lane_stride doubles apart), blocks of 64; L
+// row-major lower, ld = n.
 __global__ void __launch_bounds__(GL_THREADS)
-gl_solve_kernel(const double* __restrict__ L, int n, const double* __restrict__ rhs, const int* __restrict__ info,
+gl_solve_kernel(const double* __restrict__ L, int n, const double* __restrict__ z, const int* __restrict__ info,
                 double* __restrict__ alpha_out, double* __restrict__ nll_terms_out, double* __restrict__ work /*[n]*/,
-                int have_z, size_t lane_stride /*doubles between the candidates of a batch (blockIdx.x); 0 = single*/) {
+                size_t lane_stride /*doubles between the candidates of a batch; 0 = single*/) {
     __shared__ double xb[GL_BLK];
     __shared__ double red[GL_THREADS / 32];
     {
         const size_t off = blockIdx.x * lane_stride;
-        L += off; rhs += off; work += off;
+        L += off; z += off; work += off;
         info += 2 * off;                                            // ints: same byte offset
         if (alpha_out) alpha_out += off;
         if (nll_terms_out) nll_terms_out += off;
     }
     if (info[0] != 0) return;
     const int tid = threadIdx.x, lane = tid & 31;
-    for (int i = tid; i < n; i += GL_THREADS) work[i] = rhs[i];
+    for (int i = tid; i < n; i += GL_THREADS) work[i] = z[i];
     __syncthreads();
-    // ---- forward: L z = r
-    for (int kb = have_z ? n : 0; kb < n; kb += GL_BLK) {
-        const int nb = min(GL_BLK, n - kb);
-        if (tid < 32) {
-            for (int c = 0; c < nb; ++c) {
-                double s = 0.0;
-                for (int p = lane; p < c; p += 32) s = fma(L[(size_t)(kb + c) * n + kb + p], xb[p], s);
-                s = warp_sum(s);
-                if (lane == 0) xb[c] = (work[kb + c] - s) / L[(size_t)(kb + c) * n + kb + c];
-                __syncwarp();
-            }
-        }
-        __syncthreads();
-        for (int i = kb + nb + tid; i < n; i += GL_THREADS) {
-            const double* row = L + (size_t)i * n + kb;
-            double s = 0.0;
-            for (int c = 0; c < nb; ++c) s = fma(row[c], xb[c], s);
-            work[i] -= s;
-        }
-        if (tid < nb) work[kb + tid] = xb[tid];
-        __syncthreads();
-    }
     // ---- NLL pieces: sum log L_ii and z.z
     double lg = 0.0, zz = 0.0;
     for (int i = tid; i < n; i += GL_THREADS) {
@@ -268,7 +247,7 @@ int b200id_gp_fit_large(int kernel_id, const double* theta, const double* X, con
     const LargeWs w = carve(ws, n, 0);
     int rc = large_factor(kernel_id, theta, X, y, n, diag_add, w, info_out, st);
     if (rc) return rc;
-    gl_solve_kernel<<<1, GL_THREADS, 0, st>>>(w.A, n, w.A + (size_t)n * n, info_out, alpha_out, w.terms, w.work, 1, 0);
+    gl_solve_kernel<<<1, GL_THREADS, 0, st>>>(w.A, n, w.A + (size_t)n * n, info_out, alpha_out, w.terms, w.work, 0);
     B200ID_LAUNCH_CHECK("gl_solve_kernel");
     if (Kinv_out) {
         double* T = (double*)((char*)ws + base);
@@ -315,7 +294,7 @@ int b200id_gp_batch_eval_large(int kernel_id, const int* kernel_ids_host_or_null
         if (rc) return rc;
         // z = L^-1 y came back as row n of each array: only the NLL pieces (and, for the validation metric, the
         // backward sweep) are left; alpha lives in `work` (in place) when the validation metric needs it
-        gl_solve_kernel<<<b, GL_THREADS, 0, st>>>(w.A, n, w.A + (size_t)n * n, info, val ? w.work : nullptr, w.terms, w.work, 1, lane_d);
+        gl_solve_kernel<<<b, GL_THREADS, 0, st>>>(w.A, n, w.A + (size_t)n * n, info, val ? w.work : nullptr, w.terms, w.work, lane_d);
         B200ID_LAUNCH_CHECK("gl_solve_kernel");
         if (val) {
             for (int z = 0; z < b; ++z) {

@@ -1,5 +1,11 @@
 #!/bin/bash
+# One GPU call: the full GPU suite, then the timings of BASELINE configs 3, 4 and 5 (profiles/run_configs.py).
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gp_gpu.py -m gpu -q -k "chol or config4 or noise" 2>&1 | tail -3
-python profiles/run_cfg4_batch.py 3
-python profiles/run_chol.py 2>&1 | grep "n=2048\|n=4096"
+python -m pytest tests -m gpu -q 2>&1 | tail -4 > gpurun_out/pytest_gpu.log
+cat gpurun_out/pytest_gpu.log
+timeout 300 python profiles/run_configs.py > gpurun_out/configs.json 2> gpurun_out/configs.err
+tail -c 300 gpurun_out/configs.err; python - <<'PY'
+import json
+d=json.load(open('gpurun_out/configs.json'))
+b=d['cfg4']['batch_nll']; print({k:v for k,v in b.items() if k not in ('metrics','note')}); print(d['cfg4']['chol_blocked'], d['cfg4']['fit_with_kinv'])
+PY

@@ -360,6 +360,24 @@ __device__ __forceinline__ void stage_tile_rowmajor(const double* __restrict__ M
 #ifndef CB_SYRK_CTAS
 #define CB_SYRK_CTAS 2
 #endif
+#ifndef CB_CPASYNC
+#define CB_CPASYNC 1            // 1: operands go global -> shared with cp.async in two k-halves (no staging registers,
+#endif                          //    the second half lands while the first is multiplied)
+// k-columns [kh, kh + 32) of rows [r0, r0 + 64) x cols [c0 + kh, ...) of row-major M into Ts[r][k]; rows >= r_end are
+// zero filled (cp.async with source size 0)
+__device__ __forceinline__ void stage_half_async(const double* __restrict__ M, int ld, int r0, int r_end, int c0, int kh,
+                                                 double* __restrict__ T) {
+#pragma unroll
+    for (int it = 0; it < CB_NB * 32 / CB_THREADS; ++it) {
+        const int e = threadIdx.x + it * CB_THREADS;
+        const int r = e >> 5, k = kh + (e & 31);
+        const bool ok = r0 + r < r_end;
+        const double* src = M + (size_t)(ok ? r0 + r : r0) * ld + c0 + k;
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(T + r * CB_LDR + k);
+        const int sz = ok ? 8 : 0;
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+    }
+}
 #ifndef CB_EARLY_C
 #define CB_EARLY_C 1            // 1: the C tile is loaded before the product instead of after it (more live registers)
 #endif
@@ -379,9 +397,18 @@ cholb_syrk_mma_kernel(double* __restrict__ A, int lda, int n, int n_rows, int k0
     const int tj = lin - ti * (ti + 1) / 2;
     const int s = k0 + CB_NB;
     const int r0 = s + ti * CB_NB, c0 = s + tj * CB_NB;
+#if CB_CPASYNC
+    stage_half_async(A, lda, r0, n_rows, k0, 0, As);
+    stage_half_async(A, lda, c0, n, k0, 0, Bs);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    stage_half_async(A, lda, r0, n_rows, k0, 32, As);
+    stage_half_async(A, lda, c0, n, k0, 32, Bs);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+#else
     stage_tile_rowmajor(A, lda, r0, n_rows, k0, As);
     stage_tile_rowmajor(A, lda, c0, n, k0, Bs);
     __syncthreads();
+#endif
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int wy = warp >> 1, wx = warp & 1, fr = lane >> 2, fk = lane & 3;
     // this lane's elements: tile row 16 wy + 8 i + fr, tile columns 32 wx + 8 j + 2 fk + {0, 1}
@@ -403,17 +430,25 @@ cholb_syrk_mma_kernel(double* __restrict__ A, int lda, int n, int n_rows, int k0
     double acc[2][4][2] = {};
     const double* pa = As + (16 * wy + fr) * CB_LDR + fk;
     const double* pb = Bs + (32 * wx + fr) * CB_LDR + fk;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+#if CB_CPASYNC
+        if (half == 0) asm volatile("cp.async.wait_group 1;" ::: "memory");
+        else asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+#endif
 #pragma unroll 4
-    for (int kk = 0; kk < CB_NB; kk += 4) {
-        double a[2], b[4];
+        for (int kk = 32 * half; kk < 32 * half + 32; kk += 4) {
+            double a[2], b[4];
 #pragma unroll
-        for (int i = 0; i < 2; ++i) a[i] = pa[8 * i * CB_LDR + kk];
+            for (int i = 0; i < 2; ++i) a[i] = pa[8 * i * CB_LDR + kk];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) b[j] = pb[8 * j * CB_LDR + kk];
+            for (int j = 0; j < 4; ++j) b[j] = pb[8 * j * CB_LDR + kk];
 #pragma unroll
-        for (int i = 0; i < 2; ++i)
+            for (int i = 0; i < 2; ++i)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+                for (int j = 0; j < 4; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        }
     }
     if (!CB_EARLY_C) load_c();
     if (lin == 0) {

@@ -43,6 +43,8 @@ SIGNATURES = {
     "b200id_gp_batch_eval_pair": (I, [I, P, P, L, P, P, P, I, D, I, P, P, P, I, D, D, D, D, P, P, P, Z, P]),
     "b200id_gp_batch_eval_noise": (I, [I, P, P, P, L, P, P, I, I, P, P, I, D, D, P, P, Z, P]),
     "b200id_first_strict_min": (I, [P, L, P, P, P, Z, P]),
+    "b200id_argmin_pack": (I, [P, I, P, P, P]),
+    "b200id_argmin_pick": (I, [P, I, I, P, P, P]),
     "b200id_gp_fit_workspace_bytes": (Z, [I]),
     "b200id_gp_fit": (I, [I, P, P, P, I, D, P, P, P, P, Z, P]),
     "b200id_gp_fit_batch": (I, [I, P, P, P, I, I, D, P, P, P, Z, P]),
@@ -117,6 +119,27 @@ def call(name: str, *args) -> None:
         e1.record()
         event_log.setdefault(name, []).append((e0, e1))
     launch_count += LAUNCHES_PER_CALL.get(name, 1)
+
+
+class timed_region:
+    """``with timed_region("host:label"):`` -- CUDA-event timing of a host-side region (collectives, torch glue) into the
+    same per-call log as the entry points; free when the log is off."""
+
+    def __init__(self, name: str):
+        self.name = name
+
+    def __enter__(self):
+        if event_log is not None:
+            import torch
+            self.e0, self.e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if event_log is not None and exc[0] is None:
+            self.e1.record()
+            event_log.setdefault(self.name, []).append((self.e0, self.e1))
+        return False
 
 
 def device_info():

@@ -303,12 +303,41 @@ def _device_pick(cs: "CandidateSet", pends: Sequence[torch.Tensor]) -> List[Tupl
 
     pends[k] = [best metric, local index] on the device.  With several ranks the (metric, global index) pairs
     of ALL searches travel in one all-gather and the first strict minimum in global scan order is taken on the
-    device (ties -> smallest global index, NaN / empty shards skipped), reproducing grid_search.py:186-196."""
+    device (ties -> smallest global index, NaN / empty shards skipped), reproducing grid_search.py:186-196.
+    Two small kernels either side of the exchange (b200id_argmin_pack / b200id_argmin_pick); the tensor-op version
+    of the same rule was ~30 dependent launches, 0.4 ms of a 3.5 ms multi-GPU step."""
+    import ctypes as C
+    from . import _lib
+    from .runtime import ptr, stream_ptr
     k = len(pends)
-    pend = torch.stack(list(pends))                                   # [k, 2]
+    pend = torch.stack(list(pends)).contiguous()                      # [k, 2]
+    dev = pend.device
+    if not pend.is_cuda:
+        return _device_pick_tensor_ops(cs, pend)      # gloo host tests of the exchange: same rule in tensor operations
+    mine = empty(2 * k, dev)
+    _lib.call("b200id_argmin_pack", ptr(pend), C.c_int(k), ptr(cs.global_index_dev if cs.global_index is not None else None),
+              ptr(mine), stream_ptr())
+    ws = 1
+    tab = mine
+    if cs.global_index is not None:
+        import torch.distributed as dist
+        ws = bdist.world()[1]
+        tab = empty(ws * 2 * k, dev)
+        dist.all_gather_into_tensor(tab, mine)
+    out = empty(5 * k, dev)
+    _lib.call("b200id_argmin_pick", ptr(tab), C.c_int(ws), C.c_int(k), ptr(cs.full_theta_dev), ptr(out), stream_ptr())
+    out = out.view(k, 5)
+    return [(out[j, :3], out[j, 3], out[j, 4]) for j in range(k)]
+
+
+def _device_pick_tensor_ops(cs: "CandidateSet", pend: torch.Tensor):
+    """The rule of :func:`_device_pick` written in tensor operations on whatever device ``pend`` lives on: what the
+    CPU (gloo) tests of the exchange run, and the reference the two CUDA kernels are checked against."""
+    k = pend.shape[0]
     best, lidx = pend[:, 0], pend[:, 1].to(torch.int64)
     if cs.global_index is None:
         gidx = lidx
+        best = torch.where(lidx >= 0, best, torch.full_like(best, float("inf")))
     else:
         import torch.distributed as dist
         gmap = cs.global_index_dev
@@ -394,7 +423,8 @@ def identify_device(train: Sequence[Tuple[torch.Tensor, torch.Tensor, torch.Tens
     else:
         if use_val_metric:
             val_sums()
-        bdist.allreduce_sum_(sums_all)
+        with _lib.timed_region("collective:frf_sums"):
+            bdist.allreduce_sum_(sums_all)
     # ---- G, StandardScaler statistics of Re G / Im G and the standardised targets: one kernel; the statistics
     # travel to the host asynchronously
     G, stats_d, yr, yi = bfrf.gp_targets_device(sums_all[:3 * nd], nd, standardise=True)
@@ -421,7 +451,8 @@ def identify_device(train: Sequence[Tuple[torch.Tensor, torch.Tensor, torch.Tens
     if candidates is not None:
         # the two searches share inputs, candidates and noise: one factorisation per candidate serves both
         pend_r, pend_i = select_candidates_pair_async(candidates, X_d, yr, yi, noise, Xv_d, yv_r, yv_i, sr, si)
-        (th_r_d, gidx_r, best_r), (th_i_d, gidx_i, best_i) = _device_pick(candidates, [pend_r, pend_i])
+        with _lib.timed_region("collective:argmin_pick"):
+            (th_r_d, gidx_r, best_r), (th_i_d, gidx_i, best_i) = _device_pick(candidates, [pend_r, pend_i])
         sel = torch.stack([gidx_r.to(F64), best_r, gidx_i.to(F64), best_i])
     else:
         th = bgp._theta_block(np.asarray(theta0, dtype=np.float64))[0]
@@ -463,7 +494,8 @@ def identify_device(train: Sequence[Tuple[torch.Tensor, torch.Tensor, torch.Tens
             skip = min(10, taps.numel() // 10)
             y0 = val[4] if len(val) > 4 else float(val[2][skip].item())
             sums, _ = bfir.fir_eval_device(val[1], val[2], taps, skip, y0)
-            bdist.allreduce_sum_(sums)
+            with _lib.timed_region("collective:fir_sums"):
+                bdist.allreduce_sum_(sums)
         return G_uni, taps, sums
 
     G_uni, taps, sums = tail(alphas[0][0], alphas[1][0])

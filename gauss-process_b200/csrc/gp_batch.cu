@@ -407,6 +407,49 @@ extern "C" int b200id_gp_batch_eval_pair(int kernel_id, const int* kernel_ids, c
                                         y_b, yv_b, y_mean_b, y_scale_b, metric_out_b);
 }
 
+namespace b200id {
+__global__ void argmin_pack_kernel(const double* __restrict__ pend, int k, const int64_t* __restrict__ gmap,
+                                   double* __restrict__ mine) {
+    const int j = threadIdx.x;
+    if (j >= k) return;
+    const int64_t l = (int64_t)pend[2 * j + 1];
+    mine[2 * j] = pend[2 * j];
+    mine[2 * j + 1] = l >= 0 ? (gmap ? (double)gmap[l] : (double)l) : -1.0;
+}
+// same rule as b200id.dist.pick_first_strict_min: m < best, or m == best with a smaller global index
+__global__ void argmin_pick_kernel(const double* __restrict__ tab, int ws, int k, const double* __restrict__ full_theta,
+                                   double* __restrict__ out) {
+    const int j = threadIdx.x;
+    if (j >= k) return;
+    double best = INFINITY, gsel = -1.0;
+    for (int r = 0; r < ws; ++r) {
+        const double m = tab[((size_t)r * k + j) * 2], g = tab[((size_t)r * k + j) * 2 + 1];
+        if (g < 0.0 || !(m == m)) continue;
+        if (m < best || (m == best && g < gsel)) { best = m; gsel = g; }
+    }
+    const int64_t row = gsel >= 0.0 ? (int64_t)gsel : 0;
+    for (int p = 0; p < B200ID_MAX_PARAMS; ++p) out[5 * j + p] = full_theta[row * B200ID_MAX_PARAMS + p];
+    out[5 * j + 3] = gsel;
+    out[5 * j + 4] = best;
+}
+}  // namespace b200id
+
+extern "C" int b200id_argmin_pack(const double* pend, int n_searches, const int64_t* global_index_map, double* mine_out,
+                                  void* stream) {
+    B200ID_REQUIRE(pend && mine_out && n_searches > 0 && n_searches <= 256, B200ID_E_ARG, "argmin_pack: bad argument");
+    b200id::argmin_pack_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(pend, n_searches, global_index_map, mine_out);
+    B200ID_LAUNCH_CHECK("argmin_pack_kernel");
+    return B200ID_OK;
+}
+extern "C" int b200id_argmin_pick(const double* gathered, int n_ranks, int n_searches, const double* full_theta, double* out,
+                                  void* stream) {
+    B200ID_REQUIRE(gathered && full_theta && out && n_ranks > 0 && n_searches > 0 && n_searches <= 256, B200ID_E_ARG,
+                   "argmin_pick: bad argument");
+    b200id::argmin_pick_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(gathered, n_ranks, n_searches, full_theta, out);
+    B200ID_LAUNCH_CHECK("argmin_pick_kernel");
+    return B200ID_OK;
+}
+
 extern "C" int b200id_first_strict_min(const double* metric, int64_t n_candidates, double* best_out, int64_t* idx_out,
                                        void* ws, size_t ws_bytes, void* stream) {
     (void)ws; (void)ws_bytes;

@@ -198,6 +198,19 @@ int b200id_gp_batch_eval_noise(int kernel_id, const int* kernel_ids, const doubl
 int b200id_first_strict_min(const double* metric, int64_t n_candidates,
                             double* best_out, int64_t* idx_out, void* ws, size_t ws_bytes, void* stream);
 
+/* The two small steps either side of the ranks' argmin exchange (candidates are sharded round
+ * robin, every rank reports (best metric, global index), the first strict minimum in GLOBAL scan order wins --
+ * grid_search.py:186-196 over the whole list), for n_searches independent searches at once, as one launch each instead
+ * of a few dozen tensor operations:
+ *   argmin_pack : pend [S][2] = (best metric, LOCAL index as a double, -1 = none) -> mine [S][2] = (best metric,
+ *                 global index = global_index_map[local] (or local itself when the map is NULL), -1 = none)
+ *   argmin_pick : gathered [W][S][2] (rank-major; W = 1 without an exchange) -> out [S][5] = (theta[0..2] of the winner
+ *                 from full_theta [C][B200ID_MAX_PARAMS], global index or -1, best metric or +inf); ties go to the
+ *                 smallest global index, NaN metrics and empty shards are skipped. */
+int b200id_argmin_pack(const double* pend, int n_searches, const int64_t* global_index_map, double* mine_out, void* stream);
+int b200id_argmin_pick(const double* gathered, int n_ranks, int n_searches, const double* full_theta, double* out,
+                       void* stream);
+
 /* Final fit: K + diag_add*I, Cholesky, alpha = K^-1 y, K_inv (from the factor).  gpr_fitting.py:73-83.
  * Kinv_out may be NULL when only alpha is needed (n <= 127).
  * info_out[0] = 0 ok, k > 0 = non-positive pivot at column k (caller then uses b200id_gp_fit_pinv). */

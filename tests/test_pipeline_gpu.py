@@ -146,3 +146,49 @@ def test_identify_host_two_training_records_and_no_search():
     ref = P.identify_device(train_d, None, nd, "matern52", 1e-6, candidates=None, theta0=[0.7, 1.3])
     tr, tg = ref.taps.cpu().numpy(), got.taps.cpu().numpy()
     assert float(np.max(np.abs(tg - tr)) / np.max(np.abs(tr))) < 1e-6 and got.fir == {}
+
+
+def test_argmin_pack_and_pick_kernels_follow_the_scan_rule():
+    """b200id_argmin_pack / b200id_argmin_pick (the two launches either side of the ranks' argmin exchange) against
+    b200id.dist.pick_first_strict_min, the host statement of grid_search.py:186-196 over a sharded list: ties go to the
+    smallest global index, NaN metrics and empty shards are skipped, nothing finite anywhere gives index -1."""
+    import ctypes as C
+    import torch
+    from b200id import _lib, dist as bdist
+    from b200id.runtime import require_cuda, to_device, ptr, stream_ptr, empty
+    dev = require_cuda()
+    rng = np.random.default_rng(9)
+    n_cand, W, S = 57, 4, 3
+    full = rng.uniform(0.1, 5.0, (n_cand, 3))
+    full_d = to_device(full, dev)
+    for case in range(40):
+        # pack: local (best, index) -> (best, global index) through a rank's index map
+        gmap = np.sort(rng.choice(n_cand, 15, replace=False)).astype(np.int64)
+        lidx = rng.integers(-1, 15, S).astype(np.float64)
+        lbest = np.where(lidx >= 0, rng.integers(0, 4, S).astype(np.float64), np.inf)
+        pend = to_device(np.c_[lbest, lidx].ravel(), dev)
+        mine = empty(2 * S, dev)
+        _lib.call("b200id_argmin_pack", ptr(pend), C.c_int(S), ptr(torch.as_tensor(gmap, device=dev)), ptr(mine), stream_ptr())
+        got = mine.cpu().numpy().reshape(S, 2)
+        want_g = np.where(lidx >= 0, gmap[np.maximum(lidx.astype(int), 0)], -1)
+        assert np.array_equal(got[:, 0], lbest) and np.array_equal(got[:, 1], want_g)
+        _lib.call("b200id_argmin_pack", ptr(pend), C.c_int(S), ptr(None), ptr(mine), stream_ptr())
+        assert np.array_equal(mine.cpu().numpy().reshape(S, 2)[:, 1], lidx)
+        # pick: gathered [W][S][2] -> winner per search
+        m = rng.integers(0, 3, (W, S)).astype(np.float64)
+        g = rng.permuted(np.arange(n_cand))[:W * S].reshape(W, S).astype(np.float64)
+        m[rng.random((W, S)) < 0.2] = np.nan
+        g[rng.random((W, S)) < 0.2] = -1.0
+        if case % 7 == 0:
+            g[:, 0] = -1.0                                   # search 0: every shard empty
+        if case % 5 == 0:
+            m[:, 1] = 1e10                                   # search 1: every candidate failed -> smallest index wins
+        tab = to_device(np.stack([m, g], axis=2).ravel(), dev)
+        out = empty(5 * S, dev)
+        _lib.call("b200id_argmin_pick", ptr(tab), C.c_int(W), C.c_int(S), ptr(full_d), ptr(out), stream_ptr())
+        out = out.cpu().numpy().reshape(S, 5)
+        for j in range(S):
+            ei, eb = bdist.pick_first_strict_min([(float(m[r, j]), int(g[r, j])) for r in range(W)])
+            assert int(out[j, 3]) == ei, (case, j, out[j], ei)
+            assert out[j, 4] == eb or (ei < 0 and np.isinf(out[j, 4]))
+            assert np.array_equal(out[j, :3], full[max(ei, 0)])

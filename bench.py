@@ -226,6 +226,9 @@ def main():
 
     rank, world, local = bdist.init_from_env()
     dev = require_cuda()
+    # one process per GPU: keep this rank's host buffers on the NUMA node its GPU hangs off (matters for the e2e
+    # figure at N > 1, where every rank pulls 480 MB per step over its own link); B200ID_NUMA_BIND=0 switches it off
+    numa = bdist.bind_to_gpu_numa_node(local) if os.environ.get("B200ID_NUMA_BIND", "1") != "0" else {"bound": False}
     sm, major, minor = _lib.device_info()
     peaks = {}
     pk = ROOT / "MEASURED_PEAKS.json"
@@ -464,7 +467,7 @@ def main():
         "result": {"theta_real": res.theta_real.tolist(), "theta_imag": res.theta_imag.tolist(), "fir_rmse": res.fir.get("rmse"),
                    "e2e_fir_rmse": metrics_e.get("rmse"), "e2e_theta_real": res_e.theta_real.tolist(),
                    "e2e_theta_imag": res_e.theta_imag.tolist(), "e2e_call_by_call_fir_rmse": metrics_c.get("rmse")},
-        "device": {"sm_count": sm, "cc": f"{major}.{minor}"},
+        "device": {"sm_count": sm, "cc": f"{major}.{minor}"}, "host_numa": numa,
     }
     print(json.dumps(line), flush=True)
 

@@ -41,6 +41,36 @@ def init_from_env(backend: str = None) -> Tuple[int, int, int]:
     return rank, ws, local
 
 
+def bind_to_gpu_numa_node(local_rank: int = None) -> dict:
+    """Pin this process (CPU affinity, hence first-touch memory placement of the pinned host buffers it allocates
+    afterwards) to the NUMA node its GPU hangs off, from sysfs.  With one process per GPU on a two-socket host the
+    host->device copies of the ranks otherwise cross the socket interconnect and share its bandwidth.  No-op (and says
+    so) when the topology cannot be read or the host has a single node.  Call before allocating host buffers."""
+    info = {"bound": False}
+    try:
+        if not torch.cuda.is_available():
+            return info
+        dev = torch.cuda.current_device() if local_rank is None else local_rank
+        pr = torch.cuda.get_device_properties(dev)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        base = f"/sys/bus/pci/devices/{bdf}"
+        node = int(open(f"{base}/numa_node").read().strip())
+        info.update(pci=bdf, numa_node=node)
+        if node < 0:
+            return info
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if allowed and allowed != os.sched_getaffinity(0):
+            os.sched_setaffinity(0, allowed)
+            info.update(bound=True, cpus=len(allowed))
+    except Exception as exc:                              # topology not readable: leave the affinity alone
+        info["error"] = f"{type(exc).__name__}: {exc}"
+    return info
+
+
 def allreduce_sum_(t: torch.Tensor) -> torch.Tensor:
     """In-place sum over ranks (identity for a single process)."""
     if world()[1] > 1:

@@ -288,15 +288,6 @@ def _probe_paths(probes):
     return paths
 
 
-def _async_to_host(t: torch.Tensor):
-    """Start a device->host copy into pinned memory; returns (host tensor, event)."""
-    host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
-    host.copy_(t, non_blocking=True)
-    ev = torch.cuda.Event()
-    ev.record()
-    return host, ev
-
-
 def _device_pick(cs: "CandidateSet", pends: Sequence[torch.Tensor]) -> List[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]]:
     """[(theta [3] on the device, global index, metric)] of the selected candidate of each search in ``pends``
     WITHOUT a host round trip.
@@ -375,13 +366,13 @@ def identify_device(train: Sequence[Tuple[torch.Tensor, torch.Tensor, torch.Tens
     use_validation_metric.  candidates: grid (None -> no search, theta0 is used as is).
 
     train_frf / val_frf: per-record coefficients (U, Y) already enqueued on this stream; val_frf may also be a
-    callable returning them, which is then invoked AFTER the training targets are on their way to the host (identify_host projects
+    callable returning them, which is then invoked after the training targets have been queued (identify_host projects
     each record while it is still being uploaded); the records themselves are then only read by the FIR pass.
     frf_checks: 1-element device tensors that must be 0 for those coefficients to stand (time-base guess of a
     streamed record); they ride in the final host read and a non-zero one raises TimebaseGuessFailed.
 
-    The host only blocks twice: once for the timebase probes, once at the end.  Everything in between is
-    enqueued ahead of the GPU (the selected hyperparameters, the fit status and the all-gathered argmin stay
+    The host only blocks for the timebase probes (not at all when the coefficients are handed in) and once at the
+    end.  Everything in between is enqueued ahead of the GPU (the selected hyperparameters, the fit status and the all-gathered argmin stay
     on the device), so the stream never drains while Python prepares the next launch.
     """
     import ctypes as C
@@ -425,24 +416,25 @@ def identify_device(train: Sequence[Tuple[torch.Tensor, torch.Tensor, torch.Tens
             val_sums()
         with _lib.timed_region("collective:frf_sums"):
             bdist.allreduce_sum_(sums_all)
-    # ---- G, StandardScaler statistics of Re G / Im G and the standardised targets: one kernel; the statistics
-    # travel to the host asynchronously
+    # ---- G, StandardScaler statistics of Re G / Im G and the standardised targets: one kernel; the statistics stay
+    # on the device (they reach the host with the final read)
     G, stats_d, yr, yi = bfrf.gp_targets_device(sums_all[:3 * nd], nd, standardise=True)
     mean2, sd2 = stats_d[0:2], stats_d[2:4]
-    stats_host, stats_ev = _async_to_host(stats_d)
     Xv_d = yv_r = yv_i = None
     if lazy_val:
-        # the validation coefficients are enqueued only now: the statistics' copy above completes as soon as the
-        # training records are done, so the host wait below ends while the validation record is still arriving
-        # and everything after it is queued ahead of the GPU
         val_sums()
         bdist.allreduce_sum_(sums_all[3 * nd:])
     if use_val_metric:
         _, _, yv_r, yv_i = bfrf.gp_targets_device(sums_all[3 * nd:], nv, standardise=False)   # frf_estimator.py:239-252
         Xv_d = gi.Xv_d
-    stats_ev.synchronize()
-    st = stats_host.tolist()
-    sr, si = Standardizer(st[0], st[2]), Standardizer(st[1], st[3])
+        # The search metric is RMSE(y_val - (pred * scale + mean)) (grid_search.py:112-118 with the y scaler of
+        # gp_pipeline.py:132).  scale > 0 is a property of the target, not of the candidate, so the same scan order
+        # follows from RMSE((y_val - mean) / scale - pred) = RMSE / scale: the validation values are standardised ON
+        # THE DEVICE, the kernel runs with (mean, scale) = (0, 1), and the winner's metric is scaled back on the host
+        # at the end -- which removes the only mid-pass host read (the statistics), so the host queues the whole
+        # pass without ever waiting for the GPU.
+        yv_r = ((yv_r - mean2[0]) / sd2[0]).contiguous()
+        yv_i = ((yv_i - mean2[1]) / sd2[1]).contiguous()
     # ---- model selection (grid_search.py:48-203): Re and Im searches on two streams, winners stay on the device
     diag = float(noise) + 1e-10
     kid = bgp.KERNEL_IDS[kernel][0]
@@ -450,7 +442,7 @@ def identify_device(train: Sequence[Tuple[torch.Tensor, torch.Tensor, torch.Tens
     sel = None
     if candidates is not None:
         # the two searches share inputs, candidates and noise: one factorisation per candidate serves both
-        pend_r, pend_i = select_candidates_pair_async(candidates, X_d, yr, yi, noise, Xv_d, yv_r, yv_i, sr, si)
+        pend_r, pend_i = select_candidates_pair_async(candidates, X_d, yr, yi, noise, Xv_d, yv_r, yv_i, None, None)
         with _lib.timed_region("collective:argmin_pick"):
             (th_r_d, gidx_r, best_r), (th_i_d, gidx_i, best_i) = _device_pick(candidates, [pend_r, pend_i])
         sel = torch.stack([gidx_r.to(F64), best_r, gidx_i.to(F64), best_i])
@@ -503,6 +495,7 @@ def identify_device(train: Sequence[Tuple[torch.Tensor, torch.Tensor, torch.Tens
     pack = [infos.to(F64), th_r_d.reshape(-1)[:3], th_i_d.reshape(-1)[:3]]
     if sel is not None:
         pack.append(sel)
+        pack.append(sd2)
     if sums is not None:
         pack.append(sums)
     if frf_checks:
@@ -517,7 +510,12 @@ def identify_device(train: Sequence[Tuple[torch.Tensor, torch.Tensor, torch.Tens
     mr = mi = float("nan")
     if sel is not None:
         gr, mr, gi_, mi = host[pos:pos + 4]
-        pos += 4
+        sd_r, sd_i = host[pos + 4:pos + 6]
+        pos += 6
+        if use_val_metric:
+            # back to the reference's units; the failure constant (1e10) and NaN are not metrics and stay as they are
+            mr = mr * sd_r if (mr == mr and mr != bgp.FAIL_METRIC) else mr
+            mi = mi * sd_i if (mi == mi and mi != bgp.FAIL_METRIC) else mi
         if int(gr) < 0 or int(gi_) < 0:
             raise ValueError("grid search found no finite candidate (all metrics NaN): kernel.set_params(None) in the reference")
     used_pinv = [False, False]
@@ -558,11 +556,11 @@ def identify_host(train: Sequence[Tuple[np.ndarray, np.ndarray, np.ndarray]],
     tensors, ideally pinned): what run_gp_pipeline does for .mat files (gp_pipeline.py:60-247), for arrays.
 
     Every record crosses the link exactly once per call: all uploads are queued on the copy stream up front
-    (training records first, so that their targets' statistics -- the one mid-pass host read -- are back while
-    the validation record is still arriving), each record is projected piece by piece as its time stamps land,
-    and the FIR validation reads the validation record's resident copy -- so the link never idles between
-    stages, the host has everything queued before the last byte lands, and only the last piece's projection,
-    the GP stage and the FIR pass are exposed after it.  The uniform-timebase guess of each record (host look at its
+    (training records first), each record is projected piece by piece as its time stamps land, and the FIR
+    validation reads the validation record's resident copy.  Nothing in the pass waits for the host (the
+    targets' statistics stay on the device, see identify_device), so the link never idles between stages, the
+    whole pass is queued long before the last byte lands, and only the last piece's projection, the GP stage and
+    the FIR pass are exposed after it.  The uniform-timebase guess of each record (host look at its
     first 4096 stamps) is verified on the device over the whole resident record; the verdicts come back with
     the final host read, and a failed guess reruns the pass through :func:`identify_device` on the resident
     copies (general kernel).

@@ -365,13 +365,56 @@ def golden_fourier(out: Path):
     print("fourier.npz", {k: np.shape(v) for k, v in d.items()})
 
 
+def golden_pipeline_polar(out: Path):
+    """run_gp_pipeline with gp_mode='polar' (gp_pipeline.py:159-193: GPs on log-magnitude and unwrapped phase,
+    grid search without validation data, i.e. the NLL metric) on the same synthetic .mat files."""
+    import argparse as ap
+    from src.pipeline.gp_pipeline import run_gp_pipeline
+    d = {"versions": VERSIONS}
+    n, nd = 30000, 50
+    d["n"] = np.array(n); d["nd"] = np.array(nd)
+    tt, ut, yt = synth.make_record(n, nd, "multisine", seed=0)
+    tv, uv, yv = synth.make_record(n, nd, "square", seed=1)
+    with tempfile.TemporaryDirectory() as tmp:
+        cwd = os.getcwd(); os.chdir(tmp)
+        try:
+            ptrain = synth.write_mat(Path(tmp) / "train.mat", tt, ut, yt)
+            pval = synth.write_mat(Path(tmp) / "val.mat", tv, uv, yv)
+            for tag, kernel, opt, grid, noise in (("m52_polar_plain", "matern52", False, False, 1e-6),
+                                                  ("m52_polar_grid", "matern52", True, True, 1e-6),
+                                                  ("rbf_polar_grid", "rbf", True, True, 1e-6)):
+                np.random.seed(42)
+                cfg = ap.Namespace(
+                    mat_files=[str(ptrain)], use_existing=None, n_files=1, time_duration=None, nd=nd,
+                    freq_method="frf", kernel=kernel, nu=None, gp_mode="polar", noise_variance=noise,
+                    normalize=True, log_frequency=True, optimize=opt, n_restarts=3,
+                    out_dir=str(Path(tmp) / tag), extract_fir=True, fir_length=1024,
+                    fir_validation_mat=str(pval), method="gp", is_gp=True, use_grid_search=grid,
+                    grid_search_max_combinations=5000, validation_mat=None, n_numerator=2, n_denominator=4)
+                res = quiet(run_gp_pipeline, cfg)
+                d[f"{tag}_theta_mag"] = np.array(res["kernel_params"]["magnitude"])
+                d[f"{tag}_theta_phase"] = np.array(res["kernel_params"]["phase"])
+                d[f"{tag}_gp_rmse"] = np.array([res["magnitude"]["rmse"], res["phase"]["rmse"],
+                                                res["magnitude"]["r2"], res["phase"]["r2"]])
+                f = res["fir_extraction"]
+                d[f"{tag}_taps"] = f["fir_coefficients"]
+                d[f"{tag}_fir"] = np.array([f["rmse"], f["fit_percent"], f["r2"]])
+                print(" ", tag, "theta", res["kernel_params"]["magnitude"], res["kernel_params"]["phase"],
+                      "fir rmse", f["rmse"])
+        finally:
+            os.chdir(cwd)
+    np.savez_compressed(out / "pipeline_polar.npz", **d)
+    print("pipeline_polar.npz", len(d), "arrays")
+
+
 def main():
     ap_ = argparse.ArgumentParser()
     ap_.add_argument("--out", default=str(ROOT / "tests" / "golden"))
     ap_.add_argument("--only", default="")
     a = ap_.parse_args()
     out = Path(a.out); out.mkdir(parents=True, exist_ok=True)
-    todo = {"frf": golden_frf, "gp": golden_gp, "fir": golden_fir, "pipeline": golden_pipeline, "fourier": golden_fourier}
+    todo = {"frf": golden_frf, "gp": golden_gp, "fir": golden_fir, "pipeline": golden_pipeline, "fourier": golden_fourier,
+            "pipeline_polar": golden_pipeline_polar}
     for name, fn in todo.items():
         if a.only and name not in a.only.split(","):
             continue

@@ -9,7 +9,7 @@ from sklearn.preprocessing import StandardScaler
 
 
 def run(train_mat, val_mat, out_dir, kernel="matern52", nd=50, noise=1e-6, optimize=False, grid=False,
-        max_comb=5000, n_restarts=3):
+        max_comb=5000, n_restarts=3, mode="separate"):
     from src.frequency_transform.transform import estimate_frequency_response
     from src.frequency_transform.frf_estimator import (load_time_u_y, matlab_freq_grid, synchronous_coefficients_trapz,
                                                        frf_cross_power_average)
@@ -35,6 +35,8 @@ def run(train_mat, val_mat, out_dir, kernel="matern52", nd=50, noise=1e-6, optim
         Gv = frf_cross_power_average([synchronous_coefficients_trapz(t, u, wv, 0.0, True)],
                                      [synchronous_coefficients_trapz(t, y, wv, 0.0, True)])
         vX = Xs.transform(np.log10(wv).reshape(-1, 1)); vyr, vyi = np.real(Gv), np.imag(Gv)
+    if mode == "polar":                                            # gp_pipeline.py:159-193
+        return _run_polar(omega, G, Xs, Xn, frf, kernel, noise, optimize, grid, max_comb, n_restarts, val_mat, out_dir)
     fitted = []
     for target, scaler, vy in ((yr, ysr, vyr), (yi, ysi, vyi)):
         gp = GaussianProcessRegressor(kernel=create_kernel(kernel), noise_variance=noise)
@@ -57,6 +59,45 @@ def run(train_mat, val_mat, out_dir, kernel="matern52", nd=50, noise=1e-6, optim
         return a + 1j * b
 
     res["fir_extraction"] = gp_to_fir_direct_pipeline(omega=omega, G=pr + 1j * pi_, gp_predict_func=predict_at,
+                                                      mat_file=Path(val_mat) if val_mat else None,
+                                                      output_dir=out_dir, fir_length=1024)
+    return res
+
+
+def _run_polar(omega, G, Xs, Xn, frf, kernel, noise, optimize, grid, max_comb, n_restarts, val_mat, out_dir):
+    """gp_mode='polar': GPs on log|G| and the unwrapped phase; the search gets no validation data, so its metric
+    is the NLL (gp_pipeline.py:159-193), and the predictor recombines exp(a) * exp(jb) (:207-226)."""
+    from src.gpr.kernels import create_kernel
+    from src.gpr.gpr_fitting import GaussianProcessRegressor
+    from src.gpr.visualization import plot_gp_results
+    from src.fir_model.fir_fitting import gp_to_fir_direct_pipeline
+
+    mag = np.abs(G); phase = np.unwrap(np.angle(G))
+    ms = StandardScaler(); ym = ms.fit_transform(np.log(mag).reshape(-1, 1)).ravel()
+    ps = StandardScaler(); yp = ps.fit_transform(phase.reshape(-1, 1)).ravel()
+    fitted = []
+    for target, scaler in ((ym, ms), (yp, ps)):
+        gp = GaussianProcessRegressor(kernel=create_kernel(kernel), noise_variance=noise)
+        gp.fit(Xn, target, optimize=optimize, n_restarts=n_restarts, use_grid_search=grid, max_grid_combinations=max_comb)
+        pred, std = gp.predict(Xn, return_std=True)
+        fitted.append((gp, scaler.inverse_transform(pred.reshape(-1, 1)).ravel(), std * scaler.scale_))
+    (gp_m, pm, _), (gp_p, pp, sp) = fitted
+    mag_pred = np.exp(pm)
+    res = {"magnitude": plot_gp_results(omega, mag, mag_pred, None, "", None),
+           "phase": plot_gp_results(omega, phase, pp, sp, "", None),
+           "kernel_params": {"magnitude": gp_m.kernel.get_params().tolist(), "phase": gp_p.kernel.get_params().tolist()},
+           "frf": frf.to_numpy()}
+
+    def predict_at(omega_new):
+        X = omega_new.reshape(-1, 1).copy()
+        omin = np.min(omega[omega > 0])
+        X[X.ravel() <= omin * 0.1] = omin
+        Xq = Xs.transform(np.log10(X))
+        a = ms.inverse_transform(gp_m.predict(Xq).reshape(-1, 1)).ravel()
+        b = ps.inverse_transform(gp_p.predict(Xq).reshape(-1, 1)).ravel()
+        return np.exp(a) * np.exp(1j * b)
+
+    res["fir_extraction"] = gp_to_fir_direct_pipeline(omega=omega, G=mag_pred * np.exp(1j * pp), gp_predict_func=predict_at,
                                                       mat_file=Path(val_mat) if val_mat else None,
                                                       output_dir=out_dir, fir_length=1024)
     return res

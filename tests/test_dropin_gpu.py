@@ -190,3 +190,32 @@ def test_whole_pipeline_against_reference_run(tmp_path, golden, tag, kernel, opt
     e_fir = record(f"dropin.pipeline.{tag}.fir_metrics.rel_each",
                    rel_each(np.array([f["rmse"], f["fit_percent"], f["r2"]]), g[f"{tag}_fir"]))
     assert e_taps < 1e-7 and e_fir < 1e-7
+
+
+@pytest.mark.parametrize("tag,kernel,opt,grid", [("m52_polar_plain", "matern52", False, False),
+                                                 ("m52_polar_grid", "matern52", True, True),
+                                                 ("rbf_polar_grid", "rbf", True, True)])
+def test_whole_pipeline_polar_mode_against_reference_run(tmp_path, golden, tag, kernel, opt, grid):
+    """gp_mode='polar' of the reference's run_gp_pipeline (gp_pipeline.py:159-193: log-magnitude and unwrapped-phase
+    GPs, grid search on the NLL because no validation data reaches it) vs the same public calls on the drop-in
+    surface.  Golden: tests/golden/pipeline_polar.npz (oracle/make_golden.py)."""
+    from b200id import synth
+    import pipeline_flow
+    g = golden("pipeline_polar")
+    n, nd = int(g["n"]), int(g["nd"])
+    tt, ut, yt = synth.make_record(n, nd, "multisine", seed=0)
+    tv, uv, yv = synth.make_record(n, nd, "square", seed=1)
+    ptrain = synth.write_mat(tmp_path / "train.mat", tt, ut, yt)
+    pval = synth.write_mat(tmp_path / "val.mat", tv, uv, yv)
+    np.random.seed(42)
+    res = quiet(pipeline_flow.run, ptrain, pval, tmp_path / tag, kernel=kernel, nd=nd, noise=1e-6, optimize=opt,
+                grid=grid, mode="polar")
+    assert np.array_equal(np.array(res["kernel_params"]["magnitude"]), g[f"{tag}_theta_mag"])
+    assert np.array_equal(np.array(res["kernel_params"]["phase"]), g[f"{tag}_theta_phase"])
+    gp_m = np.array([res["magnitude"]["rmse"], res["phase"]["rmse"], res["magnitude"]["r2"], res["phase"]["r2"]])
+    e_gp = record(f"dropin.pipeline.{tag}.gp_metrics.rel_each", rel_each(gp_m, g[f"{tag}_gp_rmse"]))
+    f = res["fir_extraction"]
+    e_taps = record(f"dropin.pipeline.{tag}.taps.rel_max", rel_max(f["fir_coefficients"], g[f"{tag}_taps"]))
+    e_fir = record(f"dropin.pipeline.{tag}.fir_metrics.rel_each",
+                   rel_each(np.array([f["rmse"], f["fit_percent"], f["r2"]]), g[f"{tag}_fir"]))
+    assert e_gp < 1e-6 and e_taps < 1e-7 and e_fir < 1e-7

@@ -61,7 +61,8 @@ def _compare_metrics(got, ref, tag, cond=None):
     cg, cr = _categories(got), _categories(ref)
     flips = int(np.sum(cg != cr))
     both = (cg == 0) & (cr == 0)
-    err = np.abs(got - ref) / np.maximum(np.abs(ref), 1e-300)
+    with np.errstate(invalid="ignore"):  # NaN / inf entries are compared by category above, not by value
+        err = np.abs(got - ref) / np.maximum(np.abs(ref), 1e-300)
     record(f"gp.metric.{tag}.flips", flips)
     record(f"gp.metric.{tag}.n_compared", int(both.sum()))
     record(f"gp.metric.{tag}.rel_max", float(err[both].max()) if both.any() else 0.0)

@@ -15,6 +15,16 @@ one 10^7-sample square-wave validation record (dt = 2 ms, FP64), N_d = 100:
 value = training samples processed by all ranks / step time (device-resident inputs, CUDA events,
 max over ranks).  e2e = same metric with HOST (pinned) buffers: H2D of both records and D2H of the
 result inside the timed region.  See DESIGN.md section "Measurement" for the roofline arithmetic.
+
+Besides the headline fields the line carries
+  parity   -- the step's own results against the CPU oracle on the bench's own inputs (outside the timed region)
+  configs  -- BASELINE configs 3 (11 kernels x 4096 restarts, sharded over the ranks), 4 (N_d = 2048, 16 candidates)
+              and, with more than one rank, 5 (R = 100 records x 10^7 samples round-robin over the ranks + FIR)
+  e2e_full_upload / e2e_pageable -- the same call with the time vectors uploaded every step / from pageable memory
+
+--impl reference times the reference's CPU algorithm (oracle port) on the SAME records at the SAME n; when the run
+would not fit the time budget (B200ID_REF_BUDGET_S, default 240 s) the O(n) stages (FRF, FIR) run on a slice and are
+scaled linearly while the GP stage is timed in full -- the line says which (config.n_samples_per_record_run).
 """
 from __future__ import annotations
 
@@ -57,17 +67,24 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n", type=int, default=10_000_000, help="samples per record (per rank)")
     ap.add_argument("--nd", type=int, default=100)
-    ap.add_argument("--cpu-sample", type=int, default=400_000, help="samples of the bounded CPU-baseline pass")
+    ap.add_argument("--cpu-sample", type=int, default=0,
+                    help="samples per record of the CPU-baseline pass (0 = the bench's own n, one pass ~15 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the configs block (cfg 3 / 4 / 5)")
+    ap.add_argument("--cfg5", default="auto", choices=["auto", "on", "off"],
+                    help="config 5 (100 records x 1e7 samples over the ranks): auto = when WORLD_SIZE > 1")
+    ap.add_argument("--cfg5-records", type=int, default=100)
+    ap.add_argument("--restarts", type=int, default=4096, help="config 3: start points per kernel")
     return ap.parse_args()
 
 
-def workload_config(a, world):
+def workload_config(a, world, n_run=None):
+    n_run = a.n if n_run is None else n_run
     return {
         "workload": f"cfg2 full pipeline per rank: {a.n}-sample multisine train record + {a.n}-sample square-wave "
                     f"validation record, N_d={a.nd}, validation FRF {VAL_ND} bins, Matern-5/2 grid 900 candidates x 2 "
                     f"targets (val-RMSE), 1000-pt GP mean, Hermitian IDFT -> {N_TAPS} taps, FIR validation",
-        "n_samples_per_record": a.n, "n_d": a.nd, "records_per_rank": 2, "ranks": world,
+        "n_samples_per_record": a.n, "n_samples_per_record_run": n_run, "n_d": a.nd, "records_per_rank": 2, "ranks": world,
         "gp_candidates_per_step": 1800, "fir_taps": N_TAPS, "noise_variance": NOISE,
         "l2_policy": "inputs larger than L2 (2 records x 240 MB per rank vs 126 MB L2)",
         "parallelism": f"records x{world} (weak), candidates round-robin over ranks",
@@ -143,12 +160,11 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-def cpu_pipeline_pass(n_s, nd, threads):
-    """One pass of the SAME pipeline through the NumPy oracle (the reference's algorithm) on a bounded
-    sample of n_s samples per record.  Returns seconds per stage."""
-    from b200id import synth
+def cpu_pipeline_pass(train, val, nd, threads):
+    """One pass of the SAME pipeline through the NumPy oracle (the reference's algorithm, oracle/*.py) on the given
+    host records.  Returns (seconds per stage, results): the results are what the parity block compares with."""
     from oracle import frf as ofrf, gp as ogp, fir as ofir
-    (t, u, y), (tv, uv, yv) = make_records(n_s, nd, seed=0)
+    (t, u, y), (tv, uv, yv) = train, val
     st = {}
     t0 = time.perf_counter()
     w, G = ofrf.estimate_frf([(t, u, y)], nd, threads=threads)
@@ -163,50 +179,228 @@ def cpu_pipeline_pass(n_s, nd, threads):
     with np.errstate(all="ignore"):
         for target, tv_ in ((G.real, Gv.real), (G.imag, Gv.imag)):
             z, m, s = ogp.standardize(target)
-            best, _, _, _ = ogp.grid_search(KERNEL, X, z, NOISE, 5000, Xv=Xv, yv=tv_, y_mean=m, y_scale=s)
+            best, best_metric, _, _ = ogp.grid_search(KERNEL, X, z, NOISE, 5000, Xv=Xv, yv=tv_, y_mean=m, y_scale=s)
             alpha, Kinv, _ = ogp.fit(KERNEL, best, X, z, NOISE)
-            fits.append((best, alpha, Kinv, m, s))
+            fits.append((best, alpha, Kinv, m, s, best_metric))
     st["gp"] = time.perf_counter() - t0
     t0 = time.perf_counter()
 
     def predict(w_new):
         Xn = (np.log10(w_new) - xm) / xs
-        parts = [ogp.predict(KERNEL, b, X, a, K, Xn) * s + m for (b, a, K, m, s) in fits]
+        parts = [ogp.predict(KERNEL, b, X, a, K, Xn) * s + m for (b, a, K, m, s, _) in fits]
         return parts[0] + 1j * parts[1]
 
     taps, *_ = ofir.paper_fir(w, G, predict=predict)
     metrics, _ = ofir.fir_validate(uv, yv, taps)
     st["fir"] = time.perf_counter() - t0
-    return st, metrics
+    res = {"omega": w, "G": G, "Gv": Gv, "theta_real": np.asarray(fits[0][0]), "theta_imag": np.asarray(fits[1][0]),
+           "metric_real": float(fits[0][5]), "metric_imag": float(fits[1][5]), "taps": taps, "fir": metrics}
+    return st, res
+
+
+def scaled_step_seconds(st, n_run, n_full):
+    """Step time at n_full from stage seconds measured at n_run: FRF and FIR are O(n) (frf_estimator.py:226-231,
+    fir_fitting.py:285), the GP stage does not depend on n."""
+    f = n_full / float(n_run)
+    return (st["frf_train"] + st["frf_val"] + st["fir"]) * f + st["gp"]
+
+
+def slice_records(train, val, n_s):
+    return tuple(a[:n_s] for a in train), tuple(a[:n_s] for a in val)
 
 
 def run_reference_arm(a, rank, world):
     """--impl reference: the reference's CPU algorithm (oracle port; the reference itself is pure Python and
-    /root/reference does not exist on the GPU box) on the host cores, bounded sample per step."""
+    /root/reference does not exist on the GPU box) on the host cores with all the threads the per-bin loop can use,
+    on the bench's own records.  Runs at the bench's own n when (steps + warmup) passes fit the budget; otherwise
+    the O(n) stages run on a slice and are scaled (the line carries the n actually run and the stage seconds)."""
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    n_s = min(a.n, a.cpu_sample)
-    times = []
-    for i in range(a.warmup + a.steps):
-        t0 = time.perf_counter()
-        st, _ = cpu_pipeline_pass(n_s, a.nd, threads)
-        dt = sum(st.values())
+    dev = None
+    try:
+        import torch
+        if torch.cuda.is_available():
+            dev = torch.device("cuda", 0)       # only to synthesise the multisine quickly; nothing timed runs there
+    except Exception:
+        dev = None
+    train, val = make_records(a.n, a.nd, seed=0, dev=dev)
+    budget = float(os.environ.get("B200ID_REF_BUDGET_S", "240"))
+    # calibration on a small slice: seconds per sample of the O(n) stages and the fixed GP cost
+    n_cal = min(a.n, 200_000)
+    st_cal, _ = cpu_pipeline_pass(*slice_records(train, val, n_cal), a.nd, threads)
+    passes = a.warmup + a.steps
+    est_full = scaled_step_seconds(st_cal, n_cal, a.n)
+    if passes * est_full <= budget:
+        n_s = a.n
+    else:
+        per_sample = (st_cal["frf_train"] + st_cal["frf_val"] + st_cal["fir"]) / n_cal
+        n_s = int(max(n_cal, min(a.n, (budget / passes - st_cal["gp"]) / per_sample)))
+    tr_s, va_s = slice_records(train, val, n_s)
+    times, stages = [], []
+    for i in range(passes):
+        st, _ = cpu_pipeline_pass(tr_s, va_s, a.nd, threads)
         if i >= a.warmup:
-            times.append(dt)
+            times.append(scaled_step_seconds(st, n_s, a.n))
+            stages.append(st)
     sec = float(np.mean(times))
-    value = n_s / sec
+    value = a.n / sec
+    stage_mean = {k: float(np.mean([st[k] for st in stages])) for k in stages[0]}
+    sample = (f"{n_s} of {a.n} samples per record actually run per step"
+              + ("" if n_s == a.n else "; FRF and FIR seconds scaled by n/n_run, GP stage as measured")
+              + f"; same bins, same 1800 GP candidates, same {N_TAPS}-tap FIR; per-bin FRF loop on a {threads}-thread pool; "
+              f"stage seconds at n_run {json.dumps({k: round(v, 4) for k, v in stage_mean.items()})}")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic", "config": workload_config(a, 1),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{n_s} samples per record of the same workload (same bins, same 1800 GP candidates, "
-                                   f"same {N_TAPS}-tap FIR); per-bin FRF loop on a {threads}-thread pool"},
+        "dtype": "f64", "data": "synthetic", "config": workload_config(a, 1, n_run=n_s),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                         "n_samples_run": n_s, "stage_seconds_at_n_run": stage_mean,
+                         "note": "the oracle port spreads the reference's single-threaded per-bin loop over all host cores "
+                                 "(conservative: the reference itself uses one core outside BLAS)"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def run_configs(a, rank, world, dev, res, timed, hbm_peak):
+    """BASELINE configs 3, 4 and 5 measured in the same run (every rank takes part; CUDA events, max over ranks).
+    Returns the `configs` block of the line (fp64 fractions are filled in by the caller, which owns the peak probe)."""
+    import torch
+    from b200id import fir as bfir, frf as bfrf, gp as bgp, pipeline as P, synth
+    from b200id.runtime import empty, to_device
+    out = {}
+    gi = P.GridInputs.get(a.nd, dev)
+    # ---- cfg 3: 11 kernels x R restart start points x 2 targets at N_d = nd, NLL, candidates round-robin over ranks
+    Gh = res.G.cpu().numpy()
+    targets = []
+    for v in (Gh.real, Gh.imag):
+        sd = v.std()
+        targets.append(to_device((v - v.mean()) / (sd if sd != 0 else 1.0), dev))
+    pop = P.Population.build(a.restarts, dev, rank=rank, world_size=world)
+    ms3, picks, _, _ = timed(lambda: P.population_search_async(pop, gi.X_d, targets, NOISE), 3, 2)
+    picks = picks.cpu().numpy()                                   # [2, n_kernels, 5]
+    n_eval = 2 * pop.n_total
+    best_k = [P.select_best(pop.names, picks[j, :, 4].tolist()) for j in range(2)]
+    out["cfg3"] = {
+        "workload": f"{len(pop.names)} kernels x {a.restarts} restart start points (gpr_fitting.py:132-145, np.random.seed(42) per "
+                    f"kernel) x 2 targets at N_d={a.nd}, NLL, noise {NOISE}; round-robin over {world} rank(s), one all-gather",
+        "candidate_evaluations": n_eval, "ms": ms3, "candidates_per_s": n_eval / (ms3 * 1e-3),
+        "algorithmic_flops": n_eval * (a.nd ** 3 / 3.0 + 2.0 * a.nd ** 2),
+        "per_kernel_best_nll": {t: {k: float(picks[j, i, 4]) for i, k in enumerate(pop.names)} for j, t in enumerate(("real", "imag"))},
+        "cross_kernel_pick": {t: {"kernel": pop.names[best_k[j]], "theta": picks[j, best_k[j], :3].tolist(),
+                                  "global_index": int(picks[j, best_k[j], 3])} for j, t in enumerate(("real", "imag"))},
+    }
+    # ---- cfg 4: N_d = 2048, 16 candidates (NLL) in lockstep + one blocked Cholesky; every rank runs a replica
+    n4, nc4 = 2048, 16
+    _, w4 = synth.log_grid(n4)
+    X4 = np.log10(w4); X4 = (X4 - X4.mean()) / X4.std()
+    y4 = np.sin(2.0 * X4) + 0.05 * np.random.default_rng(4).standard_normal(n4)
+    X4_d, y4_d = to_device(X4, dev), to_device(y4, dev)
+    th4 = to_device(bgp._theta_block(np.column_stack([np.linspace(0.5, 2.0, nc4), np.linspace(0.3, 1.0, nc4)])), dev)
+    kid = bgp.KERNEL_IDS["rbf"][0]
+    ms4, m4, _, _ = timed(lambda: bgp.batch_eval_device(kid, None, th4, X4_d, y4_d, 1e-3, bgp.METRIC_NLL), 3, 2)
+    K4 = to_device(bgp.gram(kid, np.array([1.0, 0.5]), X4) + 1e-3 * np.eye(n4), dev)
+    A4 = torch.empty_like(K4)
+    info4 = torch.zeros(1, dtype=torch.int32, device=dev)
+    import ctypes as C
+    from b200id import _lib
+    from b200id.runtime import Workspace, ptr, stream_ptr
+    ws4 = Workspace.get("cholb", _lib.load().b200id_chol_blocked_workspace_bytes(n4), dev)
+
+    def chol_once():
+        A4.copy_(K4)
+        _lib.call("b200id_chol_blocked", ptr(A4), C.c_int(n4), C.c_int(n4), ptr(info4), ptr(ws4), C.c_size_t(ws4.numel()), stream_ptr())
+
+    ms_copy, _, _, _ = timed(lambda: A4.copy_(K4), 3, 1)
+    ms_chol, _, _, _ = timed(chol_once, 3, 2)
+    out["cfg4"] = {
+        "workload": f"N_d={n4} RBF candidates: {nc4} in lockstep (Gram + blocked FP64 Cholesky with y riding along + NLL), replicas on every rank",
+        "batch_candidates": nc4, "batch_ms": ms4, "candidates_per_s_per_gpu": nc4 / (ms4 * 1e-3),
+        "algorithmic_flops": nc4 * (n4 ** 3 / 3.0 + 2.0 * n4 ** 2),
+        "single_cholesky_ms": ms_chol - ms_copy, "single_cholesky_flops": n4 ** 3 / 3.0, "info": int(info4.item()),
+        "nll_first": float(m4[0]),
+    }
+    # ---- cfg 5: R records x n samples round-robin over the ranks: per-record FRF + cross-power sums, ONE all-reduce;
+    # FIR validation of the step's taps over the same samples, one 4-double all-reduce
+    want5 = a.cfg5 == "on" or (a.cfg5 == "auto" and world > 1)
+    if want5:
+        R = a.cfg5_records
+        mine = list(range(rank, R, world))
+        n = a.n
+        t_h = np.arange(n, dtype=np.float64) * synth.DT
+        t_d = to_device(t_h, dev)
+        span, t0 = float(t_h[-1] - t_h[0]), 0.0
+        f, w = synth.log_grid(a.nd)
+        w_d = gi.w_d
+        # plant as its truncated impulse response (2048 taps) so that the records are synthesised on the device
+        imp = np.zeros(2048); imp[0] = 1.0
+        g_true = to_device(synth.apply_plant(imp, noise=0.0), dev)
+        recs = []
+        for r in mine:
+            rng = np.random.default_rng(1000 + r)
+            amp = to_device(rng.uniform(0.0, 20.0 / a.nd, size=a.nd), dev)
+            ph = to_device(rng.uniform(0.0, 2.0 * np.pi, size=a.nd), dev)
+            u_d = empty(n, dev)
+            chunk = 1 << 20
+            for s0 in range(0, n, chunk):
+                e0 = min(n, s0 + chunk)
+                u_d[s0:e0] = torch.sin(t_d[s0:e0, None] * w_d[None, :] + ph[None, :]) @ amp
+            _, y_d = bfir.fir_eval_device(u_d, None, g_true, 0, 0.0, want_pred=True)
+            gen = torch.Generator(device=dev); gen.manual_seed(2000 + r)
+            y_d = y_d + 1e-3 * torch.randn(n, dtype=torch.float64, device=dev, generator=gen)
+            recs.append((u_d, y_d.contiguous()))
+        torch.cuda.synchronize()
+        path = bfrf.choose_path(t_d, span, gi.w_max, t0)
+        sums = empty(3 * a.nd, dev)
+        taps = res.taps
+        skip = min(10, taps.numel() // 10)
+        y0s = [float(y_d[skip].item()) for _, y_d in recs]
+
+        def frf5():
+            if not recs:
+                sums.zero_()
+            for k, (u_d, y_d) in enumerate(recs):
+                U, Y = bfrf.record_coefficients_device(t_d, u_d, y_d, w_d, span, path=path)
+                bfrf.cross_power_sums_device(U, Y, sums, accumulate=k > 0)
+            bdist_allreduce(sums)
+            return bfrf.gp_targets_device(sums, a.nd, standardise=False)[0]
+
+        def fir5():
+            acc = torch.zeros(4, dtype=torch.float64, device=dev)
+            for (u_d, y_d), y0 in zip(recs, y0s):
+                sm, _ = bfir.fir_eval_device(u_d, y_d, taps, skip, y0)
+                acc += sm
+            bdist_allreduce(acc)
+            return acc
+
+        from b200id.dist import allreduce_sum_ as bdist_allreduce
+        ms_frf5, G5, _, _ = timed(frf5, 2, 1)
+        ms_fir5, acc5, _, _ = timed(fir5, 2, 1)
+        total = R * n
+        G5h = G5.cpu().numpy()
+        Gtrue = synth.plant_response(w)
+        out["cfg5"] = {
+            "workload": f"R={R} records x {n} samples (distinct multisine records, same plant) round-robin over {world} rank(s): "
+                        f"per-record FRF at N_d={a.nd} + cross-power sums, one all-reduce of 3 N_d doubles; FIR validation "
+                        f"({taps.numel()} taps) of the same samples, one 4-double all-reduce",
+            "records": R, "records_on_rank0": len(mine), "total_samples": total, "frf_path": path[0],
+            "frf_ms": ms_frf5, "frf_samples_per_s": total / (ms_frf5 * 1e-3),
+            "frf_hbm_gbs_per_gpu": FRF_BYTES_PER_SAMPLE * total / world / (ms_frf5 * 1e-3) / 1e9,
+            "frf_hbm_frac": FRF_BYTES_PER_SAMPLE * total / world / (ms_frf5 * 1e-3) / 1e9 / hbm_peak,
+            "frf_algorithmic_flops": 8.0 * a.nd * total,
+            "fir_ms": ms_fir5, "fir_samples_per_s": total / (ms_fir5 * 1e-3),
+            "fir_hbm_gbs_per_gpu": FIR_BYTES_PER_SAMPLE * total / world / (ms_fir5 * 1e-3) / 1e9,
+            "fir_hbm_frac": FIR_BYTES_PER_SAMPLE * total / world / (ms_fir5 * 1e-3) / 1e9 / hbm_peak,
+            "frf_plus_fir_samples_per_s": total / ((ms_frf5 + ms_fir5) * 1e-3),
+            "G_vs_continuous_plant_median_rel": float(np.median(np.abs(G5h - Gtrue) / np.abs(Gtrue))),
+            "fir_sums": acc5.cpu().tolist(),
+        }
+        del recs
+        torch.cuda.empty_cache()
+    return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -296,6 +490,18 @@ def main():
         r = P.identify_host([tuple(host[0])], tuple(host[1]), a.nd, KERNEL, NOISE, cands, n_taps=N_TAPS)
         return r.fir, r.taps.cpu().numpy(), r
 
+    def step_e2e_full_upload():
+        # the same call with the per-array time-base facts switched off: t goes up with u and y every step
+        r = P.identify_host([tuple(host[0])], tuple(host[1]), a.nd, KERNEL, NOISE, cands, n_taps=N_TAPS, reuse_timebase=False)
+        return r.fir, r.taps.cpu().numpy(), r
+
+    pageable = None
+
+    def step_e2e_pageable():
+        # what a caller holding plain NumPy arrays (loadmat output) gets: the driver stages pageable memory itself
+        r = P.identify_host([tuple(pageable[0])], tuple(pageable[1]), a.nd, KERNEL, NOISE, cands, n_taps=N_TAPS)
+        return r.fir, r.taps.cpu().numpy(), r
+
     def step_e2e_calls():
         with contextlib.redirect_stdout(io.StringIO()):
             (t, u, y), (tv, uv, yv) = host
@@ -360,11 +566,21 @@ def main():
     ms_inst, _, log, _ = timed(step_resident, a.steps, 1, with_events=True)
     stage_ms = {k: sum(s.elapsed_time(e) for s, e in v) / a.steps for k, v in (log or {}).items()}
     # ---- e2e timing: host pinned buffers in, result out
-    ms_e2e, (metrics_e, taps_e, res_e), _, _ = timed(step_e2e, a.steps, a.warmup)
-    # per step: train (t,u,y) + validation (t,u,y), each once; back: StandardScaler statistics (4), the final pack
-    # (status 2, theta 6, selection 4, FIR sums 4, time-base verdicts 2) and the taps
-    h2d = 8 * a.n * (3 + 3)
-    d2h = 8 * (4 + 2 + 6 + 4 + 4 + 2) + 8 * N_TAPS
+    from b200id.records import FACTS
+    FACTS.clear()
+    ms_e2e, (metrics_e, taps_e, res_e), _, _ = timed(step_e2e, a.steps, max(a.warmup, 3))
+    # per step: train (u, y) + validation (u, y), each once -- the two time vectors were found to be exactly
+    # fl(i dt) + t0 during the warm-up steps and are rebuilt on the device (b200id.records.FACTS); back: the final pack
+    # (status 2, theta 6, selection 4 + 2, FIR sums 4, time-base verdict 1) and the taps
+    exact_tb = all(bool(FACTS.get(torch.from_numpy(rec[0])).get("exact")) for rec in host)
+    h2d = 8 * a.n * ((2 + 2) if exact_tb else (3 + 3))
+    d2h = 8 * (2 + 6 + 4 + 2 + 4 + 1) + 8 * N_TAPS
+    ms_e2e_full, (metrics_f, _, res_f), _, _ = timed(step_e2e_full_upload, a.steps, a.warmup)
+    h2d_full = 8 * a.n * (3 + 3)
+    # pageable host arrays: plain NumPy copies of the records (outside the timed region)
+    pageable = [[np.array(x.numpy(), copy=True) for x in rec] for rec in pinned]
+    ms_e2e_pg, (metrics_p, _, _), _, _ = timed(step_e2e_pageable, max(2, a.steps // 2), max(a.warmup, 3))
+    pageable = None
     # the same work as the reference's call sequence (drop-in surface, one synchronous call per stage, NumPy in
     # and out of every call): the validation record goes up twice (FRF, then FIR) and nothing overlaps across calls
     ms_calls, (metrics_c, taps_c), _, _ = timed(step_e2e_calls, a.steps, a.warmup)
@@ -394,6 +610,10 @@ def main():
                 torch.cuda.synchronize()
                 best = max(best, flops.value / (s.elapsed_time(e) * 1e-3) / 1e12)
             fp64[name + "_tflops"] = best
+
+    configs = None
+    if not a.no_configs:
+        configs = run_configs(a, rank, world, dev, res, timed, hbm_peak)
 
     if rank != 0:
         return
@@ -437,6 +657,16 @@ def main():
             "gp_frac": (gp_flops / (gp_ms * 1e-3) / 1e12 / fp64_peak) if (fp64_peak and gp_ms > 0) else None,
         },
     }
+    if configs and fp64_peak:
+        c3, c4 = configs["cfg3"], configs["cfg4"]
+        c3["algorithmic_tflops"] = c3["algorithmic_flops"] / (c3["ms"] * 1e-3) / 1e12
+        c3["fp64_frac"] = c3["algorithmic_tflops"] / (fp64_peak * world)
+        c4["algorithmic_tflops_per_gpu"] = c4["algorithmic_flops"] / (c4["batch_ms"] * 1e-3) / 1e12
+        c4["fp64_frac"] = c4["algorithmic_tflops_per_gpu"] / fp64_peak
+        c4["single_cholesky_tflops"] = c4["single_cholesky_flops"] / (c4["single_cholesky_ms"] * 1e-3) / 1e12
+        if "cfg5" in configs:
+            c5 = configs["cfg5"]
+            c5["frf_fp64_frac"] = c5["frf_algorithmic_flops"] / (c5["frf_ms"] * 1e-3) / 1e12 / (fp64_peak * world)
     stages = {
         "ms_per_step_by_call": stage_ms,
         "frf_samples_per_s_kernel": 2 * a.n / (frf_ms * 1e-3) if frf_ms > 0 else None,
@@ -445,25 +675,66 @@ def main():
         "fir_hbm_gbs": fir_bytes / (fir_ms * 1e-3) / 1e9 if fir_ms > 0 else None,
     }
 
-    cpu = None
+    # ---- CPU baseline = the oracle port on the bench's OWN records (rank 0, N = 1 only), one pass; its results are
+    # also what the parity block compares the GPU step with.  --cpu-sample m < n runs both sides on the first m samples.
+    cpu, parity = None, None
     if world == 1 and not a.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        n_s = min(a.n, a.cpu_sample)
-        st, cpu_metrics = cpu_pipeline_pass(n_s, a.nd, threads)
-        cpu_s = sum(st.values())
-        cpu = {"value": n_s / cpu_s, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": f"{n_s} samples per record of the same workload; stage seconds {json.dumps({k: round(v, 3) for k, v in st.items()})}"}
+        n_s = a.n if a.cpu_sample <= 0 else min(a.n, a.cpu_sample)
+        tr_s, va_s = slice_records(train_h, val_h, n_s)
+        st, ref = cpu_pipeline_pass(tr_s, va_s, a.nd, threads)
+        cpu_s = scaled_step_seconds(st, n_s, a.n)
+        cpu = {"value": a.n / cpu_s, "unit": UNIT, "cores": threads, "kind": "port", "n_samples_run": n_s,
+               "stage_seconds_at_n_run": {k: round(v, 4) for k, v in st.items()},
+               "sample": f"{n_s} of {a.n} samples per record of the same records, one pass"
+                         + ("" if n_s == a.n else "; FRF and FIR seconds scaled by n/n_run, GP stage as measured")}
+        if n_s == a.n:
+            res_p = res
+        else:
+            tr = [tuple(x[:n_s] for x in dev_recs[0]) + (float(tr_s[0][-1] - tr_s[0][0]), float(tr_s[0][0]))]
+            va = tuple(x[:n_s] for x in dev_recs[1]) + (float(va_s[0][-1] - va_s[0][0]), float(va_s[2][skip]), float(va_s[0][0]))
+            res_p = P.identify_device(tr, va, a.nd, KERNEL, NOISE, cands, n_taps=N_TAPS)
+        Gd = res_p.G.cpu().numpy()
+        taps_d = res_p.taps.cpu().numpy()
+        rel = lambda x, r: abs(x - r) / abs(r) if r != 0 else abs(x - r)
+        parity = {
+            "against": "oracle/ (NumPy restatement of the reference, pinned to reference-generated golden vectors)",
+            "n_samples_compared": n_s,
+            "frf_max_rel_err_per_bin": float(np.max(np.abs(Gd - ref["G"]) / np.abs(ref["G"]))),
+            "frf_tolerance": 1e-9,
+            "theta_identical": bool(np.array_equal(res_p.theta_real, ref["theta_real"]) and np.array_equal(res_p.theta_imag, ref["theta_imag"])),
+            "theta_gpu": [res_p.theta_real.tolist(), res_p.theta_imag.tolist()],
+            "theta_oracle": [ref["theta_real"].tolist(), ref["theta_imag"].tolist()],
+            "selection_metric_rel_err": [rel(res_p.metric_real, ref["metric_real"]), rel(res_p.metric_imag, ref["metric_imag"])],
+            "taps_max_rel_err": float(np.max(np.abs(taps_d - ref["taps"])) / np.max(np.abs(ref["taps"]))),
+            "fir_rmse_rel_err": rel(res_p.fir["rmse"], ref["fir"]["rmse"]),
+            "fir_fit_percent_abs_err": abs(res_p.fir["fit_percent"] - ref["fir"]["fit_percent"]),
+            "e2e_theta_identical_to_resident": bool(np.array_equal(res_e.theta_real, res.theta_real) and np.array_equal(res_e.theta_imag, res.theta_imag)),
+            "e2e_fir_rmse_rel_err_vs_resident": rel(metrics_e["rmse"], res.fir["rmse"]),
+        }
+        parity["pass"] = bool(parity["frf_max_rel_err_per_bin"] < 1e-9 and parity["theta_identical"]
+                              and parity["taps_max_rel_err"] < 1e-6 and parity["fir_rmse_rel_err"] < 1e-6)
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "config": workload_config(a, world),
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "call": "b200id.pipeline.identify_host (host NumPy records in pinned memory -> taps, metrics, theta on the host)"},
+                "call": "b200id.pipeline.identify_host (host NumPy records in pinned memory -> taps, metrics, theta on the host)",
+                "timebase": ("u and y cross the link every step; both time vectors are exactly fl(i dt) + t0 (checked on the device over "
+                             "the whole record in the first warm-up step) and are rebuilt on the device" if exact_tb else
+                             "t, u and y cross the link every step")},
+        "e2e_full_upload": {"value": total_samples / (ms_e2e_full * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e_full,
+                            "h2d_bytes_per_step": h2d_full, "d2h_bytes_per_step": d2h,
+                            "call": "identify_host(..., reuse_timebase=False): t, u, y uploaded every step"},
+        "e2e_pageable": {"value": total_samples / (ms_e2e_pg * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e_pg,
+                         "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                         "call": "identify_host on plain (pageable) NumPy arrays, as scipy.io.loadmat returns them"},
         "e2e_call_by_call": {"value": total_samples / (ms_calls * 1e-3), "unit": UNIT, "ms_per_step": ms_calls,
                              "h2d_bytes_per_step": h2d_calls, "d2h_bytes_per_step": d2h_calls,
                              "call": "src.frequency_transform / src.gpr / src.fir_model drop-in functions, one synchronous call per stage"},
-        "gpu_launches": launches, "clocks": clk, "roofline": roofline, "cpu_baseline": cpu, "stages": stages,
+        "gpu_launches": launches, "clocks": clk, "roofline": roofline, "cpu_baseline": cpu, "parity": parity,
+        "configs": configs, "stages": stages,
         "result": {"theta_real": res.theta_real.tolist(), "theta_imag": res.theta_imag.tolist(), "fir_rmse": res.fir.get("rmse"),
                    "e2e_fir_rmse": metrics_e.get("rmse"), "e2e_theta_real": res_e.theta_real.tolist(),
                    "e2e_theta_imag": res_e.theta_imag.tolist(), "e2e_call_by_call_fir_rmse": metrics_c.get("rmse")},

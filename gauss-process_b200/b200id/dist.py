@@ -29,15 +29,18 @@ def init_from_env(backend: str = None) -> Tuple[int, int, int]:
     ws = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    n_dev = torch.cuda.device_count() if torch.cuda.is_available() else 0
     if ws > 1 and not dist.is_initialized():
         if backend is None:
-            backend = "nccl" if torch.cuda.is_available() else "gloo"
-        if backend == "nccl":
-            torch.cuda.set_device(local)
+            # B200ID_DIST_BACKEND=gloo: several ranks sharing ONE GPU (NCCL refuses that) -- the kernels still run on
+            # the device, only the small exchanges go through gloo; used by the shard tests on a one-GPU box
+            backend = os.environ.get("B200ID_DIST_BACKEND") or ("nccl" if n_dev > 0 else "gloo")
+        if n_dev > 0:
+            torch.cuda.set_device(local % n_dev)
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group(backend=backend, rank=rank, world_size=ws)
-    elif torch.cuda.is_available():
-        torch.cuda.set_device(local)
+    elif n_dev > 0:
+        torch.cuda.set_device(local % n_dev)
     return rank, ws, local
 
 
@@ -71,10 +74,34 @@ def bind_to_gpu_numa_node(local_rank: int = None) -> dict:
     return info
 
 
+def _host_staged() -> bool:
+    """gloo has no device all-gather: device tensors are staged through the host for it (shard tests that run two
+    ranks on one GPU); NCCL takes them as they are."""
+    return dist.get_backend() == "gloo"
+
+
+def all_gather_into(out: torch.Tensor, mine: torch.Tensor) -> torch.Tensor:
+    """dist.all_gather_into_tensor for small FP64 tables, on NCCL (device) or gloo (host-staged)."""
+    if _host_staged() and mine.is_cuda:
+        tmp = torch.empty(out.shape, dtype=out.dtype)
+        dist.all_gather_into_tensor(tmp, mine.cpu())
+        out.copy_(tmp)
+        return out
+    dist.all_gather_into_tensor(out, mine)
+    return out
+
+
 def allreduce_sum_(t: torch.Tensor) -> torch.Tensor:
     """In-place sum over ranks (identity for a single process)."""
     if world()[1] > 1:
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t
+
+
+def allreduce_max_(t: torch.Tensor) -> torch.Tensor:
+    """In-place max over ranks (identity for a single process)."""
+    if world()[1] > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return t
 
 
@@ -99,7 +126,7 @@ def argmin_gather(local_best: float, local_global_idx: int, device=None) -> Tupl
     rank, ws = world()
     if ws == 1:
         return int(local_global_idx), float(local_best)
-    if device is None:
+    if device is None or _host_staged():
         device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
     mine = torch.tensor([float(local_best), float(local_global_idx)], dtype=torch.float64, device=device)
     allv = [torch.empty_like(mine) for _ in range(ws)]
@@ -113,7 +140,7 @@ def argmin_gather_multi(local_pairs: Sequence[Tuple[float, int]], device=None) -
     rank, ws = world()
     if ws == 1:
         return [(int(i), float(m)) for m, i in local_pairs]
-    if device is None:
+    if device is None or _host_staged():
         device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
     k = len(local_pairs)
     mine = torch.tensor([[float(m), float(i)] for m, i in local_pairs], dtype=torch.float64, device=device).reshape(-1)

@@ -53,14 +53,15 @@ def fir_eval_device(u_d: torch.Tensor, y_d: Optional[torch.Tensor], g_d: torch.T
     return sums, pred
 
 
-def metrics_from_sums(sums, skip: int) -> Dict[str, float]:
-    """RMSE / FIT% / R2 from the fused sums (fir_validation.py:115-128, fir_fitting.py:296-306)."""
+def metrics_from_sums(sums, skip: int, detrend: bool = False) -> Dict[str, float]:
+    """RMSE / FIT% / R2 from the fused sums (fir_validation.py:115-128, fir_fitting.py:296-306); ``detrend`` is
+    reported as the caller applied it (fir_validation.py:205)."""
     se, sy, st, cnt = (float(v) for v in sums)
     rmse = math.sqrt(se / cnt)
     norm_y = math.sqrt(sy)
     fit = float(100 * (1.0 - math.sqrt(se) / norm_y)) if norm_y > 0 else 0.0
     r2 = float(1.0 - se / st) if st > 0 else 0.0
-    return {"rmse": rmse, "fit_percent": fit, "r2": r2, "transient_skip": skip, "detrend": False}
+    return {"rmse": rmse, "fit_percent": fit, "r2": r2, "transient_skip": skip, "detrend": bool(detrend)}
 
 
 def fir_predict(u, g, n_out: Optional[int] = None) -> np.ndarray:
@@ -125,6 +126,9 @@ def fir_validate(u, y, g, detrend: bool = False, want_pred: bool = True,
         u, y = u - np.mean(u), y - np.mean(y)
     skip = min(10, g.size // 10) if skip is None else int(skip)
     n = min(u.size, y.size)
+    if not (0 <= skip < n):
+        # the reference slices y[skip:] and would fail on the empty slice further down (fir_fitting.py:288-306)
+        raise ValueError(f"record of {n} samples is not longer than the transient skip ({skip})")
     g_d = to_device(g, dev)
     if rec is not None:
         _, u_d, y_d = STORE.on_device(rec, dev)            # normally already in HBM, from the FRF of this file
@@ -133,7 +137,7 @@ def fir_validate(u, y, g, detrend: bool = False, want_pred: bool = True,
         sums, pred = fir_eval_streamed(u[:n], y[:n], g_d, skip, float(y[skip]), n, want_pred=want_pred)
     else:
         sums, pred = fir_eval_device(to_device(u, dev), to_device(y, dev), g_d, skip, float(y[skip]), want_pred=want_pred, n=n)
-    m = metrics_from_sums(sums.cpu().numpy(), skip)
+    m = metrics_from_sums(sums.cpu().numpy(), skip, detrend=detrend)
     return m, (pred.cpu().numpy() if want_pred else None)
 
 

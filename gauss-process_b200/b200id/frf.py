@@ -55,6 +55,19 @@ UNIFORM_PHASE_TOL = 2e-6
 _FORCE_PATH = os.environ.get("B200ID_FRF_PATH", "auto")     # auto | general | uniform
 
 
+PHASE_LIMIT = 2.0 ** 36           # |w t| up to which the device sincos (two-constant Cody-Waite) is valid
+
+
+def check_phase_range(w_max: float, t_first: float, t_last: float) -> None:
+    """The FRF kernels reduce the phase fl(w t) with a two-constant Cody-Waite scheme that is exact up to 2^36 rad
+    (~7e10: 1e9 samples at 500 Hz and 200 Hz bins stay below 3e9).  Epoch-style time stamps would silently lose the
+    phase; there is no CPU fallback on this path, so they are refused with the remedy."""
+    tmax = max(abs(float(t_first)), abs(float(t_last)))
+    if float(w_max) * tmax >= PHASE_LIMIT:
+        raise ValueError(f"FRF phase w*t reaches {float(w_max) * tmax:.3e} rad (limit 2^36 = {PHASE_LIMIT:.3e}): "
+                         "shift the time origin (t - t[0]) before estimating the FRF")
+
+
 def uniformity_device_async(t_d: torch.Tensor, t0: float, dt: float, own=None) -> torch.Tensor:
     """max |t_i - (t0 + i dt)| over i in ``own`` (default: all) as a 1-element device tensor."""
     dev = t_d.device
@@ -69,6 +82,24 @@ def uniformity_device_async(t_d: torch.Tensor, t0: float, dt: float, own=None) -
 def uniformity_device(t_d: torch.Tensor, t0: float, dt: float, own=None) -> float:
     """max_i |t_i - (t0 + i dt)| (one small D2H read)."""
     return float(uniformity_device_async(t_d, t0, dt, own).item())
+
+
+def timebase_check_async(t_d: torch.Tensor, t0: float, dt: float) -> torch.Tensor:
+    """Device [2] tensor whose [0] is the number of samples with t_i != fl(fl(i dt) + t0) (0 = the record's time
+    vector is exactly regenerable from (t0, dt), see b200id_frf_timebase_fill)."""
+    dev = t_d.device
+    out = empty(2, dev)
+    ws, _ = _ws(1, dev)
+    _lib.call("b200id_frf_timebase_check", ptr(t_d), C.c_int64(t_d.numel()), C.c_double(t0), C.c_double(dt), ptr(out),
+              ptr(ws), C.c_size_t(ws.numel()), stream_ptr())
+    return out
+
+
+def timebase_fill_device(n: int, t0: float, dt: float, dev) -> torch.Tensor:
+    """t_i = fl(fl(i dt) + t0), i < n, built on the device (bit-identical to ``np.arange(n) * dt + t0``)."""
+    t_d = empty(n, dev)
+    _lib.call("b200id_frf_timebase_fill", ptr(t_d), C.c_int64(n), C.c_double(t0), C.c_double(dt), stream_ptr())
+    return t_d
 
 
 def project_uniform_device(t_d, u_d, y_d, w_d, t0: float, dt: float, own=None, sums=None, inv_count: float = 0.0):
@@ -166,6 +197,8 @@ def record_coefficients_device(t_d, u_d, y_d, w_d, span: float, subtract_mean: b
     sums = moments_device(u_d, y_d, (0, n)) if subtract_mean else None
     if path is None:
         w_max = float(w_d.max().item()) if w_max is None else w_max
+        t0 = float(t_d[0].item()) if t0 is None else float(t0)
+        check_phase_range(w_max, t0, t0 + span)
         path = choose_path(t_d, span, w_max, t0)
     if path[0] == "uniform":
         part = project_uniform_device(t_d, u_d, y_d, w_d, path[1], path[2], (0, n), sums, 1.0 / n)
@@ -196,7 +229,7 @@ class StreamedRecord:
     """
 
     def __init__(self, t_h, u_h, y_h, w_d, span: float, subtract_mean: bool = True, w_max: Optional[float] = None,
-                 n_chunks: int = STREAM_CHUNKS, trace: Optional[list] = None):
+                 n_chunks: int = STREAM_CHUNKS, trace: Optional[list] = None, reuse_timebase: bool = False):
         self.dev = dev = w_d.device
         self.th, self.uh = host_f64(t_h), host_f64(u_h)
         self.yh = None if y_h is None else host_f64(y_h)
@@ -205,7 +238,7 @@ class StreamedRecord:
         self.n, self.nd = n, w_d.numel()
         self.edges = stream_edges(n, n_chunks)
         self.n_chunks = len(self.edges) - 1
-        self.t_d, self.u_d = empty(n, dev), empty(n, dev)
+        self.u_d = empty(n, dev)
         self.y_d = None if self.yh is None else empty(n, dev)
         timing = trace is not None
         self.landed = [torch.cuda.Event(enable_timing=timing) for _ in range(self.n_chunks)]
@@ -223,6 +256,22 @@ class StreamedRecord:
             grid = self.t0 + np.arange(head.size, dtype=np.float64) * self.dt
             if float(np.max(np.abs(head - grid))) * self.w_max < UNIFORM_PHASE_TOL:
                 self.kind = "uniform"
+        check_phase_range(self.w_max, self.t0, self.t0 + self.span)
+        # ---- what earlier calls on this very array established (b200id.records.FACTS): a time vector that is
+        # exactly fl(fl(i dt) + t0) and passed the uniformity check over its whole length is rebuilt on the device
+        # instead of being uploaded, so u and y are the only per-call inputs
+        from .records import FACTS, FACTS_ENABLED
+        self.facts = FACTS.get(self.th) if (reuse_timebase and FACTS_ENABLED and n >= 3) else None
+        self.exact_dt = None
+        if self.facts is not None:
+            pend = self.facts.pop("exact_pending", None)
+            if pend is not None:
+                flags = torch.stack([p[0] for p in pend]).cpu().tolist()     # resolved long ago: the call that queued it has ended
+                hit = [p[1] for p, f in zip(pend, flags) if f[0] == 0.0]
+                self.facts["exact"] = hit[0] if hit else False
+            if self.kind == "uniform" and self.facts.get("exact") and self.facts.get("uniform_ok") == (self.t0, self.dt, self.w_max):
+                self.exact_dt = float(self.facts["exact"])
+        self.t_d = None if self.exact_dt is not None else empty(n, dev)
 
     def _mark(self, label, stream=None):
         if self.trace is not None:
@@ -238,6 +287,16 @@ class StreamedRecord:
             self.trace.append(("signals_up", self.signals_up))
             self.trace.extend((f"t_landed[{k}]", self.landed[k]) for k in range(self.n_chunks))
         e = self.edges
+        if self.exact_dt is not None:
+            # known time base: nothing but the signals crosses the link, piece by piece (u, y interleaved)
+            with torch.cuda.stream(side):
+                for k in range(self.n_chunks):
+                    self.u_d[e[k]:e[k + 1]].copy_(self.uh[e[k]:e[k + 1]], non_blocking=True)
+                    if self.y_d is not None:
+                        self.y_d[e[k]:e[k + 1]].copy_(self.yh[e[k]:e[k + 1]], non_blocking=True)
+                    self.landed[k].record(side)
+                self.signals_up.record(side)
+            return
         with torch.cuda.stream(side):
             self.u_d.copy_(self.uh, non_blocking=True)
             if self.y_d is not None:
@@ -251,6 +310,8 @@ class StreamedRecord:
         """Partial sums [4*nd] of the whole record, enqueued on the current stream piece by piece."""
         main = torch.cuda.current_stream()
         n, e = self.n, self.edges
+        if self.exact_dt is not None:
+            return self._project_known_timebase()
         main.wait_event(self.signals_up)
         self.sums = moments_device(self.u_d, self.y_d, (0, n)) if self.subtract_mean else None
         self._mark("moments_done")
@@ -267,8 +328,56 @@ class StreamedRecord:
             self._mark(f"projected[{k}]")
         return part
 
+    def _project_known_timebase(self) -> torch.Tensor:
+        """Partial sums when t is rebuilt on the device: every piece of (u, y) is projected RAW as it lands and the
+        mean is taken off at the end through linearity,
+            sum_i w_i (x_i - m) c_ki = sum_i w_i x_i c_ki - m E_k,   E_k = sum_i w_i c_ki   (same for the sine sums),
+        with the window sums E of this (time vector, grid) computed once by projecting a vector of ones and kept
+        with the array's facts.  Nothing but the last piece's projection is exposed after the copy."""
+        main = torch.cuda.current_stream()
+        n, e, nd, dev = self.n, self.edges, self.nd, self.dev
+        self.t_d = timebase_fill_device(n, self.t0, self.exact_dt, dev)
+        ekey = ("window_sums", self.w_d.data_ptr(), nd, self.t0, self.dt)
+        E = self.facts.get(ekey) if self.subtract_mean else None
+        if self.subtract_mean and E is None:
+            ones = torch.ones(n, dtype=F64, device=dev)
+            E = project_uniform_device(self.t_d, ones, None, self.w_d, self.t0, self.dt, (0, n), None, 0.0)[:2 * nd].clone()
+            del ones
+            self.facts[ekey] = E
+        part, sums = None, None
+        for k in range(self.n_chunks):
+            main.wait_event(self.landed[k])
+            own = (e[k], e[k + 1])
+            if self.subtract_mean:
+                sk = moments_device(self.u_d, self.y_d, own)
+                sums = sk if sums is None else sums.add_(sk)
+            pk = project_uniform_device(self.t_d, self.u_d, self.y_d, self.w_d, self.t0, self.dt, own, None, 0.0)
+            part = pk if part is None else part.add_(pk)
+            self._mark(f"projected[{k}]")
+        if self.subtract_mean:
+            self.sums = sums
+            mean = sums / float(n)                                       # [2] = (mean u, mean y)
+            part.view(2, 2, nd).sub_(mean.view(2, 1, 1) * E.view(1, 2, nd))
+        return part
+
     def needs_check(self) -> bool:
-        return self.kind == "uniform" and _FORCE_PATH != "uniform"
+        return self.kind == "uniform" and _FORCE_PATH != "uniform" and self.exact_dt is None
+
+    def queue_exactness_probe(self) -> None:
+        """After a full upload: ask the device whether t is exactly fl(fl(i dt) + t0) for one of the obvious dt
+        candidates; the answer is read at the start of the NEXT call on this array (no wait here)."""
+        if self.facts is None or "exact" in self.facts or "exact_pending" in self.facts or self.t_d is None or self.n < 3:
+            return
+        cands = []
+        for dt in (float(self.th[1]) - self.t0, self.dt, float(f"{self.dt:.12g}")):
+            if dt > 0.0 and dt not in cands:
+                cands.append(dt)
+        self.facts["exact_pending"] = [(timebase_check_async(self.t_d, self.t0, dt), dt) for dt in cands]
+
+    def remember_uniform_ok(self) -> None:
+        """The whole-record uniformity check of this call came back clean."""
+        if self.facts is not None and self.kind == "uniform":
+            self.facts["uniform_ok"] = (self.t0, self.dt, self.w_max)
 
     def uniformity_async(self) -> torch.Tensor:
         """max |t_i - (t0 + i dt)| of the resident record as a 1-element device tensor (after :meth:`project`)."""

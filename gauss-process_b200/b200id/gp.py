@@ -38,10 +38,27 @@ def _flat(X) -> np.ndarray:
     return np.ascontiguousarray(np.asarray(X, dtype=np.float64).reshape(-1))
 
 
+def _points(X, what: str = "X") -> np.ndarray:
+    """1-D GP inputs as a flat vector.  The device Gram templates are written for scalar inputs -- what the
+    pipeline feeds them (log10 omega, gp_pipeline.py:281-282); the reference kernels built on ``cdist`` would also
+    accept (N, D > 1), which is refused here instead of being silently read as N*D points."""
+    a = np.asarray(X, dtype=np.float64)
+    if a.ndim > 2 or (a.ndim == 2 and a.shape[1] != 1):
+        raise ValueError(f"{what} must have shape (n,) or (n, 1): the b200id GP kernels take 1-D inputs, got {a.shape}")
+    return np.ascontiguousarray(a.reshape(-1))
+
+
+def _targets(y, n: int, what: str = "y") -> np.ndarray:
+    a = np.ascontiguousarray(np.asarray(y, dtype=np.float64).reshape(-1))
+    if a.size != n:
+        raise ValueError(f"{what} has {a.size} values for {n} input points")
+    return a
+
+
 def gram(kernel_id: int, theta, X1, X2=None) -> np.ndarray:
     dev = require_cuda()
-    x1 = to_device(_flat(X1), dev)
-    x2 = x1 if X2 is None else to_device(_flat(X2), dev)
+    x1 = to_device(_points(X1, "X1"), dev)
+    x2 = x1 if X2 is None else to_device(_points(X2, "X2"), dev)
     th = to_device(_theta_block(theta)[0], dev)
     K = empty(x1.numel() * x2.numel(), dev)
     _lib.call("b200id_gp_gram", C.c_int(kernel_id), ptr(th), ptr(x1), C.c_int(x1.numel()), ptr(x2),
@@ -98,11 +115,13 @@ def batch_eval_pair(kernel, thetas, X, y_a, y_b, noise: float, Xv=None, yv_a=Non
     th = to_device(_theta_block(thetas), dev)
     ids = None if kernel_ids is None else torch.as_tensor(np.asarray(kernel_ids, dtype=np.int32), device=dev)
     use_val = Xv is not None and yv_a is not None and yv_b is not None
-    d = lambda a: to_device(_flat(a), dev)
-    ma, mb = batch_eval_pair_device(kid, ids, th, d(X), d(y_a), d(y_b), float(noise),
-                                    METRIC_VAL_RMSE if use_val else METRIC_NLL,
-                                    d(Xv) if use_val else None, d(yv_a) if use_val else None, d(yv_b) if use_val else None,
-                                    scale_a, scale_b)
+    d = lambda a: to_device(a, dev)
+    x_h = _points(X)
+    xv_h = _points(Xv, "Xv") if use_val else None
+    ma, mb = batch_eval_pair_device(kid, ids, th, d(x_h), d(_targets(y_a, x_h.size, "y_a")), d(_targets(y_b, x_h.size, "y_b")),
+                                    float(noise), METRIC_VAL_RMSE if use_val else METRIC_NLL,
+                                    d(xv_h) if use_val else None, d(_targets(yv_a, xv_h.size, "yv_a")) if use_val else None,
+                                    d(_targets(yv_b, xv_h.size, "yv_b")) if use_val else None, scale_a, scale_b)
     both = torch.cat([ma, mb]).cpu().numpy()
     return both[:len(both) // 2], both[len(both) // 2:]
 
@@ -133,10 +152,12 @@ def batch_eval(kernel, thetas, X, y, noise, Xv=None, yv=None, y_mean: Optional[f
         noise_arg = to_device(np.ascontiguousarray(noise, dtype=np.float64).ravel(), dev)
         if noise_arg.numel() != th.shape[0]:
             raise ValueError(f"batch_eval: {noise_arg.numel()} noise values for {th.shape[0]} candidates")
+    x_h = _points(X)
+    xv_h = _points(Xv, "Xv") if use_val else None
     m = batch_eval_device(
-        kid, ids, th, to_device(_flat(X), dev), to_device(_flat(y), dev), noise_arg,
+        kid, ids, th, to_device(x_h, dev), to_device(_targets(y, x_h.size), dev), noise_arg,
         METRIC_VAL_RMSE if use_val else METRIC_NLL,
-        to_device(_flat(Xv), dev) if use_val else None, to_device(_flat(yv), dev) if use_val else None,
+        to_device(xv_h, dev) if use_val else None, to_device(_targets(yv, xv_h.size, "yv"), dev) if use_val else None,
         0.0 if y_mean is None else float(y_mean), 1.0 if y_scale is None else float(y_scale))
     return m.cpu().numpy()
 
@@ -149,10 +170,12 @@ def select(kernel, thetas, X, y, noise: float, **kw) -> Tuple[int, float, np.nda
     Xv, yv = kw.get("Xv"), kw.get("yv")
     use_val = Xv is not None and yv is not None
     ym, ys = kw.get("y_mean"), kw.get("y_scale")
+    x_h = _points(X)
+    xv_h = _points(Xv, "Xv") if use_val else None
     m = batch_eval_device(
-        kid, None, th, to_device(_flat(X), dev), to_device(_flat(y), dev), float(noise),
+        kid, None, th, to_device(x_h, dev), to_device(_targets(y, x_h.size), dev), float(noise),
         METRIC_VAL_RMSE if use_val else METRIC_NLL,
-        to_device(_flat(Xv), dev) if use_val else None, to_device(_flat(yv), dev) if use_val else None,
+        to_device(xv_h, dev) if use_val else None, to_device(_targets(yv, xv_h.size, "yv"), dev) if use_val else None,
         0.0 if ym is None else float(ym), 1.0 if ys is None else float(ys))
     best, idx = first_strict_min_device(m)
     return int(idx.item()), float(best.item()), m.cpu().numpy()
@@ -184,11 +207,13 @@ def _memo_put(key, alpha, kinv, used_pinv):
 def fit(kernel_id: int, theta, X, y, diag_add: float, want_kinv: bool = True):
     """(alpha[n], K_inv[n,n] or None, used_pinv) -- Cholesky path, pseudo-inverse path when a pivot is <= 0."""
     dev = require_cuda()
-    key = _fit_key(kernel_id, theta, X, y, diag_add)
+    x_h = _points(X)
+    y_h = _targets(y, x_h.size)
+    key = _fit_key(kernel_id, theta, x_h, y_h, diag_add)
     hit = _memo_get(key, want_kinv)
     if hit is not None:
         return hit
-    x, yy = to_device(_flat(X), dev), to_device(_flat(y), dev)
+    x, yy = to_device(x_h, dev), to_device(y_h, dev)
     n = x.numel()
     th = to_device(_theta_block(theta)[0], dev)
     want_kinv = want_kinv or (127 < n <= SMEM_NMAX)
@@ -215,8 +240,10 @@ def fit_batch(kernel_id: int, thetas, X, ys, diag_add: float):
     dev = require_cuda()
     th = to_device(_theta_block(thetas), dev)
     yy = to_device(np.ascontiguousarray(np.asarray(ys, dtype=np.float64)).reshape(th.shape[0], -1), dev)
-    x = to_device(_flat(X), dev)
+    x = to_device(_points(X), dev)
     b, n = yy.shape
+    if n != x.numel():
+        raise ValueError(f"fit_batch: ys has {n} values per problem for {x.numel()} input points")
     alpha = empty(b * n, dev)
     info = torch.zeros(b, dtype=torch.int32, device=dev)
     ws = Workspace.get("gpfit", b * _lib.load().b200id_gp_fit_workspace_bytes(n), dev)
@@ -237,12 +264,14 @@ def search_and_fit(kernel_id: int, start_theta, candidates, X, y, noise: float, 
     dev = require_cuda()
     cand = _theta_block(candidates)
     c = cand.shape[0]
-    x_h, y_h = _flat(X), _flat(y)
+    x_h = _points(X)
     n = x_h.size
+    y_h = _targets(y, n)
     use_val = Xv is not None and yv is not None
-    nv = _flat(Xv).size if use_val else 0
+    xv_h = _points(Xv, "Xv") if use_val else None
+    nv = xv_h.size if use_val else 0
     # one staging buffer up: [thetas (c+1)*3 | X n | y n | Xv nv | yv nv]
-    parts = [np.vstack([_theta_block(start_theta), cand]).ravel(), x_h, y_h] + ([_flat(Xv), _flat(yv)] if use_val else [])
+    parts = [np.vstack([_theta_block(start_theta), cand]).ravel(), x_h, y_h] + ([xv_h, _targets(yv, nv, "yv")] if use_val else [])
     up = to_device(np.concatenate(parts), dev)
     o = 0
     th = up[o:o + 3 * (c + 1)].view(c + 1, MAX_PARAMS); o += 3 * (c + 1)
@@ -285,10 +314,10 @@ def search_and_fit(kernel_id: int, start_theta, candidates, X, y, noise: float, 
 
 def predict(kernel_id: int, theta, X_train, alpha, K_inv, Xs, return_std: bool = False):
     dev = require_cuda()
-    x, xs = to_device(_flat(X_train), dev), to_device(_flat(Xs), dev)
+    x, xs = to_device(_points(X_train, "X_train"), dev), to_device(_points(Xs, "Xs"), dev)
     n, m = x.numel(), xs.numel()
     th = to_device(_theta_block(theta)[0], dev)
-    a = to_device(_flat(alpha), dev)
+    a = to_device(_targets(alpha, n, "alpha"), dev)
     kinv = to_device(_flat(K_inv), dev) if return_std else None
     mean = empty(m, dev)
     std = empty(m, dev) if return_std else None

@@ -297,14 +297,21 @@ def _device_pick(cs: "CandidateSet", pends: Sequence[torch.Tensor]) -> List[Tupl
     device (ties -> smallest global index, NaN / empty shards skipped), reproducing grid_search.py:186-196.
     Two small kernels either side of the exchange (b200id_argmin_pack / b200id_argmin_pick); the tensor-op version
     of the same rule was ~30 dependent launches, 0.4 ms of a 3.5 ms multi-GPU step."""
+    pend = torch.stack(list(pends)).contiguous()                      # [k, 2]
+    if not pend.is_cuda:
+        return _device_pick_tensor_ops(cs, pend)      # gloo host tests of the exchange: same rule in tensor operations
+    out = _device_pick_block(cs, pend)
+    return [(out[j, :3], out[j, 3], out[j, 4]) for j in range(out.shape[0])]
+
+
+def _device_pick_block(cs: "CandidateSet", pend: torch.Tensor) -> torch.Tensor:
+    """pend [k, 2] (best metric, local index) on the device -> [k, 5] = (theta[0..2], global index, metric) of the first
+    strict minimum in global scan order of each of the k searches (see :func:`_device_pick`)."""
     import ctypes as C
     from . import _lib
     from .runtime import ptr, stream_ptr
-    k = len(pends)
-    pend = torch.stack(list(pends)).contiguous()                      # [k, 2]
+    k = pend.shape[0]
     dev = pend.device
-    if not pend.is_cuda:
-        return _device_pick_tensor_ops(cs, pend)      # gloo host tests of the exchange: same rule in tensor operations
     mine = empty(2 * k, dev)
     _lib.call("b200id_argmin_pack", ptr(pend), C.c_int(k), ptr(cs.global_index_dev if cs.global_index is not None else None),
               ptr(mine), stream_ptr())
@@ -314,11 +321,10 @@ def _device_pick(cs: "CandidateSet", pends: Sequence[torch.Tensor]) -> List[Tupl
         import torch.distributed as dist
         ws = bdist.world()[1]
         tab = empty(ws * 2 * k, dev)
-        dist.all_gather_into_tensor(tab, mine)
+        bdist.all_gather_into(tab, mine)
     out = empty(5 * k, dev)
     _lib.call("b200id_argmin_pick", ptr(tab), C.c_int(ws), C.c_int(k), ptr(cs.full_theta_dev), ptr(out), stream_ptr())
-    out = out.view(k, 5)
-    return [(out[j, :3], out[j, 3], out[j, 4]) for j in range(k)]
+    return out.view(k, 5)
 
 
 def _device_pick_tensor_ops(cs: "CandidateSet", pend: torch.Tensor):
@@ -498,10 +504,15 @@ def identify_device(train: Sequence[Tuple[torch.Tensor, torch.Tensor, torch.Tens
         pack.append(sd2)
     if sums is not None:
         pack.append(sums)
-    if frf_checks:
-        pack.append(torch.cat([c.reshape(1) for c in frf_checks]))
+    if frf_checks is not None:
+        # ONE verdict for the whole job: a rank whose guess failed must not redo its pass (and its collectives) alone,
+        # so the flags are folded to one number and max-reduced over the ranks before anybody reads them
+        verdict = (torch.cat([c.reshape(1) for c in frf_checks]).max().reshape(1) if len(frf_checks)
+                   else torch.zeros(1, dtype=F64, device=dev))
+        bdist.allreduce_max_(verdict)
+        pack.append(verdict)
     host = torch.cat(pack).cpu().tolist()
-    if frf_checks and any(v != 0.0 for v in host[-len(frf_checks):]):
+    if frf_checks is not None and host[-1] != 0.0:
         raise TimebaseGuessFailed()
     flags = (int(host[0]), int(host[1]))
     nparams = bgp.KERNEL_IDS[kernel][1]
@@ -551,7 +562,7 @@ def identify_host(train: Sequence[Tuple[np.ndarray, np.ndarray, np.ndarray]],
                   nd: int, kernel: str = "matern52", noise: float = 1e-6,
                   candidates: Optional[CandidateSet] = None, theta0: Optional[Sequence[float]] = None,
                   use_validation_metric: bool = True, n_taps: int = PAPER_TAPS,
-                  n_chunks: int = bfrf.STREAM_CHUNKS) -> IdentifyResult:
+                  n_chunks: int = bfrf.STREAM_CHUNKS, reuse_timebase: bool = True) -> IdentifyResult:
     """The same pass as :func:`identify_device` for records that live in HOST memory (NumPy arrays or CPU
     tensors, ideally pinned): what run_gp_pipeline does for .mat files (gp_pipeline.py:60-247), for arrays.
 
@@ -563,7 +574,14 @@ def identify_host(train: Sequence[Tuple[np.ndarray, np.ndarray, np.ndarray]],
     the FIR pass are exposed after it.  The uniform-timebase guess of each record (host look at its
     first 4096 stamps) is verified on the device over the whole resident record; the verdicts come back with
     the final host read, and a failed guess reruns the pass through :func:`identify_device` on the resident
-    copies (general kernel).
+    copies (general kernel) -- on EVERY rank: the verdict is max-reduced over the ranks first, so the collectives of
+    the second pass pair up.
+
+    reuse_timebase: a time vector that an earlier call on the same array (identity + content probes,
+    b200id.records.FACTS) found to be exactly ``fl(fl(i dt) + t0)`` is rebuilt on the device instead of being
+    uploaded again; the call then moves 16 bytes per sample instead of 24 and projects every piece of (u, y) as it
+    lands (StreamedRecord._project_known_timebase).  Same coefficients as the full upload up to the order of the
+    final additions.  Pass False for arrays that are rewritten in place between calls.
     """
     dev = require_cuda()
     gi = GridInputs.get(nd, dev)
@@ -573,17 +591,22 @@ def identify_host(train: Sequence[Tuple[np.ndarray, np.ndarray, np.ndarray]],
     if val is not None:
         # the validation grid is only projected when the search metric needs it; the upload serves the FIR pass
         val_sr = bfrf.StreamedRecord(val[0], val[1], val[2], gi.wv_d, span(val[0]), True, gi.wv_max,
-                                     n_chunks if use_val_metric else 1)
-    train_sr = [bfrf.StreamedRecord(t, u, y, gi.w_d, span(t), True, gi.w_max, n_chunks) for (t, u, y) in train]
+                                     n_chunks if use_val_metric else 1, reuse_timebase=reuse_timebase)
+    train_sr = [bfrf.StreamedRecord(t, u, y, gi.w_d, span(t), True, gi.w_max, n_chunks, reuse_timebase=reuse_timebase)
+                for (t, u, y) in train]
     order = train_sr + ([val_sr] if val_sr is not None else [])
     for sr in order:
         sr.enqueue_copies()
     checks = []
 
+    checked = []
+
     def coefficients(sr):
         part = sr.project()
         if sr.needs_check():
             checks.append((sr.uniformity_async() * sr.w_max >= bfrf.UNIFORM_PHASE_TOL).to(F64))
+            checked.append(sr)
+        sr.queue_exactness_probe()
         return sr.finalize(part)
 
     train_frf = [coefficients(sr) for sr in train_sr]
@@ -595,11 +618,22 @@ def identify_host(train: Sequence[Tuple[np.ndarray, np.ndarray, np.ndarray]],
         skip = min(10, min(n_taps, 2 * PAPER_ND - 1) // 10)
         val_d = (val_sr.t_d, val_sr.u_d, val_sr.y_d, val_sr.span, float(val_sr.yh[skip]), val_sr.t0)
     try:
-        return identify_device(train_d, val_d, nd, kernel, noise, candidates, theta0, use_validation_metric, n_taps,
-                               val_frf=(lambda: coefficients(val_sr)) if use_val_metric else None,
-                               train_frf=train_frf, frf_checks=checks)
+        res = identify_device(train_d, val_d, nd, kernel, noise, candidates, theta0, use_validation_metric, n_taps,
+                              val_frf=(lambda: coefficients(val_sr)) if use_val_metric else None,
+                              train_frf=train_frf, frf_checks=checks)
     except TimebaseGuessFailed:
+        # some rank's guess failed (the verdict is common to all ranks): everybody redoes the pass on the resident
+        # copies with probed paths, so the collectives of the second pass pair up across ranks
+        for sr in order:
+            if sr.t_d is None:
+                sr.t_d = bfrf.timebase_fill_device(sr.n, sr.t0, sr.exact_dt, dev)
+        train_d = [(sr.t_d, sr.u_d, sr.y_d, sr.span, sr.t0) for sr in train_sr]
+        if val_sr is not None:
+            val_d = (val_sr.t_d,) + tuple(val_d[1:])
         return identify_device(train_d, val_d, nd, kernel, noise, candidates, theta0, use_validation_metric, n_taps)
+    for sr in checked:
+        sr.remember_uniform_ok()
+    return res
 
 
 _SIDE_STREAMS: Dict[int, "torch.cuda.Stream"] = {}
@@ -751,3 +785,45 @@ def population_search_device(theta: np.ndarray, kernel_ids: np.ndarray, X_d, y_d
                 best, arg = float(v), int(i)
         out.append(bdist.argmin_gather(best, arg, device=dev))
     return m_host, gidx, out
+
+
+@dataclass
+class Population:
+    """BASELINE config 3 on the device: a mixed-kernel candidate population (this rank's round-robin shard), the
+    segment of every kernel inside the shard, and the names in METHOD_ORDER."""
+    cs: CandidateSet
+    offsets_d: torch.Tensor          # [n_kernels + 1] int64: kernel k owns shard rows [offsets[k], offsets[k+1])
+    names: List[str]
+    n_per_kernel: int
+    n_total: int
+
+    @staticmethod
+    def build(n_restarts: int, dev, kernels: Sequence[str] = tuple(BASELINE_KERNELS), seed: int = 42,
+              rank: int = 0, world_size: int = 1) -> "Population":
+        theta, ids, _ = restart_candidates(n_restarts, kernels, seed)
+        cs = CandidateSet.build(None, theta, dev, kernel_ids=ids, rank=rank, world_size=world_size)
+        gidx = cs.global_index if cs.global_index is not None else np.arange(theta.shape[0], dtype=np.int64)
+        edges = np.searchsorted(gidx, np.arange(len(kernels) + 1, dtype=np.int64) * n_restarts).astype(np.int64)
+        return Population(cs, torch.as_tensor(edges, device=dev), list(kernels), n_restarts, theta.shape[0])
+
+
+def population_search_async(pop: Population, X_d: torch.Tensor, targets: Sequence[torch.Tensor], noise: float) -> torch.Tensor:
+    """NLL of every (kernel, start point) candidate of this rank's shard for each target (one mixed-kernel launch per
+    target), the per-kernel first strict minima (one launch per target) and, under torch.distributed, ONE all-gather
+    for all len(targets) x n_kernels searches.  Returns a device tensor [len(targets), n_kernels, 5] =
+    (theta[0..2], global index, NLL) of each kernel's winner, nothing read back (gpr_fitting.py:104-123,132-145 as a
+    batched population; the cross-kernel pick is :func:`select_best` on the last column)."""
+    import ctypes as C
+    from . import _lib
+    from .runtime import ptr, stream_ptr
+    nk = len(pop.names)
+    dev = X_d.device
+    pends = []
+    for y_d in targets:
+        m = bgp.batch_eval_device(0, pop.cs.kernel_ids, pop.cs.theta, X_d, y_d, noise, bgp.METRIC_NLL)
+        pend = empty(2 * nk, dev)
+        _lib.call("b200id_first_strict_min_segments", ptr(m), ptr(pop.offsets_d), C.c_int(nk), ptr(pend), stream_ptr())
+        pends.append(pend.view(nk, 2))
+    with _lib.timed_region("collective:population_pick"):
+        out = _device_pick_block(pop.cs, torch.cat(pends).contiguous())
+    return out.view(len(targets), nk, 5)

@@ -214,3 +214,42 @@ class RecordStore:
 
 
 STORE = RecordStore()
+
+
+# ------------------------------------------------------------------------------------- host-array facts
+class ArrayFacts:
+    """Small facts about HOST arrays that callers hand in again and again (the time vector of a record that is
+    identified once per kernel, per noise level, per step ...), keyed by identity AND content probes: data
+    pointer, length and 16 evenly spaced values.  An array that is rewritten in place between two calls changes
+    at least its probes unless the writer deliberately preserves all of them; callers that mutate time vectors
+    in place pass ``reuse_timebase=False`` (or set B200ID_TIMEBASE_FACTS=0).  LRU-bounded."""
+
+    PROBES = 16
+
+    def __init__(self, capacity: int = 64):
+        self.capacity = capacity
+        self.table: "OrderedDict[tuple, dict]" = OrderedDict()
+
+    @classmethod
+    def key(cls, th: "torch.Tensor") -> tuple:
+        n = th.numel()
+        idx = torch.linspace(0, n - 1, min(cls.PROBES, n)).to(torch.int64)
+        return (th.data_ptr(), n, th[idx].numpy().tobytes())
+
+    def get(self, th: "torch.Tensor") -> dict:
+        k = self.key(th)
+        d = self.table.get(k)
+        if d is None:
+            d = self.table[k] = {}
+            while len(self.table) > self.capacity:
+                self.table.popitem(last=False)
+        else:
+            self.table.move_to_end(k)
+        return d
+
+    def clear(self) -> None:
+        self.table.clear()
+
+
+FACTS_ENABLED = os.environ.get("B200ID_TIMEBASE_FACTS", "1") != "0"
+FACTS = ArrayFacts()

@@ -94,13 +94,14 @@ def empty(n, dev, dtype=F64) -> torch.Tensor:
 
 
 class Workspace:
-    """Grow-only device scratch buffer, one per (device, purpose)."""
+    """Grow-only device scratch buffer, one per (device, purpose, stream): calls on different streams never share
+    scratch, calls on one stream are ordered by it."""
 
     _pool = {}
 
     @classmethod
     def get(cls, key: str, nbytes: int, dev: torch.device) -> torch.Tensor:
-        k = (key, dev.index)
+        k = (key, dev.index, torch.cuda.current_stream(dev).cuda_stream if dev.type == "cuda" else 0)
         buf = cls._pool.get(k)
         if buf is None or buf.numel() < nbytes:
             buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=dev)

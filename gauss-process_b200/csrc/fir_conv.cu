@@ -13,6 +13,7 @@
 // folded per CTA and then by a fixed-order tree (deterministic).
 #include <stdlib.h>
 #include "common.cuh"
+#include <mutex>
 
 namespace b200id {
 
@@ -53,6 +54,18 @@ constexpr int FIR_CONST_TAPS = 4104;                // taps up to this count are
 // acc (register), u window (register) and the tap through a uniform register -- two distinct
 // register operands, which is what lets the FP64 pipe issue at its full rate (see fp64_math.cuh).
 __constant__ double c_taps[FIR_CONST_TAPS];
+
+// The constant bank is one per process: a call stages its taps there only while it OWNS the bank -- the stream that
+// used it last keeps it, another stream takes it over once the previous owner's kernel has finished (event query, no
+// wait), and otherwise the call runs the shared-memory tap path (same arithmetic, same order of operations).  Staging
+// and launch happen under one host mutex, so two host threads cannot interleave them either.
+struct ConstTapsOwner {
+    std::mutex mu;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr;
+    bool init = false;
+};
+static ConstTapsOwner g_ctaps;
 
 __host__ __device__ inline int fir_pad(int x) { return x + (x >> 4); }
 static inline size_t fir_smem_bytes(int taps_padded) {
@@ -210,8 +223,21 @@ extern "C" int b200id_fir_eval(const double* u, const double* y, int64_t n, int6
     const int taps_padded = (n_taps + FIR_TAP_GROUP - 1) / FIR_TAP_GROUP * FIR_TAP_GROUP;
     const size_t smem = fir_smem_bytes(taps_padded);
     cudaStream_t st = (cudaStream_t)stream;
-    const bool use_const = taps_padded <= FIR_CONST_TAPS;
+    bool use_const = taps_padded <= FIR_CONST_TAPS;
     int rc;
+    std::unique_lock<std::mutex> bank(g_ctaps.mu, std::defer_lock);
+    if (use_const) {
+        bank.lock();
+        if (!g_ctaps.init) {
+            rc = check_cuda(cudaEventCreateWithFlags(&g_ctaps.done, cudaEventDisableTiming), "cudaEventCreate(c_taps)");
+            if (rc) return rc;
+            g_ctaps.init = true;
+            g_ctaps.stream = st;
+        } else if (g_ctaps.stream != st) {
+            if (cudaEventQuery(g_ctaps.done) == cudaSuccess) g_ctaps.stream = st;     // previous owner is done: take over
+            else { use_const = false; bank.unlock(); (void)cudaGetLastError(); }      // busy on another stream: shared-memory taps
+        }
+    }
     if (use_const) {
         // stage the (zero padded) taps into the constant bank on the caller's stream
         void* sym = nullptr;
@@ -227,6 +253,9 @@ extern "C" int b200id_fir_eval(const double* u, const double* y, int64_t n, int6
         if (rc) return rc;
         fir_eval_kernel<true><<<(unsigned)ctas, FIR_THREADS, smem, st>>>(u, y, n, lead, g, n_taps, taps_padded, skip, y0,
                                                                         y_pred_out, (double*)ws);
+        rc = check_cuda(cudaEventRecord(g_ctaps.done, st), "cudaEventRecord(c_taps)");
+        if (rc) return rc;
+        bank.unlock();
     } else {
         rc = check_cuda(cudaFuncSetAttribute(fir_eval_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute(fir)");
         if (rc) return rc;

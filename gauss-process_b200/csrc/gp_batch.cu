@@ -127,6 +127,43 @@ first_strict_min_kernel(const double* __restrict__ metric, int64_t n, double* be
     }
 }
 
+// Same rule per segment [offsets[s], offsets[s+1]) of one metric array, one CTA per segment: the per-kernel minima of a
+// mixed-kernel candidate population (BASELINE config 3: 11 kernels x 4096 start points in one launch).
+// pend_out[s] = (best metric or +inf, index into metric[] as a double or -1) -- the layout b200id_argmin_pack takes.
+__global__ void __launch_bounds__(ARGMIN_THREADS)
+first_strict_min_segments_kernel(const double* __restrict__ metric, const int64_t* __restrict__ offsets,
+                                 double* __restrict__ pend_out) {
+    __shared__ double sv[ARGMIN_THREADS];
+    __shared__ long long si[ARGMIN_THREADS];
+    const int64_t lo = offsets[blockIdx.x], hi = offsets[blockIdx.x + 1];
+    double bv = INFINITY;
+    long long bi = -1;
+    for (int64_t i = lo + threadIdx.x; i < hi; i += ARGMIN_THREADS) {
+        const double v = metric[i];
+        if (v < bv) { bv = v; bi = i; }
+    }
+    sv[threadIdx.x] = bv;
+    si[threadIdx.x] = bi;
+    __syncthreads();
+    for (int s = ARGMIN_THREADS / 2; s > 0; s >>= 1) {
+        if (threadIdx.x < s) {
+            const double ov = sv[threadIdx.x + s];
+            const long long oi = si[threadIdx.x + s];
+            const double mv = sv[threadIdx.x];
+            const long long mi = si[threadIdx.x];
+            if (oi >= 0 && (mi < 0 || ov < mv || (ov == mv && oi < mi))) {
+                sv[threadIdx.x] = ov;
+                si[threadIdx.x] = oi;
+            }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        pend_out[2 * blockIdx.x] = sv[0];
+        pend_out[2 * blockIdx.x + 1] = (double)si[0];
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 __global__ void gram_kernel(int kernel_id, const double* __restrict__ theta, const double* __restrict__ X1,
                             int n1, const double* __restrict__ X2, int n2, double* __restrict__ K) {
@@ -456,6 +493,15 @@ extern "C" int b200id_first_strict_min(const double* metric, int64_t n_candidate
     B200ID_REQUIRE(metric && best_out && idx_out && n_candidates > 0, B200ID_E_ARG, "first_strict_min: bad argument");
     first_strict_min_kernel<<<1, ARGMIN_THREADS, 0, (cudaStream_t)stream>>>(metric, n_candidates, best_out, idx_out);
     B200ID_LAUNCH_CHECK("first_strict_min_kernel");
+    return B200ID_OK;
+}
+
+extern "C" int b200id_first_strict_min_segments(const double* metric, const int64_t* offsets, int n_segments,
+                                                double* pend_out, void* stream) {
+    B200ID_REQUIRE(metric && offsets && pend_out && n_segments > 0 && n_segments <= 65535, B200ID_E_ARG,
+                   "first_strict_min_segments: bad argument");
+    first_strict_min_segments_kernel<<<n_segments, ARGMIN_THREADS, 0, (cudaStream_t)stream>>>(metric, offsets, pend_out);
+    B200ID_LAUNCH_CHECK("first_strict_min_segments_kernel");
     return B200ID_OK;
 }
 

@@ -94,7 +94,16 @@ class GaussianProcessRegressor:
 
         def batched_map(_fun, points):
             points = list(points)
-            return [float(v) for v in nll_many(points)] if points else []
+            if not points:
+                return []
+            vals = [float(v) for v in nll_many(points)]
+            # the reference's objective mutates the model on EVERY evaluation (reference :105-106), finite-difference
+            # points included, and the next restart starts from log(self.noise_variance) (:143): leave the model in
+            # the state the sequential evaluation would have left it in, i.e. that of the last point
+            last = np.asarray(points[-1], dtype=np.float64)
+            self.kernel.set_params(last[:-1])
+            self.noise_variance = np.exp(last[-1])
+            return vals
 
         options = {"workers": batched_map} if _LBFGSB_TAKES_WORKERS else {}
         bounds = self.kernel.bounds + [LOG_NOISE_BOUNDS]

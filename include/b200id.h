@@ -104,6 +104,16 @@ int b200id_frf_project_uniform(const double* t, const double* u, const double* y
                                const double* sums /*[2] or NULL*/, double inv_count, double t0, double dt,
                                double* partial_out /*[4*nd]*/, void* ws, size_t ws_bytes, void* stream);
 
+/* Exactly regenerable time base (what `np.arange(n) * dt`, MATLAB's `(0:n-1) * dt` and files saved from them hold):
+ * b200id_frf_timebase_check writes to mismatches_out[0] the number of samples with t_i != fl(fl(i dt) + t0)
+ * (mismatches_out needs TWO doubles; [1] is scratch) and b200id_frf_timebase_fill writes exactly that progression.
+ * A host record whose stamps passed the check once can skip the upload of t afterwards (the load_time_u_y ->
+ * synchronous_coefficients_trapz sequence of frf_estimator.py:70-134,194-232 run again on the same arrays):
+ * u and y are the only per-call inputs.  Workspace: b200id_frf_workspace_bytes(1). */
+int b200id_frf_timebase_check(const double* t, int64_t n, double t0, double dt, double* mismatches_out /*[2]*/,
+                              void* ws, size_t ws_bytes, void* stream);
+int b200id_frf_timebase_fill(double* t_out, int64_t n, double t0, double dt, void* stream);
+
 /* Which recurrence b200id_frf_project_uniform runs for the well-conditioned bins: 0 = three-term recurrence on
  * the basis values (frf_project_uniform3_kernel), 1 = Goertzel recurrence on the accumulators with the rounding
  * term in packed FP32 (frf_project_uniform_g_kernel), -1 = back to the default (environment B200ID_FRF_GOERTZEL,
@@ -197,6 +207,13 @@ int b200id_gp_batch_eval_noise(int kernel_id, const int* kernel_ids, const doubl
  * best_out[0] = metric (+inf if none), idx_out[0] = index (-1 if none). */
 int b200id_first_strict_min(const double* metric, int64_t n_candidates,
                             double* best_out, int64_t* idx_out, void* ws, size_t ws_bytes, void* stream);
+
+/* The same scan per segment [offsets[s], offsets[s+1]) of one metric array (offsets: n_segments + 1 device int64), one
+ * launch for all segments: the per-kernel minima of a mixed-kernel candidate population (BASELINE config 3, the
+ * restart rule of gpr_fitting.py:132-145 applied to all 11 kernels of run_baseline.py:37-41 at once).
+ * pend_out [n_segments][2] = (best metric or +inf, index into metric[] as a double or -1): what b200id_argmin_pack takes. */
+int b200id_first_strict_min_segments(const double* metric, const int64_t* offsets, int n_segments,
+                                     double* pend_out /*[n_segments][2]*/, void* stream);
 
 /* The two small steps either side of the ranks' argmin exchange (candidates are sharded round
  * robin, every rank reports (best metric, global index), the first strict minimum in GLOBAL scan order wins --

@@ -407,6 +407,40 @@ def golden_pipeline_polar(out: Path):
     print("pipeline_polar.npz", len(d), "arrays")
 
 
+def golden_run_baseline(out: Path):
+    """run_baseline.py's table: all 11 GP kernels through run_gp_pipeline with build_config's settings
+    (run_baseline.py:51-86: N_d = 50, noise 0, grid search on the validation RMSE, max 500000 combinations,
+    np.random.seed(42) per method, :129) on the synthetic train / validation .mat files."""
+    import argparse as ap
+    from src.pipeline.gp_pipeline import run_gp_pipeline
+    from src.run_baseline import build_config, GP_METHODS
+    d = {"versions": VERSIONS}
+    n, nd = 30000, 50
+    d["n"] = np.array(n); d["nd"] = np.array(nd)
+    tt, ut, yt = synth.make_record(n, nd, "multisine", seed=0)
+    tv, uv, yv = synth.make_record(n, nd, "square", seed=1)
+    with tempfile.TemporaryDirectory() as tmp:
+        cwd = os.getcwd(); os.chdir(tmp)
+        try:
+            ptrain = synth.write_mat(Path(tmp) / "train.mat", tt, ut, yt)
+            pval = synth.write_mat(Path(tmp) / "val.mat", tv, uv, yv)
+            for kernel in GP_METHODS:
+                np.random.seed(42)
+                cfg = build_config(kernel, [str(ptrain)], str(pval), str(Path(tmp) / kernel))
+                res = quiet(run_gp_pipeline, cfg)
+                d[f"{kernel}_theta_real"] = np.array(res["kernel_params"]["real"])
+                d[f"{kernel}_theta_imag"] = np.array(res["kernel_params"]["imag"])
+                d[f"{kernel}_gp_rmse"] = np.array([res["real"]["rmse"], res["imag"]["rmse"], res["real"]["r2"], res["imag"]["r2"]])
+                f = res["fir_extraction"]
+                d[f"{kernel}_taps"] = f["fir_coefficients"]
+                d[f"{kernel}_fir"] = np.array([f["rmse"], f["fit_percent"], f["r2"]])
+                print(" ", kernel, "theta", res["kernel_params"]["real"], res["kernel_params"]["imag"], "fir rmse", f["rmse"])
+        finally:
+            os.chdir(cwd)
+    np.savez_compressed(out / "run_baseline.npz", **d)
+    print("run_baseline.npz", len(d), "arrays")
+
+
 def main():
     ap_ = argparse.ArgumentParser()
     ap_.add_argument("--out", default=str(ROOT / "tests" / "golden"))
@@ -414,7 +448,7 @@ def main():
     a = ap_.parse_args()
     out = Path(a.out); out.mkdir(parents=True, exist_ok=True)
     todo = {"frf": golden_frf, "gp": golden_gp, "fir": golden_fir, "pipeline": golden_pipeline, "fourier": golden_fourier,
-            "pipeline_polar": golden_pipeline_polar}
+            "pipeline_polar": golden_pipeline_polar, "run_baseline": golden_run_baseline}
     for name, fn in todo.items():
         if a.only and name not in a.only.split(","):
             continue

@@ -32,6 +32,8 @@ SIGNATURES = {
     "b200id_frf_timebase_check": (I, [P, L, D, D, P, P, Z, P]),
     "b200id_frf_timebase_fill": (I, [P, L, D, D, P]),
     "b200id_frf_select_recurrence": (I, [I]),
+    "b200id_frf_adaptive_force": (I, [I]),
+    "b200id_frf_adaptive_diag": (I, [P, Z, I, P, P]),
     "b200id_fir_select_fft": (I, [I]),
     "b200id_frf_project_uniform_mma": (I, [P, P, P, L, L, L, P, I, P, D, D, D, P, P, Z, P]),
     "b200id_cross_power_sums": (I, [P, P, I, I, I, P, P]),

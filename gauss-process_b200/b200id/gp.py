@@ -18,7 +18,7 @@ from .runtime import F64, Workspace, empty, ptr, require_cuda, stream_ptr, to_de
 KERNEL_IDS = {
     "rbf": (0, 2), "matern12": (1, 2), "matern32": (2, 2), "matern52": (3, 2), "exp": (4, 2),
     "dc": (5, 3), "di": (6, 2), "ss1": (7, 2), "ss2": (8, 2), "sshf": (9, 2), "stable_spline": (10, 2),
-    "rq": (11, 3), "tc": (12, 2),
+    "rq": (11, 3), "tc": (12, 2), "matern_nu": (13, 2),      # matern_nu: theta[2] = nu, fixed (not optimised)
 }
 MAX_PARAMS = 3
 METRIC_NLL, METRIC_VAL_RMSE = 0, 1

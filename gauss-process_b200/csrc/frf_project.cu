@@ -636,6 +636,21 @@ constexpr int FRFG_UNROLL_N = FRFG_UNROLL;
 #endif
 constexpr size_t FRFG_SMEM_BYTES = (size_t)FRFG_TILE_MAX * (16 + 8 + 16) + (size_t)8 * FRF_THREADS * sizeof(double) + FRFG_SMEM_PAD;
 
+// narrowing of the rounding residual: F2F.F32.F64 (quarter rate), or the integer re-bias of frf_dg.cuh (-DFRFG_INT_NARROW=1)
+#ifndef FRFG_INT_NARROW
+#define FRFG_INT_NARROW 0   // measured: the integer narrowing costs 4 issue slots and is SLOWER (0.94 vs 0.88 ms per 1e9 sample-bins)
+#endif
+__device__ __forceinline__ float frfg_narrow_int(double e) {
+    const int hi = __double2hiint(e);
+    const int t = max((hi & 0x7fffffff) - 0x38000000, 0);
+    return __int_as_float((t << 3) | (hi & 0x80000000));
+}
+#if FRFG_INT_NARROW
+#define FRFG_NARROW(x) frfg_narrow_int(x)
+#else
+#define FRFG_NARROW(x) ((float)(x))
+#endif
+
 template <bool HAS_Y>
 __global__ void __launch_bounds__(FRF_THREADS, FRF_CTAS_PER_SM)
 frf_project_uniform_g_kernel(const double* __restrict__ t, const double* __restrict__ u,
@@ -703,7 +718,7 @@ frf_project_uniform_g_kernel(const double* __restrict__ t, const double* __restr
 #define FRFG_BIN(wk, wkf, K, Kf, U1, U2, Y1, Y2, Q1, Q2)                                             \
     {                                                                                                \
         const double p = (wk) * tv;                                                                  \
-        const float ef = (float)fma((wk), tv, -p);                                                   \
+        const float ef = FRFG_NARROW(fma((wk), tv, -p));                                             \
         const float epsf = fmaf((wkf), fv.z, -ef);                                                   \
         U2 = fma((K), U1, abv.x - U2);                                                               \
         if (HAS_Y) Y2 = fma((K), Y1, abv.y - Y2);                                                    \
@@ -980,6 +995,7 @@ constexpr size_t FRFU_SMEM_BYTES = (size_t)(4 * FRF_TILE_MAX) * sizeof(double);
 }  // namespace b200id
 
 #include "frf_mma.cuh"
+#include "frf_adaptive.cuh"
 
 using namespace b200id;
 
@@ -992,6 +1008,23 @@ static size_t frf_partial_area_bytes(int nd) {
     return align_up(ctas * 4 * (size_t)nd * sizeof(double), 256) + align_up((size_t)sm_count() * 4 * 2 * sizeof(double), 256) + 256;
 }
 
+// bin-adaptive form: {per-CTA moments [n_cta + 8][DA_NORMS], diag [32 doubles], flag count [4 ints], flag list [nd ints]}
+// after the matrix-product tables
+static size_t frf_adaptive_area_offset(int nd) { return frf_partial_area_bytes(nd) + align_up(fm_tables_bytes(), 256); }
+static size_t frf_adaptive_area_bytes(int nd) {
+    const size_t ctas = (size_t)sm_count() * FRF_CTAS_PER_SM + 8;
+    return align_up(ctas * DA_NORMS * sizeof(double) + 32 * sizeof(double) + (4 + (size_t)nd) * sizeof(int), 256);
+}
+// B200ID_FRF_ADAPTIVE=all lists every bin (the rounding term everywhere, as forms 0 and 1 do); tests use it
+static int g_frf_force_all = -1;
+static int frf_adaptive_force_all() {
+    if (g_frf_force_all < 0) {
+        const char* e = getenv("B200ID_FRF_ADAPTIVE");
+        g_frf_force_all = (e && e[0] == 'a') ? 1 : 0;
+    }
+    return g_frf_force_all;
+}
+
 static bool frf_mma_enabled() {
     static int on = -1;
     if (on < 0) {
@@ -1001,25 +1034,47 @@ static bool frf_mma_enabled() {
     return on == 1;
 }
 
-#ifndef FRF_GOERTZEL_DEFAULT
-#define FRF_GOERTZEL_DEFAULT 1
+// Which evaluation b200id_frf_project_uniform runs for the well-conditioned bins:
+//   0 = three-term recurrence on the basis values (frf_project_uniform3_kernel)
+//   1 = Goertzel recurrence on the accumulators, rounding term in packed FP32 (frf_project_uniform_g_kernel)
+//   2 = bin-adaptive (frf_adaptive.cuh): DMMA main term for all bins, FP32 Goertzel rounding term only for the bins a
+//       device-side test lists (whole-record calls with y; everything else takes form 1)
+#ifndef FRF_FORM_DEFAULT
+#define FRF_FORM_DEFAULT 2
 #endif
-static int g_frf_goertzel = -1;
-static bool frf_goertzel_enabled() {
-    if (g_frf_goertzel < 0) {
-        const char* e = getenv("B200ID_FRF_GOERTZEL");
-        g_frf_goertzel = e ? (e[0] == '1' ? 1 : 0) : FRF_GOERTZEL_DEFAULT;
+static int g_frf_form = -1;
+static int frf_form() {
+    if (g_frf_form < 0) {
+        const char* e = getenv("B200ID_FRF_FORM");
+        const char* legacy = getenv("B200ID_FRF_GOERTZEL");
+        if (e && e[0] >= '0' && e[0] <= '2') g_frf_form = e[0] - '0';
+        else if (legacy) g_frf_form = legacy[0] == '1' ? 1 : 0;
+        else g_frf_form = FRF_FORM_DEFAULT;
     }
-    return g_frf_goertzel == 1;
+    return g_frf_form;
 }
+static bool frf_goertzel_enabled() { return frf_form() >= 1; }
 extern "C" int b200id_frf_select_recurrence(int which) {
-    const int prev = frf_goertzel_enabled() ? 1 : 0;
-    g_frf_goertzel = which < 0 ? -1 : (which ? 1 : 0);
+    const int prev = frf_form();
+    g_frf_form = which < 0 ? -1 : (which > 2 ? 2 : which);
     return prev;
 }
 
 // Matrix-product path of b200id_frf_project_uniform (two signals, nd <= FM_NDMAX).  Returns 1 when the shape does
 // not fit (caller falls back to the recurrence kernels), 0 on success, < 0 on error.
+extern "C" int b200id_frf_adaptive_force(int all_bins) {
+    const int prev = frf_adaptive_force_all();
+    g_frf_force_all = all_bins < 0 ? -1 : (all_bins ? 1 : 0);
+    return prev;
+}
+extern "C" int b200id_frf_adaptive_diag(const void* ws, size_t ws_bytes, int nd, double* diag_out, void* stream) {
+    B200ID_REQUIRE(ws && diag_out && nd > 0, B200ID_E_ARG, "frf_adaptive_diag: null pointer");
+    const size_t ad_off = frf_adaptive_area_offset(nd);
+    B200ID_REQUIRE(ws_bytes >= ad_off + frf_adaptive_area_bytes(nd), B200ID_E_WORKSPACE, "frf_adaptive_diag: workspace too small");
+    const double* diag = (const double*)((const char*)ws + ad_off) + (size_t)(sm_count() * FRF_CTAS_PER_SM + 8) * DA_NORMS;
+    return check_cuda(cudaMemcpyAsync(diag_out, diag, 2 * sizeof(double), cudaMemcpyDeviceToDevice, (cudaStream_t)stream), "diag copy");
+}
+
 static int frf_project_mma_launch(const double* t, const double* u, const double* y, int64_t n, int64_t own_begin,
                                   int64_t own_end, const double* w, int nd, const double* sums, double inv_count,
                                   double t0, double dt, double* partial_out, void* ws, size_t ws_bytes, cudaStream_t st) {
@@ -1066,7 +1121,7 @@ static int frf_project_mma_launch(const double* t, const double* u, const double
 
 extern "C" size_t b200id_frf_workspace_bytes(int nd) {
     if (nd <= 0) return 0;
-    return frf_partial_area_bytes(nd) + fm_tables_bytes();
+    return frf_adaptive_area_offset(nd) + frf_adaptive_area_bytes(nd);
 }
 
 extern "C" int b200id_frf_moments(const double* u, const double* y, int64_t n, int64_t own_begin,
@@ -1235,6 +1290,57 @@ extern "C" int b200id_frf_project_uniform(const double* t, const double* u, cons
     for (int k = 0; k < 4; ++k) {
         rc = check_cuda(cudaFuncSetAttribute(fns[k], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FRFU_SMEM_BYTES), "smem attr");
         if (rc) return rc;
+    }
+    if (y && frf_form() == 2 && own_begin == 0 && own_end == n) {
+        // bin-adaptive: main term of all bins (DMMA), device-side list of the weak bins, rounding term for those only.
+        // Sub-range calls (time-segment shards) stay on form 1: the test needs the whole record's |U_k|.
+        const int groups = da_main_groups(nd), bpg = (nd + groups - 1) / groups;
+        const int64_t nt64 = (n + DA_TS - 1) / DA_TS;
+        B200ID_REQUIRE(nt64 <= 0x7fffffff, B200ID_E_UNSUPPORTED, "frf_project_uniform: record too long for one launch");
+        const int nt = (int)nt64;
+        const int n_cta = sm_count() * FRF_CTAS_PER_SM;
+        int gx = n_cta / groups;
+        if (gx < 1) gx = 1;
+        if (gx > nt) gx = nt;
+        const size_t ad_off = frf_adaptive_area_offset(nd);
+        B200ID_REQUIRE(ws_bytes >= ad_off + frf_adaptive_area_bytes(nd), B200ID_E_WORKSPACE,
+                       "frf_project_uniform: workspace %zu < %zu", ws_bytes, ad_off + frf_adaptive_area_bytes(nd));
+        double* norm_part = (double*)((char*)ws + ad_off);
+        double* diag = norm_part + (size_t)(n_cta + 8) * DA_NORMS;
+        double* fit = diag + 8;                                      // {sum delta, sum (i - c) delta}
+        int* flag_count = (int*)(diag + 32);
+        int* flag_idx = flag_count + 4;
+        const size_t smem = da_main_smem_bytes(bpg);
+        rc = check_cuda(cudaFuncSetAttribute(frf_main_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr");
+        if (rc) return rc;
+        rc = check_cuda(cudaFuncSetAttribute(frf_round_goertzel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)da_round_smem_bytes()), "smem attr");
+        if (rc) return rc;
+        {
+            int fg = sm_count() * 4;
+            int64_t chunk = (n + fg - 1) / fg;
+            chunk = (chunk + 255) / 256 * 256;
+            fg = (int)((n + chunk - 1) / chunk);
+            frf_timebase_fit_kernel<<<fg, DA_FIT_THREADS, 0, st>>>(t, own_begin, own_end, t0, dt, chunk, part);
+            B200ID_LAUNCH_CHECK("frf_timebase_fit_kernel");
+            frf_fold_kernel<<<1, FOLD_WARPS * 32, 0, st>>>(part, fg, 2, fit);
+            B200ID_LAUNCH_CHECK("frf_fold_kernel(fit)");
+        }
+        frf_main_dmma_kernel<<<dim3(gx, groups), DA_THREADS, smem, st>>>(t, u, y, n, own_begin, own_end, w, nd, sums, inv_count, t0, dt,
+                                                                           fit, nt, bpg, part, norm_part);
+        B200ID_LAUNCH_CHECK("frf_main_dmma_kernel");
+        const int dlen = 4 * nd;
+        frf_fold_kernel<<<(dlen + 31) / 32, FOLD_WARPS * 32, 0, st>>>(part, gx, dlen, partial_out);
+        B200ID_LAUNCH_CHECK("frf_fold_kernel");
+        const double tmax_abs = fmax(fabs(t0), fabs(t0 + (double)(n - 1) * dt));
+        frf_decide_kernel<<<1, DA_DECIDE_THREADS, (size_t)nd, st>>>(partial_out, norm_part, gx, w, nd, tmax_abs, frf_adaptive_force_all(),
+                                                                    flag_count, flag_idx, diag);
+        B200ID_LAUNCH_CHECK("frf_decide_kernel");
+        frf_round_goertzel_kernel<<<n_cta, DA_THREADS, da_round_smem_bytes(), st>>>(t, u, y, n, own_begin, own_end, w, nd, sums, inv_count,
+                                                                                      t0, dt, fit, nt, flag_count, flag_idx, part);
+        B200ID_LAUNCH_CHECK("frf_round_goertzel_kernel");
+        frf_fold_add_kernel<<<dim3((nd + 31) / 32, 4), FOLD_WARPS * 32, 0, st>>>(part, n_cta, nd, flag_count, flag_idx, partial_out);
+        B200ID_LAUNCH_CHECK("frf_fold_add_kernel");
+        return B200ID_OK;
     }
     if (frf_goertzel_enabled()) {
         // Goertzel form: own tile size (its per-thread accumulators live in shared memory next to the tile)

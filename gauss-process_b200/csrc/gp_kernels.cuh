@@ -5,6 +5,7 @@
 // rounding).  Parameter order per kernel is the reference's get_params() order (include/b200id.h).
 #pragma once
 #include "common.cuh"
+#include "gp_bessel.cuh"
 
 namespace b200id {
 
@@ -35,13 +36,15 @@ B200ID_HD KernelParams make_kernel_params(int id, const double* theta) {
     k.id = id;
     k.p0 = theta[0];
     k.p1 = theta[1];
-    k.p2 = (id == B200ID_K_DC || id == B200ID_K_RQ) ? theta[2] : 0.0;
+    k.p2 = (id == B200ID_K_DC || id == B200ID_K_RQ || id == B200ID_K_MATERN_NU) ? theta[2] : 0.0;
     k.c0 = 0.0;
     k.c1 = 0.0;
     switch (id) {
         case B200ID_K_RBF: k.c0 = B200ID_MUL(k.p0, k.p0); break;                       // length_scale ** 2
         case B200ID_K_RQ:  k.c0 = B200ID_MUL(B200ID_MUL(2.0, k.p2), B200ID_MUL(k.p0, k.p0)); break;  // 2*alpha*ls**2
         case B200ID_K_SS2: k.c0 = B200ID_MUL(3.0, k.p0); break;                        // 3.0 * beta
+        case B200ID_K_MATERN_NU:                                                        // np.sqrt(2.0 * nu), 2**(1-nu) / gamma(nu)
+            k.c0 = sqrt(B200ID_MUL(2.0, k.p2)); k.c1 = matern_scale(k.p2); break;
         default: break;
     }
     return k;
@@ -75,6 +78,16 @@ B200ID_HD double kernel_entry_t(const KernelParams& k, double xa, double xb) {
                 const double a = B200ID_MUL(s5, d);
                 const double q = B200ID_MUL(5.0 / 3.0, B200ID_MUL(d, d));
                 v = B200ID_MUL(B200ID_ADD(B200ID_ADD(1.0, a), q), exp(-a));
+            }
+            return B200ID_MUL(v, k.p1);
+        }
+        case B200ID_K_MATERN_NU: {      // general nu (theta[2], fixed): kernels.py:131-135
+            const double d = B200ID_DIV(fabs(B200ID_SUB(xa, xb)), k.p0);
+            double v = 1.0;                                  // K[dists == 0] = 1.0
+            if (d != 0.0) {
+                v = pow(d, k.p2);                            // K = dists ** nu
+                v = B200ID_MUL(v, bessel_k(k.p2, B200ID_MUL(k.c0, d)));   // K *= kv(nu, sqrt(2 nu) * dists)
+                v = B200ID_MUL(v, k.c1);                     // K *= 2 ** (1 - nu) / gamma(nu)
             }
             return B200ID_MUL(v, k.p1);
         }
@@ -143,6 +156,7 @@ B200ID_HD double kernel_entry_t(const KernelParams& k, double xa, double xb) {
         case B200ID_K_STABLE_SPLINE: FN<B200ID_K_STABLE_SPLINE>(__VA_ARGS__); break; \
         case B200ID_K_RQ: FN<B200ID_K_RQ>(__VA_ARGS__); break;                \
         case B200ID_K_TC: FN<B200ID_K_TC>(__VA_ARGS__); break;                \
+        case B200ID_K_MATERN_NU: FN<B200ID_K_MATERN_NU>(__VA_ARGS__); break;  \
         default: break;                                                       \
     }
 

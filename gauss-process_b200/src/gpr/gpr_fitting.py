@@ -85,7 +85,7 @@ class GaussianProcessRegressor:
 
         def nll_many(points):
             pts = np.asarray(points, dtype=np.float64).reshape(len(points), -1)
-            return _gp.batch_eval(kid, pts[:, :-1], self.X_train, self.y_train, np.exp(pts[:, -1]))
+            return _gp.batch_eval(kid, self.kernel.with_fixed(pts[:, :-1]), self.X_train, self.y_train, np.exp(pts[:, -1]))
 
         def nll(params):
             self.kernel.set_params(params[:-1])

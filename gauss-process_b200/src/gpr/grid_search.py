@@ -76,8 +76,8 @@ def grid_search_hyperparameters(kernel: Kernel,
     # ONE device round trip: metric of the start point and of every candidate, the first-strict-minimum scan,
     # the fit of the winner (noise + 1e-10 jitter, as GaussianProcessRegressor.fit will ask for next) and its
     # fitted mean at the training inputs.  The prints below keep the reference's order.
-    res = _gp.search_and_fit(kernel.kernel_id, start, candidates, X_train, y_train, noise_variance,
-                             noise_variance + 1e-10, **val)
+    res = _gp.search_and_fit(kernel.kernel_id, kernel.with_fixed(start), kernel.with_fixed(candidates), X_train, y_train,
+                             noise_variance, noise_variance + 1e-10, **val)
     if use_validation:
         print(f"  Initial (pre-grid-search) {metric_name}: {res['start_metric']:.6e}")
         print(f"  Initial params: {start}, noise: {noise_variance:.3e} (fixed)")

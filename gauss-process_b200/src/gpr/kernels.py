@@ -35,7 +35,12 @@ class Kernel(ABC):
         """C ABI kernel id (include/b200id.h)."""
 
     def theta(self) -> np.ndarray:
-        return np.asarray(self.get_params(), dtype=np.float64)
+        """What the device receives for this kernel: the optimisable parameters followed by any fixed shape parameter."""
+        return self.with_fixed(np.asarray(self.get_params(), dtype=np.float64))
+
+    def with_fixed(self, thetas: np.ndarray) -> np.ndarray:
+        """Candidate rows [..., n_params] -> device rows (fixed shape parameters appended; none by default)."""
+        return np.asarray(thetas, dtype=np.float64)
 
     def __call__(self, X1: np.ndarray, X2: Optional[np.ndarray] = None) -> np.ndarray:
         """K(X1, X2) (X2 None -> K(X1, X1)) for 1-D inputs given as (n, 1) or (n,) arrays."""
@@ -141,11 +146,14 @@ StableSplineKernel = _simple_kernel(
 class MaternKernel(Kernel):
     """Matern kernel; nu is a fixed shape parameter, not optimised (reference :113-147).
 
-    nu in {0.5, 1.5, 2.5} runs on the device.  The general-nu branch of the reference (scipy.special.kv)
-    is outside the 11 baseline kernels and not built."""
+    nu in {0.5, 1.5, 2.5} uses the closed forms (:124-130); any other nu > 0 the Bessel form
+    dists**nu * K_nu(sqrt(2 nu) dists) * 2**(1-nu) / Gamma(nu) (:131-135) with K_nu evaluated on the device
+    (csrc/gp_bessel.cuh: Temme series / Steed continued fraction + recurrence); nu then rides along as a third,
+    fixed entry of the device parameter row."""
     PARAM_ORDER = ("length_scale", "variance")
     DEFAULT_BOUNDS = (_WIDE, _WIDE)
     _IDS = {0.5: 1, 1.5: 2, 2.5: 3}
+    GENERAL_ID = 13
 
     def __init__(self, length_scale: float = 1.0, variance: float = 1.0, nu: float = 1.5):
         super().__init__(length_scale=length_scale, variance=variance, nu=nu)
@@ -153,9 +161,18 @@ class MaternKernel(Kernel):
     @property
     def kernel_id(self) -> int:
         nu = self.params["nu"]
-        if nu not in self._IDS:
-            raise NotImplementedError(f"Matern nu={nu}: only nu in (0.5, 1.5, 2.5) has a device kernel")
-        return self._IDS[nu]
+        if nu in self._IDS:
+            return self._IDS[nu]
+        if not (isinstance(nu, (int, float)) and 0.0 < float(nu) <= 64.0):
+            raise ValueError(f"Matern nu={nu!r}: the device kernel needs 0 < nu <= 64")
+        return self.GENERAL_ID
+
+    def with_fixed(self, thetas: np.ndarray) -> np.ndarray:
+        th = np.asarray(thetas, dtype=np.float64)
+        if self.params["nu"] in self._IDS:
+            return th
+        nu = np.full(th.shape[:-1] + (1,), float(self.params["nu"]))
+        return np.concatenate([th, nu], axis=-1)
 
 
 def create_kernel(kernel_type: str, **kwargs) -> Kernel:

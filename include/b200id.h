@@ -50,7 +50,9 @@ enum b200id_kernel_id {
     B200ID_K_STABLE_SPLINE = 10, /* kernels.py:358                                  */
     B200ID_K_RQ = 11,            /* kernels.py:150  [length_scale, variance, alpha] */
     B200ID_K_TC = 12,            /* kernels.py:201  [omega, variance]               */
-    B200ID_K_COUNT = 13
+    B200ID_K_MATERN_NU = 13,     /* kernels.py:131  general nu: [length_scale, variance] optimised,
+                                    theta[2] = nu rides along as a fixed shape parameter (scipy.special.kv branch) */
+    B200ID_K_COUNT = 14
 };
 #define B200ID_MAX_PARAMS 3
 
@@ -116,10 +118,19 @@ int b200id_frf_timebase_fill(double* t_out, int64_t n, double t0, double dt, voi
 
 /* Which recurrence b200id_frf_project_uniform runs for the well-conditioned bins: 0 = three-term recurrence on
  * the basis values (frf_project_uniform3_kernel), 1 = Goertzel recurrence on the accumulators with the rounding
- * term in packed FP32 (frf_project_uniform_g_kernel), -1 = back to the default (environment B200ID_FRF_GOERTZEL,
- * else the build's default).  Process-wide, not stream-ordered: meant for tests and for timing one form against
- * the other.  Returns the previous setting. */
+ * term in packed FP32 (frf_project_uniform_g_kernel), 2 = bin-adaptive (the default; frf_adaptive.cuh: exact-phase
+ * main term of every bin as FP64 matrix products, the reference's per-sample phase-rounding term only for the bins a
+ * device-side test finds weakly excited; whole-record calls with y, anything else runs form 1), -1 = back to the
+ * default (environment B200ID_FRF_FORM, else the build's default).  Process-wide, not stream-ordered: meant for
+ * tests and for timing one form against the other.  Returns the previous setting. */
 int b200id_frf_select_recurrence(int which);
+
+/* Bin-adaptive form only.  b200id_frf_adaptive_force(1) lists every bin for the rounding term (0 = decide per bin,
+ * -1 = environment B200ID_FRF_ADAPTIVE=all / default); returns the previous setting.  b200id_frf_adaptive_diag copies
+ * {number of bins that took the rounding term, largest (16 sigma_k + rigorous_k) / |S_k| among the skipped bins} of
+ * the LAST b200id_frf_project_uniform call on this workspace to diag_out[2] (device), stream-ordered. */
+int b200id_frf_adaptive_force(int all_bins);
+int b200id_frf_adaptive_diag(const void* ws, size_t ws_bytes, int nd, double* diag_out /*[2]*/, void* stream);
 
 /* EXPERIMENTAL alternative evaluation of b200id_frf_project_uniform (same arguments, same outputs, same
  * reference lines frf_estimator.py:226-231): the exact-phase part as a blocked FP64 matrix product on

@@ -27,6 +27,8 @@ KERNELS: Dict[str, Tuple[int, Tuple[str, ...], Tuple[Tuple[float, float], ...]]]
     "stable_spline": (10, ("beta", "variance"), (WIDE, WIDE)),                        # kernels.py:358-382
     "rq":            (11, ("length_scale", "variance", "alpha"), (WIDE, WIDE, WIDE)),  # kernels.py:150-171
     "tc":            (12, ("omega", "variance"), (WIDE, WIDE)),                       # kernels.py:201-224
+    # general-nu Matern: theta = [length_scale, variance, nu]; nu is a fixed shape parameter (kernels.py:131-135)
+    "matern_nu":     (13, ("length_scale", "variance"), (WIDE, WIDE)),
 }
 BASELINE_KERNELS = ["dc", "di", "exp", "matern12", "matern32", "matern52",
                     "rbf", "ss1", "ss2", "sshf", "stable_spline"]        # run_baseline.py:37-41
@@ -54,6 +56,16 @@ def gram(name: str, theta: Sequence[float], X1, X2=None) -> np.ndarray:
             K = (1.0 + np.sqrt(3.0) * d) * np.exp(-np.sqrt(3.0) * d)
         else:
             K = (1.0 + np.sqrt(5.0) * d + 5.0 / 3.0 * d ** 2) * np.exp(-np.sqrt(5.0) * d)
+        K *= th[1]
+        return K
+    if name == "matern_nu":                             # :121,131-136 (scipy.special.kv branch)
+        from scipy.special import gamma, kv
+        d = np.sqrt((A - B) ** 2) / th[0]
+        nu = th[2]
+        K = d ** nu
+        K *= kv(nu, np.sqrt(2.0 * nu) * d)
+        K *= 2.0 ** (1.0 - nu) / gamma(nu)
+        K[d == 0] = 1.0
         K *= th[1]
         return K
     if name == "rq":                                    # :158-161

@@ -407,6 +407,87 @@ def golden_pipeline_polar(out: Path):
     print("pipeline_polar.npz", len(d), "arrays")
 
 
+def golden_matern_nu(out: Path):
+    """General-nu Matern (kernels.py:131-135, the scipy.special.kv branch of MaternKernel): Gram matrices for several
+    nu / length scales on the GP problem's inputs and on widely spaced inputs (kv arguments from 1e-5 to beyond
+    the underflow of exp(-x)), per-candidate NLL and validation RMSE over the reference's own 900-point scan list,
+    the grid-search selection, fit / predict, and one whole run_gp_pipeline (--kernel matern --nu 0.8)."""
+    import argparse as ap
+    import itertools
+    from src.gpr.kernels import MaternKernel
+    from src.pipeline.gp_pipeline import run_gp_pipeline
+    d = {"versions": VERSIONS}
+    P = gp_problem(50)
+    X, yr, Xv = P["X"], P["yr"], P["Xv"]
+    d.update(X=X, yr=yr, Xv=Xv, yv_r=P["Gv"].real, yr_mean=P["ys_r"].mean_, yr_scale=P["ys_r"].scale_)
+    Xw = np.concatenate([[0.0], np.logspace(-6, 3.2, 40)]).reshape(-1, 1)          # distances from 1e-6 to 1.6e3
+    d["Xw"] = Xw
+    nus = [0.3, 0.8, 1.0, 2.0, 3.3, 7.5, 0.50001, 12.25]
+    d["nus"] = np.array(nus)
+    thetas = [(1.0, 1.0), (0.05, 2.5), (30.0, 0.2), (1e-3, 1e3), (1e3, 1e-3)]
+    d["thetas"] = np.array(thetas)
+    for a, nu in enumerate(nus):
+        for q, (ls, var) in enumerate(thetas):
+            k = MaternKernel(length_scale=ls, variance=var, nu=nu)
+            with np.errstate(all="ignore"):
+                d[f"gram_{a}_{q}"] = k(X[:24])
+                d[f"gramx_{a}_{q}"] = k(Xv[:10], X[:24])
+                d[f"gramw_{a}_{q}"] = k(Xw)
+    for a, nu in ((1, 0.8), (4, 3.3)):
+        k = MaternKernel(nu=nu)
+        g = R_grids(k)
+        C = np.array(list(itertools.product(*[g[f"param_{i}"] for i in range(len(g))])))
+        d[f"cand_{a}"] = C
+        with np.errstate(all="ignore"):
+            d[f"nll_{a}"] = np.array([metric_ref(k, th, X, yr, 1e-6) for th in C])
+            d[f"vrmse_{a}"] = np.array([metric_ref(k, th, X, yr, 1e-6, Xv, P["Gv"].real, P["ys_r"]) for th in C])
+        for mode in ("nll", "val"):
+            gp = R_GPR(kernel=MaternKernel(nu=nu), noise_variance=1e-6)
+            kw = dict(validation_X=Xv, validation_y=P["Gv"].real, y_scaler=P["ys_r"]) if mode == "val" else {}
+            quiet(gp.fit, X, yr, optimize=True, use_grid_search=True, **kw)
+            d[f"sel_{a}_{mode}"] = gp.kernel.get_params()
+            d[f"sel_alpha_{a}_{mode}"] = gp.alpha
+            m, s_ = gp.predict(X, return_std=True)
+            d[f"sel_mean_{a}_{mode}"] = m
+            d[f"sel_std_{a}_{mode}"] = s_
+        gp = R_GPR(kernel=MaternKernel(length_scale=0.7, variance=1.3, nu=nu), noise_variance=1e-6)
+        gp.fit(X, yr, optimize=False)
+        d[f"fit_alpha_{a}"] = gp.alpha
+        Xs_new = np.linspace(X.min() - 0.2, X.max() + 0.2, 64).reshape(-1, 1)
+        d["Xs_new"] = Xs_new
+        m, s_ = gp.predict(Xs_new, return_std=True)
+        d[f"fit_mean_{a}"] = m
+        d[f"fit_std_{a}"] = s_
+    n, nd = 30000, 50
+    d["n"] = np.array(n); d["nd"] = np.array(nd)
+    tt, ut, yt = synth.make_record(n, nd, "multisine", seed=0)
+    tv, uv, yv = synth.make_record(n, nd, "square", seed=1)
+    with tempfile.TemporaryDirectory() as tmp:
+        cwd = os.getcwd(); os.chdir(tmp)
+        try:
+            ptrain = synth.write_mat(Path(tmp) / "train.mat", tt, ut, yt)
+            pval = synth.write_mat(Path(tmp) / "val.mat", tv, uv, yv)
+            np.random.seed(42)
+            cfg = ap.Namespace(
+                mat_files=[str(ptrain)], use_existing=None, n_files=1, time_duration=None, nd=nd,
+                freq_method="frf", kernel="matern", nu=0.8, gp_mode="separate", noise_variance=1e-6,
+                normalize=True, log_frequency=True, optimize=True, n_restarts=3,
+                out_dir=str(Path(tmp) / "m08"), extract_fir=True, fir_length=1024,
+                fir_validation_mat=str(pval), method="gp", is_gp=True, use_grid_search=True,
+                grid_search_max_combinations=5000, validation_mat=None, n_numerator=2, n_denominator=4)
+            res = quiet(run_gp_pipeline, cfg)
+            d["pipe_theta_real"] = np.array(res["kernel_params"]["real"])
+            d["pipe_theta_imag"] = np.array(res["kernel_params"]["imag"])
+            f = res["fir_extraction"]
+            d["pipe_taps"] = f["fir_coefficients"]
+            d["pipe_fir"] = np.array([f["rmse"], f["fit_percent"], f["r2"]])
+            print("  pipeline matern nu=0.8 theta", res["kernel_params"], "fir rmse", f["rmse"])
+        finally:
+            os.chdir(cwd)
+    np.savez_compressed(out / "matern_nu.npz", **d)
+    print("matern_nu.npz", len(d), "arrays")
+
+
 def golden_run_baseline(out: Path):
     """run_baseline.py's table: all 11 GP kernels through run_gp_pipeline with build_config's settings
     (run_baseline.py:51-86: N_d = 50, noise 0, grid search on the validation RMSE, max 500000 combinations,
@@ -448,7 +529,7 @@ def main():
     a = ap_.parse_args()
     out = Path(a.out); out.mkdir(parents=True, exist_ok=True)
     todo = {"frf": golden_frf, "gp": golden_gp, "fir": golden_fir, "pipeline": golden_pipeline, "fourier": golden_fourier,
-            "pipeline_polar": golden_pipeline_polar, "run_baseline": golden_run_baseline}
+            "pipeline_polar": golden_pipeline_polar, "run_baseline": golden_run_baseline, "matern_nu": golden_matern_nu}
     for name, fn in todo.items():
         if a.only and name not in a.only.split(","):
             continue

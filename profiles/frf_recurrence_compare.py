@@ -1,4 +1,5 @@
-"""Time the two recurrence forms of b200id_frf_project_uniform side by side (10^7 samples, N_d = 100 and 150).
+"""Time the three evaluations of b200id_frf_project_uniform side by side (10^7 samples, N_d = 100 and 150):
+three-term recurrence, Goertzel recurrence, DMMA main term + FP32 Goertzel rounding term (default).
 
     python profiles/frf_recurrence_compare.py            # on the GPU box
 """
@@ -28,7 +29,7 @@ for nd in (100, 150):
     t0, dt = float(t[0]), span / (n - 1)
     sums = frf.moments_device(u_d, y_d, (0, n))
     res = {}
-    for which, name in ((0, "three_term"), (1, "goertzel")):
+    for which, name in ((0, "three_term"), (1, "goertzel"), (2, "dmma_goertzel")):
         lib.b200id_frf_select_recurrence(C.c_int(which))
         for _ in range(3):
             p = frf.project_uniform_device(t_d, u_d, y_d, w_d, t0, dt, (0, n), sums, 1.0 / n)
@@ -46,7 +47,12 @@ for nd in (100, 150):
     magy = np.hypot(a[2 * nd:3 * nd], a[3 * nd:])
     du = np.hypot(a[:nd] - b[:nd], a[nd:2 * nd] - b[nd:2 * nd]) / mag
     dy = np.hypot(a[2 * nd:3 * nd] - b[2 * nd:3 * nd], a[3 * nd:] - b[3 * nd:]) / magy
+    c = res["dmma_goertzel"]["partial"]
+    du2 = np.hypot(b[:nd] - c[:nd], b[nd:2 * nd] - c[nd:2 * nd]) / mag
+    dy2 = np.hypot(b[2 * nd:3 * nd] - c[2 * nd:3 * nd], b[3 * nd:] - c[3 * nd:]) / magy
     out[f"nd{nd}"] = {"three_term_ms": res["three_term"]["ms"], "goertzel_ms": res["goertzel"]["ms"],
+                      "dmma_goertzel_ms": res["dmma_goertzel"]["ms"],
+                      "max_rel_diff_dmma_vs_goertzel_u": float(du2.max()), "max_rel_diff_dmma_vs_goertzel_y": float(dy2.max()),
                       "ms_per_1e9_sample_bins": {k2: v["ms"] / (n * nd / 1e9) for k2, v in res.items()},
                       "max_rel_diff_u": float(du.max()), "max_rel_diff_y": float(dy.max())}
 lib.b200id_frf_select_recurrence(C.c_int(-1))

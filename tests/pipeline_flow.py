@@ -9,7 +9,7 @@ from sklearn.preprocessing import StandardScaler
 
 
 def run(train_mat, val_mat, out_dir, kernel="matern52", nd=50, noise=1e-6, optimize=False, grid=False,
-        max_comb=5000, n_restarts=3, mode="separate"):
+        max_comb=5000, n_restarts=3, mode="separate", kernel_kwargs=None):
     from src.frequency_transform.transform import estimate_frequency_response
     from src.frequency_transform.frf_estimator import (load_time_u_y, matlab_freq_grid, synchronous_coefficients_trapz,
                                                        frf_cross_power_average)
@@ -39,7 +39,7 @@ def run(train_mat, val_mat, out_dir, kernel="matern52", nd=50, noise=1e-6, optim
         return _run_polar(omega, G, Xs, Xn, frf, kernel, noise, optimize, grid, max_comb, n_restarts, val_mat, out_dir)
     fitted = []
     for target, scaler, vy in ((yr, ysr, vyr), (yi, ysi, vyi)):
-        gp = GaussianProcessRegressor(kernel=create_kernel(kernel), noise_variance=noise)
+        gp = GaussianProcessRegressor(kernel=create_kernel(kernel, **(kernel_kwargs or {})), noise_variance=noise)   # gp_pipeline.py:282-286
         gp.fit(Xn, target, optimize=optimize, n_restarts=n_restarts, use_grid_search=grid,
                max_grid_combinations=max_comb, validation_X=vX, validation_y=vy, y_scaler=scaler)
         pred, std = gp.predict(Xn, return_std=True)

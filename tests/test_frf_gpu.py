@@ -323,6 +323,9 @@ def test_cross_power_sums_and_gp_targets(frf, nd, R):
     assert stats.cpu().tolist() == [2.0, -3.0, 1.0, 1.0] and float(y_re.abs().max()) == 0.0
 
 
+BUDGET = 4e-10          # DA_BUDGET of csrc/frf_adaptive.cuh
+
+
 @pytest.mark.parametrize("n,nd,kind,t_shift", [(200_000, 100, "multisine", 0.0), (300_001, 150, "square", 0.0),
                                                (100_000, 50, "multisine", 1.9e6), (65_537, 150, "square", 123.4567),
                                                (4_097, 7, "multisine", 0.0), (70_000, 160, "square", -33.3)])
@@ -403,3 +406,154 @@ def test_goertzel_form_matches_three_term_and_oracle(frf, n, nd, kind, t_shift):
     assert record(f"frf.goertzel.{kind}.n{n}.segments", float((a1 + a2 - a).abs().max()) / scale) < 1e-12
     assert torch.equal(again, a), "deterministic run to run"
     assert torch.equal(only_u[:2 * nd], a[:2 * nd]), "u sums do not depend on whether y rides along"
+
+
+@pytest.mark.parametrize("n,nd,kind,t_shift", [(200_000, 100, "multisine", 0.0), (300_001, 150, "square", 0.0),
+                                               (100_000, 50, "multisine", 1.9e6), (65_537, 150, "square", 123.4567),
+                                               (4_097, 7, "multisine", 0.0), (70_000, 160, "square", -33.3),
+                                               (1_000_003, 100, "square", 0.0), (50_000, 601, "multisine", 0.0),
+                                               (1_537, 37, "square", 0.0), (1_000, 1, "multisine", 5.0)])
+def test_adaptive_form_matches_goertzel_and_oracle(frf, n, nd, kind, t_shift):
+    """The default evaluation of the uniform path (frf_adaptive.cuh: exact-phase main term of every bin as block-phasor
+    FP64 matrix products on the FP64 tensor pipe; the reference's per-sample phase-rounding term as a packed-FP32
+    Goertzel recurrence ONLY for the bins a device-side test finds weakly excited) against the all-recurrence Goertzel
+    kernel and the oracle, on the records that stress it: weak bins of the square-wave record, phases ~1e9 rad, ragged
+    tiles, bin counts that are not a multiple of 4, several bin groups, a single bin, negative times.  Run twice: with
+    the per-bin decision and with every bin listed (the decision may only ever skip what does not matter); run-to-run
+    determinism; sub-range calls (form 1) still add up to the whole-record call."""
+    import ctypes as C
+    import torch
+    from b200id import _lib, synth
+    from b200id.runtime import require_cuda, to_device
+    dev = require_cuda()
+    t, u, y = synth.make_record(n, min(nd, 100), kind, seed=5)
+    t = t + t_shift
+    _, w = ofrf.freq_grid(nd)
+    span = float(t[-1] - t[0])
+    t_d, u_d, y_d, w_d = (to_device(a, dev) for a in (t, u, y, w))
+    t0, dt = float(t[0]), span / (n - 1)
+    sums = frf.moments_device(u_d, y_d, (0, n))
+    lib = _lib.load()
+    prev = lib.b200id_frf_select_recurrence(C.c_int(2))
+    prev_force = lib.b200id_frf_adaptive_force(C.c_int(0))
+    try:
+        a = frf.project_uniform_device(t_d, u_d, y_d, w_d, t0, dt, (0, n), sums, 1.0 / n)
+        listed, worst_skipped = frf.adaptive_diag(nd, dev)
+        cut = n // 3 + 5
+        a1 = frf.project_uniform_device(t_d, u_d, y_d, w_d, t0, dt, (0, cut), sums, 1.0 / n)
+        a2 = frf.project_uniform_device(t_d, u_d, y_d, w_d, t0, dt, (cut, n), sums, 1.0 / n)
+        again = frf.project_uniform_device(t_d, u_d, y_d, w_d, t0, dt, (0, n), sums, 1.0 / n)
+        lib.b200id_frf_adaptive_force(C.c_int(1))
+        full = frf.project_uniform_device(t_d, u_d, y_d, w_d, t0, dt, (0, n), sums, 1.0 / n)
+        listed_full, _ = frf.adaptive_diag(nd, dev)
+        lib.b200id_frf_select_recurrence(C.c_int(1))
+        b = frf.project_uniform_device(t_d, u_d, y_d, w_d, t0, dt, (0, n), sums, 1.0 / n)
+    finally:
+        lib.b200id_frf_select_recurrence(C.c_int(prev))
+        lib.b200id_frf_adaptive_force(C.c_int(prev_force))
+    tag = f"frf.adaptive.{kind}.n{n}.nd{nd}.shift{t_shift:g}"
+    record(f"{tag}.bins_with_rounding_term", listed)
+    record(f"{tag}.worst_skipped_bound_over_budget", worst_skipped / BUDGET)
+    assert listed_full == nd and 0 <= listed <= nd and worst_skipped <= BUDGET
+    Ua, Ya = (x.cpu().numpy() for x in frf.finalize_device(a, nd, 2.0 / span))
+    Uf, Yf = (x.cpu().numpy() for x in frf.finalize_device(full, nd, 2.0 / span))
+    Ub, Yb = (x.cpu().numpy() for x in frf.finalize_device(b, nd, 2.0 / span))
+    Ur, Yr = ofrf.demod_trapz(t, u, w, threads=8), ofrf.demod_trapz(t, y, w, threads=8)
+    e_r = record(f"{tag}.vs_goertzel", max(rel_each(Ua, Ub), rel_each(Ya, Yb)))
+    e_o = record(f"{tag}.vs_oracle", max(rel_each(Ua, Ur), rel_each(Ya, Yr)))
+    e_f = record(f"{tag}.all_listed.vs_oracle", max(rel_each(Uf, Ur), rel_each(Yf, Yr)))
+    # what skipping cost: the adaptive result against the same kernels with every bin listed
+    record(f"{tag}.skipped_vs_all_listed", max(rel_each(Ua, Uf), rel_each(Ya, Yf)))
+    assert e_r < TOL and e_o < TOL and e_f < TOL
+    # sub-range calls run form 1 (every bin with its rounding term): against the whole-record call the sum differs by
+    # what the decision skipped, i.e. by less than the budget relative to the largest sum
+    scale = float(a.abs().max())
+    assert record(f"{tag}.segments", float((a1 + a2 - a).abs().max()) / scale) < BUDGET
+    assert torch.equal(again, a), "deterministic run to run"
+
+
+def test_adaptive_form_lists_by_excitation(frf):
+    """What the device-side decision does on the two kinds of record of BASELINE config 2: on a multisine record
+    whose lines sit on the bins only the weak output bins need the rounding term; on the square-wave record the weakly
+    excited input bins do as well.  A real timebase deviation (jitter far above the rounding level of t, here 5e-11 s against
+    ulp(t) ~ 1e-13 s) is never treated as noise: its first-order bound w_k sum |a_i delta_i| lists every bin but the few
+    lowest-frequency ones."""
+    import ctypes as C
+    from b200id import _lib, synth
+    from b200id.runtime import require_cuda, to_device
+    dev = require_cuda()
+    lib = _lib.load()
+    n = 500_000
+    out = {}
+    prev = lib.b200id_frf_select_recurrence(C.c_int(2))
+    prev_force = lib.b200id_frf_adaptive_force(C.c_int(0))
+    try:
+        for kind, nd, jitter in (("multisine", 100, 0.0), ("square", 150, 0.0), ("multisine", 100, 5e-11)):
+            t, u, y = synth.make_record(n, 100, kind, seed=11)
+            if jitter:
+                t = t + jitter * np.random.default_rng(3).standard_normal(n)
+            _, w = ofrf.freq_grid(nd)
+            span = float(t[-1] - t[0])
+            t_d, u_d, y_d, w_d = (to_device(a, dev) for a in (t, u, y, w))
+            t0, dt = float(t[0]), span / (n - 1)
+            sums = frf.moments_device(u_d, y_d, (0, n))
+            a = frf.project_uniform_device(t_d, u_d, y_d, w_d, t0, dt, (0, n), sums, 1.0 / n)
+            listed, _ = frf.adaptive_diag(nd, dev)
+            out[(kind, jitter)] = listed
+            Ua, Ya = (x.cpu().numpy() for x in frf.finalize_device(a, nd, 2.0 / span))
+            Ur, Yr = ofrf.demod_trapz(t, u, w, threads=8), ofrf.demod_trapz(t, y, w, threads=8)
+            e = record(f"frf.adaptive.listing.{kind}.jitter{jitter:g}.vs_oracle", max(rel_each(Ua, Ur), rel_each(Ya, Yr)))
+            lib.b200id_frf_select_recurrence(C.c_int(1))
+            b = frf.project_uniform_device(t_d, u_d, y_d, w_d, t0, dt, (0, n), sums, 1.0 / n)
+            lib.b200id_frf_select_recurrence(C.c_int(2))
+            Ub, Yb = (x.cpu().numpy() for x in frf.finalize_device(b, nd, 2.0 / span))
+            record(f"frf.adaptive.listing.{kind}.jitter{jitter:g}.form1_vs_oracle", max(rel_each(Ub, Ur), rel_each(Yb, Yr)))
+            record(f"frf.adaptive.listing.{kind}.jitter{jitter:g}.bins_with_rounding_term", listed)
+            assert e < TOL
+    finally:
+        lib.b200id_frf_select_recurrence(C.c_int(prev))
+        lib.b200id_frf_adaptive_force(C.c_int(prev_force))
+    # the multisine's lines are all excited in u; what is listed are the OUTPUT's bins above the plant's corner
+    # (|Y_k| rolls off as 1/f^4 there), about a third of the grid; the square wave adds its own weak input bins
+    assert 0 < out[("multisine", 0.0)] <= 45
+    assert out[("multisine", 0.0)] < out[("square", 0.0)] < 150
+    assert out[("multisine", 5e-11)] >= 80
+
+
+def test_adaptive_form_ill_conditioned_chain_step(frf):
+    """Listed bins whose Goertzel chain step is ill-conditioned (|sin(w R dt)| < 1e-3) take the FP32 rotation inside
+    the rounding-term kernel.  With every one of 50 bins listed its threads would walk R = 20 samples per step and the
+    kernel lowers R (up to five times) to get away from such bins; bins planted at w = m pi / (R dt) for EVERY R it
+    may try (20 ... 15) leave it no way out, so the rotation path runs; neighbours just inside and outside the
+    threshold ride along."""
+    import ctypes as C
+    from b200id import _lib, synth
+    from b200id.runtime import require_cuda, to_device
+    dev = require_cuda()
+    n, nd = 120_000, 50
+    t, u, y = synth.make_record(n, 100, "square", seed=9)
+    _, w = ofrf.freq_grid(nd)
+    w = w.copy()
+    dt_nom = 0.002
+    for i, R in enumerate(range(20, 14, -1)):
+        w[10 + i] = (1 + i % 3) * np.pi / (R * dt_nom)
+    w[30] = 3.0 * np.pi / (15 * dt_nom) * (1.0 - 2e-4)
+    w[49] = 2.0 * np.pi / (15 * dt_nom) * (1.0 + 1e-5)
+    span = float(t[-1] - t[0])
+    t_d, u_d, y_d, w_d = (to_device(a, dev) for a in (t, u, y, w))
+    t0, dt = float(t[0]), span / (n - 1)
+    sums = frf.moments_device(u_d, y_d, (0, n))
+    lib = _lib.load()
+    prev = lib.b200id_frf_select_recurrence(C.c_int(2))
+    prev_force = lib.b200id_frf_adaptive_force(C.c_int(1))
+    try:
+        a = frf.project_uniform_device(t_d, u_d, y_d, w_d, t0, dt, (0, n), sums, 1.0 / n)
+        listed, _ = frf.adaptive_diag(nd, dev)
+    finally:
+        lib.b200id_frf_select_recurrence(C.c_int(prev))
+        lib.b200id_frf_adaptive_force(C.c_int(prev_force))
+    assert listed == nd
+    Ua, Ya = (x.cpu().numpy() for x in frf.finalize_device(a, nd, 2.0 / span))
+    Ur, Yr = ofrf.demod_trapz(t, u, w, threads=8), ofrf.demod_trapz(t, y, w, threads=8)
+    e = record("frf.adaptive.ill_conditioned_step.vs_oracle", max(rel_each(Ua, Ur), rel_each(Ya, Yr)))
+    assert e < TOL

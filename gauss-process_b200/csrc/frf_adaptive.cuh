@@ -64,6 +64,8 @@ constexpr int DA_RESEED = 64;                    // tiles between exact re-seeds
 constexpr int DA_NORMS = 6;                      // {sum au^2, sum ay^2, sum au^2 ds^2, sum ay^2 ds^2, sum |au dr|, sum |ay dr|}
 constexpr size_t DA_SMEM_LIMIT = 115712;         // (228 KB - 2 x 1 KB) / 2: two CTAs per SM
 constexpr int DA_BPB = 64;                       // bins per CTA pass of the rounding-term kernel (stripes R >= 16)
+constexpr double DA_MAGIC = 4503599627370496.0 + 1262485504.0;   // 2^52 + 0x4B400000: low word of (DA_MAGIC + n) = bits of the float 2^23 + 2^22 + n
+constexpr float DA_MAGIC_F = 12582912.0f;                        // 2^23 + 2^22
 constexpr int DA_CM = DA_TS + DA_THREADS;        // entries of the chain-major arrays (R ceil(TS / R) < TS + R)
 #ifndef DA_SIGMAS
 #define DA_SIGMAS 4.0
@@ -433,8 +435,9 @@ __global__ void __launch_bounds__(DA_THREADS, 2)
 frf_round_goertzel_kernel(const double* __restrict__ t, const double* __restrict__ u, const double* __restrict__ y,
                           int64_t n, int64_t own_begin, int64_t own_end, const double* __restrict__ w, int nd,
                           const double* __restrict__ sums, double inv_count, double t0, double dt,
-                          const double* __restrict__ fit, int n_tiles, const int* __restrict__ flag_count,
-                          const int* __restrict__ flag_idx, double* __restrict__ cta_partial) {
+                          const double* __restrict__ fit, double tmax_abs, int n_tiles,
+                          const int* __restrict__ flag_count, const int* __restrict__ flag_idx,
+                          double* __restrict__ cta_partial) {
     const int nf = flag_count[0];
     if (nf <= 0) return;
     const DaRoundGeom geo = da_round_geom(nf, gridDim.x);
@@ -480,11 +483,17 @@ frf_round_goertzel_kernel(const double* __restrict__ t, const double* __restrict
     const bool active = r < R;
     const int kA = b2, kB = (b2 + nb2 < nb_all) ? b2 + nb2 : b2;     // odd count: the last pair's second bin is a dummy
 
-    const double wA = ws[kA], wB = ws[kB];
-    const float wAf = (float)wA, wBf = (float)wB;
-    const float2 sdA = SD[kA], sdB = SD[kB];
-    const float KA = 2.0f * sdA.x, KB = 2.0f * sdB.x;
-    const bool bad = fabsf(sdA.y) < (float)FRFU_SIN_MIN || fabsf(sdB.y) < (float)FRFU_SIN_MIN;
+    // The residual e = w t - fl(w t) reaches FP32 WITHOUT a conversion instruction (F2F.F32.F64 runs at a quarter of the
+    // FP64 rate and was the busiest pipe of this loop): with S_k = 2^21 / ulp(w_k t_max) a power of two, w' = w S gives
+    // p' = fl(w' t) = S fl(w t) and e' = fma(w', t, -p') = S e exactly, |e'| <= 2^20; adding 2^52 + 0x4B400000 rounds e'
+    // to an integer whose low word IS the FP32 number 2^23 + 2^22 + e'.  The recurrence then runs on S eps and the
+    // chain ends are scaled back by 1 / S.
+    const double SA = fmin(2097152.0 / da_ulp(ws[kA] * tmax_abs), 0x1p100), SB = fmin(2097152.0 / da_ulp(ws[kB] * tmax_abs), 0x1p100);
+    const double wSA = ws[kA] * SA, wSB = ws[kB] * SB;
+    const float wSAf = (float)wSA, wSBf = (float)wSB;
+    const float invSA = (float)(1.0 / SA), invSB = (float)(1.0 / SB);
+    const float KA = 2.0f * SD[kA].x, KB = 2.0f * SD[kB].x;
+    const bool bad = fabsf(SD[kA].y) < (float)FRFU_SIN_MIN || fabsf(SD[kB].y) < (float)FRFU_SIN_MIN;
     // float accumulators of the rounding term: (d S_c, d S_s) of u and y for bins A and B
     float2 gAc = make_float2(0.f, 0.f), gAs = gAc, gBc = gAc, gBs = gAc;      // .x: u, .y: y
 
@@ -526,9 +535,10 @@ frf_round_goertzel_kernel(const double* __restrict__ t, const double* __restrict
             // eps of one step for both bins: e = w t - fl(w t) exactly, narrowed, then w delta - e
 #define DA_EPS(tv, dv, eA, eB)                                                                       \
     {                                                                                                \
-        const double pA_ = wA * (tv), pB_ = wB * (tv);                                               \
-        const float fA_ = (float)fma(wA, (tv), -pA_), fB_ = (float)fma(wB, (tv), -pB_);              \
-        eA = fmaf(wAf, (dv), -fA_); eB = fmaf(wBf, (dv), -fB_);                                      \
+        const double pA_ = wSA * (tv), pB_ = wSB * (tv);                                             \
+        const double rA_ = fma(wSA, (tv), -pA_) + DA_MAGIC, rB_ = fma(wSB, (tv), -pB_) + DA_MAGIC;   \
+        eA = fmaf(wSAf, (dv), DA_MAGIC_F) - __int_as_float(__double2loint(rA_));                     \
+        eB = fmaf(wSBf, (dv), DA_MAGIC_F) - __int_as_float(__double2loint(rB_));                     \
     }
             // one Goertzel step of one bin: Q1 holds s[m-1], Q2 holds s[m-2] and receives s[m] = a eps + K s[m-1] - s[m-2]
 #define DA_STEP(av, e, K, Q1, Q2)                                                                    \
@@ -564,19 +574,20 @@ frf_round_goertzel_kernel(const double* __restrict__ t, const double* __restrict
             // is <= 1e-6 of the sum and needs three digits.
             const DD xl = da_time(tb, (double)(i0 + r + (int64_t)R * (M - 1)));
             // E = (s1 - cd s2) + j (sd s2);  d S_c = cl Ei - sl Er,  d S_s = sl Ei + cl Er
-#define DA_FOLD(wk, sd_, Q1, Q2, GC, GS)                                                             \
+#define DA_FOLD(k_, inv_, Q1, Q2, GC, GS)                                                            \
     {                                                                                                \
-        const double tr_ = (wk) * 0.15915494309189535 * xl.hi;                                       \
+        const double tr_ = ws[k_] * 0.15915494309189535 * xl.hi;                                     \
         const float fr_ = (float)(tr_ - rint(tr_));                                                  \
         float sl_, cl_;                                                                              \
         sincospif(2.0f * fr_, &sl_, &cl_);                                                           \
-        const float eru = fmaf(-sd_.x, Q2.x, Q1.x), eiu = sd_.y * Q2.x;                              \
-        const float ery = fmaf(-sd_.x, Q2.y, Q1.y), eiy = sd_.y * Q2.y;                              \
+        const float2 sd_ = SD[k_];                                                                   \
+        const float eru = (inv_) * fmaf(-sd_.x, Q2.x, Q1.x), eiu = (inv_) * (sd_.y * Q2.x);          \
+        const float ery = (inv_) * fmaf(-sd_.x, Q2.y, Q1.y), eiy = (inv_) * (sd_.y * Q2.y);          \
         GC.x += cl_ * eiu - sl_ * eru; GS.x += sl_ * eiu + cl_ * eru;                                \
         GC.y += cl_ * eiy - sl_ * ery; GS.y += sl_ * eiy + cl_ * ery;                                \
     }
-            DA_FOLD(wA, sdA, qA1, qA2, gAc, gAs)
-            DA_FOLD(wB, sdB, qB1, qB2, gBc, gBs)
+            DA_FOLD(kA, invSA, qA1, qA2, gAc, gAs)
+            DA_FOLD(kB, invSB, qB1, qB2, gBc, gBs)
 #undef DA_FOLD
         } else {
             // ill-conditioned chain step for one of this thread's bins: plain FP32 rotation along the chain
@@ -584,9 +595,9 @@ frf_round_goertzel_kernel(const double* __restrict__ t, const double* __restrict
             const DD x0 = da_time(tb, (double)(i0 + r));
 #pragma unroll 1
             for (int which = 0; which < 2; ++which) {
-                const double wk = which ? wB : wA;
-                const float wkf = which ? wBf : wAf;
-                const float2 sd = which ? sdB : sdA;
+                const double wk = ws[which ? kB : kA];
+                const float wkf = (float)wk;
+                const float2 sd = SD[which ? kB : kA];
                 double s0, c0;
                 sincos_dd(wk, x0, s0, c0);
                 float c = (float)c0, s = (float)s0;

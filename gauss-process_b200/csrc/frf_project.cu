@@ -1336,7 +1336,7 @@ extern "C" int b200id_frf_project_uniform(const double* t, const double* u, cons
                                                                     flag_count, flag_idx, diag);
         B200ID_LAUNCH_CHECK("frf_decide_kernel");
         frf_round_goertzel_kernel<<<n_cta, DA_THREADS, da_round_smem_bytes(), st>>>(t, u, y, n, own_begin, own_end, w, nd, sums, inv_count,
-                                                                                      t0, dt, fit, nt, flag_count, flag_idx, part);
+                                                                                      t0, dt, fit, tmax_abs, nt, flag_count, flag_idx, part);
         B200ID_LAUNCH_CHECK("frf_round_goertzel_kernel");
         frf_fold_add_kernel<<<dim3((nd + 31) / 32, 4), FOLD_WARPS * 32, 0, st>>>(part, n_cta, nd, flag_count, flag_idx, partial_out);
         B200ID_LAUNCH_CHECK("frf_fold_add_kernel");

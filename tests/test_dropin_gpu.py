@@ -5,6 +5,7 @@ import contextlib
 
 import numpy as np
 import pytest
+from oracle import gp as ogp
 
 from parity_util import rel_each, rel_max, record
 
@@ -89,8 +90,9 @@ def test_gpr_plain_fit_predict_and_errors(golden):
     np.testing.assert_allclose(K, g["gram_matern52_0"], rtol=2e-15)
     with pytest.raises(ValueError, match="Unknown kernel type"):
         create_kernel("laplace")
-    with pytest.raises(NotImplementedError):
-        create_kernel("matern", nu=0.7)(g["X"][:4])
+    # any other nu: the scipy.special.kv branch of kernels.py:131-135, evaluated on the device (tests/test_matern_nu_gpu.py)
+    K07 = create_kernel("matern", nu=0.7)(g["X"][:4])
+    np.testing.assert_allclose(K07, ogp.gram("matern_nu", [1.0, 1.0, 0.7], g["X"][:4]), rtol=1e-12)
 
 
 def test_gpr_lbfgs_path(golden):

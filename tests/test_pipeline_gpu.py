@@ -90,7 +90,9 @@ def test_identify_host_matches_identify_device(n, pinned):
     ref, got = _host_vs_device(t, u, y, tv, uv, yv, nd)
     assert np.array_equal(ref.theta_real, got.theta_real) and np.array_equal(ref.theta_imag, got.theta_imag)
     Gr, Gg = ref.G.cpu().numpy(), got.G.cpu().numpy()
-    assert record(f"identify_host.frf.{n}", float(np.max(np.abs(Gg - Gr) / np.abs(Gr)))) < 1e-11
+    # the resident pass projects whole records (bin-adaptive form: the rounding term of strongly excited bins is skipped
+    # within a 4e-10 budget per spectrum), the host pass projects pieces as they land (form 1, every bin's rounding term)
+    assert record(f"identify_host.frf.{n}", float(np.max(np.abs(Gg - Gr) / np.abs(Gr)))) < 1e-9
     tr, tg = ref.taps.cpu().numpy(), got.taps.cpu().numpy()
     assert record(f"identify_host.taps.{n}", float(np.max(np.abs(tg - tr)) / np.max(np.abs(tr)))) < 1e-8
     assert abs(got.fir["rmse"] - ref.fir["rmse"]) <= 1e-8 * ref.fir["rmse"]

@@ -57,6 +57,10 @@ SIGNATURES = {
     "b200id_gp_predict": (I, [I, P, P, I, P, P, P, I, P, P, P]),
     "b200id_chol_blocked_workspace_bytes": (Z, [I]),
     "b200id_chol_blocked": (I, [P, I, I, P, P, Z, P]),
+    "b200id_kr_workspace_bytes": (Z, [I, I]),
+    "b200id_kr_summaries": (I, [P, P, L, I, P, P, P, P, Z, P]),
+    "b200id_kr_nll_batch": (I, [I, P, I, P, P, D, D, I, D, P, P, P, Z, P]),
+    "b200id_kr_posterior": (I, [I, P, P, P, I, P, P, P, P, P, Z, P]),
     "b200id_idft_hermitian": (I, [P, I, P, I, P]),
     "b200id_fir_workspace_bytes": (Z, [L]),
     "b200id_fir_eval": (I, [P, P, L, L, P, I, L, D, P, P, P, Z, P]),

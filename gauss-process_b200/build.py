@@ -22,7 +22,7 @@ CSRC = PKG / "csrc"
 LIB_DIR = PKG / "lib"
 LIB = LIB_DIR / "libb200id.so"
 STAMP = LIB_DIR / "libb200id.stamp"
-SOURCES = ["capi.cu", "frf_project.cu", "gp_batch.cu", "gp_batch_tiled.cu", "gp_pinv.cu", "gp_large.cu", "chol_blocked.cu", "fir_conv.cu", "fir_fft.cu"]
+SOURCES = ["capi.cu", "frf_project.cu", "gp_batch.cu", "gp_batch_tiled.cu", "gp_pinv.cu", "gp_large.cu", "chol_blocked.cu", "fir_conv.cu", "fir_fft.cu", "kr_fir.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 

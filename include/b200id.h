@@ -273,6 +273,29 @@ int b200id_gp_predict(int kernel_id, const double* theta, const double* X, int n
 size_t b200id_chol_blocked_workspace_bytes(int n);
 int b200id_chol_blocked(double* A, int n, int lda, int* info_out, void* ws, size_t ws_bytes, void* stream);
 
+/* ------------------------------------------------------------------ kernel-regularised FIR (time domain)
+ * Reference src/fir_model/kernel_regularized.py.  kernel: 0 = 'dc' (theta = [log c, logit lam, atanh rho]),
+ * 1 = 'ss' ([log c, logit lam]), 2 = 'si' ([logit r, logit(omega / pi), log q, logit barlam]); every theta row
+ * carries log sigma^2 as its last entry (kernel_regularized.py:192-217, :236-238).
+ *
+ * b200id_kr_summaries: G = U^T U [L*L], b = U^T y [L], yy = y^T y [1] of the zero-padded Toeplitz regressor
+ * (:84-92, :337-340), all on the device.
+ * b200id_kr_nll_batch: negative log marginal likelihood (:224-261) of `batch` hyper-parameter points, one CTA each.
+ *   info_out[b]: 0 ok, 2 = S took the reference's 1e-6 fallback jitter (:246-250), 1 = K + jitter I not positive
+ *   definite, 3 = S not positive definite even so; nll_out[b] is NaN for 1 and 3 (the reference raises LinAlgError).
+ * b200id_kr_posterior: g_hat [L], sigma^2 [1] and (optionally) K [L*L] for one point (:264-291, jitter 1e-10);
+ *   with g_out == NULL only the covariance K of theta's kernel part is built (_build_kernel, :192-217).
+ * Workspace: b200id_kr_workspace_bytes(L, batch) (batch = 1 for summaries and posterior). */
+size_t b200id_kr_workspace_bytes(int L, int batch);
+int b200id_kr_summaries(const double* u, const double* y, int64_t n, int L, double* G_out, double* b_out,
+                        double* yy_out, void* ws, size_t ws_bytes, void* stream);
+int b200id_kr_nll_batch(int kernel, const double* theta /*[batch][kdim+1]*/, int batch, const double* G,
+                        const double* b, double yy, double n_samples, int L, double jitter, double* nll_out,
+                        int* info_out, void* ws, size_t ws_bytes, void* stream);
+int b200id_kr_posterior(int kernel, const double* theta /*[kdim+1]*/, const double* G, const double* b, int L,
+                        double* g_out, double* K_out /*may be NULL*/, double* sig2_out, int* info_out, void* ws,
+                        size_t ws_bytes, void* stream);
+
 /* ------------------------------------------------------------------ FIR (K5, K6)
  * h[m] = Re( (1/M) sum_k X[k] e^{+2 pi j k m / M} ), m < n_taps, with X the two-sided Hermitian
  * extension of G_pos (M = 2 nd - 1, X[0] = Re G[0]).  fir_helpers.py:75-137. */

@@ -13,6 +13,7 @@ from __future__ import annotations
 
 import argparse
 import io
+import math
 import contextlib
 import os
 import sys
@@ -522,6 +523,48 @@ def golden_run_baseline(out: Path):
     print("run_baseline.npz", len(d), "arrays")
 
 
+def golden_kr(out: Path):
+    """Kernel-regularised FIR (src/fir_model/kernel_regularized.py): regressor summaries, the three covariances behind
+    the unconstrained parameters, the marginal likelihood at scattered hyper-parameter points (including ones that
+    take the 1e-6 fallback jitter), the posterior mean, and whole run_fir_experiment runs (L-BFGS-B multi-start) on the
+    reference's own synthetic fallback data and on a .mat record."""
+    from src.fir_model import kernel_regularized as R_kr
+    d = {"versions": VERSIONS}
+    rng = np.random.default_rng(3)
+    t, u, y = synth.make_record(6000, 50, "multisine", seed=4)
+    u, y = u - u.mean(), y - y.mean()
+    d["u"], d["y"] = u, y
+    theta0 = {"dc": [math.log(1.0), math.log(0.98 / 0.02), np.arctanh(0.8)], "ss": [math.log(1.0), math.log(0.96 / 0.04)],
+              "si": [math.log(0.98 / 0.02), math.log(0.25), math.log(1e-2), math.log(0.96 / 0.04)]}
+    for L in (24, 128):
+        U = R_kr._build_regressor(u, L)
+        G, b, yy = U.T @ U, U.T @ y, float(y @ y)
+        d[f"G_{L}"], d[f"b_{L}"], d[f"yy_{L}"] = G, b, np.array([yy])
+        for kname, th0 in theta0.items():
+            pts = [np.array(th0 + [math.log(1e-2)])]
+            for _ in range(7):
+                pts.append(pts[0] + np.concatenate([0.6 * rng.standard_normal(len(th0)), [2.0 * rng.standard_normal()]]))
+            pts = np.array(pts)
+            d[f"theta_{kname}_{L}"] = pts
+            d[f"nll_{kname}_{L}"] = np.array([R_kr._nll(p, G, b, yy, len(u), L, kname) for p in pts])
+            d[f"K_{kname}_{L}"] = R_kr._build_kernel(L, kname, pts[1][:len(th0)])
+            g_hat, sig2, K = R_kr._posterior_mean_g(pts[0], G, b, L, kname)
+            d[f"ghat_{kname}_{L}"], d[f"sig2_{kname}_{L}"] = g_hat, np.array([sig2])
+    tmp = Path(tempfile.mkdtemp(prefix="b200id_golden_kr_"))
+    mat = synth.write_mat(tmp / "io.mat", t, u + 0.3, y - 0.1)
+    for kname, L, src in (("dc", 48, "synthetic"), ("ss", 32, "synthetic"), ("si", 24, "synthetic"), ("dc", 64, "mat")):
+        cfg = R_kr.FIRConfig(io_mat=(mat if src == "mat" else tmp / "missing.mat"), out_dir=tmp / f"out_{kname}_{L}_{src}",
+                             kernel=kname, L=L, multi_starts=2, maxiter=60)
+        res = quiet(R_kr.run_fir_experiment, cfg)
+        co = np.load(res["coeff_npz"])
+        tag = f"run_{kname}_{L}_{src}"
+        d[f"{tag}_ghat"], d[f"{tag}_K"] = co["g_hat"], co["K"]
+        d[f"{tag}_metrics"] = np.array([res["rmse"], res["nrmse"], res["r2"], res["fit_percent"], res["sigma2"]])
+    d["mat_t"], d["mat_u"], d["mat_y"] = t, u + 0.3, y - 0.1
+    np.savez_compressed(out / "kr_fir.npz", **d)
+    print("kr_fir.npz", len(d), "arrays")
+
+
 def main():
     ap_ = argparse.ArgumentParser()
     ap_.add_argument("--out", default=str(ROOT / "tests" / "golden"))
@@ -529,7 +572,7 @@ def main():
     a = ap_.parse_args()
     out = Path(a.out); out.mkdir(parents=True, exist_ok=True)
     todo = {"frf": golden_frf, "gp": golden_gp, "fir": golden_fir, "pipeline": golden_pipeline, "fourier": golden_fourier,
-            "pipeline_polar": golden_pipeline_polar, "run_baseline": golden_run_baseline, "matern_nu": golden_matern_nu}
+            "pipeline_polar": golden_pipeline_polar, "run_baseline": golden_run_baseline, "matern_nu": golden_matern_nu, "kr": golden_kr}
     for name, fn in todo.items():
         if a.only and name not in a.only.split(","):
             continue

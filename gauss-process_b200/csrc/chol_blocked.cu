@@ -15,6 +15,7 @@
 // so the forward substitution of the solve costs no launch of its own (cholb_factor_rows; gp_large.cu).
 // One factorisation is a chain of 2 n / 64 dependent launches, i.e. latency bound at n = 2048 (1.9 ms where the flops
 // alone would take 0.1 ms); throughput comes from running several candidates side by side (gp_large.cu).
+#include <stdint.h>
 #include "common.cuh"
 #include "gp_linalg.cuh"
 
@@ -64,84 +65,102 @@ __device__ __forceinline__ void stage_tile_kmajor(const double* __restrict__ M, 
 }
 
 // (1) diagonal block: factorise in shared memory, write L back.
-// This kernel is the serial link of the factorisation (one CTA, n / 64 times), so it is written for latency:
-// right-looking with ONE barrier per column -- the scaled column goes to the unused upper triangle, so nobody
-// overwrites what the trailing update of the same step still reads; each thread forms l_i = a_ik * (1/d) itself (the
-// same product the scaled column holds: potf2's SCAL + SYR arithmetic).
+// This routine is the serial link of the factorisation (one CTA, n / 64 times), so it is written for latency.
 constexpr int CB_LDD = CB_NB + 1;
-// Factorises the nb x nb block held in D (lower triangle, column-major D[j * CB_LDD + i]) and writes L to
-// A[k0 + i][k0 + j].  Once column j is final its scaled copy L[i][j] goes to the UPPER triangle at D[i * CB_LDD + j]
-// (i > j) and the pivot root to dg[j], so the trailing update of the same step still reads the unscaled column.
-// All CB_THREADS threads call; D must be complete (caller synchronised).  Returns false on a failed pivot.
+// Factorises the nb x nb block held in D (lower triangle, column-major D[j * CB_LDD + i]) in place and writes L to
+// A[k0 + i][k0 + j].  All CB_THREADS threads call; D must be complete (caller synchronised); dg needs 17 doubles.
+// Returns false on a failed pivot.
 __device__ __forceinline__ bool cholb_factor_block(double* __restrict__ D, double* __restrict__ dg, int nb,
                                                    double* __restrict__ A, int lda, int k0, int* __restrict__ info) {
+    // Two-level: four 16-wide block columns.  Per block column
+    //   (i)   warp 0 factorises the 16 x 16 diagonal sub-block in REGISTERS (lane = row, columns broadcast by shuffle:
+    //         the only serial latency per pivot is one rsqrt + Newton pair, no barrier),
+    //   (ii)  one thread per row below solves x L^T = a by forward substitution in registers (reciprocal diagonal),
+    //   (iii) all threads apply the rank-16 update to what is left.
+    // 12 block barriers per 64 x 64 block instead of 64 (this routine is the serial link of the whole factorisation:
+    // 39 us -> measured in profiles/r02_chol_blocked.txt).  dg[0..15] holds the reciprocal pivots of the current
+    // sub-block, dg[16] the failure flag.
     constexpr int ld = CB_LDD;
-    const int tid = threadIdx.x;
-    // thread (ty, tx) of a 16 x 16 grid owns rows i = ty (mod 16) and columns j = tx (mod 16): no index division in the
-    // loop that runs once per pivot
-    const int ty = tid >> 4, tx = tid & 15;
-    for (int k = 0; k < nb; ++k) {
-        const double* colk = D + k * ld;
-        const double piv = colk[k];
-        // pivot <= 0 or +inf -> failure, NaN goes on: the rule of chol_smem (gp_linalg.cuh); every thread reads the
-        // same value, so the branch is uniform
-        if (piv <= 0.0 || piv == INFINITY) {
-            if (tid == 0) info[0] = k0 + k + 1;
-            return false;
-        }
-        // 1 / sqrt(piv): hardware approximation (2^-22) + two Newton steps -- the shortest dependent chain that reaches
-        // 1 ulp; the root itself (only stored) is taken off the critical path
-        double inv;
-        asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(inv) : "d"(piv));
-        inv = fma(0.5 * inv, fma(-piv * inv, inv, 1.0), inv);
-        inv = fma(0.5 * inv, fma(-piv * inv, inv, 1.0), inv);
-        if (tid == 0) {
-            double d = piv * inv;
-            d = fma(0.5 * inv, fma(-d, d, piv), d);
-            dg[k] = d;
-        }
-        // loads first, then the FMAs, then the stores: a shared-memory store keeps the compiler from moving later loads
-        // of the same array above it, which would serialise the 16 element updates of a thread
-        double lj[4], li[4], dv[4][4];
+    constexpr int SB = 16;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) dg[SB] = 0.0;
+    __syncthreads();
+    for (int c0 = 0; c0 < nb; c0 += SB) {
+        const int w = min(SB, nb - c0);
+        if (warp == 0) {
+            double d[SB];
 #pragma unroll
-        for (int b = 0; b < 4; ++b) {
-            const int j = tx + 16 * b;
-            lj[b] = (j > k && j < nb) ? colk[j] : 0.0;
-        }
+            for (int c = 0; c < SB; ++c) d[c] = (lane < w && c <= lane) ? D[(c0 + c) * ld + c0 + lane] : 0.0;
+            int fail = 0;
 #pragma unroll
-        for (int a = 0; a < 4; ++a) {
-            const int i = ty + 16 * a;
-            li[a] = (i > k && i < nb) ? colk[i] : 0.0;
+            for (int k = 0; k < SB; ++k) {
+                if (k < w && fail == 0) {
+                    const double piv = __shfl_sync(0xffffffffu, d[k], k);
+                    if (piv <= 0.0 || piv == INFINITY) {           // NaN compares false: the factorisation goes on
+                        fail = k + 1;
+                    } else {
+                        double inv = rsqrt(piv);
+                        double dk = piv * inv;
+                        dk = fma(0.5 * inv, fma(-dk, dk, piv), dk);
+                        inv = fma(inv, fma(-dk, inv, 1.0), inv);
+                        const double l = (lane == k) ? dk : d[k] * inv;
+                        d[k] = l;
+                        if (lane == k) dg[k] = inv;
 #pragma unroll
-            for (int b = 0; b < 4; ++b) {
-                const int j = tx + 16 * b;
-                dv[a][b] = (i > k && i < nb && j > k && j <= i) ? D[j * ld + i] : 0.0;
+                        for (int c = k + 1; c < SB; ++c) {
+                            const double lc = __shfl_sync(0xffffffffu, l, c);
+                            d[c] = fma(-l, lc, d[c]);
+                        }
+                    }
+                }
             }
-        }
-        const double lnew = (k + 1 + tid < nb) ? colk[k + 1 + tid] * inv : 0.0;
+            if (fail != 0) {
+                if (lane == 0) { dg[SB] = 1.0; info[0] = k0 + c0 + fail; }
+            } else {
 #pragma unroll
-        for (int b = 0; b < 4; ++b) lj[b] *= inv;
-#pragma unroll
-        for (int a = 0; a < 4; ++a) {
-            li[a] *= inv;
-#pragma unroll
-            for (int b = 0; b < 4; ++b) dv[a][b] = fma(-li[a], lj[b], dv[a][b]);
-        }
-        if (k + 1 + tid < nb) D[(k + 1 + tid) * ld + k] = lnew;
-#pragma unroll
-        for (int a = 0; a < 4; ++a) {
-            const int i = ty + 16 * a;
-#pragma unroll
-            for (int b = 0; b < 4; ++b) {
-                const int j = tx + 16 * b;
-                if (i > k && i < nb && j > k && j <= i) D[j * ld + i] = dv[a][b];
+                for (int c = 0; c < SB; ++c)
+                    if (lane < w && c <= lane) D[(c0 + c) * ld + c0 + lane] = d[c];
             }
         }
         __syncthreads();
+        if (dg[SB] != 0.0) return false;
+        const int below = nb - (c0 + w);
+        if (below > 0) {
+            if (tid < below) {
+                const int i = c0 + w + tid;
+                double x[SB];
+#pragma unroll
+                for (int c = 0; c < SB; ++c) {
+                    if (c < w) {
+                        double v = D[(c0 + c) * ld + i];
+#pragma unroll
+                        for (int k = 0; k < c; ++k) v = fma(-x[k], D[(c0 + k) * ld + c0 + c], v);
+                        x[c] = v * dg[c];
+                    } else {
+                        x[c] = 0.0;
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < SB; ++c)
+                    if (c < w) D[(c0 + c) * ld + i] = x[c];
+            }
+            __syncthreads();
+            // rank-w update of the lower triangle of rows / columns [c0 + w, nb): thread (ty, tx) of a 16 x 16 grid
+            const int ty = tid >> 4, tx = tid & 15, base = c0 + w;
+            for (int i = base + ty; i < nb; i += 16)
+                for (int j = base + tx; j <= i; j += 16) {
+                    double v = D[j * ld + i];
+#pragma unroll
+                    for (int k = 0; k < SB; ++k)
+                        if (k < w) v = fma(-D[(c0 + k) * ld + i], D[(c0 + k) * ld + j], v);
+                    D[j * ld + i] = v;
+                }
+            __syncthreads();
+        }
     }
     for (int e = tid; e < CB_NB * CB_NB; e += CB_THREADS) {
         const int i = e >> 6, j = e & 63;
-        if (i < nb && j <= i) A[(size_t)(k0 + i) * lda + k0 + j] = (i == j) ? dg[i] : D[i * ld + j];
+        if (i < nb && j <= i) A[(size_t)(k0 + i) * lda + k0 + j] = D[j * ld + i];
     }
     return true;
 }
@@ -383,7 +402,7 @@ __device__ __forceinline__ void stage_half_async(const double* __restrict__ M, i
 #endif
 __global__ void __launch_bounds__(CB_THREADS, CB_SYRK_CTAS)
 cholb_syrk_mma_kernel(double* __restrict__ A, int lda, int n, int n_rows, int k0, int* __restrict__ info,
-                      size_t a_stride, size_t info_stride) {
+                      size_t a_stride, size_t info_stride, int first_column_only) {
     extern __shared__ __align__(16) double cb_sm[];
     double* As = cb_sm;
     double* Bs = cb_sm + CB_NB * CB_LDR;
@@ -391,10 +410,14 @@ cholb_syrk_mma_kernel(double* __restrict__ A, int lda, int n, int n_rows, int k0
     info += blockIdx.z * info_stride;
     if (info[0] != 0) return;
     const int lin = blockIdx.x;
-    int ti = (int)((sqrt(8.0 * lin + 1.0) - 1.0) * 0.5);
-    while ((ti + 1) * (ti + 2) / 2 <= lin) ++ti;
-    while (ti * (ti + 1) / 2 > lin) --ti;
-    const int tj = lin - ti * (ti + 1) / 2;
+    // first_column_only: the grid is one CTA per tile ROW and only the first block column of the trailing matrix is
+    // updated (the second half of a 128-wide super-panel; the rest waits for the rank-128 update below)
+    int ti = first_column_only ? lin : (int)((sqrt(8.0 * lin + 1.0) - 1.0) * 0.5);
+    if (!first_column_only) {
+        while ((ti + 1) * (ti + 2) / 2 <= lin) ++ti;
+        while (ti * (ti + 1) / 2 > lin) --ti;
+    }
+    const int tj = first_column_only ? 0 : lin - ti * (ti + 1) / 2;
     const int s = k0 + CB_NB;
     const int r0 = s + ti * CB_NB, c0 = s + tj * CB_NB;
 #if CB_CPASYNC
@@ -488,6 +511,174 @@ cholb_syrk_mma_kernel(double* __restrict__ A, int lda, int n, int n_rows, int k0
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// (3') rank-128 trailing update over 128 x 64 tiles: A[i, j] -= P_i P_j^T with P = the 128-wide super-panel
+// [k0, k0 + 128), tiles of the matrix starting at s = k0 + 128 that touch its lower triangle.  Twice the panel width
+// and twice the tile area of cholb_syrk_mma_kernel: 6.4 flop per byte moved instead of 4, half as many dependent
+// update launches.  Operands arrive by TMA bulk copies (cp.async.bulk, one 256-byte row segment each, completion
+// counted on an mbarrier) in four k-chunks of 32 through a two-stage ring: the copy of chunk c + 2 is issued as soon as
+// chunk c has been multiplied and lands under the DMMAs of chunk c + 1; no thread spends registers or issue slots on
+// staging.  8 warps, warp (wy, wx) owns rows [32 wy, +32) x columns [32 wx, +32) of the tile = 4 x 4 accumulator
+// fragments: 8 conflict-free LDS.64 feed 16 DMMAs.  Two CTAs per SM, so one CTA's prologue and read-modify-write of C
+// run under the other's products.
+constexpr int CW_TM = 128;                // tile rows and panel width
+constexpr int CW_TN = 64;                 // tile columns
+constexpr int CW_KC = 32;                 // k-chunk
+constexpr int CW_NCHUNK = CW_TM / CW_KC;  // 4
+constexpr int CW_STAGES = 2;
+constexpr int CW_THREADS = 256;
+constexpr int CW_LD = CW_KC + 4;          // row pitch of a staged chunk (doubles): 288 bytes, fragments conflict-free
+constexpr size_t CW_STAGE_DOUBLES = (size_t)(CW_TM + CW_TN) * CW_LD;
+constexpr size_t CW_SMEM_BYTES = CW_STAGES * CW_STAGE_DOUBLES * sizeof(double) + 64;
+
+__device__ __forceinline__ unsigned cw_smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cw_mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void cw_mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cw_bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void cw_mbar_wait(unsigned bar, unsigned parity) {
+    unsigned ok = 0;
+    while (!ok) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    }
+}
+// tiles of a trailing matrix of t128 row tiles: row tile ti has column tiles tj = 0 .. 2 ti + 1
+__host__ __device__ inline int cw_tile_count(int t128) { return t128 * (t128 + 1); }
+
+__global__ void __launch_bounds__(CW_THREADS, 2)
+cholb_syrk_wide_kernel(double* __restrict__ A, int lda, int n, int n_rows, int k0, int* __restrict__ info,
+                       size_t a_stride, size_t info_stride) {
+    extern __shared__ __align__(128) double cb_sm[];
+    A += blockIdx.z * a_stride;
+    info += blockIdx.z * info_stride;
+    if (info[0] != 0) return;
+    const int lin = blockIdx.x;
+    int ti = (int)((sqrt(4.0 * lin + 1.0) - 1.0) * 0.5);
+    while ((ti + 1) * (ti + 2) <= lin) ++ti;
+    while (ti * (ti + 1) > lin) --ti;
+    const int tj = lin - ti * (ti + 1);
+    const int s = k0 + CW_TM;
+    const int r0 = s + ti * CW_TM, c0 = s + tj * CW_TN;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int validA = max(0, min(CW_TM, n_rows - r0)), validB = max(0, min(CW_TN, n - c0));
+    if (validB == 0) return;                                      // tile entirely right of the matrix
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(cb_sm + CW_STAGES * CW_STAGE_DOUBLES);
+
+    // rows past the matrix are never copied: they stay zero in every stage
+    for (int e = tid; e < CW_STAGES * (CW_TM + CW_TN); e += CW_THREADS) {
+        const int st = e / (CW_TM + CW_TN), row = e - st * (CW_TM + CW_TN);
+        const bool is_b = row >= CW_TM;
+        const int rr = is_b ? row - CW_TM : row;
+        if (rr >= (is_b ? validB : validA)) {
+            double* dst = cb_sm + st * CW_STAGE_DOUBLES + (size_t)row * CW_LD;
+            for (int k = 0; k < CW_LD; ++k) dst[k] = 0.0;
+        }
+    }
+    if (tid == 0) {
+        for (int st = 0; st < CW_STAGES; ++st) cw_mbar_init(cw_smem_addr(bars + st), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+
+    // chunk c -> stage c % 2: A rows r0.. and B rows c0.., columns [k0 + 32 c, +32).  Every warp issues the copies of
+    // its own 24 rows (a bulk copy takes its addresses from uniform registers, so a warp issues its lanes' copies one
+    // after the other: spread over the 8 warps that is 24 short issues each instead of 192 on one warp that also has
+    // products to do); thread 0 arms the barrier with the byte count -- the transaction count may run negative until
+    // then, the phase cannot complete before thread 0's arrival.
+    auto issue = [&](int c) {
+        const int st = c % CW_STAGES;
+        const unsigned bar = cw_smem_addr(bars + st);
+        double* base = cb_sm + st * CW_STAGE_DOUBLES;
+        if (tid == 0) cw_mbar_expect_tx(bar, (unsigned)((validA + validB) * CW_KC * sizeof(double)));
+        constexpr int ROWS_PER_WARP = (CW_TM + CW_TN) / (CW_THREADS / 32);
+        if (lane < ROWS_PER_WARP) {
+            const int row = warp * ROWS_PER_WARP + lane;
+            const bool is_b = row >= CW_TM;
+            const int rr = is_b ? row - CW_TM : row;
+            if (rr < (is_b ? validB : validA)) {
+                const double* src = A + (size_t)((is_b ? c0 : r0) + rr) * lda + k0 + CW_KC * c;
+                cw_bulk_g2s(cw_smem_addr(base + (size_t)row * CW_LD), src, CW_KC * sizeof(double), bar);
+            }
+        }
+    };
+    issue(0); issue(1);
+    const int wy = warp >> 1, wx = warp & 1, fr = lane >> 2, fk = lane & 3;
+    double acc[4][4][2] = {};
+#pragma unroll 1
+    for (int c = 0; c < CW_NCHUNK; ++c) {
+        const int st = c % CW_STAGES;
+        cw_mbar_wait(cw_smem_addr(bars + st), (unsigned)((c / CW_STAGES) & 1));
+        const double* pa = cb_sm + st * CW_STAGE_DOUBLES + (size_t)(32 * wy + fr) * CW_LD + fk;
+        const double* pb = cb_sm + st * CW_STAGE_DOUBLES + (size_t)(CW_TM + 32 * wx + fr) * CW_LD + fk;
+#pragma unroll 2
+        for (int kk = 0; kk < CW_KC; kk += 4) {
+            double a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = pa[8 * i * CW_LD + kk];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = pb[8 * j * CW_LD + kk];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        }
+        if (c + CW_STAGES < CW_NCHUNK) {
+            // this stage is free once every warp has finished the chunk: refill it with chunk c + 2
+            __syncthreads();
+            issue(c + CW_STAGES);
+        }
+    }
+    if (lin == 0) {
+        // tile (0, 0) holds the NEXT diagonal block (its top 64 rows): update it with plain loads and factorise it
+        // here, so the serial chain of the factorisation has no launch of its own for it
+        __syncthreads();                                         // every warp is done with the staged operands
+        double* D = cb_sm;
+        double* dg = cb_sm + CB_NB * CB_LDD;
+        const int nb = min(CB_NB, n - s);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int ii = 32 * wy + 8 * i + fr, r = r0 + ii;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int jj = 32 * wx + 8 * j + 2 * fk + q, c = c0 + jj;
+                    if (r < n_rows && c <= r && c < n) {
+                        const double v = A[(size_t)r * lda + c] - acc[i][j][q];
+                        if (ii < nb) D[jj * CB_LDD + ii] = v;
+                        else A[(size_t)r * lda + c] = v;
+                    }
+                }
+        }
+        __syncthreads();
+        cholb_factor_block(D, dg, nb, A, lda, s, const_cast<int*>(info));
+        return;
+    }
+    // C -= acc on the lower triangle (c <= r), inside the matrix.  Every element has exactly one contribution per
+    // launch, so the subtraction is handed to the L2 as a reduction (RED.ADD.F64: same IEEE addition, same result):
+    // nothing waits for a load of C, and C never occupies a register.
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int r = r0 + 32 * wy + 8 * i + fr;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int c = c0 + 32 * wx + 8 * j + 2 * fk + q;
+                if (r < n_rows && c <= r && c < n) atomicAdd(A + (size_t)r * lda + c, -acc[i][j][q]);
+            }
+    }
+}
+
 }  // namespace b200id
 
 using namespace b200id;
@@ -518,9 +709,40 @@ int cholb_factor_rows(double* A, int n, int n_rows, int lda, int* info_out, cuda
     if (rc) return rc;
     rc = check_cuda(cudaFuncSetAttribute(cholb_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute(syrk)");
     if (rc) return rc;
+    rc = check_cuda(cudaFuncSetAttribute(cholb_syrk_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CW_SMEM_BYTES), "cudaFuncSetAttribute(syrk wide)");
+    if (rc) return rc;
+    static int use_wide = -1;                    // B200ID_CHOL_WIDE=0: 64-wide updates only (round-1 schedule, timing comparisons)
+    if (use_wide < 0) { const char* e = getenv("B200ID_CHOL_WIDE"); use_wide = (e && e[0] == '0') ? 0 : 1; }
+    // the bulk copies and the paired stores of the wide update need 16-byte aligned row segments
+    const bool aligned = (lda % 2 == 0) && (a_stride % 2 == 0) && (((uintptr_t)A & 15) == 0);
+    const bool wide = use_wide && use_mma && aligned;
     // the first diagonal block has a launch of its own; every later one is factorised by the update kernel of the
     // block column before it (CTA of tile (0, 0))
     cholb_diag_kernel<<<dim3(1, 1, batch), CB_THREADS, 0, st>>>(A, lda, n, 0, info_out, a_stride, info_stride);
+    if (wide) {
+        // super-panels of 128 columns: panel | update of the second block column (its tile (0, 0) factorises the next
+        // diagonal block) | panel | rank-128 update of everything to the right (tile (0, 0) factorises the next one)
+        for (int k0 = 0; k0 < n; k0 += CW_TM) {
+            for (int h = 0; h < 2; ++h) {
+                const int kk = k0 + h * CB_NB;
+                if (kk >= n) break;
+                const int nb = n - kk < CB_NB ? n - kk : CB_NB;
+                const int below = n_rows - (kk + nb);
+                if (below <= 0) break;
+                cholb_panel_kernel<<<dim3((below + CB_NB - 1) / CB_NB, 1, batch), CB_THREADS, smem_panel, st>>>(A, lda, n, n_rows, kk, info_out, a_stride, info_stride);
+                if (h == 0 && n - (kk + CB_NB) > 0) {
+                    const int tiles = (n_rows - (kk + CB_NB) + CB_NB - 1) / CB_NB;
+                    cholb_syrk_mma_kernel<<<dim3(tiles, 1, batch), CB_THREADS, smem, st>>>(A, lda, n, n_rows, kk, info_out, a_stride, info_stride, 1);
+                }
+            }
+            if (n - (k0 + CW_TM) > 0) {
+                const int t128 = (n_rows - (k0 + CW_TM) + CW_TM - 1) / CW_TM;
+                cholb_syrk_wide_kernel<<<dim3(cw_tile_count(t128), 1, batch), CW_THREADS, CW_SMEM_BYTES, st>>>(A, lda, n, n_rows, k0, info_out, a_stride, info_stride);
+            }
+        }
+        B200ID_LAUNCH_CHECK("chol_blocked kernels");
+        return B200ID_OK;
+    }
     for (int k0 = 0; k0 < n; k0 += CB_NB) {
         const int nb = n - k0 < CB_NB ? n - k0 : CB_NB;
         const int below = n_rows - (k0 + nb);                // rows under this diagonal block (incl. extra rows)
@@ -529,7 +751,7 @@ int cholb_factor_rows(double* A, int n, int n_rows, int lda, int* info_out, cuda
         if (n - (k0 + CB_NB) > 0) {                           // trailing columns left
             const int tiles = (n_rows - (k0 + CB_NB) + CB_NB - 1) / CB_NB;
             if (use_mma)
-                cholb_syrk_mma_kernel<<<dim3(tiles * (tiles + 1) / 2, 1, batch), CB_THREADS, smem, st>>>(A, lda, n, n_rows, k0, info_out, a_stride, info_stride);
+                cholb_syrk_mma_kernel<<<dim3(tiles * (tiles + 1) / 2, 1, batch), CB_THREADS, smem, st>>>(A, lda, n, n_rows, k0, info_out, a_stride, info_stride, 0);
             else
                 cholb_syrk_kernel<<<dim3(tiles * (tiles + 1) / 2, 1, batch), CB_THREADS, smem, st>>>(A, lda, n, n_rows, k0, info_out, a_stride, info_stride);
         }

@@ -53,7 +53,8 @@ N_TAPS = 1024
 VAL_ND = 150
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures
 # (profiles/r01_ncu_*.txt), 10^7-sample record: FRF reads t,u,y once (240 MB), FIR reads u,y (160 MB)
-NCU_TRAFFIC_BYTES = {"frf_project_uniform_g_kernel": 245.9e6, "fir_fft16_kernel": 167.5e6, "frf_project_uniform3_kernel": 245.2e6, "frf_project_uniform_kernel": 245.2e6, "frf_project_kernel": 245.3e6, "fir_eval_kernel": 167.3e6,
+NCU_TRAFFIC_BYTES = {"frf_main_dmma_kernel": 240.0e6, "frf_round_goertzel_kernel": 240.1e6, "frf_timebase_fit_kernel": 80.0e6,
+                     "frf_project_uniform_g_kernel": 245.9e6, "fir_fft16_kernel": 167.5e6, "frf_project_uniform3_kernel": 245.2e6, "frf_project_uniform_kernel": 245.2e6, "frf_project_kernel": 245.3e6, "fir_eval_kernel": 167.3e6,
                      "fir_fft_kernel": 163.6e6, "gp_batch_tiled_kernel": 0.33e6}
 FRF_BYTES_PER_SAMPLE = 24        # t, u, y FP64 read once
 FIR_BYTES_PER_SAMPLE = 16        # u, y FP64 read once, y_pred not materialised
@@ -265,6 +266,49 @@ def run_reference_arm(a, rank, world):
 
 
 # ------------------------------------------------------------------------------------------------
+def measure_frf_phases(dev_recs, a, dev):
+    """{frf_main_ms, frf_main_tflops, frf_round_ms, bins listed} of one step's two b200id_frf_project_uniform calls."""
+    import ctypes as C
+    import torch
+    from b200id import _lib, frf as bfrf, pipeline as P
+    from b200id.runtime import to_device
+    lib = _lib.load()
+    out = {}
+    recs = [("train", dev_recs[0], a.nd), ("val", dev_recs[1], VAL_ND)]
+    tot = {"full": 0.0, "main": 0.0}
+    listed = {}
+    for tag, rec, nd in recs:
+        t_d, u_d, y_d = rec[0], rec[1], rec[2]
+        n = t_d.numel()
+        w_d = to_device(P.log_grid_omega(nd), dev)
+        t0 = float(t_d[0].item()); span = float(t_d[-1].item()) - t0
+        dt = span / (n - 1)
+        sums = bfrf.moments_device(u_d, y_d, (0, n))
+        for mode, key in ((0, "full"), (2, "main")):
+            prev = lib.b200id_frf_adaptive_force(C.c_int(mode))
+            try:
+                for _ in range(2):
+                    bfrf.project_uniform_device(t_d, u_d, y_d, w_d, t0, dt, (0, n), sums, 1.0 / n)
+                torch.cuda.synchronize()
+                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s.record()
+                for _ in range(5):
+                    bfrf.project_uniform_device(t_d, u_d, y_d, w_d, t0, dt, (0, n), sums, 1.0 / n)
+                e.record()
+                torch.cuda.synchronize()
+                tot[key] += s.elapsed_time(e) / 5
+                if mode == 0:
+                    listed[tag] = bfrf.adaptive_diag(nd, dev)[0]
+            finally:
+                lib.b200id_frf_adaptive_force(C.c_int(prev))
+    flops = 8.0 * a.n * (a.nd + VAL_ND)
+    out["frf_main_ms"] = tot["main"]
+    out["frf_main_tflops"] = flops / (tot["main"] * 1e-3) / 1e12
+    out["frf_round_ms"] = tot["full"] - tot["main"]
+    out["frf_bins_with_rounding_term"] = listed
+    return out
+
+
 def run_configs(a, rank, world, dev, res, timed, hbm_peak):
     """BASELINE configs 3, 4 and 5 measured in the same run (every rank takes part; CUDA events, max over ranks).
     Returns the `configs` block of the line (fp64 fractions are filled in by the caller, which owns the peak probe)."""
@@ -323,6 +367,36 @@ def run_configs(a, rank, world, dev, res, timed, hbm_peak):
         "single_cholesky_ms": ms_chol - ms_copy, "single_cholesky_flops": n4 ** 3 / 3.0, "info": int(info4.item()),
         "nll_first": float(m4[0]),
     }
+    # ---- kernel-regularised FIR (kernel_regularized.py): regressor summaries of a 1e5-sample record at
+    # L = 128 and the marginal likelihood at the 5 forward-difference points of one L-BFGS-B gradient (DC kernel), device
+    # against the oracle's NumPy / LAPACK evaluation of the same points on this host (rank 0 only)
+    if rank == 0:
+        try:
+            import math
+            import time as _time
+            from b200id import kr as bkr
+            from oracle import kr_fir as okr
+            n_kr, L_kr = 100_000, 128
+            _, u_kr, y_kr = synth.make_record(n_kr, a.nd, "multisine", seed=21)
+            u_kr, y_kr = u_kr - u_kr.mean(), y_kr - y_kr.mean()
+            ms_sum, summ, _, _ = timed(lambda: bkr.summaries(u_kr, y_kr, L_kr), 3, 1)
+            th0 = np.array([0.0, math.log(0.98 / 0.02), math.atanh(0.8), math.log(1e-2)])
+            pts = np.vstack([th0] + [th0 + 1e-8 * np.eye(4)[k] for k in range(4)])
+            ms_nll, (v_gpu, info_kr), _, _ = timed(lambda: bkr.nll_batch("dc", pts, summ), 5, 2)
+            G_h, b_h = summ.G.cpu().numpy(), summ.b.cpu().numpy()
+            t0_ = _time.perf_counter()
+            v_cpu = np.array([okr.nll(p_, G_h, b_h, summ.yy, n_kr, L_kr, "dc") for p_ in pts])
+            cpu_ms = (_time.perf_counter() - t0_) * 1e3
+            t0_ = _time.perf_counter()
+            okr.summaries(u_kr, y_kr, L_kr)
+            cpu_sum_ms = (_time.perf_counter() - t0_) * 1e3
+            out["kr_fir"] = {
+                "workload": f"kernel-regularised FIR, DC kernel, L={L_kr}, {n_kr} samples: summaries (host u, y in) and 5-point NLL batch",
+                "summaries_ms": ms_sum, "summaries_cpu_ms": cpu_sum_ms, "nll_batch_ms": ms_nll, "nll_batch_cpu_ms": cpu_ms,
+                "nll_rel_err_max": float(np.max(np.abs(v_gpu - v_cpu) / np.abs(v_cpu))), "info": info_kr.tolist(),
+            }
+        except Exception as exc:
+            out["kr_fir"] = {"error": repr(exc)}
     # ---- cfg 5: R records x n samples round-robin over the ranks: per-record FRF + cross-power sums, ONE all-reduce;
     # FIR validation of the step's taps over the same samples, one 4-double all-reduce
     want5 = a.cfg5 == "on" or (a.cfg5 == "auto" and world > 1)
@@ -618,9 +692,18 @@ def main():
     if rank != 0:
         return
 
+    # ---- bin-adaptive FRF: time of the main-term phase alone (rounding term switched off), both launches of a step,
+    # measured live with CUDA events on the records of this run; the rounding-term phase is the difference
+    frf_phases = {}
+    try:
+        frf_phases = measure_frf_phases(dev_recs, a, dev)
+    except Exception as exc:                                  # never lose the bench line over a diagnostic
+        frf_phases = {"frf_phases_error": repr(exc)}
+
     # ---- roofline of the dominant kernel (largest share of the step among the instrumented calls)
     frf_ms = stage_ms.get("b200id_frf_project", 0.0) + stage_ms.get("b200id_frf_project_uniform", 0.0)
-    frf_uniform_kernel = "frf_project_uniform3_kernel" if os.environ.get("B200ID_FRF_GOERTZEL", "1") == "0" else "frf_project_uniform_g_kernel"
+    frf_form = os.environ.get("B200ID_FRF_FORM", "0" if os.environ.get("B200ID_FRF_GOERTZEL", "1") == "0" else "2")
+    frf_uniform_kernel = {"0": "frf_project_uniform3_kernel", "1": "frf_project_uniform_g_kernel"}.get(frf_form, "frf_main_dmma_kernel")
     fir_kernel = "fir_fft_kernel" if os.environ.get("B200ID_FIR_RADIX4", "0") == "1" else "fir_fft16_kernel"
     frf_kernel = frf_uniform_kernel if stage_ms.get("b200id_frf_project_uniform", 0.0) > stage_ms.get("b200id_frf_project", 0.0) else "frf_project_kernel"
     fir_ms = stage_ms.get("b200id_fir_eval", 0.0)
@@ -643,16 +726,21 @@ def main():
         "kernel": dominant, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
         "traffic": NCU_TRAFFIC_BYTES.get(dominant), "peak_source": peak_src,
         "launches_per_step": 2 if dominant.startswith("frf") else 1,
-        "note": "FP64-issue bound by construction: the reference rounds the phase per sample, so each sample-bin costs 7 "
-                "FP64-pipe instructions (uniform timebase, Goertzel form) or 24 (general) where 4 are algorithmic; see the "
-                "fp64 block and DESIGN.md",
+        "note": "FP64 bound by construction (8 FP64 flops per sample-bin against 24 bytes per sample).  Bin-adaptive form: "
+                "'achieved' is the whole b200id_frf_project_uniform call (least-squares time base 80 MB, main-term DMMA "
+                "kernel 240 MB, rounding-term kernel for the listed bins 240 MB: 560 MB of DRAM traffic per launch in "
+                "three passes, none of them bandwidth bound); the kernel named here is the largest of the three, its own "
+                "time and FP64 fraction are in fp64.frf_main_*; see DESIGN.md K1",
+        "call_traffic": 560.2e6 if dominant == "frf_main_dmma_kernel" else None,
         "fp64": {
             "peak_tflops_measured": fp64_peak, **fp64,
             "frf_algorithmic_tflops": frf_flops / (frf_ms * 1e-3) / 1e12 if frf_ms > 0 else None,
+            **frf_phases,
             # direct-form-equivalent rate: the overlap-save FFT path executes ~90 flops per output, not 2*taps
             "fir_direct_form_equivalent_tflops": fir_flops / (fir_ms * 1e-3) / 1e12 if fir_ms > 0 else None,
             "gp_algorithmic_tflops": gp_flops / (gp_ms * 1e-3) / 1e12 if gp_ms > 0 else None,
             "frf_frac": (frf_flops / (frf_ms * 1e-3) / 1e12 / fp64_peak) if (fp64_peak and frf_ms > 0) else None,
+            "frf_main_frac": (frf_phases["frf_main_tflops"] / fp64_peak) if (fp64_peak and "frf_main_tflops" in frf_phases) else None,
             "fir_hbm_frac": (fir_bytes / (fir_ms * 1e-3) / 1e9 / hbm_peak) if fir_ms > 0 else None,
             "gp_frac": (gp_flops / (gp_ms * 1e-3) / 1e12 / fp64_peak) if (fp64_peak and gp_ms > 0) else None,
         },

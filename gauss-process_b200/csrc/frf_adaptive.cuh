@@ -405,6 +405,7 @@ frf_decide_kernel(const double* __restrict__ main, const double* __restrict__ no
             if (!(bound <= DA_BUDGET * mag)) need = true;              // also true for NaN / Inf anywhere
             ratio = fmax(ratio, bound / mag);
         }
+        if (force_all == 2) need = false;                               // timing experiments only: main term alone
         flags[k] = need ? 1 : 0;
         if (!need) wr = fmax(wr, ratio);
     }

@@ -1064,7 +1064,7 @@ extern "C" int b200id_frf_select_recurrence(int which) {
 // not fit (caller falls back to the recurrence kernels), 0 on success, < 0 on error.
 extern "C" int b200id_frf_adaptive_force(int all_bins) {
     const int prev = frf_adaptive_force_all();
-    g_frf_force_all = all_bins < 0 ? -1 : (all_bins ? 1 : 0);
+    g_frf_force_all = all_bins < 0 ? -1 : (all_bins > 2 ? 1 : all_bins);
     return prev;
 }
 extern "C" int b200id_frf_adaptive_diag(const void* ws, size_t ws_bytes, int nd, double* diag_out, void* stream) {

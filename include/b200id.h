@@ -126,7 +126,8 @@ int b200id_frf_timebase_fill(double* t_out, int64_t n, double t0, double dt, voi
 int b200id_frf_select_recurrence(int which);
 
 /* Bin-adaptive form only.  b200id_frf_adaptive_force(1) lists every bin for the rounding term (0 = decide per bin,
- * -1 = environment B200ID_FRF_ADAPTIVE=all / default); returns the previous setting.  b200id_frf_adaptive_diag copies
+ * 2 = list none: the main term alone, for timing its kernel -- NOT a valid result at weak bins, -1 = environment
+ * B200ID_FRF_ADAPTIVE=all / default); returns the previous setting.  b200id_frf_adaptive_diag copies
  * {number of bins that took the rounding term, largest (16 sigma_k + rigorous_k) / |S_k| among the skipped bins} of
  * the LAST b200id_frf_project_uniform call on this workspace to diag_out[2] (device), stream-ordered. */
 int b200id_frf_adaptive_force(int all_bins);

@@ -373,6 +373,293 @@ frf_main_dmma_kernel(const double* __restrict__ t, const double* __restrict__ u,
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// 1'. main term, warp-specialised (the default): ONE CTA of 1024 threads per SM, the tables once per SM.
+//   * producer warps 0-3: the raw t / u / y segments of a tile arrive by TMA bulk copies (cp.async.bulk, completion on
+//     an mbarrier) two tiles ahead; the producers turn them into the weighted block rows As[tile & 1], the tile's seed
+//     phasors and the moments of delta, then hand the buffer to the consumers and re-arm the copies of tile + 2;
+//   * consumer warps 4-31: the block-phasor matrix products of frf_main_dmma_kernel on the buffer the producers
+//     filled while the previous tile was multiplied.
+// Named barriers full[b] / empty[b] (b = tile parity) carry the hand-over; there is no CTA-wide barrier in the tile
+// loop, so the DMMA pipe never waits for a global load or for the staging arithmetic.
+constexpr int DW_THREADS = 1024;
+constexpr int DW_PRODUCERS = 128;                       // threads of warps 0-3
+constexpr int DW_CWARPS = (DW_THREADS - DW_PRODUCERS) / 32;
+constexpr int DW_RAW_T = DA_TS + 4;                     // t[i0 - 2 .. i0 + TS + 2): 16-byte aligned start, halo for the weights
+constexpr int DW_RAW_DOUBLES = DW_RAW_T + 2 * DA_TS;    // t, u, y of one tile
+constexpr size_t DA_SMEM_LIMIT_1CTA = 227 * 1024;
+static inline size_t dw_smem_bytes(int bins_per_group) {
+    const size_t bp = (size_t)da_pad4(bins_per_group);
+    return (size_t)2 * bp * DA_LD * sizeof(double)              // Qt
+           + (size_t)2 * 2 * DA_NB * DA_LD * sizeof(double)     // A rows, two tiles
+           + (size_t)2 * DW_RAW_DOUBLES * sizeof(double)        // raw t, u, y, two tiles
+           + (size_t)8 * bp * sizeof(double2)                   // P1
+           + (size_t)bp * sizeof(double2)                       // R8
+           + (size_t)3 * bp * sizeof(double2)                   // Pt0 (two tiles), RT
+           + (size_t)4 * bp * sizeof(double)                    // main-term sums
+           + bp * sizeof(double)                                // w
+           + 64;                                                // mbarriers
+}
+static inline int dw_groups(int nd) {
+    int g = 1;
+    while (dw_smem_bytes((nd + g - 1) / g) > DA_SMEM_LIMIT_1CTA) ++g;
+    return g;
+}
+__device__ __forceinline__ unsigned dw_smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void dw_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void dw_bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void dw_mbar_wait(unsigned bar, unsigned parity) {
+    unsigned ok = 0;
+    while (!ok) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    }
+}
+
+__global__ void __launch_bounds__(DW_THREADS, 1)
+frf_main_ws_kernel(const double* __restrict__ t, const double* __restrict__ u, const double* __restrict__ y,
+                   int64_t n, int64_t own_begin, int64_t own_end, const double* __restrict__ w, int nd,
+                   const double* __restrict__ sums, double inv_count, double t0, double dt,
+                   const double* __restrict__ fit, int n_tiles, int bins_per_group, double* __restrict__ cta_partial,
+                   double* __restrict__ norm_partial) {
+    extern __shared__ __align__(128) unsigned char da_smem[];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = (int)__reduce_max_sync(0xffffffffu, (unsigned)(tid >> 5));      // uniform register
+    const int bin0 = blockIdx.y * bins_per_group;
+    const int nb_all = min(nd - bin0, bins_per_group);
+    const int bp = da_pad4(nb_all);
+    const int ncg = bp >> 2;
+    if (nb_all <= 0) return;
+
+    double* raw = reinterpret_cast<double*>(da_smem);                // [2][DW_RAW_DOUBLES]  t (halo 2 + 2), u, y
+    double* Qt = raw + 2 * DW_RAW_DOUBLES;                           // [2 bp][DA_LD]
+    double* As = Qt + (size_t)2 * bp * DA_LD;                        // [2][2 DA_NB][DA_LD]
+    double2* P1 = reinterpret_cast<double2*>(As + (size_t)2 * 2 * DA_NB * DA_LD);   // [8][bp]
+    double2* R8 = P1 + (size_t)8 * bp;                               // [bp]
+    double2* Pt0 = R8 + bp;                                          // [2][bp]  tile seed phasors of the tile in As[b]
+    double2* RT = Pt0 + 2 * bp;                                      // [bp]     tile-to-tile rotation
+    double* accM = reinterpret_cast<double*>(RT + bp);               // [4][bp]
+    double* ws = accM + (size_t)4 * bp;                              // [bp]
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(ws + bp);      // [2] raw[b] landed
+
+    const double mean_u = sums ? sums[0] * inv_count : 0.0;
+    const double mean_y = sums ? sums[1] * inv_count : 0.0;
+    const bool do_norms = blockIdx.y == 0 && norm_partial != nullptr;
+    const DaBase tb = da_base(fit, t0, dt, own_begin, own_end);
+
+    for (int k = tid; k < bp; k += DW_THREADS) ws[k] = k < nb_all ? w[bin0 + k] : 0.0;
+    if (tid == 0) {
+        for (int b = 0; b < 2; ++b) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(dw_smem_addr(bars + b)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    for (int e = tid; e < bp * 32; e += DW_THREADS) {
+        const int k = e >> 5, rr = e & 31;
+        double s, c;
+        da_sincos_steps(ws[k], (double)rr, tb, s, c);
+        Qt[(size_t)(2 * k) * DA_LD + rr] = c;
+        Qt[(size_t)(2 * k + 1) * DA_LD + rr] = s;
+    }
+    for (int e = tid; e < bp * 9; e += DW_THREADS) {
+        const int g = e / bp, k = e - g * bp;
+        double s, c;
+        da_sincos_steps(ws[k], (double)(32 * g), tb, s, c);
+        if (g < 8) P1[g * bp + k] = make_double2(c, s);
+        else R8[k] = make_double2(c, s);
+    }
+    for (int k = tid; k < bp; k += DW_THREADS) {
+        double s, c;
+        da_sincos_steps(ws[k], (double)gridDim.x * (double)DA_TS, tb, s, c);
+        RT[k] = make_double2(c, s);
+        accM[k] = 0.0; accM[bp + k] = 0.0; accM[2 * bp + k] = 0.0; accM[3 * bp + k] = 0.0;
+    }
+    __syncthreads();
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+
+    // a tile whose raw segments lie inside the record goes through the TMA; the first and the last tile of the record
+    // (halo or length not a whole number of 16-byte pieces) are fetched by the producers themselves
+    auto tile_i0 = [&](int tl) { return own_begin + (int64_t)tl * DA_TS; };
+    auto uses_tma = [&](int tl) { const int64_t i0 = tile_i0(tl); return i0 >= 2 && i0 + DA_TS + 2 <= n && i0 + DA_TS <= own_end; };
+
+    if (warp < DW_PRODUCERS / 32) {
+        // =========================================== producers
+        auto issue = [&](int tl, int b) {                      // one thread: arm the barrier, three bulk copies
+            const int64_t i0 = tile_i0(tl);
+            double* dst = raw + (size_t)b * DW_RAW_DOUBLES;
+            const unsigned bar = dw_smem_addr(bars + b);
+            const unsigned bytes_t = DW_RAW_T * sizeof(double), bytes_s = DA_TS * sizeof(double);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes_t + 2 * bytes_s) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(dw_smem_addr(dst)), "l"(t + i0 - 2), "r"(bytes_t), "r"(bar) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(dw_smem_addr(dst + DW_RAW_T)), "l"(u + i0), "r"(bytes_s), "r"(bar) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(dw_smem_addr(dst + DW_RAW_T + DA_TS)), "l"(y + i0), "r"(bytes_s), "r"(bar) : "memory");
+        };
+        if (tid == 0) {
+            const int tl0 = blockIdx.x, tl1 = blockIdx.x + gridDim.x;
+            if (tl0 < n_tiles && uses_tma(tl0)) issue(tl0, 0);
+            if (tl1 < n_tiles && uses_tma(tl1)) issue(tl1, 1);
+        }
+        // moments for the decision, in FP32 (they only need a digit or two, and every FP64 instruction of a producer
+        // queues behind the consumers' DMMAs on the same pipe); delta is scaled by 2^40 so that its squares stay normal
+        float nrm[DA_NORMS];
+#pragma unroll
+        for (int c = 0; c < DA_NORMS; ++c) nrm[c] = 0.f;
+        unsigned phase0 = 0u, phase1 = 0u;                          // parity of the next landing in raw[0], raw[1]
+        int it = 0;
+        for (int tl = blockIdx.x; tl < n_tiles; tl += gridDim.x, ++it) {
+            const int b = it & 1;
+            const int64_t i0 = tile_i0(tl);
+            const int cnt = (int)min((int64_t)DA_TS, own_end - i0);
+            double* rw = raw + (size_t)b * DW_RAW_DOUBLES;
+            if (uses_tma(tl)) {
+                dw_mbar_wait(dw_smem_addr(bars + b), b ? phase1 : phase0);
+                if (b) phase1 ^= 1u; else phase0 ^= 1u;
+            } else {
+                // edge tile: the producers fetch it (zeros past the owned range, clamped halo)
+                for (int j = tid; j < DW_RAW_T; j += DW_PRODUCERS) {
+                    const int64_t i = i0 - 2 + j;
+                    rw[j] = __ldg(t + (i < 0 ? 0 : (i > n - 1 ? n - 1 : i)));
+                }
+                for (int j = tid; j < DA_TS; j += DW_PRODUCERS) {
+                    const bool ok = j < cnt;
+                    rw[DW_RAW_T + j] = ok ? __ldg(u + i0 + j) : 0.0;
+                    rw[DW_RAW_T + DA_TS + j] = ok ? __ldg(y + i0 + j) : 0.0;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // these plain stores precede later bulk copies into raw[b]
+                dw_bar_sync(5, DW_PRODUCERS);                        // producers only: the tile is complete
+            }
+            if (it >= 2) dw_bar_sync(3 + b, DW_THREADS);             // consumers are done with As[b] / Pt0[b] (tile it - 2)
+            // ---- raw -> weighted block rows, moments of delta
+            const double* rt = rw + 2;                               // rt[j] = t[i0 + j], j = -2 .. TS + 1
+            const double ti0 = rt[0];
+            const DD x0 = da_time(tb, (double)i0);
+            const double d0 = (ti0 - x0.hi) - x0.lo;
+            double* Ab = As + (size_t)b * 2 * DA_NB * DA_LD;
+#pragma unroll 4
+            for (int j = tid; j < DA_TS; j += DW_PRODUCERS) {
+                double au = 0.0, ay = 0.0;
+                if (j < cnt) {
+                    const int64_t i = i0 + j;
+                    const double ti = rt[j];
+                    const double tm = i > 0 ? rt[j - 1] : ti, tp = i < n - 1 ? rt[j + 1] : ti;
+                    const double wt = 0.5 * (tp - tm);
+                    au = wt * (rw[DW_RAW_T + j] - mean_u);
+                    ay = wt * (rw[DW_RAW_T + DA_TS + j] - mean_y);
+                    if (do_norms) {
+                        const double jd = (double)j;
+                        const double dl = fma(-jd, tb.dtl, fma(-jd, tb.dth, ti - ti0)) + d0;
+                        const double ad = fabs(dl);
+                        const bool noise = ad <= da_ulp(ti);
+                        const float adf = (float)(ad * 0x1p40), fu = fabsf((float)au), fy = fabsf((float)ay);
+                        const float ds = noise ? adf : 0.f, dr = noise ? 0.f : adf;
+                        const float u2 = fu * fu, y2 = fy * fy, ds2 = ds * ds;
+                        nrm[0] += u2; nrm[1] += y2;
+                        nrm[2] = fmaf(u2, ds2, nrm[2]); nrm[3] = fmaf(y2, ds2, nrm[3]);
+                        nrm[4] = fmaf(fu, dr, nrm[4]); nrm[5] = fmaf(fy, dr, nrm[5]);
+                    }
+                }
+                const int blk = j >> 5, rr = j & 31;
+                Ab[(size_t)blk * DA_LD + rr] = au;
+                Ab[(size_t)(DA_NB + blk) * DA_LD + rr] = ay;
+            }
+            // ---- phasor of the tile start: exact seed every DA_RESEED tiles, the exact tile-to-tile rotation in between
+            if (tid < bp) {
+                if (it % DA_RESEED == 0) {
+                    double s, c;
+                    sincos_dd(ws[tid], x0, s, c);
+                    Pt0[b * bp + tid] = make_double2(c, s);
+                } else {
+                    const double2 p = Pt0[(b ^ 1) * bp + tid], q = RT[tid];
+                    Pt0[b * bp + tid] = make_double2(fma(p.x, q.x, -(p.y * q.y)), fma(p.y, q.x, p.x * q.y));
+                }
+            }
+            dw_bar_sync(5, DW_PRODUCERS);                            // every producer is done with raw[b] (and wrote As[b])
+            dw_bar_arrive(1 + b, DW_THREADS);                        // full[b]
+            if (tid == 0) {
+                const int tl2 = tl + 2 * (int)gridDim.x;
+                if (tl2 < n_tiles && uses_tma(tl2)) issue(tl2, b);
+            }
+        }
+        if (do_norms) {
+            double* red = raw;                                       // producers own raw[] once their loop is over
+            dw_bar_sync(5, DW_PRODUCERS);
+#pragma unroll
+            for (int c = 0; c < DA_NORMS; ++c) {
+                double v = (double)nrm[c] * (c < 2 ? 1.0 : (c < 4 ? 0x1p-80 : 0x1p-40));
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                if (lane == 0) red[c * (DW_PRODUCERS / 32) + warp] = v;
+            }
+            dw_bar_sync(5, DW_PRODUCERS);
+            if (tid < DA_NORMS) {
+                double v = 0.0;
+                for (int q = 0; q < DW_PRODUCERS / 32; ++q) v += red[tid * (DW_PRODUCERS / 32) + q];
+                norm_partial[(size_t)blockIdx.x * DA_NORMS + tid] = v;
+            }
+        }
+    } else {
+        // =========================================== consumers
+        const int cw = warp - DW_PRODUCERS / 32;
+        const int g4 = lane >> 2, l4 = lane & 3;
+        int it = 0;
+        for (int tl = blockIdx.x; tl < n_tiles; tl += gridDim.x, ++it) {
+            const int b = it & 1;
+            dw_bar_sync(1 + b, DW_THREADS);                          // full[b]
+            const double* Ab = As + (size_t)b * 2 * DA_NB * DA_LD;
+            const double2* Ptb = Pt0 + b * bp;
+            for (int unit = cw; unit < 2 * ncg; unit += DW_CWARPS) {
+                const int sig = unit & 1, cg = unit >> 1;
+                const int k = cg * 4 + l4;
+                double c[DA_NBG][2];
+#pragma unroll
+                for (int bg = 0; bg < DA_NBG; ++bg) { c[bg][0] = 0.0; c[bg][1] = 0.0; }
+                const double* bq = Qt + (size_t)(cg * 8 + g4) * DA_LD + l4;
+                const double* ap = Ab + (size_t)(sig * DA_NB + g4) * DA_LD + l4;
+#pragma unroll 1
+                for (int ks = 0; ks < 8; ++ks) {
+                    const double bv = bq[ks * 4];
+                    double a[DA_NBG];
+#pragma unroll
+                    for (int bg = 0; bg < DA_NBG; ++bg) a[bg] = ap[(size_t)(bg * 8) * DA_LD + ks * 4];
+#pragma unroll
+                    for (int bg = 0; bg < DA_NBG; ++bg) da_dmma(c[bg][0], c[bg][1], a[bg], bv);
+                }
+                const double2 r8 = R8[k];
+                double hr = c[DA_NBG - 1][0], hi = c[DA_NBG - 1][1];
+#pragma unroll
+                for (int bg = DA_NBG - 2; bg >= 0; --bg) {
+                    const double nr = fma(hr, r8.x, fma(-hi, r8.y, c[bg][0]));
+                    hi = fma(hr, r8.y, fma(hi, r8.x, c[bg][1]));
+                    hr = nr;
+                }
+                const double2 p1 = P1[g4 * bp + k];
+                double sre = fma(hr, p1.x, -(hi * p1.y)), sim = fma(hr, p1.y, hi * p1.x);
+#pragma unroll
+                for (int o = 4; o < 32; o <<= 1) {
+                    sre += __shfl_xor_sync(0xffffffffu, sre, o);
+                    sim += __shfl_xor_sync(0xffffffffu, sim, o);
+                }
+                if (g4 == 0) {
+                    const double2 pt = Ptb[k];
+                    accM[(2 * sig) * bp + k] += fma(sre, pt.x, -(sim * pt.y));
+                    accM[(2 * sig + 1) * bp + k] += fma(sre, pt.y, sim * pt.x);
+                }
+            }
+            dw_bar_arrive(3 + b, DW_THREADS);                        // empty[b]
+        }
+    }
+    // the producers' last two empty[] waits never happen (they only wait from their third tile on): every barrier
+    // phase that was armed by an arrive has been consumed or is abandoned at exit, which PTX allows.
+    __syncthreads();
+    if (tid < nb_all) {
+        double* out = cta_partial + (size_t)blockIdx.x * 4 * nd + bin0 + tid;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) out[(size_t)c * nd] = accM[c * bp + tid];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // 3. which bins need the rounding term (one CTA).  main = folded main-term sums [4][nd] = {uc, us, yc, ys}.
 //    diag (optional) receives {count, max over skipped bins of (DA_SIGMAS sigma + rigorous) / |S|}.
 constexpr int DA_DECIDE_THREADS = 256;

@@ -1000,6 +1000,7 @@ constexpr size_t FRFU_SMEM_BYTES = (size_t)(4 * FRF_TILE_MAX) * sizeof(double);
 using namespace b200id;
 
 #include <stdlib.h>
+#include <stdint.h>
 
 // bytes of the per-CTA partial area + the moments area (the layout every FRF entry point shares); the tables of the
 // matrix-product path follow it
@@ -1294,12 +1295,17 @@ extern "C" int b200id_frf_project_uniform(const double* t, const double* u, cons
     if (y && frf_form() == 2 && own_begin == 0 && own_end == n) {
         // bin-adaptive: main term of all bins (DMMA), device-side list of the weak bins, rounding term for those only.
         // Sub-range calls (time-segment shards) stay on form 1: the test needs the whole record's |U_k|.
-        const int groups = da_main_groups(nd), bpg = (nd + groups - 1) / groups;
+        // main-term kernel: warp-specialised with TMA bulk staging (one CTA per SM) when the three arrays are 16-byte
+        // aligned, else the plain two-CTAs-per-SM kernel (B200ID_FRF_MAIN=plain forces it, for timing comparisons)
+        static int main_ws = -1;
+        if (main_ws < 0) { const char* e = getenv("B200ID_FRF_MAIN"); main_ws = (e && e[0] == 'p') ? 0 : 1; }
+        const bool ws_ok = main_ws && ((((uintptr_t)t | (uintptr_t)u | (uintptr_t)y) & 15) == 0);
+        const int groups = ws_ok ? dw_groups(nd) : da_main_groups(nd), bpg = (nd + groups - 1) / groups;
         const int64_t nt64 = (n + DA_TS - 1) / DA_TS;
         B200ID_REQUIRE(nt64 <= 0x7fffffff, B200ID_E_UNSUPPORTED, "frf_project_uniform: record too long for one launch");
         const int nt = (int)nt64;
         const int n_cta = sm_count() * FRF_CTAS_PER_SM;
-        int gx = n_cta / groups;
+        int gx = (ws_ok ? sm_count() : n_cta) / groups;
         if (gx < 1) gx = 1;
         if (gx > nt) gx = nt;
         const size_t ad_off = frf_adaptive_area_offset(nd);
@@ -1310,8 +1316,10 @@ extern "C" int b200id_frf_project_uniform(const double* t, const double* u, cons
         double* fit = diag + 8;                                      // {sum delta, sum (i - c) delta}
         int* flag_count = (int*)(diag + 32);
         int* flag_idx = flag_count + 4;
-        const size_t smem = da_main_smem_bytes(bpg);
-        rc = check_cuda(cudaFuncSetAttribute(frf_main_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr");
+        const size_t smem = ws_ok ? dw_smem_bytes(bpg) : da_main_smem_bytes(bpg);
+        rc = check_cuda(cudaFuncSetAttribute(frf_main_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)da_main_smem_bytes(ws_ok ? 1 : bpg)), "smem attr");
+        if (rc) return rc;
+        rc = check_cuda(cudaFuncSetAttribute(frf_main_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dw_smem_bytes(ws_ok ? bpg : 1)), "smem attr");
         if (rc) return rc;
         rc = check_cuda(cudaFuncSetAttribute(frf_round_goertzel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)da_round_smem_bytes()), "smem attr");
         if (rc) return rc;
@@ -1325,9 +1333,13 @@ extern "C" int b200id_frf_project_uniform(const double* t, const double* u, cons
             frf_fold_kernel<<<1, FOLD_WARPS * 32, 0, st>>>(part, fg, 2, fit);
             B200ID_LAUNCH_CHECK("frf_fold_kernel(fit)");
         }
-        frf_main_dmma_kernel<<<dim3(gx, groups), DA_THREADS, smem, st>>>(t, u, y, n, own_begin, own_end, w, nd, sums, inv_count, t0, dt,
-                                                                           fit, nt, bpg, part, norm_part);
-        B200ID_LAUNCH_CHECK("frf_main_dmma_kernel");
+        if (ws_ok)
+            frf_main_ws_kernel<<<dim3(gx, groups), DW_THREADS, smem, st>>>(t, u, y, n, own_begin, own_end, w, nd, sums, inv_count, t0, dt,
+                                                                             fit, nt, bpg, part, norm_part);
+        else
+            frf_main_dmma_kernel<<<dim3(gx, groups), DA_THREADS, smem, st>>>(t, u, y, n, own_begin, own_end, w, nd, sums, inv_count, t0, dt,
+                                                                               fit, nt, bpg, part, norm_part);
+        B200ID_LAUNCH_CHECK("frf_main kernel");
         const int dlen = 4 * nd;
         frf_fold_kernel<<<(dlen + 31) / 32, FOLD_WARPS * 32, 0, st>>>(part, gx, dlen, partial_out);
         B200ID_LAUNCH_CHECK("frf_fold_kernel");

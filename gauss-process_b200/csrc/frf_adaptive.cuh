@@ -63,7 +63,7 @@ constexpr int DA_NBG = DA_NB / 8;                // block groups (8 blocks = one
 constexpr int DA_RESEED = 64;                    // tiles between exact re-seeds of the tile phasor
 constexpr int DA_NORMS = 6;                      // {sum au^2, sum ay^2, sum au^2 ds^2, sum ay^2 ds^2, sum |au dr|, sum |ay dr|}
 constexpr size_t DA_SMEM_LIMIT = 115712;         // (228 KB - 2 x 1 KB) / 2: two CTAs per SM
-constexpr int DA_BPB = 64;                       // bins per CTA pass of the rounding-term kernel (stripes R >= 16)
+constexpr int DA_BPB = 128;                      // bins per CTA pass of the rounding-term kernel (stripes R >= 8)
 constexpr double DA_MAGIC = 4503599627370496.0 + 1262485504.0;   // 2^52 + 0x4B400000: low word of (DA_MAGIC + n) = bits of the float 2^23 + 2^22 + n
 constexpr float DA_MAGIC_F = 12582912.0f;                        // 2^23 + 2^22
 constexpr int DA_CM = DA_TS + DA_THREADS;        // entries of the chain-major arrays (R ceil(TS / R) < TS + R)

@@ -17,6 +17,7 @@
 //   * the circular convolution is valid for m in [taps-1, N): each block yields V = N - taps + 1 outputs.
 // Data (N complex, padded one element per 8 against bank conflicts) + N/4 twiddles = 90 KB per CTA -> 2 CTAs
 // per SM, persistent grid, error sums fused into the epilogue (y_pred is optional).
+#include <stdint.h>
 #include "common.cuh"
 
 namespace b200id {
@@ -323,6 +324,42 @@ fir_fft16_kernel(const double* __restrict__ u, const double* __restrict__ y, int
     const int gB = tid >> 4, jB = tid & 15;          // pass B / B': group of 256, offset inside the group's 16-blocks
     cplx v[4][4];
 
+    // ---- TMA staging of the input window.  A unit reads 2V + hist CONSECUTIVE samples of u (block B's window is block
+    // A's shifted by V).  The FFT buffer x is idle from the moment pass A' has read it until the next unit's pass A
+    // writes it, i.e. for the whole epilogue: one thread sends the NEXT unit's window into it with a bulk copy
+    // (cp.async.bulk, completion on an mbarrier), and pass A then takes its 32 samples per thread from shared memory
+    // instead of issuing 32 global loads whose latency nothing covers at 16 warps per SM.  Units whose window leaves
+    // the record (first / last) keep the predicated global loads.
+    __shared__ unsigned long long ff_bar;
+    const unsigned bar = (unsigned)__cvta_generic_to_shared(&ff_bar);
+    double* rawd = reinterpret_cast<double*>(x);
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    // window of `unit` as [g0, g0 + len): g0 = sA - sh with sh in {0, 1} making u + g0 16-byte aligned, len even
+    auto stage_next = [&](int64_t unit_n, int& sh_out) -> bool {
+        if (unit_n >= n_units) return false;
+        const int64_t sA_n = unit_n * 2 * (int64_t)V - hist;
+        const int sh = (int)((reinterpret_cast<uintptr_t>(u + sA_n) >> 3) & 1);
+        const int64_t g0 = sA_n - sh;
+        const int len = (2 * V + hist + sh + 1) & ~1;
+        if (g0 < -lead || g0 + len > n) return false;
+        sh_out = sh;
+        if (tid == 0) {
+            const unsigned bytes = (unsigned)len * (unsigned)sizeof(double);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"((unsigned)__cvta_generic_to_shared(rawd)), "l"(u + g0), "r"(bytes), "r"(bar) : "memory");
+        }
+        return true;
+    };
+    int sh_cur = 0;
+    unsigned bar_parity = 0;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    bool staged = stage_next(blockIdx.x, sh_cur);
+
     for (int64_t unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
         const int64_t oA = unit * 2 * (int64_t)V, oB = oA + V;       // first output of blocks A and B
         // ---- pass A: element a*1024 + b*256 + tid of z = uA + j uB straight from global memory.  Index windows as
@@ -342,16 +379,34 @@ fir_fft16_kernel(const double* __restrict__ u, const double* __restrict__ y, int
                 const int64_t iy = oA + (int64_t)ln * 16;
                 if (y && iy < n && ln * 16 < 2 * V + 16) asm volatile("prefetch.global.L2 [%0];" ::"l"(y + iy));
             }
-            const double* pa = u + sA + tid;
-            const double* pb = u + sB + tid;
+            if (staged) {
+                // the window landed in x during the previous unit's epilogue: block A at rawd[sh + m], block B V further
+                unsigned ok = 0;
+                while (!ok)
+                    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                                 : "=r"(ok) : "r"(bar), "r"(bar_parity) : "memory");
+                bar_parity ^= 1u;
+                const double* pa = rawd + sh_cur + tid;
+                const double* pb = pa + V;
 #pragma unroll
-            for (int a = 0; a < 4; ++a)
+                for (int a = 0; a < 4; ++a)
 #pragma unroll
-                for (int b = 0; b < 4; ++b) {
-                    const int m = a * 1024 + b * 256 + tid;
-                    v[a][b].x = (m >= loA && m < hiA) ? __ldg(pa + (a * 1024 + b * 256)) : 0.0;
-                    v[a][b].y = (m >= loB && m < hiB) ? __ldg(pb + (a * 1024 + b * 256)) : 0.0;
-                }
+                    for (int b = 0; b < 4; ++b) {
+                        v[a][b].x = pa[a * 1024 + b * 256];
+                        v[a][b].y = pb[a * 1024 + b * 256];
+                    }
+            } else {
+                const double* pa = u + sA + tid;
+                const double* pb = u + sB + tid;
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        const int m = a * 1024 + b * 256 + tid;
+                        v[a][b].x = (m >= loA && m < hiA) ? __ldg(pa + (a * 1024 + b * 256)) : 0.0;
+                        v[a][b].y = (m >= loB && m < hiB) ? __ldg(pb + (a * 1024 + b * 256)) : 0.0;
+                    }
+            }
         }
         __syncthreads();                                             // twiddles ready / previous unit's pass A' has read x
 #pragma unroll
@@ -431,6 +486,11 @@ fir_fft16_kernel(const double* __restrict__ u, const double* __restrict__ y, int
         for (int a = 0; a < 4; ++a)
 #pragma unroll
             for (int b = 0; b < 4; ++b) v[a][b] = lds(x, a * 1024 + b * 256 + tid);
+        // x is free now: once every thread has its elements, the next unit's window goes into it (the plain stores of
+        // the passes precede the bulk copy's writes: cross-proxy fence, then the barrier)
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        staged = stage_next(unit + gridDim.x, sh_cur);
         {
             const cplx w = ldtw(tw, 4 * tid);
 #pragma unroll

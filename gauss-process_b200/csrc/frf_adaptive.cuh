@@ -374,15 +374,21 @@ frf_main_dmma_kernel(const double* __restrict__ t, const double* __restrict__ u,
 
 // ------------------------------------------------------------------------------------------------------------------
 // 1'. main term, warp-specialised (the default): ONE CTA of 1024 threads per SM, the tables once per SM.
-//   * producer warps 0-3: the raw t / u / y segments of a tile arrive by TMA bulk copies (cp.async.bulk, completion on
+//   * producer warps 0-11: the raw t / u / y segments of a tile arrive by TMA bulk copies (cp.async.bulk, completion on
 //     an mbarrier) two tiles ahead; the producers turn them into the weighted block rows As[tile & 1], the tile's seed
 //     phasors and the moments of delta, then hand the buffer to the consumers and re-arm the copies of tile + 2;
-//   * consumer warps 4-31: the block-phasor matrix products of frf_main_dmma_kernel on the buffer the producers
+//   * consumer warps 12-31: the block-phasor matrix products of frf_main_dmma_kernel on the buffer the producers
 //     filled while the previous tile was multiplied.
 // Named barriers full[b] / empty[b] (b = tile parity) carry the hand-over; there is no CTA-wide barrier in the tile
 // loop, so the DMMA pipe never waits for a global load or for the staging arithmetic.
 constexpr int DW_THREADS = 1024;
-constexpr int DW_PRODUCERS = 128;                       // threads of warps 0-3
+// producer threads: measured 128 / 256 / 384 / 512 -> 0.689 / 0.677 / 0.666 / 0.682 ms (N_d = 100) and 1.039 / 0.996 /
+// 0.982 / 0.991 ms (150 bins) per adaptive call: a producer's FP64 instructions queue behind the consumers' DMMAs, so
+// the per-tile staging chain is short only when it is spread over many warps
+#ifndef DW_PRODUCER_THREADS
+#define DW_PRODUCER_THREADS 384
+#endif
+constexpr int DW_PRODUCERS = DW_PRODUCER_THREADS;       // threads of the producer warps (warps 0 .. DW_PRODUCERS/32 - 1)
 constexpr int DW_CWARPS = (DW_THREADS - DW_PRODUCERS) / 32;
 constexpr int DW_RAW_T = DA_TS + 4;                     // t[i0 - 2 .. i0 + TS + 2): 16-byte aligned start, halo for the weights
 constexpr int DW_RAW_DOUBLES = DW_RAW_T + 2 * DA_TS;    // t, u, y of one tile

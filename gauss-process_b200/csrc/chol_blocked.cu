@@ -556,7 +556,7 @@ __host__ __device__ inline int cw_tile_count(int t128) { return t128 * (t128 + 1
 __global__ void __launch_bounds__(CW_THREADS, 2)
 cholb_syrk_wide_kernel(double* __restrict__ A, int lda, int n, int n_rows, int k0, int* __restrict__ info,
                        size_t a_stride, size_t info_stride) {
-    extern __shared__ __align__(128) double cb_sm[];
+    extern __shared__ __align__(16) double cb_sm[];
     A += blockIdx.z * a_stride;
     info += blockIdx.z * info_stride;
     if (info[0] != 0) return;

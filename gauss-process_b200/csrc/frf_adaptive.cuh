@@ -113,15 +113,23 @@ __device__ __forceinline__ void da_dmma(double& d0, double& d1, double a, double
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                  : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
-// Time base t0 + i dt in double-double: (t0, dt) from the caller, the low words from the least-squares fit
-// fit = {sum_i delta_i, sum_i (i - c) delta_i} over [begin, end), c = (begin + end - 1) / 2.
+// Time base t0 + i dt in double-double: (t0, dt) from the caller, the low words from the least-squares line through
+// delta_i = t_i - (t0 + i dt) over the SAMPLED stamps i = begin, begin + DA_FIT_STRIDE, ...:
+// fit = {sum delta, sum (i - c) delta, m, sum (i - c), sum (i - c)^2}, c = (begin + end - 1) / 2.
+constexpr int DA_FIT_STRIDE = 16;
+constexpr int DA_FIT_SUMS = 5;
 struct DaBase { double t0h, t0l, dth, dtl; };
 __device__ __forceinline__ DaBase da_base(const double* __restrict__ fit, double t0, double dt, int64_t begin, int64_t end) {
     DaBase b; b.t0h = t0; b.t0l = 0.0; b.dth = dt; b.dtl = 0.0;
     if (fit) {
-        const double cnt = (double)(end - begin), c = 0.5 * (double)(begin + end - 1);
-        const double alpha = fit[0] / cnt;
-        const double beta = cnt > 1.5 ? fit[1] * 12.0 / (cnt * (cnt * cnt - 1.0)) : 0.0;
+        const double c = 0.5 * (double)(begin + end - 1);
+        const double sd = fit[0], sxd = fit[1], m = fit[2], sx = fit[3], sxx = fit[4];
+        const double det = m * sxx - sx * sx;
+        double alpha = m > 0.0 ? sd / m : 0.0, beta = 0.0;
+        if (m > 1.5 && det > 0.0) {
+            beta = (m * sxd - sx * sd) / det;
+            alpha = (sd - beta * sx) / m;
+        }
         b.t0l = alpha - beta * c; b.dtl = beta;
     }
     return b;
@@ -170,25 +178,33 @@ __device__ __forceinline__ DaSample da_sample(const double* __restrict__ t, cons
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// 0. sums of delta_i and (i - c) delta_i against the caller's (t0, dt): the least-squares line through the stamps
+// 0. sums for the least-squares line through the stamps against the caller's (t0, dt).  Every DA_FIT_STRIDE-th stamp is
+// enough: the line is determined to a small fraction of an ulp by 1e5+ points, and whatever line comes out, delta is
+// taken against it consistently afterwards (a quarter of the DRAM sectors of t instead of all of them)
 constexpr int DA_FIT_THREADS = 256;
 __global__ void __launch_bounds__(DA_FIT_THREADS)
 frf_timebase_fit_kernel(const double* __restrict__ t, int64_t begin, int64_t end, double t0, double dt, int64_t chunk,
                         double* __restrict__ cta_partial) {
     __shared__ double scratch[DA_FIT_THREADS / 32];
-    const int64_t lo = begin + (int64_t)blockIdx.x * chunk, hi = min(lo + chunk, end);
+    const int64_t lo = begin + (int64_t)blockIdx.x * chunk, hi = min(lo + chunk, end);        // chunk is a multiple of the stride
     const double c = 0.5 * (double)(begin + end - 1);
     DaBase b; b.t0h = t0; b.t0l = 0.0; b.dth = dt; b.dtl = 0.0;
-    double s0 = 0.0, s1 = 0.0;
-    for (int64_t i = lo + threadIdx.x; i < hi; i += DA_FIT_THREADS) {
+    double s[DA_FIT_SUMS] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    for (int64_t i = lo + (int64_t)threadIdx.x * DA_FIT_STRIDE; i < hi; i += (int64_t)DA_FIT_THREADS * DA_FIT_STRIDE) {
         const DD x = da_time(b, (double)i);
         const double d = (__ldg(t + i) - x.hi) - x.lo;
-        s0 += d;
-        s1 = fma((double)i - c, d, s1);
+        const double xi = (double)i - c;
+        s[0] += d;
+        s[1] = fma(xi, d, s[1]);
+        s[2] += 1.0;
+        s[3] += xi;
+        s[4] = fma(xi, xi, s[4]);
     }
-    s0 = block_sum(s0, scratch);
-    s1 = block_sum(s1, scratch);
-    if (threadIdx.x == 0) { cta_partial[2 * blockIdx.x] = s0; cta_partial[2 * blockIdx.x + 1] = s1; }
+#pragma unroll
+    for (int q = 0; q < DA_FIT_SUMS; ++q) {
+        const double v = block_sum(s[q], scratch);
+        if (threadIdx.x == 0) cta_partial[DA_FIT_SUMS * blockIdx.x + q] = v;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -427,7 +443,7 @@ frf_main_ws_kernel(const double* __restrict__ t, const double* __restrict__ u, c
                    const double* __restrict__ sums, double inv_count, double t0, double dt,
                    const double* __restrict__ fit, int n_tiles, int bins_per_group, double* __restrict__ cta_partial,
                    double* __restrict__ norm_partial) {
-    extern __shared__ __align__(128) unsigned char da_smem[];
+    extern __shared__ __align__(16) unsigned char da_smem[];
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = (int)__reduce_max_sync(0xffffffffu, (unsigned)(tid >> 5));      // uniform register
     const int bin0 = blockIdx.y * bins_per_group;

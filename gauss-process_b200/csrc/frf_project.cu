@@ -1313,7 +1313,7 @@ extern "C" int b200id_frf_project_uniform(const double* t, const double* u, cons
                        "frf_project_uniform: workspace %zu < %zu", ws_bytes, ad_off + frf_adaptive_area_bytes(nd));
         double* norm_part = (double*)((char*)ws + ad_off);
         double* diag = norm_part + (size_t)(n_cta + 8) * DA_NORMS;
-        double* fit = diag + 8;                                      // {sum delta, sum (i - c) delta}
+        double* fit = diag + 8;                                      // DA_FIT_SUMS sums of the sampled least-squares line
         int* flag_count = (int*)(diag + 32);
         int* flag_idx = flag_count + 4;
         const size_t smem = ws_ok ? dw_smem_bytes(bpg) : da_main_smem_bytes(bpg);
@@ -1324,13 +1324,13 @@ extern "C" int b200id_frf_project_uniform(const double* t, const double* u, cons
         rc = check_cuda(cudaFuncSetAttribute(frf_round_goertzel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)da_round_smem_bytes()), "smem attr");
         if (rc) return rc;
         {
-            int fg = sm_count() * 4;
+            int fg = sm_count() * 2;
             int64_t chunk = (n + fg - 1) / fg;
-            chunk = (chunk + 255) / 256 * 256;
+            chunk = (chunk + 4095) / 4096 * 4096;                    // a multiple of the sampling stride
             fg = (int)((n + chunk - 1) / chunk);
             frf_timebase_fit_kernel<<<fg, DA_FIT_THREADS, 0, st>>>(t, own_begin, own_end, t0, dt, chunk, part);
             B200ID_LAUNCH_CHECK("frf_timebase_fit_kernel");
-            frf_fold_kernel<<<1, FOLD_WARPS * 32, 0, st>>>(part, fg, 2, fit);
+            frf_fold_kernel<<<1, FOLD_WARPS * 32, 0, st>>>(part, fg, DA_FIT_SUMS, fit);
             B200ID_LAUNCH_CHECK("frf_fold_kernel(fit)");
         }
         if (ws_ok)

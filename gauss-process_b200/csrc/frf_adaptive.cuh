@@ -66,7 +66,7 @@ constexpr size_t DA_SMEM_LIMIT = 115712;         // (228 KB - 2 x 1 KB) / 2: two
 constexpr int DA_BPB = 128;                      // bins per CTA pass of the rounding-term kernel (stripes R >= 8)
 constexpr double DA_MAGIC = 4503599627370496.0 + 1262485504.0;   // 2^52 + 0x4B400000: low word of (DA_MAGIC + n) = bits of the float 2^23 + 2^22 + n
 constexpr float DA_MAGIC_F = 12582912.0f;                        // 2^23 + 2^22
-constexpr int DA_CM = DA_TS + DA_THREADS;        // entries of the chain-major arrays (R ceil(TS / R) < TS + R)
+constexpr int DA_CM = DA_TS + 2 * DA_THREADS;    // entries of the chain-major arrays (R (ceil(TS / R) | 1) < TS + 2 R)
 #ifndef DA_SIGMAS
 #define DA_SIGMAS 4.0
 #endif
@@ -788,7 +788,10 @@ frf_round_goertzel_kernel(const double* __restrict__ t, const double* __restrict
         --R;
     }
     __syncthreads();
-    const int Mmax = (DA_TS + R - 1) / R;                            // steps of the longest chain
+    // steps of the longest chain, made ODD: consecutive samples of a tile go to consecutive chains, i.e. Mmax entries
+    // apart, and an even pitch puts the 16 lanes of a 64-bit store on a handful of banks (measured: 33.5 M bank
+    // conflicts per launch with Mmax = 48)
+    const int Mmax = ((DA_TS + R - 1) / R) | 1;
     const int b2 = tid % nb2, r = tid / nb2;
     const bool active = r < R;
     const int kA = b2, kB = (b2 + nb2 < nb_all) ? b2 + nb2 : b2;     // odd count: the last pair's second bin is a dummy

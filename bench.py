@@ -53,7 +53,7 @@ N_TAPS = 1024
 VAL_ND = 150
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures
 # (profiles/r01_ncu_*.txt), 10^7-sample record: FRF reads t,u,y once (240 MB), FIR reads u,y (160 MB)
-NCU_TRAFFIC_BYTES = {"frf_main_ws_kernel": 240.1e6, "frf_main_dmma_kernel": 240.0e6, "frf_round_goertzel_kernel": 240.1e6, "frf_timebase_fit_kernel": 80.0e6,
+NCU_TRAFFIC_BYTES = {"frf_main_ws_kernel": 240.1e6, "frf_main_dmma_kernel": 240.0e6, "frf_round_goertzel_kernel": 240.1e6, "frf_timebase_fit_kernel": 20.0e6,
                      "frf_project_uniform_g_kernel": 245.9e6, "fir_fft16_kernel": 167.5e6, "frf_project_uniform3_kernel": 245.2e6, "frf_project_uniform_kernel": 245.2e6, "frf_project_kernel": 245.3e6, "fir_eval_kernel": 167.3e6,
                      "fir_fft_kernel": 163.6e6, "gp_batch_tiled_kernel": 0.33e6}
 FRF_BYTES_PER_SAMPLE = 24        # t, u, y FP64 read once
@@ -741,11 +741,11 @@ def main():
         "traffic": NCU_TRAFFIC_BYTES.get(dominant), "peak_source": peak_src,
         "launches_per_step": 2 if dominant.startswith("frf") else 1,
         "note": "FP64 bound by construction (8 FP64 flops per sample-bin against 24 bytes per sample).  Bin-adaptive form: "
-                "'achieved' is the whole b200id_frf_project_uniform call (least-squares time base 80 MB, main-term DMMA "
-                "kernel 240 MB, rounding-term kernel for the listed bins 240 MB: 560 MB of DRAM traffic per launch in "
-                "three passes, none of them bandwidth bound); the kernel named here is the largest of the three, its own "
+                "'achieved' is the whole b200id_frf_project_uniform call (least-squares time base on every 64th stamp 20 MB, "
+                "main-term DMMA kernel 240 MB, rounding-term kernel for the listed bins 240 MB: 500 MB of DRAM traffic per "
+                "launch in three passes, none of them bandwidth bound); the kernel named here is the largest of the three, its own "
                 "time and FP64 fraction are in fp64.frf_main_*; see DESIGN.md K1",
-        "call_traffic": 560.2e6 if dominant == "frf_main_ws_kernel" else None,
+        "call_traffic": 500.2e6 if dominant == "frf_main_ws_kernel" else None,
         "fp64": {
             "peak_tflops_measured": fp64_peak, **fp64,
             "frf_algorithmic_tflops": frf_flops / (frf_ms * 1e-3) / 1e12 if frf_ms > 0 else None,

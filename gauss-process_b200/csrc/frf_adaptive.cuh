@@ -116,7 +116,7 @@ __device__ __forceinline__ void da_dmma(double& d0, double& d1, double a, double
 // Time base t0 + i dt in double-double: (t0, dt) from the caller, the low words from the least-squares line through
 // delta_i = t_i - (t0 + i dt) over the SAMPLED stamps i = begin, begin + DA_FIT_STRIDE, ...:
 // fit = {sum delta, sum (i - c) delta, m, sum (i - c), sum (i - c)^2}, c = (begin + end - 1) / 2.
-constexpr int DA_FIT_STRIDE = 16;
+constexpr int DA_FIT_STRIDE = 64;
 constexpr int DA_FIT_SUMS = 5;
 struct DaBase { double t0h, t0l, dth, dtl; };
 __device__ __forceinline__ DaBase da_base(const double* __restrict__ fit, double t0, double dt, int64_t begin, int64_t end) {
@@ -179,7 +179,7 @@ __device__ __forceinline__ DaSample da_sample(const double* __restrict__ t, cons
 
 // ------------------------------------------------------------------------------------------------------------------
 // 0. sums for the least-squares line through the stamps against the caller's (t0, dt).  Every DA_FIT_STRIDE-th stamp is
-// enough: the line is determined to a small fraction of an ulp by 1e5+ points, and whatever line comes out, delta is
+// enough (one 32-byte sector out of four 128-byte lines): the line is determined to a small fraction of an ulp by 1e5+ points, and whatever line comes out, delta is
 // taken against it consistently afterwards (a quarter of the DRAM sectors of t instead of all of them)
 constexpr int DA_FIT_THREADS = 256;
 __global__ void __launch_bounds__(DA_FIT_THREADS)

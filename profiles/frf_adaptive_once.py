@@ -1,5 +1,5 @@
 """One bin-adaptive projection call of the multisine record (10^7 samples, N_d = 100) for `ncu -k regex:...`:
-    python profiles/frf_adaptive_once.py [all]        # all = every bin listed for the rounding term"""
+    python profiles/frf_adaptive_once.py [all] [square]   # all = every bin listed; square = the 150-bin validation record"""
 import ctypes as C, sys
 from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
@@ -8,8 +8,8 @@ import numpy as np, torch
 from b200id import _lib, frf, synth
 from b200id.runtime import require_cuda, to_device
 dev = require_cuda(); lib = _lib.load()
-n = 10_000_000; nd = 100
-t, u, y = synth.make_record(n, 100, "multisine", seed=1)
+n = 10_000_000; nd = 150 if "square" in sys.argv else 100
+t, u, y = synth.make_record(n, 100, "square" if "square" in sys.argv else "multisine", seed=1)
 _, w = synth.log_grid(nd)
 t_d, u_d, y_d, w_d = (to_device(a, dev) for a in (t, u, y, w))
 span = float(t[-1] - t[0]); t0, dt = float(t[0]), span / (n - 1)

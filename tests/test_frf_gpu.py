@@ -557,3 +557,39 @@ def test_adaptive_form_ill_conditioned_chain_step(frf):
     Ur, Yr = ofrf.demod_trapz(t, u, w, threads=8), ofrf.demod_trapz(t, y, w, threads=8)
     e = record("frf.adaptive.ill_conditioned_step.vs_oracle", max(rel_each(Ua, Ur), rel_each(Ya, Yr)))
     assert e < TOL
+
+
+def test_adaptive_form_unaligned_arrays(frf):
+    """Views that start 8 bytes into an allocation are not 16-byte aligned: the TMA-staged main-term kernel does not
+    apply and the plain build of the same arithmetic runs (frf_main_dmma_kernel); same result as on aligned copies up
+    to the order of the tile sums (and, for a bin at the edge of the decision, the skipped rounding term), and within
+    tolerance of the oracle."""
+    import ctypes as C
+    import torch
+    from b200id import _lib, synth
+    from b200id.runtime import require_cuda, to_device
+    dev = require_cuda()
+    n, nd = 150_001, 60
+    t, u, y = synth.make_record(n + 1, 60, "multisine", seed=13)
+    _, w = ofrf.freq_grid(nd)
+    big = [to_device(a, dev) for a in (t, u, y)]
+    t_d, u_d, y_d = (b[1:] for b in big)                                  # data_ptr() % 16 == 8
+    assert all(v.data_ptr() % 16 == 8 for v in (t_d, u_d, y_d))
+    w_d = to_device(w, dev)
+    t1, u1, y1 = t[1:], u[1:], y[1:]
+    span = float(t1[-1] - t1[0])
+    t0, dt = float(t1[0]), span / (n - 1)
+    lib = _lib.load()
+    prev = lib.b200id_frf_select_recurrence(C.c_int(2))
+    try:
+        sums = frf.moments_device(u_d, y_d, (0, n))
+        a = frf.project_uniform_device(t_d, u_d, y_d, w_d, t0, dt, (0, n), sums, 1.0 / n)
+        tc, uc, yc = (v.clone() for v in (t_d, u_d, y_d))                 # aligned copies -> warp-specialised kernel
+        b = frf.project_uniform_device(tc, uc, yc, w_d, t0, dt, (0, n), sums, 1.0 / n)
+    finally:
+        lib.b200id_frf_select_recurrence(C.c_int(prev))
+    Ua, Ya = (x.cpu().numpy() for x in frf.finalize_device(a, nd, 2.0 / span))
+    Ub, Yb = (x.cpu().numpy() for x in frf.finalize_device(b, nd, 2.0 / span))
+    Ur, Yr = ofrf.demod_trapz(t1, u1, w, threads=8), ofrf.demod_trapz(t1, y1, w, threads=8)
+    assert record("frf.adaptive.unaligned.vs_oracle", max(rel_each(Ua, Ur), rel_each(Ya, Yr))) < TOL
+    assert record("frf.adaptive.unaligned.vs_aligned", max(rel_each(Ua, Ub), rel_each(Ya, Yb))) < BUDGET

@@ -12,13 +12,14 @@
 // It only MATTERS where a bin is weakly excited: e_ki is rounding noise of size ulp(w_k t), so the rounding term is a
 // random walk of standard deviation  sigma_k ~ ulp(w_k t_max) ||a||_2 / sqrt(12),  to be compared with |U_k|.
 //
-//   0. frf_timebase_fit_kernel   least-squares line through the time stamps: the caller's (t0, dt) are FP64 numbers, and
+//   0. frf_timebase_fit_kernel   least-squares line through (every 64th of) the time stamps: the caller's (t0, dt) are FP64 numbers, and
 //                                dt = span / (n - 1) is off by up to half an ulp of t_end over the record -- a RAMP in
 //                                delta_i that is coherent with every excited bin (w_k ulp(t_end) / 4 ~ 1e-9 rad at the top
 //                                bin of a 1e7-sample record).  The fit's (alpha, beta) extend (t0, dt) to double-double,
 //                                so the ramp is part of the exact phase theta_ki and delta_i is what remains.
-//   1. frf_main_dmma_kernel      main term of ALL bins on the FP64 tensor pipe (DMMA), every warp of the CTA;
-//                                also ||a||^2 and the moments of delta that the decision needs.
+//   1. frf_main_ws_kernel        main term of ALL bins on the FP64 tensor pipe (DMMA): warp-specialised, raw samples by
+//      (frf_main_dmma_kernel      TMA bulk copies (the plain build where the arrays are not 16-byte aligned);
+//       = plain build)           also ||a||^2 and the moments of delta that the decision needs.
 //   2. frf_fold_kernel           per-CTA partials -> sums (fixed order)
 //   3. frf_decide_kernel         per bin, on the device: the rounding term is SKIPPED when
 //                                    DA_SIGMAS sigma_k + rigorous_k  <=  DA_BUDGET |S_k|     for u and for y,
@@ -30,8 +31,9 @@
 //                                together), geometry from the device-side count: no host read in between.
 //   5. frf_fold_add_kernel       adds the listed bins' rounding terms to the sums (fixed order).
 //
-// On a multisine record every bin is excited: step 4 finds an empty list and returns.  On the square-wave record
-// the bins above the plant's corner are weak and take the rounding term as before.  DA_BUDGET = 4e-10 leaves the
+// On a multisine record every INPUT bin is excited; what gets listed there are the output's bins above the plant's corner
+// (|Y_k| rolls off as 1/f^4), about a third of the grid; on the square-wave record about half.  If the list is empty
+// step 4 returns at once.  DA_BUDGET = 4e-10 leaves the
 // 1e-9 per-bin parity of U and Y (and of G = Y/U) intact: a skipped rounding term above the budget needs a
 // DA_SIGMAS = 4 sigma event, one above 1e-9 a 10 sigma event (measured |rounding term| / sigma_k <= 2 over the test
 // records, sigma_k itself an over-estimate: it takes ulp(w_k t) at the END of the record for every sample).  What the noise model cannot
@@ -43,8 +45,8 @@
 // the bracket a dense [blocks x 32] x [32 x 2 bins] product on mma.sync.m8n8k4.f64: one DMMA = 256 FMAs from ONE issue
 // slot.  A warp owns (4-bin column group, signal) units; per k-step one B fragment (table Qt) and the A fragments of
 // ALL block groups of the tile are loaded and the block groups' DMMAs issue back to back, so a DMMA never waits for
-// its accumulator.  The block phasors (tile seed x in-superblock table x block-group table, all exact) are applied
-// to the accumulator fragments with independent FMAs and a tree sum; rows are reduced with three shuffles per unit.
+// its accumulator.  The block phasors (tile seed x row table x block-group phasor, all exact) are applied by Horner over
+// the block groups (one phasor per bin), the row phasor once, the tile seed after the three-shuffle row sum.
 //
 // Deterministic for a given grid: every accumulator entry has exactly one owner and a fixed order.
 #pragma once

@@ -411,11 +411,11 @@ constexpr int DW_CWARPS = (DW_THREADS - DW_PRODUCERS) / 32;
 constexpr int DW_RAW_T = DA_TS + 4;                     // t[i0 - 2 .. i0 + TS + 2): 16-byte aligned start, halo for the weights
 constexpr int DW_RAW_DOUBLES = DW_RAW_T + 2 * DA_TS;    // t, u, y of one tile
 constexpr size_t DA_SMEM_LIMIT_1CTA = 227 * 1024;
-static inline size_t dw_smem_bytes(int bins_per_group) {
+static inline size_t dw_smem_bytes(int bins_per_group, int raw_bufs = 2) {
     const size_t bp = (size_t)da_pad4(bins_per_group);
     return (size_t)2 * bp * DA_LD * sizeof(double)              // Qt
            + (size_t)2 * 2 * DA_NB * DA_LD * sizeof(double)     // A rows, two tiles
-           + (size_t)2 * DW_RAW_DOUBLES * sizeof(double)        // raw t, u, y, two tiles
+           + (size_t)raw_bufs * DW_RAW_DOUBLES * sizeof(double) // raw t, u, y, one or two tiles
            + (size_t)8 * bp * sizeof(double2)                   // P1
            + (size_t)bp * sizeof(double2)                       // R8
            + (size_t)3 * bp * sizeof(double2)                   // Pt0 (two tiles), RT
@@ -423,11 +423,14 @@ static inline size_t dw_smem_bytes(int bins_per_group) {
            + bp * sizeof(double)                                // w
            + 64;                                                // mbarriers
 }
-static inline int dw_groups(int nd) {
+static inline int dw_groups(int nd, int raw_bufs = 2) {
     int g = 1;
-    while (dw_smem_bytes((nd + g - 1) / g) > DA_SMEM_LIMIT_1CTA) ++g;
+    while (dw_smem_bytes((nd + g - 1) / g, raw_bufs) > DA_SMEM_LIMIT_1CTA) ++g;
     return g;
 }
+// one raw buffer instead of two when that saves a bin group: every group stages the whole record again, and the
+// producers -- not the copies -- are what the consumers wait for (150 bins: one group of 150 instead of two of 75)
+static inline int dw_raw_bufs(int nd) { return dw_groups(nd, 1) < dw_groups(nd, 2) ? 1 : 2; }
 __device__ __forceinline__ unsigned dw_smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void dw_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void dw_bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
@@ -443,8 +446,8 @@ __global__ void __launch_bounds__(DW_THREADS, 1)
 frf_main_ws_kernel(const double* __restrict__ t, const double* __restrict__ u, const double* __restrict__ y,
                    int64_t n, int64_t own_begin, int64_t own_end, const double* __restrict__ w, int nd,
                    const double* __restrict__ sums, double inv_count, double t0, double dt,
-                   const double* __restrict__ fit, int n_tiles, int bins_per_group, double* __restrict__ cta_partial,
-                   double* __restrict__ norm_partial) {
+                   const double* __restrict__ fit, int n_tiles, int bins_per_group, int raw_bufs,
+                   double* __restrict__ cta_partial, double* __restrict__ norm_partial) {
     extern __shared__ __align__(16) unsigned char da_smem[];
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = (int)__reduce_max_sync(0xffffffffu, (unsigned)(tid >> 5));      // uniform register
@@ -454,8 +457,8 @@ frf_main_ws_kernel(const double* __restrict__ t, const double* __restrict__ u, c
     const int ncg = bp >> 2;
     if (nb_all <= 0) return;
 
-    double* raw = reinterpret_cast<double*>(da_smem);                // [2][DW_RAW_DOUBLES]  t (halo 2 + 2), u, y
-    double* Qt = raw + 2 * DW_RAW_DOUBLES;                           // [2 bp][DA_LD]
+    double* raw = reinterpret_cast<double*>(da_smem);                // [raw_bufs][DW_RAW_DOUBLES]  t (halo 2 + 2), u, y
+    double* Qt = raw + (size_t)raw_bufs * DW_RAW_DOUBLES;            // [2 bp][DA_LD]
     double* As = Qt + (size_t)2 * bp * DA_LD;                        // [2][2 DA_NB][DA_LD]
     double2* P1 = reinterpret_cast<double2*>(As + (size_t)2 * 2 * DA_NB * DA_LD);   // [8][bp]
     double2* R8 = P1 + (size_t)8 * bp;                               // [bp]
@@ -522,7 +525,7 @@ frf_main_ws_kernel(const double* __restrict__ t, const double* __restrict__ u, c
         if (tid == 0) {
             const int tl0 = blockIdx.x, tl1 = blockIdx.x + gridDim.x;
             if (tl0 < n_tiles && uses_tma(tl0)) issue(tl0, 0);
-            if (tl1 < n_tiles && uses_tma(tl1)) issue(tl1, 1);
+            if (raw_bufs == 2 && tl1 < n_tiles && uses_tma(tl1)) issue(tl1, 1);
         }
         // moments for the decision, in FP32 (they only need a digit or two, and every FP64 instruction of a producer
         // queues behind the consumers' DMMAs on the same pipe); delta is scaled by 2^40 so that its squares stay normal
@@ -533,12 +536,13 @@ frf_main_ws_kernel(const double* __restrict__ t, const double* __restrict__ u, c
         int it = 0;
         for (int tl = blockIdx.x; tl < n_tiles; tl += gridDim.x, ++it) {
             const int b = it & 1;
+            const int rb = raw_bufs == 2 ? b : 0;                    // raw buffer of this tile
             const int64_t i0 = tile_i0(tl);
             const int cnt = (int)min((int64_t)DA_TS, own_end - i0);
-            double* rw = raw + (size_t)b * DW_RAW_DOUBLES;
+            double* rw = raw + (size_t)rb * DW_RAW_DOUBLES;
             if (uses_tma(tl)) {
-                dw_mbar_wait(dw_smem_addr(bars + b), b ? phase1 : phase0);
-                if (b) phase1 ^= 1u; else phase0 ^= 1u;
+                dw_mbar_wait(dw_smem_addr(bars + rb), rb ? phase1 : phase0);
+                if (rb) phase1 ^= 1u; else phase0 ^= 1u;
             } else {
                 // edge tile: the producers fetch it (zeros past the owned range, clamped halo)
                 for (int j = tid; j < DW_RAW_T; j += DW_PRODUCERS) {
@@ -601,8 +605,8 @@ frf_main_ws_kernel(const double* __restrict__ t, const double* __restrict__ u, c
             dw_bar_sync(5, DW_PRODUCERS);                            // every producer is done with raw[b] (and wrote As[b])
             dw_bar_arrive(1 + b, DW_THREADS);                        // full[b]
             if (tid == 0) {
-                const int tl2 = tl + 2 * (int)gridDim.x;
-                if (tl2 < n_tiles && uses_tma(tl2)) issue(tl2, b);
+                const int tl2 = tl + raw_bufs * (int)gridDim.x;      // the tile that will use this raw buffer next
+                if (tl2 < n_tiles && uses_tma(tl2)) issue(tl2, rb);
             }
         }
         if (do_norms) {

@@ -1300,7 +1300,8 @@ extern "C" int b200id_frf_project_uniform(const double* t, const double* u, cons
         static int main_ws = -1;
         if (main_ws < 0) { const char* e = getenv("B200ID_FRF_MAIN"); main_ws = (e && e[0] == 'p') ? 0 : 1; }
         const bool ws_ok = main_ws && ((((uintptr_t)t | (uintptr_t)u | (uintptr_t)y) & 15) == 0);
-        const int groups = ws_ok ? dw_groups(nd) : da_main_groups(nd), bpg = (nd + groups - 1) / groups;
+        const int raw_bufs = dw_raw_bufs(nd);
+        const int groups = ws_ok ? dw_groups(nd, raw_bufs) : da_main_groups(nd), bpg = (nd + groups - 1) / groups;
         const int64_t nt64 = (n + DA_TS - 1) / DA_TS;
         B200ID_REQUIRE(nt64 <= 0x7fffffff, B200ID_E_UNSUPPORTED, "frf_project_uniform: record too long for one launch");
         const int nt = (int)nt64;
@@ -1316,10 +1317,10 @@ extern "C" int b200id_frf_project_uniform(const double* t, const double* u, cons
         double* fit = diag + 8;                                      // DA_FIT_SUMS sums of the sampled least-squares line
         int* flag_count = (int*)(diag + 32);
         int* flag_idx = flag_count + 4;
-        const size_t smem = ws_ok ? dw_smem_bytes(bpg) : da_main_smem_bytes(bpg);
+        const size_t smem = ws_ok ? dw_smem_bytes(bpg, raw_bufs) : da_main_smem_bytes(bpg);
         rc = check_cuda(cudaFuncSetAttribute(frf_main_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)da_main_smem_bytes(ws_ok ? 1 : bpg)), "smem attr");
         if (rc) return rc;
-        rc = check_cuda(cudaFuncSetAttribute(frf_main_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dw_smem_bytes(ws_ok ? bpg : 1)), "smem attr");
+        rc = check_cuda(cudaFuncSetAttribute(frf_main_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dw_smem_bytes(ws_ok ? bpg : 1, ws_ok ? raw_bufs : 2)), "smem attr");
         if (rc) return rc;
         rc = check_cuda(cudaFuncSetAttribute(frf_round_goertzel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)da_round_smem_bytes()), "smem attr");
         if (rc) return rc;
@@ -1335,7 +1336,7 @@ extern "C" int b200id_frf_project_uniform(const double* t, const double* u, cons
         }
         if (ws_ok)
             frf_main_ws_kernel<<<dim3(gx, groups), DW_THREADS, smem, st>>>(t, u, y, n, own_begin, own_end, w, nd, sums, inv_count, t0, dt,
-                                                                             fit, nt, bpg, part, norm_part);
+                                                                             fit, nt, bpg, raw_bufs, part, norm_part);
         else
             frf_main_dmma_kernel<<<dim3(gx, groups), DA_THREADS, smem, st>>>(t, u, y, n, own_begin, own_end, w, nd, sums, inv_count, t0, dt,
                                                                                fit, nt, bpg, part, norm_part);

@@ -667,6 +667,13 @@ def main():
     h2d_full = 8 * a.n * (3 + 3)
     # pageable host arrays: plain NumPy copies of the records (outside the timed region)
     pageable = [[np.array(x.numpy(), copy=True) for x in rec] for rec in pinned]
+    # first call on fresh pageable arrays: the host layer page-locks them in place (cudaHostRegister) while it uploads
+    # them for the first time; every later call on the same arrays runs at the pinned rate (b200id/runtime.py)
+    torch.cuda.synchronize()
+    t_first = time.perf_counter()
+    step_e2e_pageable()
+    torch.cuda.synchronize()
+    ms_e2e_pg_first = (time.perf_counter() - t_first) * 1e3
     ms_e2e_pg, (metrics_p, _, _), _, _ = timed(step_e2e_pageable, max(2, a.steps // 2), max(a.warmup, 3))
     pageable = None
     # the same work as the reference's call sequence (drop-in surface, one synchronous call per stage, NumPy in
@@ -831,7 +838,10 @@ def main():
                             "call": "identify_host(..., reuse_timebase=False): t, u, y uploaded every step"},
         "e2e_pageable": {"value": total_samples / (ms_e2e_pg * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e_pg,
                          "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                         "call": "identify_host on plain (pageable) NumPy arrays, as scipy.io.loadmat returns them"},
+                         "first_call_ms": ms_e2e_pg_first,
+                         "call": "identify_host on plain (pageable) NumPy arrays, as scipy.io.loadmat returns them: the first call "
+                                 "page-locks them in place while uploading (first_call_ms, host clock), later calls on the same "
+                                 "arrays are the timed ones; B200ID_PIN_HOST=0 restores driver-staged pageable copies"},
         "e2e_call_by_call": {"value": total_samples / (ms_calls * 1e-3), "unit": UNIT, "ms_per_step": ms_calls,
                              "h2d_bytes_per_step": h2d_calls, "d2h_bytes_per_step": d2h_calls,
                              "call": "src.frequency_transform / src.gpr / src.fir_model drop-in functions, one synchronous call per stage"},

@@ -221,3 +221,48 @@ def test_run_baseline_table_all_kernels_noise0(tmp_path, golden, kernel):
     else:
         # a different rounding-noise winner is a different, equally "valid" model: it must still be a sane one
         assert np.isfinite(rmse) and 0.5 < rmse / rmse_ref < 2.0, (kernel, rmse, rmse_ref)
+
+
+@pytest.mark.parametrize("kernel", ["dc", "di", "exp", "matern12", "matern32", "matern52", "rbf", "ss1", "ss2", "sshf", "stable_spline"])
+def test_resident_pipeline_selection_against_run_baseline_goldens(tmp_path, golden, kernel):
+    """The RESIDENT pipeline (b200id.pipeline.identify_device: validation targets standardised on the device, search run
+    with (mean, scale) = (0, 1), the winner's metric scaled back at the end) on run_baseline.py's settings (N_d = 50,
+    noise 0, validation-RMSE grid search over the full grid) against the selections of the reference's own run
+    (golden run_baseline.npz) and against the drop-in classes, whose arithmetic follows the reference's
+    inverse_transform form.  The reordering may only ever matter where the drop-in path itself departs from the
+    reference (numerically singular winners, tests/test_gp_gpu.py::test_selection_identical): wherever the drop-in path
+    reproduces the reference's selection the resident path must reproduce it too."""
+    import contextlib
+    import io
+    import torch
+    import pipeline_flow
+    from b200id import pipeline as P, synth
+    from b200id.runtime import require_cuda, to_device
+    dev = require_cuda()
+    g = golden("run_baseline")
+    n, nd = int(g["n"]), int(g["nd"])
+    tt, ut, yt = synth.make_record(n, nd, "multisine", seed=0)
+    tv, uv, yv = synth.make_record(n, nd, "square", seed=1)
+    skip = min(10, 1024 // 10)
+    train = [(to_device(tt, dev), to_device(ut, dev), to_device(yt, dev), float(tt[-1] - tt[0]), float(tt[0]))]
+    val = (to_device(tv, dev), to_device(uv, dev), to_device(yv, dev), float(tv[-1] - tv[0]), float(yv[skip]), float(tv[0]))
+    cands = P.CandidateSet.build(kernel, P.grid_candidates(kernel, max_combinations=500000), dev)
+    res = P.identify_device(train, val, nd, kernel, 0.0, cands, use_validation_metric=True)
+    torch.cuda.synchronize()
+    ptrain = synth.write_mat(tmp_path / "train.mat", tt, ut, yt)
+    pval = synth.write_mat(tmp_path / "val.mat", tv, uv, yv)
+    np.random.seed(42)
+    with contextlib.redirect_stdout(io.StringIO()):
+        drop = pipeline_flow.run(ptrain, pval, tmp_path / kernel, kernel=kernel, nd=nd, noise=0.0, optimize=True, grid=True,
+                                 max_comb=500000)
+    d_r, d_i = np.array(drop["kernel_params"]["real"]), np.array(drop["kernel_params"]["imag"])
+    g_r, g_i = g[f"{kernel}_theta_real"], g[f"{kernel}_theta_imag"]
+    same_dropin = np.array_equal(res.theta_real, d_r) and np.array_equal(res.theta_imag, d_i)
+    same_golden = np.array_equal(res.theta_real, g_r) and np.array_equal(res.theta_imag, g_i)
+    dropin_golden = np.array_equal(d_r, g_r) and np.array_equal(d_i, g_i)
+    record(f"resident_vs_golden.{kernel}", {"resident_equals_dropin": bool(same_dropin), "resident_equals_reference": bool(same_golden),
+                                            "dropin_equals_reference": bool(dropin_golden),
+                                            "theta_real": res.theta_real.tolist(), "theta_imag": res.theta_imag.tolist()})
+    if dropin_golden:
+        assert same_golden, (kernel, res.theta_real, g_r, res.theta_imag, g_i)
+    assert np.isfinite(res.fir["rmse"])

@@ -72,6 +72,9 @@ def parse_args():
                     help="samples per record of the CPU-baseline pass (0 = the bench's own n, one pass ~15 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the configs block (cfg 3 / 4 / 5)")
+    ap.add_argument("--resident-only", action="store_true",
+                    help="profiling aid (ncu launch lists): only the device-resident step, the same launches the "
+                         "headline 'value' times; prints a reduced line, not a bench line")
     ap.add_argument("--cfg5", default="auto", choices=["auto", "on", "off"],
                     help="config 5 (100 records x 1e7 samples over the ranks): auto = when WORLD_SIZE > 1")
     ap.add_argument("--cfg5-records", type=int, default=100)
@@ -653,6 +656,11 @@ def main():
     # ---- per-stage kernel times from a second, event-instrumented run (same work, same stream)
     ms_inst, _, log, _ = timed(step_resident, a.steps, 1, with_events=True)
     stage_ms = {k: sum(s.elapsed_time(e) for s, e in v) / a.steps for k, v in (log or {}).items()}
+    if a.resident_only:
+        if rank == 0:
+            print(json.dumps({"resident_only": True, "ms_per_step": ms_step, "steps": a.steps, "warmup": a.warmup,
+                              "ms_per_step_by_call": stage_ms}), flush=True)
+        return
     # ---- e2e timing: host pinned buffers in, result out
     from b200id.records import FACTS
     FACTS.clear()

@@ -38,6 +38,16 @@ __device__ unsigned long long g_gt_prof[16];
 #define GT_TICK_INIT
 #endif
 
+// independent covariance entries in flight per thread in the Gram fill and the validation prediction (each entry is a
+// ~45-instruction FP64 chain through exp; with 16 warps per SM nothing else covers its latency)
+#ifndef GT_FILL_UNROLL
+#define GT_FILL_UNROLL 1
+#endif
+#ifndef GT_PRED_UNROLL
+#define GT_PRED_UNROLL 4
+#endif
+constexpr int GT_FILL_UNROLL_N = GT_FILL_UNROLL;
+constexpr int GT_PRED_UNROLL_N = GT_PRED_UNROLL;
 constexpr int GT_THREADS = 128;
 constexpr int GT_NB = 16;
 constexpr int GT_NMAX = 127;            // n + 1 rows <= 128 = 4 warps x 32 rows
@@ -83,6 +93,7 @@ __device__ __forceinline__ void gt_fill(const KernelParams& kp, const double* __
         const double xj = j < n ? xs[j] : 0.0;
         const double yj = j < n ? y[j] : 0.0;
         const double y2j = (y2 && j < n) ? y2[j] : 0.0;
+#pragma unroll GT_FILL_UNROLL_N
         for (int r = r8; r < ld; r += 8) {
             const int i = GT_NB * J + r;
             double v = 0.0;
@@ -107,6 +118,7 @@ template <int ID>
 __device__ __forceinline__ void gt_predict_point(const KernelParams& kp, double xv, const double* __restrict__ xs,
                                                  const double* __restrict__ alpha, int n, double* out) {
     double pred = 0.0;
+#pragma unroll GT_PRED_UNROLL_N
     for (int j = 0; j < n; ++j) pred = fma(kernel_entry_t<ID>(kp, xv, xs[j]), alpha[j], pred);
     *out = pred;
 }
@@ -117,6 +129,7 @@ __device__ __forceinline__ void gt_predict_point2(const KernelParams& kp, double
                                                   const double* __restrict__ alpha, const double* __restrict__ alpha2,
                                                   int n, double* out, double* out2) {
     double pred = 0.0, pred2 = 0.0;
+#pragma unroll GT_PRED_UNROLL_N
     for (int j = 0; j < n; ++j) {
         const double kv = kernel_entry_t<ID>(kp, xv, xs[j]);
         pred = fma(kv, alpha[j], pred);

@@ -1,5 +1,7 @@
 #!/usr/bin/env python3
-"""Phase timing of gp_batch_tiled_kernel (needs a -DGT_PROFILE build: B200ID_NVCC_FLAGS=-DGT_PROFILE)."""
+"""Phase timing of gp_batch_tiled_kernel (needs a -DGT_PROFILE build of the library, e.g. B200ID_LIB=variants/gtprof.so):
+per-warp clock64 deltas per phase, NLL mode and the bench's validation-RMSE pair mode, for one CTA per SM (the
+latency of one candidate alone), one full wave (4 per SM) and many waves."""
 import ctypes as C, sys
 from pathlib import Path
 import numpy as np, torch
@@ -9,17 +11,23 @@ from b200id import gp, pipeline as P, _lib
 from b200id.runtime import require_cuda, to_device
 dev = require_cuda()
 lib = _lib.load()
-n, cands = int(sys.argv[1]) if len(sys.argv) > 1 else 100, 8192
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 100
+rng = np.random.default_rng(0)
 X = to_device(np.linspace(-1.7, 1.7, n), dev)
-y = torch.randn(n, dtype=torch.float64, device=dev)
-th = to_device(gp._theta_block(P.restart_population("matern52", cands)), dev)
-gp.batch_eval_device(3, None, th, X, y, 1e-6); torch.cuda.synchronize()
+y = to_device(rng.standard_normal(n), dev); y2 = to_device(rng.standard_normal(n), dev)
+Xv = to_device(np.linspace(-1.6, 1.6, 150), dev); yv = to_device(rng.standard_normal(150), dev); yv2 = to_device(rng.standard_normal(150), dev)
+names = ["fill", "sync(fill)", "update_finish", "sync(update)", "diag", "lookahead", "sync(diag)", "panel", "sync(panel)", "backsub", "predict", "deferred_fill", "bs_diag", "bs_sync1", "bs_update", "bs_sync2"]
 buf = (C.c_ulonglong * 16)()
-lib.b200id_debug_gt_profile(buf, 1)
-gp.batch_eval_device(3, None, th, X, y, 1e-6); torch.cuda.synchronize()
-lib.b200id_debug_gt_profile(buf, 0)
-names = ["fill", "sync(fill)", "update_finish", "sync(update)", "diag", "lookahead", "sync(diag)", "panel", "sync(panel)"]
-tot = sum(buf[:9])
-for k, nm in enumerate(names):
-    print(f"{nm:16s} {buf[k] / (cands * 4):10.0f} cycles per warp per candidate  {buf[k] / tot * 100:5.1f}%")
-print("total per warp per candidate", tot / (cands * 4))
+def run(label, cands, fn):
+    fn(); torch.cuda.synchronize()
+    lib.b200id_debug_gt_profile(buf, 1)
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record(); fn(); e.record(); torch.cuda.synchronize()
+    lib.b200id_debug_gt_profile(buf, 0)
+    tot = sum(buf[:16])
+    print(f"== {label}: {cands} candidates, {s.elapsed_time(e):.4f} ms, {tot / (cands * 4):.0f} cycles per warp per candidate")
+    print("   " + "  ".join(f"{nm} {buf[k] / (cands * 4):.0f} ({buf[k] / tot * 100:.0f}%)" for k, nm in enumerate(names) if buf[k]))
+for cands in (148, 592, 900, 8192):
+    th = to_device(gp._theta_block(P.restart_population("matern52", cands)), dev)
+    run("NLL", cands, lambda: gp.batch_eval_device(3, None, th, X, y, 1e-6, gp.METRIC_NLL))
+    run("val-RMSE pair", cands, lambda: gp.batch_eval_pair_device(3, None, th, X, y, y2, 1e-6, gp.METRIC_VAL_RMSE, Xv, yv, yv2, (0.0, 1.0), (0.0, 1.0)) if hasattr(gp, "batch_eval_pair_device") else None)

@@ -45,6 +45,8 @@ SIGNATURES = {
     "b200id_gp_batch_workspace_bytes": (Z, [L, I]),
     "b200id_gp_batch_eval": (I, [I, P, P, L, P, P, I, D, I, P, P, I, D, D, P, P, Z, P]),
     "b200id_gp_batch_eval_pair": (I, [I, P, P, L, P, P, P, I, D, I, P, P, P, I, D, D, D, D, P, P, P, Z, P]),
+    "b200id_gp_shared_workspace_bytes": (Z, [I, I, I, I]),
+    "b200id_gp_batch_eval_shared": (I, [I, P, L, P, P, I, P, P, P, I, D, I, P, P, P, I, D, D, D, D, P, P, P, Z, P]),
     "b200id_gp_batch_eval_noise": (I, [I, P, P, P, L, P, P, I, I, P, P, I, D, D, P, P, Z, P]),
     "b200id_first_strict_min": (I, [P, L, P, P, P, Z, P]),
     "b200id_first_strict_min_segments": (I, [P, P, I, P, P]),
@@ -86,7 +88,7 @@ _lib = None
 # kernels launched per successful entry-point call (bench.py reports the sum as gpu_launches)
 LAUNCHES_PER_CALL = {
     "b200id_frf_moments": 2, "b200id_frf_project": 2, "b200id_frf_project_uniform": 3, "b200id_frf_uniformity": 2, "b200id_frf_timebase_check": 2, "b200id_frf_timebase_fill": 1, "b200id_frf_finalize": 1, "b200id_cross_power": 1, "b200id_dft_bins": 2,
-    "b200id_gp_gram": 1, "b200id_gp_batch_eval": 1, "b200id_gp_batch_eval_noise": 1, "b200id_gp_batch_eval_pair": 1, "b200id_first_strict_min": 1, "b200id_gp_fit": 1,
+    "b200id_gp_gram": 1, "b200id_gp_batch_eval": 1, "b200id_gp_batch_eval_noise": 1, "b200id_gp_batch_eval_pair": 1, "b200id_gp_batch_eval_shared": 2, "b200id_first_strict_min": 1, "b200id_gp_fit": 1,
     "b200id_gp_fit_pinv": 1, "b200id_gp_predict": 1, "b200id_idft_hermitian": 1, "b200id_fir_eval": 3,
     "b200id_fp64_peak_probe": 1,
 }

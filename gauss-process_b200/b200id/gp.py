@@ -25,6 +25,12 @@ METRIC_NLL, METRIC_VAL_RMSE = 0, 1
 FAIL_METRIC = 1e10
 PINV_RCOND = 1e-15          # np.linalg.pinv default (gpr_fitting.py:86)
 SMEM_NMAX = 160             # largest n the in-shared-memory kernels accept
+TILED_NMAX = 127            # largest n of the register-tiled candidate kernel (126 with two targets)
+# shared covariance shapes (b200id_gp_batch_eval_shared): used when a list has at least SHARED_MIN_GAIN candidates per
+# distinct shape and the shape tables stay below SHARED_MAX_TABLE_BYTES; B200ID_GP_SHARED=0 switches it off
+SHARED_MIN_GAIN = 4
+SHARED_MAX_TABLE_BYTES = 256 << 20
+AMPLITUDE_SLOT = 1
 
 
 def _theta_block(thetas) -> np.ndarray:
@@ -32,6 +38,24 @@ def _theta_block(thetas) -> np.ndarray:
     out = np.zeros((th.shape[0], MAX_PARAMS), dtype=np.float64)
     out[:, :th.shape[1]] = th
     return out
+
+
+def shape_groups(kernel_id: int, thetas) -> Optional[Tuple[np.ndarray, np.ndarray]]:
+    """Candidates that differ only in the amplitude theta[1] share the shape of their covariance (every kernel but DI
+    multiplies by theta[1] last, kernels.py:98-372), and a grid-search list is a product of 1-D grids
+    (grid_search.py:173).  Returns (shape_of [C] int32, shape_theta [S, 3]) when sharing pays, else None."""
+    import os
+    if os.environ.get("B200ID_GP_SHARED", "1") == "0" or kernel_id == KERNEL_IDS["di"][0]:
+        return None
+    th = _theta_block(thetas)
+    if th.shape[0] < 2 * SHARED_MIN_GAIN:
+        return None
+    key = th.copy()
+    key[:, AMPLITUDE_SLOT] = 0.0
+    _, first, inverse = np.unique(key, axis=0, return_index=True, return_inverse=True)
+    if first.size * SHARED_MIN_GAIN > th.shape[0]:
+        return None
+    return np.ascontiguousarray(inverse.reshape(-1), dtype=np.int32), np.ascontiguousarray(th[first])
 
 
 def _flat(X) -> np.ndarray:
@@ -105,6 +129,37 @@ def batch_eval_pair_device(kernel_id: int, kernel_ids_d: Optional[torch.Tensor],
               C.c_double(scale_a[0]), C.c_double(scale_a[1]), C.c_double(scale_b[0]), C.c_double(scale_b[1]),
               ptr(out[:c]), ptr(out[c:]), ptr(ws), C.c_size_t(ws.numel()), stream_ptr())
     return out[:c], out[c:]
+
+
+def shared_fits(n_shapes: int, n: int, nv: int, two_targets: bool) -> bool:
+    """Can b200id_gp_batch_eval_shared take this problem (kernel size limit, table size cap)?"""
+    if n > (TILED_NMAX - 1 if two_targets else TILED_NMAX):
+        return False
+    return 0 < _lib.load().b200id_gp_shared_workspace_bytes(n_shapes, n, nv, int(two_targets)) <= SHARED_MAX_TABLE_BYTES
+
+
+def batch_eval_shared_device(kernel_id: int, theta_d: torch.Tensor, shape_of_d: torch.Tensor, shape_theta_d: torch.Tensor,
+                             X_d: torch.Tensor, y_a: torch.Tensor, y_b: Optional[torch.Tensor], noise: float,
+                             metric: int = METRIC_NLL, Xv_d: Optional[torch.Tensor] = None,
+                             yv_a: Optional[torch.Tensor] = None, yv_b: Optional[torch.Tensor] = None,
+                             scale_a=(0.0, 1.0), scale_b=(0.0, 1.0), out: Optional[torch.Tensor] = None):
+    """Metrics of a candidate list with shared covariance shapes (see :func:`shape_groups`): the shape tables are
+    evaluated once per distinct shape, every candidate scales its table (b200id_gp_batch_eval_shared); values
+    bit-identical to :func:`batch_eval_device` / :func:`batch_eval_pair_device`.  Returns metric_a, or
+    (metric_a, metric_b) when a second target ``y_b`` is given."""
+    dev = theta_d.device
+    c, n, s = theta_d.shape[0], X_d.numel(), shape_theta_d.shape[0]
+    two = y_b is not None
+    nv = 0 if (Xv_d is None or metric != METRIC_VAL_RMSE) else Xv_d.numel()
+    if out is None:
+        out = empty(2 * c if two else c, dev)
+    ws = Workspace.get("gpshape", _lib.load().b200id_gp_shared_workspace_bytes(s, n, nv, int(two)), dev)
+    _lib.call("b200id_gp_batch_eval_shared", C.c_int(kernel_id), ptr(theta_d), C.c_int64(c), ptr(shape_of_d), ptr(shape_theta_d),
+              C.c_int(s), ptr(X_d), ptr(y_a), ptr(y_b), C.c_int(n), C.c_double(noise), C.c_int(metric), ptr(Xv_d), ptr(yv_a),
+              ptr(yv_b), C.c_int(0 if Xv_d is None else Xv_d.numel()),
+              C.c_double(scale_a[0]), C.c_double(scale_a[1]), C.c_double(scale_b[0]), C.c_double(scale_b[1]),
+              ptr(out[:c]), ptr(out[c:]) if two else ptr(None), ptr(ws), C.c_size_t(ws.numel()), stream_ptr())
+    return (out[:c], out[c:]) if two else out
 
 
 def batch_eval_pair(kernel, thetas, X, y_a, y_b, noise: float, Xv=None, yv_a=None, yv_b=None,
@@ -284,9 +339,16 @@ def search_and_fit(kernel_id: int, start_theta, candidates, X, y, noise: float, 
     # one result buffer down: [metrics c+1 | best | idx | info | alpha n | pred n]
     down = empty(c + 4 + 2 * n, dev)
     m = down[:c + 1]
-    batch_eval_device(kernel_id, None, th, x_d, y_d, float(noise), METRIC_VAL_RMSE if use_val else METRIC_NLL,
-                      xv_d, yv_d, 0.0 if y_mean is None else float(y_mean), 1.0 if y_scale is None else float(y_scale),
-                      out=m)
+    metric = METRIC_VAL_RMSE if use_val else METRIC_NLL
+    scale = (0.0 if y_mean is None else float(y_mean), 1.0 if y_scale is None else float(y_scale))
+    groups = shape_groups(kernel_id, cand)
+    if groups is not None and shared_fits(groups[1].shape[0], n, nv, False):
+        # product grid: the start point alone, then the list through its shared covariance shapes
+        batch_eval_device(kernel_id, None, th[:1], x_d, y_d, float(noise), metric, xv_d, yv_d, scale[0], scale[1], out=m[:1])
+        batch_eval_shared_device(kernel_id, th[1:], torch.as_tensor(groups[0], device=dev), to_device(groups[1], dev),
+                                 x_d, y_d, None, float(noise), metric, xv_d, yv_d, None, scale, out=m[1:])
+    else:
+        batch_eval_device(kernel_id, None, th, x_d, y_d, float(noise), metric, xv_d, yv_d, scale[0], scale[1], out=m)
     best, idx = first_strict_min_device(m[1:])
     th_best = th[(idx + 1).clamp_(min=0)].reshape(-1).contiguous()        # idx = -1 (no finite metric) -> start theta
     alpha = down[c + 4:c + 4 + n]

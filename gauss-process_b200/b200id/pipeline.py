@@ -114,6 +114,9 @@ class CandidateSet:
     full_theta: Optional[np.ndarray] = None        # the whole host-side list (every rank can index it)
     full_theta_dev: Optional[torch.Tensor] = None  # same on the device (device-side pick of the winner)
     global_index_dev: Optional[torch.Tensor] = None
+    # shared covariance shapes of a product grid (gp.shape_groups): shape index per candidate, one theta per shape
+    shape_of: Optional[torch.Tensor] = None
+    shape_theta: Optional[torch.Tensor] = None
 
     @staticmethod
     def build(kernel: Optional[str], thetas: np.ndarray, dev, kernel_ids: Optional[np.ndarray] = None,
@@ -128,7 +131,28 @@ class CandidateSet:
                 kernel_ids = np.asarray(kernel_ids)[gidx]
         ids = None if kernel_ids is None else torch.as_tensor(np.asarray(kernel_ids, dtype=np.int32), device=dev)
         gdev = None if gidx is None else torch.as_tensor(gidx, device=dev)
-        return CandidateSet(kernel, th, to_device(th, dev), ids, gidx, full, to_device(full, dev), gdev)
+        cs = CandidateSet(kernel, th, to_device(th, dev), ids, gidx, full, to_device(full, dev), gdev)
+        if kernel is not None and kernel_ids is None:
+            groups = bgp.shape_groups(bgp.KERNEL_IDS[kernel][0], th)
+            if groups is not None:
+                cs.shape_of = torch.as_tensor(groups[0], device=dev)
+                cs.shape_theta = to_device(groups[1], dev)
+        return cs
+
+    def shared(self, n: int, nv: int, two_targets: bool) -> bool:
+        """Does this list go through b200id_gp_batch_eval_shared for a problem of this size?"""
+        return self.shape_of is not None and bgp.shared_fits(self.shape_theta.shape[0], n, nv, two_targets)
+
+
+def _candidate_metrics(cs: CandidateSet, kid: int, X_d, y_d, noise: float, Xv_d, yv_d, scaler, out=None) -> torch.Tensor:
+    """metric[C] of one target: through the shared covariance shapes when the list is a product grid."""
+    use_val = Xv_d is not None
+    metric = bgp.METRIC_VAL_RMSE if use_val else bgp.METRIC_NLL
+    mean, scale = (scaler.mean, scaler.scale) if (use_val and scaler) else (0.0, 1.0)
+    if cs.shared(X_d.numel(), Xv_d.numel() if use_val else 0, False):
+        return bgp.batch_eval_shared_device(kid, cs.theta, cs.shape_of, cs.shape_theta, X_d, y_d, None, noise, metric,
+                                            Xv_d, yv_d, None, (mean, scale), out=out)
+    return bgp.batch_eval_device(kid, cs.kernel_ids, cs.theta, X_d, y_d, noise, metric, Xv_d, yv_d, mean, scale, out=out)
 
 
 def select_candidates(cs: CandidateSet, X_d, y_d, noise: float, Xv_d=None, yv_d=None, scaler: Optional[Standardizer] = None,
@@ -136,10 +160,7 @@ def select_candidates(cs: CandidateSet, X_d, y_d, noise: float, Xv_d=None, yv_d=
     """(global index, metric) of the first strict minimum; ranks exchange 16 bytes each."""
     kid = bgp.KERNEL_IDS[cs.kernel][0] if cs.kernel is not None else 0
     use_val = Xv_d is not None
-    m = bgp.batch_eval_device(kid, cs.kernel_ids, cs.theta, X_d, y_d, noise,
-                              bgp.METRIC_VAL_RMSE if use_val else bgp.METRIC_NLL, Xv_d, yv_d,
-                              scaler.mean if (use_val and scaler) else 0.0, scaler.scale if (use_val and scaler) else 1.0,
-                              out=metric_buf)
+    m = _candidate_metrics(cs, kid, X_d, y_d, noise, Xv_d, yv_d, scaler, out=metric_buf)
     best, idx = bgp.first_strict_min_device(m)
     bi = torch.stack([best[0], idx[0].to(F64)]).cpu()
     local_idx, local_best = int(bi[1]), float(bi[0])
@@ -653,9 +674,7 @@ def select_candidates_async(cs: CandidateSet, X_d, y_d, noise: float, Xv_d=None,
     (best metric, local index as double) without synchronising."""
     kid = bgp.KERNEL_IDS[cs.kernel][0] if cs.kernel is not None else 0
     use_val = Xv_d is not None
-    m = bgp.batch_eval_device(kid, cs.kernel_ids, cs.theta, X_d, y_d, noise,
-                              bgp.METRIC_VAL_RMSE if use_val else bgp.METRIC_NLL, Xv_d, yv_d,
-                              scaler.mean if (use_val and scaler) else 0.0, scaler.scale if (use_val and scaler) else 1.0)
+    m = _candidate_metrics(cs, kid, X_d, y_d, noise, Xv_d, yv_d, scaler)
     best, idx = bgp.first_strict_min_device(m)
     return torch.stack([best[0], idx[0].to(F64)])
 
@@ -668,8 +687,12 @@ def select_candidates_pair_async(cs: CandidateSet, X_d, y_a, y_b, noise: float, 
     use_val = Xv_d is not None
     sa = (scaler_a.mean, scaler_a.scale) if (use_val and scaler_a) else (0.0, 1.0)
     sb = (scaler_b.mean, scaler_b.scale) if (use_val and scaler_b) else (0.0, 1.0)
-    ma, mb = bgp.batch_eval_pair_device(kid, cs.kernel_ids, cs.theta, X_d, y_a, y_b, noise,
-                                        bgp.METRIC_VAL_RMSE if use_val else bgp.METRIC_NLL, Xv_d, yv_a, yv_b, sa, sb)
+    metric = bgp.METRIC_VAL_RMSE if use_val else bgp.METRIC_NLL
+    if cs.shared(X_d.numel(), Xv_d.numel() if use_val else 0, True):
+        ma, mb = bgp.batch_eval_shared_device(kid, cs.theta, cs.shape_of, cs.shape_theta, X_d, y_a, y_b, noise, metric,
+                                              Xv_d, yv_a, yv_b, sa, sb)
+    else:
+        ma, mb = bgp.batch_eval_pair_device(kid, cs.kernel_ids, cs.theta, X_d, y_a, y_b, noise, metric, Xv_d, yv_a, yv_b, sa, sb)
     out = []
     for m in (ma, mb):
         best, idx = bgp.first_strict_min_device(m)

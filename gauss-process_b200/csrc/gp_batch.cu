@@ -323,7 +323,11 @@ int b200id_gp_batch_tiled_launch(int kernel_id, const int* kernel_ids, const dou
                                  const double* Xv, const double* yv, int nv, double y_mean, double y_scale,
                                  double* metric_out, const double* noise_v, cudaStream_t st,
                                  const double* y_b = nullptr, const double* yv_b = nullptr, double y_mean_b = 0.0,
-                                 double y_scale_b = 1.0, double* metric_out_b = nullptr);
+                                 double y_scale_b = 1.0, double* metric_out_b = nullptr,
+                                 const double* shape_tab = nullptr, const int* shape_of = nullptr);
+size_t b200id_gp_shape_table_doubles(int n_shapes, int n, int nv, int nrhs);
+int b200id_gp_shape_table_launch(int kernel_id, const double* shape_theta, int n_shapes, const double* X, int n,
+                                 const double* Xv, int nv, int nrhs, double* tab, cudaStream_t st);
 constexpr int GT_PAIR_NMAX = 126;       // n + 2 rows must fit the 128-row warp map of the tiled kernel
 
 // gp_large.cu: global-memory path for n > 160 (blocked Cholesky)
@@ -442,6 +446,38 @@ extern "C" int b200id_gp_batch_eval_pair(int kernel_id, const int* kernel_ids, c
     return b200id_gp_batch_tiled_launch(kernel_id, kernel_ids, theta, n_candidates, X, y_a, n, noise, metric, Xv, yv_a, nv,
                                         y_mean_a, y_scale_a, metric_out_a, nullptr, (cudaStream_t)stream,
                                         y_b, yv_b, y_mean_b, y_scale_b, metric_out_b);
+}
+
+extern "C" size_t b200id_gp_shared_workspace_bytes(int n_shapes, int n, int nv, int two_targets) {
+    if (n_shapes < 1 || n < 1 || nv < 0) return 0;
+    return b200id_gp_shape_table_doubles(n_shapes, n, nv, two_targets ? 2 : 1) * sizeof(double) + 256;
+}
+
+extern "C" int b200id_gp_batch_eval_shared(int kernel_id, const double* theta, int64_t n_candidates, const int* shape_of,
+                                           const double* shape_theta, int n_shapes,
+                                           const double* X, const double* y_a, const double* y_b, int n, double noise, int metric,
+                                           const double* Xv, const double* yv_a, const double* yv_b, int nv,
+                                           double y_mean_a, double y_scale_a, double y_mean_b, double y_scale_b,
+                                           double* metric_out_a, double* metric_out_b, void* ws, size_t ws_bytes, void* stream) {
+    const bool val = metric == B200ID_METRIC_VAL_RMSE;
+    B200ID_REQUIRE(theta && shape_of && shape_theta && X && y_a && metric_out_a, B200ID_E_ARG, "gp_batch_eval_shared: null pointer");
+    B200ID_REQUIRE((y_b == nullptr) == (metric_out_b == nullptr), B200ID_E_ARG, "gp_batch_eval_shared: second target and its output go together");
+    B200ID_REQUIRE(n_candidates > 0 && n_candidates < (1LL << 31) && n > 0 && n_shapes > 0, B200ID_E_ARG, "gp_batch_eval_shared: bad problem size");
+    B200ID_REQUIRE(kernel_id >= 0 && kernel_id < B200ID_K_COUNT, B200ID_E_ARG, "gp_batch_eval_shared: unknown kernel id %d", kernel_id);
+    B200ID_REQUIRE(kernel_id != B200ID_K_DI, B200ID_E_UNSUPPORTED, "gp_batch_eval_shared: the DI kernel's amplitude is not theta[1]");
+    B200ID_REQUIRE(metric == B200ID_METRIC_NLL || val, B200ID_E_ARG, "gp_batch_eval_shared: unknown metric %d", metric);
+    B200ID_REQUIRE(!val || (Xv && yv_a && nv > 0 && (!y_b || yv_b)), B200ID_E_ARG, "gp_batch_eval_shared: validation metric needs Xv, yv");
+    B200ID_REQUIRE(n <= (y_b ? GT_PAIR_NMAX : 127) && !force_generic_gp_path(), B200ID_E_UNSUPPORTED,
+                   "gp_batch_eval_shared: n = %d is beyond the shared-memory kernel", n);
+    if (!val) nv = 0;
+    const size_t need = b200id_gp_shared_workspace_bytes(n_shapes, n, nv, y_b != nullptr);
+    B200ID_REQUIRE(ws && ws_bytes >= need, B200ID_E_WORKSPACE, "gp_batch_eval_shared: workspace %zu < %zu bytes", ws_bytes, need);
+    double* tab = (double*)(((uintptr_t)ws + 255) & ~(uintptr_t)255);
+    int rc = b200id_gp_shape_table_launch(kernel_id, shape_theta, n_shapes, X, n, Xv, nv, y_b ? 2 : 1, tab, (cudaStream_t)stream);
+    if (rc) return rc;
+    return b200id_gp_batch_tiled_launch(kernel_id, nullptr, theta, n_candidates, X, y_a, n, noise, metric, Xv, yv_a, nv,
+                                        y_mean_a, y_scale_a, metric_out_a, nullptr, (cudaStream_t)stream,
+                                        y_b, yv_b, y_mean_b, y_scale_b, metric_out_b, tab, shape_of);
 }
 
 namespace b200id {

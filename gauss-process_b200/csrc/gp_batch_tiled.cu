@@ -139,6 +139,66 @@ __device__ __forceinline__ void gt_predict_point2(const KernelParams& kp, double
     *out2 = pred2;
 }
 
+// Shared covariance shapes (b200id_gp_batch_eval_shared).  In every kernel but DI the amplitude theta[1] is the LAST
+// factor of an entry, k = fl(theta[1] * s(x, x'; other parameters)), and a grid search is a product of 1-D grids
+// (grid_search.py:173): 900 Matern candidates are 30 shapes x 30 amplitudes.  The shape values -- the division and
+// the exp, ~50 FP64 instructions per entry -- are evaluated ONCE per distinct shape into a table (amplitude 1: 1 * s
+// is exact) and a candidate's CTA forms fl(theta[1] * s) from it: the same operations on the same operands as the
+// direct evaluation, so the metrics are bit-identical.
+//   table of shape q at tab + q * stride:  [ Gram in the CTA's block-column layout, zeros above the diagonal and in the
+//   target / padding rows : gt_off(R, nblk) ][ K(Xv, X) shape values, entry (v, j) at j * nv + v : n * nv ]
+struct GtShapes {
+    const double* tab;          // NULL -> direct evaluation
+    const int* shape_of;        // [C] table index of each candidate
+    int64_t stride;             // doubles per table
+};
+
+__host__ __device__ inline int64_t gt_shape_stride(int n, int nv, int nrhs) {
+    return ((int64_t)gt_off(gt_rows(n, nrhs), gt_nblk(n)) + (int64_t)n * nv + 1) & ~(int64_t)1;
+}
+
+template <int ID>
+__device__ __forceinline__ void gt_shape_entry(const KernelParams& kp, double xa, double xb, double* out) {
+    *out = kernel_entry_t<ID>(kp, xa, xb);
+}
+
+// grid (nblk + ceil(n * nv / GT_TAB_CHUNK), n_shapes): blockIdx.x < nblk fills block column blockIdx.x of the Gram part,
+// the other CTAs one chunk of the validation part each
+constexpr int GT_TAB_THREADS = 256;
+constexpr int GT_TAB_CHUNK = 2048;
+__global__ void __launch_bounds__(GT_TAB_THREADS)
+gp_shape_table_kernel(int kernel_id, const double* __restrict__ shape_theta, const double* __restrict__ X, int n,
+                      const double* __restrict__ Xv, int nv, int nrhs, double* __restrict__ tab, int64_t stride) {
+    const int q = blockIdx.y;
+    double th[B200ID_MAX_PARAMS];
+    for (int p = 0; p < B200ID_MAX_PARAMS; ++p) th[p] = shape_theta[(int64_t)q * B200ID_MAX_PARAMS + p];
+    th[1] = 1.0;                                         // the amplitude is applied per candidate
+    const KernelParams kp = make_kernel_params(kernel_id, th);
+    const int R = gt_rows(n, nrhs), nblk = gt_nblk(n);
+    double* out = tab + (int64_t)q * stride;
+    if ((int)blockIdx.x < nblk) {
+        const int J = blockIdx.x, ld = R - GT_NB * J;
+        double* col = out + gt_off(R, J);
+        for (int e = threadIdx.x; e < GT_NB * ld; e += GT_TAB_THREADS) {
+            const int c = e / ld, r = e - c * ld;
+            const int i = GT_NB * J + r, j = GT_NB * J + c;
+            double v = 0.0;
+            if (i < n && j < n && i >= j) { B200ID_DISPATCH_KERNEL(kernel_id, gt_shape_entry, kp, X[i], X[j], &v) }
+            col[e] = v;
+        }
+    } else {
+        double* val = out + gt_off(R, nblk);
+        const int e0 = ((int)blockIdx.x - nblk) * GT_TAB_CHUNK;
+        const int e1 = min(e0 + GT_TAB_CHUNK, n * nv);
+        for (int e = e0 + threadIdx.x; e < e1; e += GT_TAB_THREADS) {
+            const int j = e / nv, v = e - j * nv;
+            double k = 0.0;
+            B200ID_DISPATCH_KERNEL(kernel_id, gt_shape_entry, kp, Xv[v], X[j], &k)
+            val[e] = k;
+        }
+    }
+}
+
 // 4 CTAs per SM: 128 registers per thread (without the bound ptxas takes 154, i.e. 3 CTAs per SM, and the search
 // loses a quarter of its throughput: 900 x 2 validation-RMSE candidates 0.42 -> 0.26 ms, 4096 NLL 0.84 -> 0.60 ms)
 __global__ void __launch_bounds__(GT_THREADS, 4)
@@ -148,7 +208,7 @@ gp_batch_tiled_kernel(int kernel_id, const int* __restrict__ kernel_ids, const d
                       double y_mean, double y_scale, double* __restrict__ metric_out,
                       double* __restrict__ fit_alpha, double* __restrict__ fit_L, int* __restrict__ fit_info,
                       const double* __restrict__ noise_v /*per-candidate diagonal term, or NULL*/,
-                      const GtSecond sec) {
+                      const GtSecond sec, const GtShapes shp) {
     extern __shared__ __align__(16) double sm[];
     const int nrhs = sec.y ? 2 : 1;
     const int R = gt_rows(n, nrhs), nblk = gt_nblk(n);
@@ -182,7 +242,29 @@ gp_batch_tiled_kernel(int kernel_id, const int* __restrict__ kernel_ids, const d
         fit_L += cand * (int64_t)n * n;
         fit_info += cand;
     }
-    B200ID_DISPATCH_KERNEL(kid, gt_fill, kp, xs, y, n, noise, R, nblk, Lb, sec.y)
+    const double* shape = shp.tab ? shp.tab + (int64_t)shp.shape_of[cand] * shp.stride : nullptr;
+    if (shape) {
+        // shared shapes: fl(amplitude * shape value) for the whole storage (zeros stay zeros), then the diagonal term
+        // and the target rows
+        const int G = gt_off(R, nblk);
+        const double2* src = reinterpret_cast<const double2*>(shape);
+        double2* dst = reinterpret_cast<double2*>(Lb);
+#pragma unroll 4
+        for (int e = tid; e < G / 2; e += GT_THREADS) {
+            const double2 v = src[e];
+            dst[e] = make_double2(B200ID_MUL(kp.p1, v.x), B200ID_MUL(kp.p1, v.y));
+        }
+        __syncthreads();
+        for (int j = tid; j < n; j += GT_THREADS) {
+            const int J = j >> 4;
+            double* col = Lb + gt_off(R, J) + (j & 15) * (R - GT_NB * J) - GT_NB * J;      // col[i] = entry (i, j)
+            col[j] = B200ID_ADD(col[j], noise);
+            col[n] = y[j];
+            if (sec.y) col[n + 1] = sec.y[j];
+        }
+    } else {
+        B200ID_DISPATCH_KERNEL(kid, gt_fill, kp, xs, y, n, noise, R, nblk, Lb, sec.y)
+    }
     GT_TICK(0);
     __syncthreads();
     GT_TICK(1);
@@ -419,16 +501,33 @@ gp_batch_tiled_kernel(int kernel_id, const int* __restrict__ kernel_ids, const d
         return;
     }
     double se = 0.0, se2 = 0.0;
+    const double* shape_val = shape ? shape + gt_off(R, nblk) : nullptr;
     for (int v = tid; v < nv; v += GT_THREADS) {
         const double xv = Xv[v];
         double pred = 0.0, pred2 = 0.0;
-        if (sec.y) {
+        if (shape_val) {
+            // covariance entries from the shape table (coalesced over the validation points), same dot product
+            const double* kcol = shape_val + v;
+            if (sec.y) {
+#pragma unroll 10
+                for (int j = 0; j < n; ++j) {
+                    const double kv = B200ID_MUL(kp.p1, kcol[(int64_t)j * nv]);
+                    pred = fma(kv, zz[j], pred);
+                    pred2 = fma(kv, zz2[j], pred2);
+                }
+            } else {
+#pragma unroll 10
+                for (int j = 0; j < n; ++j) pred = fma(B200ID_MUL(kp.p1, kcol[(int64_t)j * nv]), zz[j], pred);
+            }
+        } else if (sec.y) {
             B200ID_DISPATCH_KERNEL(kid, gt_predict_point2, kp, xv, xs, zz, zz2, n, &pred, &pred2)
+        } else {
+            B200ID_DISPATCH_KERNEL(kid, gt_predict_point, kp, xv, xs, zz, n, &pred)
+        }
+        if (sec.y) {
             pred2 = pred2 * sec.y_scale + sec.y_mean;
             const double e2 = sec.yv[v] - pred2;
             se2 = fma(e2, e2, se2);
-        } else {
-            B200ID_DISPATCH_KERNEL(kid, gt_predict_point, kp, xv, xs, zz, n, &pred)
         }
         pred = pred * y_scale + y_mean;
         const double e = yv[v] - pred;
@@ -454,15 +553,29 @@ int b200id_gp_batch_tiled_launch(int kernel_id, const int* kernel_ids, const dou
                                  const double* Xv, const double* yv, int nv, double y_mean, double y_scale,
                                  double* metric_out, const double* noise_v, cudaStream_t st,
                                  const double* y_b, const double* yv_b, double y_mean_b, double y_scale_b,
-                                 double* metric_out_b) {
+                                 double* metric_out_b, const double* shape_tab, const int* shape_of) {
     const GtSecond sec{y_b, yv_b, y_mean_b, y_scale_b, metric_out_b};
+    const GtShapes shp{shape_tab, shape_of, gt_shape_stride(n, nv, y_b ? 2 : 1)};
     const size_t smem = gt_smem_bytes(n, y_b ? 2 : 1);
     int rc = check_cuda(cudaFuncSetAttribute(gp_batch_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute(gp tiled)");
     if (rc) return rc;
     gp_batch_tiled_kernel<<<(unsigned)n_candidates, GT_THREADS, smem, st>>>(kernel_id, kernel_ids, theta, X, y, n, noise, metric,
                                                                            Xv, yv, nv, y_mean, y_scale, metric_out,
-                                                                           nullptr, nullptr, nullptr, noise_v, sec);
+                                                                           nullptr, nullptr, nullptr, noise_v, sec, shp);
     B200ID_LAUNCH_CHECK("gp_batch_tiled_kernel");
+    return B200ID_OK;
+}
+
+// Shape tables for b200id_gp_batch_eval_shared: n_shapes tables of gt_shape_stride(n, nv, nrhs) doubles each.
+size_t b200id_gp_shape_table_doubles(int n_shapes, int n, int nv, int nrhs) {
+    return (size_t)n_shapes * (size_t)gt_shape_stride(n, nv, nrhs);
+}
+int b200id_gp_shape_table_launch(int kernel_id, const double* shape_theta, int n_shapes, const double* X, int n,
+                                 const double* Xv, int nv, int nrhs, double* tab, cudaStream_t st) {
+    const dim3 grid((unsigned)(gt_nblk(n) + ((int64_t)n * nv + GT_TAB_CHUNK - 1) / GT_TAB_CHUNK), (unsigned)n_shapes);
+    gp_shape_table_kernel<<<grid, GT_TAB_THREADS, 0, st>>>(kernel_id, shape_theta, X, n, Xv, nv, nrhs, tab,
+                                                           gt_shape_stride(n, nv, nrhs));
+    B200ID_LAUNCH_CHECK("gp_shape_table_kernel");
     return B200ID_OK;
 }
 
@@ -485,7 +598,8 @@ int b200id_gp_fit_tiled_launch(int kernel_id, const double* theta, const double*
     int rc = check_cuda(cudaFuncSetAttribute(gp_batch_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute(gp tiled)");
     if (rc) return rc;
     gp_batch_tiled_kernel<<<n_problems, GT_THREADS, smem, st>>>(kernel_id, nullptr, theta, X, y, n, diag_add, GT_METRIC_FIT,
-                                                               nullptr, nullptr, 0, 0.0, 1.0, nullptr, alpha_out, L_out, info_out, nullptr, GtSecond{nullptr, nullptr, 0.0, 1.0, nullptr});
+                                                               nullptr, nullptr, 0, 0.0, 1.0, nullptr, alpha_out, L_out, info_out, nullptr, GtSecond{nullptr, nullptr, 0.0, 1.0, nullptr},
+                                                               GtShapes{nullptr, nullptr, 0});
     B200ID_LAUNCH_CHECK("gp_batch_tiled_kernel(fit)");
     return B200ID_OK;
 }

@@ -207,6 +207,21 @@ int b200id_gp_batch_eval_pair(int kernel_id, const int* kernel_ids, const double
                               const double* Xv, const double* yv_a, const double* yv_b, int nv,
                               double y_mean_a, double y_scale_a, double y_mean_b, double y_scale_b,
                               double* metric_out_a, double* metric_out_b, void* ws, size_t ws_bytes, void* stream);
+/* Candidate lists that are products of 1-D grids (grid_search.py:173: itertools.product of the per-parameter grids):
+ * in every kernel but DI the amplitude theta[1] is the last factor of a covariance entry, k = fl(theta[1] * s(x, x')),
+ * so candidates that differ only in theta[1] share the shape values s.  shape_theta [S][B200ID_MAX_PARAMS] holds one
+ * theta per distinct shape (its amplitude slot is ignored), shape_of [C] the shape index of every candidate; the S
+ * shape tables are evaluated first (one launch) and every candidate forms its entries from its table by the same
+ * final multiplication as the direct evaluation: metrics bit-identical to b200id_gp_batch_eval(_pair).
+ * y_b / yv_b / metric_out_b NULL -> one target.  n <= 127 (126 with two targets); one kernel id per call.
+ * Workspace: b200id_gp_shared_workspace_bytes(S, n, nv (0 for NLL), two_targets). */
+size_t b200id_gp_shared_workspace_bytes(int n_shapes, int n, int nv, int two_targets);
+int b200id_gp_batch_eval_shared(int kernel_id, const double* theta, int64_t n_candidates, const int* shape_of,
+                                const double* shape_theta, int n_shapes,
+                                const double* X, const double* y_a, const double* y_b, int n, double noise, int metric,
+                                const double* Xv, const double* yv_a, const double* yv_b, int nv,
+                                double y_mean_a, double y_scale_a, double y_mean_b, double y_scale_b,
+                                double* metric_out_a, double* metric_out_b, void* ws, size_t ws_bytes, void* stream);
 /* Same, with one noise variance PER CANDIDATE (noise [C], device): the finite-difference points of the
  * L-BFGS-B hyperparameter optimisation perturb log(noise) as well, gpr_fitting.py:104-123,130,147 -- the
  * value and all forward-difference points of one gradient are one launch. */

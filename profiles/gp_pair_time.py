@@ -26,4 +26,14 @@ def timed(fn, reps=10):
 ms_val, m = timed(lambda: bgp.batch_eval_device(kid, None, cands.theta, gi.X_d, y, 1e-6, bgp.METRIC_VAL_RMSE, Xv, yv, 0.0, 1.0))
 th = to_device(bgp._theta_block(P.restart_population("matern52", 4096)), dev)
 ms_nll, m2 = timed(lambda: bgp.batch_eval_device(kid, None, th, gi.X_d, y, 1e-6, bgp.METRIC_NLL))
+y2 = to_device(rng.standard_normal(nd), dev); yv2 = to_device(rng.standard_normal(150), dev)
+ms_pair, (pa, pb) = timed(lambda: bgp.batch_eval_pair_device(kid, None, cands.theta, gi.X_d, y, y2, 1e-6, bgp.METRIC_VAL_RMSE, Xv, yv, yv2))
+line = "pair val-RMSE 900 x 2: direct %.4f ms" % ms_pair
+if cands.shape_of is not None:
+    ms_sh, (sa, sb) = timed(lambda: bgp.batch_eval_shared_device(kid, cands.theta, cands.shape_of, cands.shape_theta, gi.X_d, y, y2, 1e-6, bgp.METRIC_VAL_RMSE, Xv, yv, yv2))
+    ms_sh_nll, sn = timed(lambda: bgp.batch_eval_shared_device(kid, cands.theta, cands.shape_of, cands.shape_theta, gi.X_d, y, None, 1e-6, bgp.METRIC_NLL))
+    ms_d_nll, dn = timed(lambda: bgp.batch_eval_device(kid, None, cands.theta, gi.X_d, y, 1e-6, bgp.METRIC_NLL))
+    line += "   shared shapes (%d) %.4f ms, identical bits: %s   NLL 900: direct %.4f shared %.4f identical: %s" % (
+        cands.shape_theta.shape[0], ms_sh, bool(torch.equal(pa, sa) and torch.equal(pb, sb)), ms_d_nll, ms_sh_nll, bool(torch.equal(sn, dn)))
+print(line)
 print(os.environ.get("B200ID_LIB", "default").split("/")[-1], "val-RMSE 900: %.4f ms   NLL 4096: %.4f ms   checksums %.12e %.12e" % (ms_val, ms_nll, float(m[torch.isfinite(m)].sum()), float(m2[torch.isfinite(m2) & (m2 < 1e9)].sum())))

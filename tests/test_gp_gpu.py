@@ -452,6 +452,75 @@ def test_pair_evaluation_shares_one_factorisation(gp, n, name, mode):
     assert ogp.first_strict_min(ma) == ogp.first_strict_min(ra) and ogp.first_strict_min(mb) == ogp.first_strict_min(rb)
 
 
+@pytest.mark.parametrize("n,name,mode,two", [(100, "matern52", "val", True), (100, "matern52", "nll", False), (50, "rbf", "val", False),
+                                             (60, "dc", "val", True), (126, "rbf", "val", True), (127, "ss2", "nll", False), (64, "sshf", "val", True),
+                                             (33, "stable_spline", "nll", True), (100, "exp", "val", False),
+                                             (90, "matern12", "val", True), (17, "matern32", "nll", False)])
+def test_shared_shape_tables_are_bit_identical(gp, n, name, mode, two):
+    """b200id_gp_batch_eval_shared: a product grid evaluated through one covariance-shape table per distinct
+    (theta without its amplitude) gives the SAME BITS as the direct evaluation of every candidate -- the table holds
+    the entry with amplitude 1 and the candidate applies the reference's final multiplication (kernels.py:98-372),
+    so the operations and operands are identical.  Covers the failure (1e10) and NaN categories (ss2 / sshf at noise 0)."""
+    import torch
+    from b200id.runtime import require_cuda, to_device
+    dev = require_cuda()
+    rng = np.random.default_rng(7 * n)
+    X = np.linspace(-1.7, 1.6, n)
+    ya = np.sin(2.0 * X) + 0.1 * rng.standard_normal(n)
+    yb = np.cos(3.0 * X) * 0.5 + 0.05 * rng.standard_normal(n)
+    cands = ogp.grid_candidates(name, 5000 if name == "dc" else 900)     # grid_search.py:173-183: product of the 1-D grids (DC: sampled)
+    groups = gp.shape_groups(ogp.KERNELS[name][0], cands)
+    assert groups is not None and groups[1].shape[0] * 4 <= len(cands)
+    noise = 0.0 if name in ("ss2", "sshf") else 1e-6
+    kid = ogp.KERNELS[name][0]
+    d = lambda a: None if a is None else to_device(np.ascontiguousarray(a, dtype=np.float64), dev)
+    Xv = yva = yvb = None
+    metric, sa, sb = gp.METRIC_NLL, (0.0, 1.0), (0.0, 1.0)
+    if mode == "val":
+        Xv = np.linspace(-1.5, 1.5, 150)
+        yva, yvb = 0.7 * np.sin(2.0 * Xv) + 0.2, 1.3 * np.cos(3.0 * Xv) - 0.1
+        metric, sa, sb = gp.METRIC_VAL_RMSE, (0.2, 0.7), (-0.1, 1.3)
+    th = d(gp._theta_block(cands))
+    got = gp.batch_eval_shared_device(kid, th, torch.as_tensor(groups[0], device=dev), d(groups[1]), d(X), d(ya),
+                                      d(yb) if two else None, noise, metric, d(Xv), d(yva), d(yvb) if two else None, sa, sb)
+    if two:
+        ref = gp.batch_eval_pair_device(kid, None, th, d(X), d(ya), d(yb), noise, metric, d(Xv), d(yva), d(yvb), sa, sb)
+    else:
+        got, ref = (got,), (gp.batch_eval_device(kid, None, th, d(X), d(ya), noise, metric, d(Xv), d(yva), sa[0], sa[1]),)
+    for g_, r_ in zip(got, ref):
+        g_, r_ = g_.cpu().numpy(), r_.cpu().numpy()
+        assert np.array_equal(g_.view(np.uint64), r_.view(np.uint64)), f"max rel diff {rel_max(g_[np.isfinite(r_)], r_[np.isfinite(r_)])}"
+    record(f"gp.shared_shapes.{name}.n{n}.{mode}.bit_identical", 0.0)
+
+
+def test_shared_shapes_grouping_rules(gp):
+    """shape_groups: DI (amplitude is theta[0]) and lists without enough sharing are left to the direct evaluation;
+    B200ID_GP_SHARED=0 switches the path off; search_and_fit returns the same metrics either way."""
+    import os
+    assert gp.shape_groups(ogp.KERNELS["di"][0], ogp.grid_candidates("di", 900)) is None
+    rng = np.random.default_rng(0)
+    assert gp.shape_groups(3, rng.uniform(0.1, 2.0, size=(500, 2))) is None          # random restarts: nothing shared
+    cands = ogp.grid_candidates("matern52", 900)
+    so, st = gp.shape_groups(3, cands)
+    assert st.shape == (30, 3) and so.shape == (900,)
+    assert np.array_equal(gp._theta_block(cands)[:, [0, 2]], st[so][:, [0, 2]])
+    n = 50
+    X = np.linspace(-1.7, 1.6, n)
+    y = np.sin(2.0 * X) + 0.1 * rng.standard_normal(n)
+    Xv = np.linspace(-1.5, 1.5, 150)
+    yv = 0.7 * np.sin(2.0 * Xv) + 0.2
+    res = gp.search_and_fit(3, cands[0], cands, X, y, 1e-6, 1e-6 + 1e-10, Xv=Xv, yv=yv, y_mean=0.2, y_scale=0.7)
+    os.environ["B200ID_GP_SHARED"] = "0"
+    try:
+        assert gp.shape_groups(3, cands) is None
+        gp._fit_memo.clear()
+        ref = gp.search_and_fit(3, cands[0], cands, X, y, 1e-6, 1e-6 + 1e-10, Xv=Xv, yv=yv, y_mean=0.2, y_scale=0.7)
+    finally:
+        del os.environ["B200ID_GP_SHARED"]
+    assert res["index"] == ref["index"] and res["start_metric"] == ref["start_metric"]
+    assert np.array_equal(res["metrics"], ref["metrics"])
+
+
 @pytest.mark.parametrize("n,name", [(100, "matern52"), (33, "rbf"), (127, "dc"), (200, "matern32")])
 def test_fit_batch_equals_single_fits(gp, n, name):
     """b200id_gp_fit_batch (the Re and Im final fits as one launch) = the single fits, problem by problem,

@@ -147,6 +147,7 @@ __device__ __forceinline__ void gt_predict_point2(const KernelParams& kp, double
 // direct evaluation, so the metrics are bit-identical.
 //   table of shape q at tab + q * stride:  [ Gram in the CTA's block-column layout, zeros above the diagonal and in the
 //   target / padding rows : gt_off(R, nblk) ][ K(Xv, X) shape values, entry (v, j) at j * nv + v : n * nv ]
+//   (coalesced over the validation points; a row-per-point layout with vector loads measured slower)
 struct GtShapes {
     const double* tab;          // NULL -> direct evaluation
     const int* shape_of;        // [C] table index of each candidate
@@ -164,6 +165,10 @@ __device__ __forceinline__ void gt_shape_entry(const KernelParams& kp, double xa
 
 // grid (nblk + ceil(n * nv / GT_TAB_CHUNK), n_shapes): blockIdx.x < nblk fills block column blockIdx.x of the Gram part,
 // the other CTAs one chunk of the validation part each
+#ifndef GT_TAB_UNROLL_N
+#define GT_TAB_UNROLL_N 10
+#endif
+constexpr int GT_TAB_UNROLL = GT_TAB_UNROLL_N;     // table loads in flight per thread in the validation prediction
 constexpr int GT_TAB_THREADS = 256;
 constexpr int GT_TAB_CHUNK = 2048;
 __global__ void __launch_bounds__(GT_TAB_THREADS)
@@ -197,6 +202,14 @@ gp_shape_table_kernel(int kernel_id, const double* __restrict__ shape_theta, con
             val[e] = k;
         }
     }
+}
+
+// a[k] for a run-time k out of a register array (a chain of selects: no local-memory copy of the array)
+__device__ __forceinline__ double lc_at(const double (&a)[GT_NB], int k) {
+    double v = a[0];
+#pragma unroll
+    for (int q = 1; q < GT_NB; ++q) v = (k == q) ? a[q] : v;
+    return v;
 }
 
 // 4 CTAs per SM: 128 registers per thread (without the bound ptxas takes 154, i.e. 3 CTAs per SM, and the search
@@ -340,6 +353,31 @@ gp_batch_tiled_kernel(int kernel_id, const int* __restrict__ kernel_ids, const d
             for (int c = 0; c < GT_NB; ++c)
                 d[c] = (lane < ncols && c <= lane) ? colJ[c * ldJ + lane] : 0.0;
             int fail = 0;
+            if (ncols == GT_NB) {
+                // full block: straight-line code, no branch per pivot (the 16 pivots are the critical path of the
+                // block column; a failed pivot only raises the flag, what follows it is discarded).  The next pivot is
+                // broadcast from lane k + 1's own product l * l, ahead of the 15 shuffles of the trailing update
+                // (same value as its update below: its partner in that update is its own l).
+                double piv = __shfl_sync(0xffffffffu, d[0], 0);
+#pragma unroll
+                for (int k = 0; k < GT_NB; ++k) {
+                    const bool bad = (piv <= 0.0) || (piv == INFINITY);     // NaN compares false: the factorisation goes on
+                    fail = (fail == 0 && bad) ? k + 1 : fail;
+                    double inv = rsqrt(piv);
+                    double dk = piv * inv;
+                    dk = fma(0.5 * inv, fma(-dk, dk, piv), dk);
+                    inv = fma(inv, fma(-dk, inv, 1.0), inv);
+                    const double l = (lane == k) ? dk : d[k] * inv;
+                    d[k] = l;
+                    if (lane == k) idg[GT_NB * J + k] = inv;
+                    if (k + 1 < GT_NB) piv = __shfl_sync(0xffffffffu, fma(-l, l, d[k + 1]), k + 1);
+#pragma unroll
+                    for (int c = k + 1; c < GT_NB; ++c) {
+                        const double lc = __shfl_sync(0xffffffffu, l, c);
+                        d[c] = fma(-l, lc, d[c]);
+                    }
+                }
+            } else {
 #pragma unroll
             for (int k = 0; k < GT_NB; ++k) {
                 if (k < ncols && fail == 0) {
@@ -364,6 +402,7 @@ gp_batch_tiled_kernel(int kernel_id, const int* __restrict__ kernel_ids, const d
                         }
                     }
                 }
+            }
             }
             if (fail != 0) {
                 if (lane == 0) status = GT_NB * J + fail;
@@ -400,6 +439,19 @@ gp_batch_tiled_kernel(int kernel_id, const int* __restrict__ kernel_ids, const d
             const int r = ncols + tid;                  // row offset inside the block column
             if (r < ldJ && GT_NB * J + r < n + nrhs) {
                 double x[GT_NB];
+                if (ncols == GT_NB) {
+                    // full block: no per-column tests
+#pragma unroll
+                    for (int c = 0; c < GT_NB; ++c) x[c] = colJ[c * ldJ + r];
+#pragma unroll
+                    for (int c = 0; c < GT_NB; ++c) {
+                        x[c] *= idg[GT_NB * J + c];
+#pragma unroll
+                        for (int q = c + 1; q < GT_NB; ++q) x[q] = fma(-x[c], colJ[c * ldJ + q], x[q]);
+                    }
+#pragma unroll
+                    for (int c = 0; c < GT_NB; ++c) colJ[c * ldJ + r] = x[c];
+                } else {
 #pragma unroll
                 for (int c = 0; c < GT_NB; ++c) x[c] = (c < ncols) ? colJ[c * ldJ + r] : 0.0;
 #pragma unroll
@@ -416,6 +468,7 @@ gp_batch_tiled_kernel(int kernel_id, const int* __restrict__ kernel_ids, const d
 #pragma unroll
                 for (int c = 0; c < GT_NB; ++c)
                     if (c < ncols) colJ[c * ldJ + r] = x[c];
+                }
             }
         }
         GT_TICK(7);
@@ -457,32 +510,95 @@ gp_batch_tiled_kernel(int kernel_id, const int* __restrict__ kernel_ids, const d
         if (sec.y) zz2[j] = Lat(n + 1, j);
     }
     __syncthreads();
+    // Column `lane` of diagonal block J below its diagonal, lc[k] = L[16 J + k][16 J + lane] for lane < k < ncols (zero
+    // elsewhere): 16 consecutive doubles per lane, fetched as 8 vector loads.  Warp 0 fetches the NEXT block's column
+    // while all warps run the update of the current one.
+    auto load_lc = [&](int J, int ncols, double (&lc)[GT_NB]) {
+        const double2* colp = reinterpret_cast<const double2*>(Lb + gt_off(R, J) + min(lane, GT_NB - 1) * (R - GT_NB * J));
+#pragma unroll
+        for (int q = 0; q < GT_NB / 2; ++q) {
+            const double2 v = colp[q];
+            lc[2 * q] = (lane < 2 * q && 2 * q < ncols) ? v.x : 0.0;
+            lc[2 * q + 1] = (lane < 2 * q + 1 && 2 * q + 1 < ncols) ? v.y : 0.0;
+        }
+    };
+    double lc[GT_NB];
+    if (tid < 32) load_lc(nblk - 1, n - GT_NB * (nblk - 1), lc);
     for (int J = nblk - 1; J >= 0; --J) {
         const int ncols = min(GT_NB, n - GT_NB * J);
+        GT_TICK(12);
         if (tid < 32) {
-            // 16 x 16 upper-triangular solve inside warp 0: alpha_k = (z_k - sum_{r>k} L[r][k] alpha_r) / L[k][k]
-            for (int k = ncols - 1; k >= 0; --k) {
-                const int gk = GT_NB * J + k;
-                const double ak = zz[gk] * idg[gk];
-                const double ak2 = sec.y ? zz2[gk] * idg[gk] : 0.0;
-                __syncwarp();
-                if (lane == 0) { zz[gk] = ak; if (sec.y) zz2[gk] = ak2; }
-                if (lane < k) {
-                    const double lkj = Lat(gk, GT_NB * J + lane);
-                    zz[GT_NB * J + lane] = fma(-lkj, ak, zz[GT_NB * J + lane]);
-                    if (sec.y) zz2[GT_NB * J + lane] = fma(-lkj, ak2, zz2[GT_NB * J + lane]);
+            // 16 x 16 upper-triangular solve inside warp 0: alpha_k = (z_k - sum_{r>k} L[r][k] alpha_r) / L[k][k].
+            // Lane j keeps z_j and column j of the diagonal block in registers and alpha_k travels by one shuffle per
+            // step: the same operations in the same order as a sweep through shared memory, without its two round
+            // trips per step; straight-line code for a full block (a branch per step costs more than the arithmetic).
+            const bool own = lane < ncols;
+            double z = own ? zz[GT_NB * J + lane] : 0.0;
+            double z2 = (own && sec.y) ? zz2[GT_NB * J + lane] : 0.0;
+            const double dinv = own ? idg[GT_NB * J + lane] : 0.0;
+            GT_TICK(13);
+            if (ncols == GT_NB && sec.y) {
+#pragma unroll
+                for (int k = GT_NB - 1; k >= 0; --k) {
+                    const double ak = __shfl_sync(0xffffffffu, z * dinv, k);
+                    const double ak2 = __shfl_sync(0xffffffffu, z2 * dinv, k);
+                    const double t = fma(-lc[k], ak, z), t2 = fma(-lc[k], ak2, z2);
+                    z = (lane == k) ? ak : ((lane < k) ? t : z);
+                    z2 = (lane == k) ? ak2 : ((lane < k) ? t2 : z2);
                 }
-                __syncwarp();
+            } else if (ncols == GT_NB) {
+#pragma unroll
+                for (int k = GT_NB - 1; k >= 0; --k) {
+                    const double ak = __shfl_sync(0xffffffffu, z * dinv, k);
+                    const double t = fma(-lc[k], ak, z);
+                    z = (lane == k) ? ak : ((lane < k) ? t : z);
+                }
+            } else {
+                for (int k = ncols - 1; k >= 0; --k) {
+                    const double ak = __shfl_sync(0xffffffffu, z * dinv, k);
+                    const double ak2 = sec.y ? __shfl_sync(0xffffffffu, z2 * dinv, k) : 0.0;
+                    const double lk = lc_at(lc, k);
+                    if (lane == k) { z = ak; z2 = ak2; }
+                    else if (lane < k) { z = fma(-lk, ak, z); z2 = fma(-lk, ak2, z2); }
+                }
+            }
+            GT_TICK(14);
+            if (own) {
+                zz[GT_NB * J + lane] = z;
+                if (sec.y) zz2[GT_NB * J + lane] = z2;
             }
         }
         __syncthreads();
-        // z[j] -= sum_{k in block J} L[k][j] alpha_k for j < 16 J
+        GT_TICK(15);
+        if (tid < 32 && J > 0) load_lc(J - 1, GT_NB, lc);
+        // z[j] -= sum_{k in block J} L[k][j] alpha_k for j < 16 J (row 16 J + k of column j: consecutive k are
+        // consecutive doubles, so a full block is 8 vector loads issued ahead of the 16 dependent FMAs)
         for (int j = tid; j < GT_NB * J; j += GT_THREADS) {
             double s = zz[j], s2 = sec.y ? zz2[j] : 0.0;
-            for (int k = 0; k < ncols; ++k) {
-                const double lkj = Lat(GT_NB * J + k, j);
-                s = fma(-lkj, zz[GT_NB * J + k], s);
-                if (sec.y) s2 = fma(-lkj, zz2[GT_NB * J + k], s2);
+            const int Jc = j >> 4;
+            const double* lrow = Lb + gt_off(R, Jc) + (j & 15) * (R - GT_NB * Jc) + GT_NB * (J - Jc);
+            if (ncols == GT_NB) {
+                double2 lv[GT_NB / 2];
+#pragma unroll
+                for (int q = 0; q < GT_NB / 2; ++q) lv[q] = reinterpret_cast<const double2*>(lrow)[q];
+#pragma unroll
+                for (int q = 0; q < GT_NB / 2; ++q) {
+                    s = fma(-lv[q].x, zz[GT_NB * J + 2 * q], s);
+                    s = fma(-lv[q].y, zz[GT_NB * J + 2 * q + 1], s);
+                }
+                if (sec.y) {
+#pragma unroll
+                    for (int q = 0; q < GT_NB / 2; ++q) {
+                        s2 = fma(-lv[q].x, zz2[GT_NB * J + 2 * q], s2);
+                        s2 = fma(-lv[q].y, zz2[GT_NB * J + 2 * q + 1], s2);
+                    }
+                }
+            } else {
+                for (int k = 0; k < ncols; ++k) {
+                    const double lkj = lrow[k];
+                    s = fma(-lkj, zz[GT_NB * J + k], s);
+                    if (sec.y) s2 = fma(-lkj, zz2[GT_NB * J + k], s2);
+                }
             }
             zz[j] = s;
             if (sec.y) zz2[j] = s2;
@@ -509,14 +625,14 @@ gp_batch_tiled_kernel(int kernel_id, const int* __restrict__ kernel_ids, const d
             // covariance entries from the shape table (coalesced over the validation points), same dot product
             const double* kcol = shape_val + v;
             if (sec.y) {
-#pragma unroll 10
+#pragma unroll GT_TAB_UNROLL
                 for (int j = 0; j < n; ++j) {
                     const double kv = B200ID_MUL(kp.p1, kcol[(int64_t)j * nv]);
                     pred = fma(kv, zz[j], pred);
                     pred2 = fma(kv, zz2[j], pred2);
                 }
             } else {
-#pragma unroll 10
+#pragma unroll GT_TAB_UNROLL
                 for (int j = 0; j < n; ++j) pred = fma(B200ID_MUL(kp.p1, kcol[(int64_t)j * nv]), zz[j], pred);
             }
         } else if (sec.y) {

@@ -28,7 +28,7 @@ SMEM_NMAX = 160             # largest n the in-shared-memory kernels accept
 TILED_NMAX = 127            # largest n of the register-tiled candidate kernel (126 with two targets)
 # shared covariance shapes (b200id_gp_batch_eval_shared): used when a list has at least SHARED_MIN_GAIN candidates per
 # distinct shape and the shape tables stay below SHARED_MAX_TABLE_BYTES; B200ID_GP_SHARED=0 switches it off
-SHARED_MIN_GAIN = 4
+SHARED_MIN_GAIN = 2
 SHARED_MAX_TABLE_BYTES = 256 << 20
 AMPLITUDE_SLOT = 1
 

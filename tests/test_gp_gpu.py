@@ -470,7 +470,7 @@ def test_shared_shape_tables_are_bit_identical(gp, n, name, mode, two):
     yb = np.cos(3.0 * X) * 0.5 + 0.05 * rng.standard_normal(n)
     cands = ogp.grid_candidates(name, 5000 if name == "dc" else 900)     # grid_search.py:173-183: product of the 1-D grids (DC: sampled)
     groups = gp.shape_groups(ogp.KERNELS[name][0], cands)
-    assert groups is not None and groups[1].shape[0] * 4 <= len(cands)
+    assert groups is not None and groups[1].shape[0] * gp.SHARED_MIN_GAIN <= len(cands)
     noise = 0.0 if name in ("ss2", "sshf") else 1e-6
     kid = ogp.KERNELS[name][0]
     d = lambda a: None if a is None else to_device(np.ascontiguousarray(a, dtype=np.float64), dev)

@@ -48,6 +48,9 @@ __device__ unsigned long long g_gt_prof[16];
 #endif
 constexpr int GT_FILL_UNROLL_N = GT_FILL_UNROLL;
 constexpr int GT_PRED_UNROLL_N = GT_PRED_UNROLL;
+#ifndef GT_DMMA
+#define GT_DMMA 1
+#endif
 constexpr int GT_THREADS = 128;
 constexpr int GT_NB = 16;
 constexpr int GT_NMAX = 127;            // n + 1 rows <= 128 = 4 warps x 32 rows
@@ -282,6 +285,75 @@ gp_batch_tiled_kernel(int kernel_id, const int* __restrict__ kernel_ids, const d
     __syncthreads();
     GT_TICK(1);
 
+#if GT_DMMA
+    // Updates on the FP64 tensor pipe (mma.sync.m8n8k4.f64): a warp owns 32 rows x 16 columns of a block column as
+    // 4 x 2 accumulator fragments of 8 x 8; lane l holds C[l / 4][2 (l % 4) .. +1] of each.  Per 4 steps of k a lane
+    // loads 4 A values (its row of each 8-row block, column k + l % 4, negated) and 2 B values and the warp issues 8 DMMAs
+    // = 2048 FMAs from 8 issue slots, where the register-tiled loop needed 64 DFMAs and 16 vector loads; a DMMA adds its
+    // four products in k order, so the factor is bit-identical to that loop's.
+    const int fr = lane >> 2, fk = lane & 3;
+    const int wrow0 = 32 * wrow;                       // first row of this warp
+    double acc[4][2][2];
+    bool acc_valid = false;                            // warp-uniform
+    const bool diag_warp = (wrow == 0);
+    // rows of this warp that take part in block column J: fragments rbk with [wrow0 + 8 rbk, +8) inside [16 J, R)
+    auto frag_on = [&](int J, int rbk) { return wrow0 + 8 * rbk + 7 >= GT_NB * J && wrow0 + 8 * rbk < R; };
+    auto warp_on = [&](int J) { return wrow0 + 31 >= GT_NB * J && wrow0 < R; };
+    auto apply_columns = [&](int J, int Jk0, int Jk1) {
+        for (int Jk = Jk0; Jk < Jk1; ++Jk) {
+            const int ldk = R - GT_NB * Jk;
+            const double* base = Lb + gt_off(R, Jk) + fk * ldk - GT_NB * Jk;        // base[kk * ldk + row] = L[row][16 Jk + kk + fk]
+            int ra[4], rbx[2];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) ra[i] = min(wrow0 + 8 * i + fr, R - 1);     // rows past the storage: any finite address
+#pragma unroll
+            for (int j = 0; j < 2; ++j) rbx[j] = min(GT_NB * J + 8 * j + fr, R - 1);
+#pragma unroll
+            for (int kk = 0; kk < GT_NB; kk += 4) {
+                double av[4], bv[2];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) av[i] = -base[kk * ldk + max(ra[i], GT_NB * Jk)];
+#pragma unroll
+                for (int j = 0; j < 2; ++j) bv[j] = base[kk * ldk + rbx[j]];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (frag_on(J, i)) {
+#pragma unroll
+                        for (int j = 0; j < 2; ++j)
+                            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                                         : "+d"(acc[i][j][0]), "+d"(acc[i][j][1]) : "d"(av[i]), "d"(bv[j]));
+                    }
+            }
+        }
+    };
+    auto load_tile = [&](int J) {
+        const int ldJ = R - GT_NB * J;
+        const double* colJ = Lb + gt_off(R, J) - GT_NB * J;                        // colJ[c * ldJ + row]
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int row = wrow0 + 8 * i + fr;
+            const bool ok = row >= GT_NB * J && row < R;
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) acc[i][j][e] = ok ? colJ[(8 * j + 2 * fk + e) * ldJ + row] : 0.0;
+        }
+    };
+    auto store_tile = [&](int J) {
+        const int ldJ = R - GT_NB * J;
+        double* colJ = Lb + gt_off(R, J) - GT_NB * J;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int row = wrow0 + 8 * i + fr;
+            if (row >= GT_NB * J && row < R) {
+#pragma unroll
+                for (int j = 0; j < 2; ++j)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) colJ[(8 * j + 2 * fk + e) * ldJ + row] = acc[i][j][e];
+            }
+        }
+    };
+#else
     const int rb = lane >> 2, cb = lane & 3;           // 8 row blocks x 4 column blocks of 4 x 4
     const int i0 = 32 * wrow + 4 * rb;                 // first of this lane's 4 rows
 
@@ -325,11 +397,19 @@ gp_batch_tiled_kernel(int kernel_id, const int* __restrict__ kernel_ids, const d
         }
     };
 
+#endif
     for (int J = 0; J < nblk; ++J) {
         const int ldJ = R - GT_NB * J;
         double* colJ = Lb + gt_off(R, J);
         const int ncols = min(GT_NB, n - GT_NB * J);
         // ---------------- finish the update of block column J: the lookahead covered block columns < J-1
+#if GT_DMMA
+        if (J > 0 && warp_on(J)) {
+            if (!acc_valid) load_tile(J);
+            apply_columns(J, acc_valid ? J - 1 : 0, J);
+            store_tile(J);
+        }
+#else
         if (J > 0 && i0 >= GT_NB * J && i0 < R) {
             if (!acc_valid) load_tile(J);
             apply_columns(J, acc_valid ? J - 1 : 0, J);
@@ -340,6 +420,7 @@ gp_batch_tiled_kernel(int kernel_id, const int* __restrict__ kernel_ids, const d
                 *reinterpret_cast<double2*>(dst + 2) = make_double2(acc[2][b], acc[3][b]);
             }
         }
+#endif
         acc_valid = false;
         GT_TICK(2);
         __syncthreads();
@@ -414,11 +495,19 @@ gp_batch_tiled_kernel(int kernel_id, const int* __restrict__ kernel_ids, const d
         }
         GT_TICK(4);
         // ---------------- lookahead: block column J+1 minus block columns < J (all final), kept in registers
+#if GT_DMMA
+        if (J + 1 < nblk && J >= 1 && !diag_warp && warp_on(J + 1)) {
+            load_tile(J + 1);
+            apply_columns(J + 1, 0, J);
+            acc_valid = true;
+        }
+#else
         if (J + 1 < nblk && J >= 1 && i0 >= GT_NB * (J + 1) && i0 < R) {
             load_tile(J + 1);
             apply_columns(J + 1, 0, J);
             acc_valid = true;
         }
+#endif
         GT_TICK(5);
         __syncthreads();
         GT_TICK(6);

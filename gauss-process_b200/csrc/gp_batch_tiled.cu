@@ -51,6 +51,9 @@ constexpr int GT_PRED_UNROLL_N = GT_PRED_UNROLL;
 #ifndef GT_DMMA
 #define GT_DMMA 1
 #endif
+#ifndef GT_MIN_CTAS
+#define GT_MIN_CTAS 4
+#endif
 constexpr int GT_THREADS = 128;
 constexpr int GT_NB = 16;
 constexpr int GT_NMAX = 127;            // n + 1 rows <= 128 = 4 warps x 32 rows
@@ -217,7 +220,7 @@ __device__ __forceinline__ double lc_at(const double (&a)[GT_NB], int k) {
 
 // 4 CTAs per SM: 128 registers per thread (without the bound ptxas takes 154, i.e. 3 CTAs per SM, and the search
 // loses a quarter of its throughput: 900 x 2 validation-RMSE candidates 0.42 -> 0.26 ms, 4096 NLL 0.84 -> 0.60 ms)
-__global__ void __launch_bounds__(GT_THREADS, 4)
+__global__ void __launch_bounds__(GT_THREADS, GT_MIN_CTAS)
 gp_batch_tiled_kernel(int kernel_id, const int* __restrict__ kernel_ids, const double* __restrict__ theta,
                       const double* __restrict__ X, const double* __restrict__ y, int n, double noise,
                       int metric, const double* __restrict__ Xv, const double* __restrict__ yv, int nv,

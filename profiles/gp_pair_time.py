@@ -8,7 +8,7 @@ import numpy as np, torch
 from b200id import gp as bgp, pipeline as P, synth
 from b200id.runtime import require_cuda, to_device
 dev = require_cuda()
-nd = 100
+nd = int(sys.argv[1]) if len(sys.argv) > 1 else 100
 gi = P.GridInputs.get(nd, dev)
 rng = np.random.default_rng(0)
 y = to_device(rng.standard_normal(nd), dev)

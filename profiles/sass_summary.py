@@ -29,7 +29,7 @@ def main():
             name = re.sub(r"\(.*", "", name).replace("b200id::", "").replace("void ", "")
             cur = per.setdefault(name, Counter())
             continue
-        m = re.match(r"\s*/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", line)
+        m = re.match(r"\s*/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", line)
         if m and cur is not None:
             op = m.group(1)
             base = op.split(".")[0]

@@ -69,6 +69,9 @@ constexpr int DA_BPB = 128;                      // bins per CTA pass of the rou
 constexpr double DA_MAGIC = 4503599627370496.0 + 1262485504.0;   // 2^52 + 0x4B400000: low word of (DA_MAGIC + n) = bits of the float 2^23 + 2^22 + n
 constexpr float DA_MAGIC_F = 12582912.0f;                        // 2^23 + 2^22
 constexpr int DA_CM = DA_TS + 2 * DA_THREADS;    // entries of the chain-major arrays (R (ceil(TS / R) | 1) < TS + 2 R)
+#ifndef DA_ROUND_PREFETCH
+#define DA_ROUND_PREFETCH 1
+#endif
 #ifndef DA_SIGMAS
 #define DA_SIGMAS 4.0
 #endif
@@ -843,6 +846,18 @@ frf_round_goertzel_kernel(const double* __restrict__ t, const double* __restrict
         }
         if (tid == DA_THREADS - 1 && tl + geo.gx < n_tiles)
             seeds[(it + 1) & 1] = da_tile_seed(t, i0 + (int64_t)geo.gx * DA_TS, tb);       // read after the next loop-top barrier
+#if DA_ROUND_PREFETCH
+        // L2 prefetch of this CTA's next tile (one 128-byte line per thread: t, u, y), so that its staging loads -- the
+        // only global reads of the kernel, issued right after the chains of this tile -- find their lines in the L2
+        if (tl + geo.gx < n_tiles && tid < 3 * (DA_TS / 16)) {
+            const int arr = tid / (DA_TS / 16), ln = tid - arr * (DA_TS / 16);
+            const int64_t ip = i0 + (int64_t)geo.gx * DA_TS + 16 * ln;
+            if (ip < n) {
+                const double* src = arr == 0 ? t : (arr == 1 ? u : y);
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(src + ip));
+            }
+        }
+#endif
         __syncthreads();
         if (!active || r >= cnt) continue;
         const int M = (cnt - r + R - 1) / R;                             // steps of this chain in this tile

@@ -55,3 +55,23 @@ def test_round_robin_shards_of_the_grid_still_share(gp):
             shard = cands[rank::world]
             groups = gp.shape_groups(ogp.KERNELS["matern52"][0], shard)
             assert groups is not None and groups[1].shape[0] == 30
+
+
+@pytest.mark.parametrize("name", [k for k in ogp.KERNELS if k not in ("di", "matern_nu")])
+def test_amplitude_is_the_last_factor_in_the_reference_arithmetic(name):
+    """The basis of b200id_gp_batch_eval_shared, checked on the oracle's restatement of kernels.py:90-382 (pinned to
+    reference-generated goldens): for every kernel but DI, K(theta) is bit for bit theta[1] * K(theta with theta[1] = 1)
+    -- the amplitude multiplies last, 1 * s is exact, and (v * sign) * m == v * (sign * m) for sign = +-1 (SSHF)."""
+    rng = np.random.default_rng(len(name))
+    X = np.sort(rng.uniform(-1.7, 1.7, 40))
+    Xv = rng.uniform(-1.6, 1.6, 25)
+    cands = ogp.grid_candidates(name, 5000)
+    for th in cands[rng.choice(len(cands), 40, replace=False)]:
+        unit = np.array(th, dtype=np.float64); unit[1] = 1.0
+        for a, b in ((X, None), (Xv, X)):
+            with np.errstate(all="ignore"):
+                K, S = ogp.gram(name, th, a, b), ogp.gram(name, unit, a, b)
+                want = th[1] * S
+            assert np.array_equal(np.isnan(K), np.isnan(want))
+            ok = ~np.isnan(K)
+            assert np.array_equal(K[ok].view(np.uint64), want[ok].view(np.uint64)), name

@@ -1,23 +1,30 @@
 // gp_batch_tiled.cu -- K2 fast path (n <= 127): one CTA of 4 warps per candidate, left-looking BLOCKED
-// Cholesky with register-tiled FP64 updates.
+// Cholesky in shared memory with the trailing updates on the FP64 tensor pipe.
 //
 // Reference call sites: src/gpr/grid_search.py:91-133 (candidate metric), src/gpr/gpr_fitting.py:104-123.
 //
 // Layout in shared memory.  The (n+1) x n array [K + noise*I ; y^T] is stored by BLOCK COLUMNS of 16:
 // block column J keeps rows [16J, R) (R = n+1 rounded up to 4) column-major with leading dimension
 // ld_J = R - 16J, so a thread's 4 consecutive rows of one column are one 32-byte vector and the upper
-// triangle above each block is never stored (50 KB at n = 100 -> 4 CTAs per SM).
+// triangle above each block is never stored (50 KB at n = 100 -> 4 CTAs per SM, which the launch bound keeps).
+//
+// Gram entries: evaluated per candidate (gt_fill), or -- b200id_gp_batch_eval_shared, product grids -- taken from a
+// table of covariance SHAPES (gp_shape_table_kernel, one table per distinct theta-without-amplitude) and scaled by the
+// candidate's amplitude with the reference's own final multiplication; same bits either way.
 //
 // Per block column J:
-//   update : C[i, c] -= sum_{k < 16J} L[i, k] L[16J + c, k].  Each warp owns 32 rows x 16 columns, each
-//            lane a 4 x 4 register tile; per k a lane reads 4 + 4 doubles (broadcast across the lanes that
-//            share the rows / columns: 4 shared-memory wavefronts per 16 DFMA warp instructions).
-//   diag   : one warp factorises the 16 x 16 diagonal block in registers (shuffles, reciprocal scaling)
-//            while the other warps already apply block columns < J to block column J+1 (lookahead).
+//   update : C[i, c] -= sum_{k < 16J} L[i, k] L[16J + c, k].  Each warp owns 32 rows x 16 columns as 4 x 2
+//            accumulator fragments of mma.sync.m8n8k4.f64 (GT_DMMA; the register-tiled DFMA loop it replaced, 4 x 4
+//            per lane, is kept under GT_DMMA=0); both add the products in k order: the factor is bit-identical.
+//   diag   : one warp factorises the 16 x 16 diagonal block in registers (shuffles, reciprocal scaling; straight-line
+//            code for a full block) while the other warps already apply block columns < J to block column J+1 (lookahead).
 //   panel  : one thread per row below solves x L_JJ^T = c by forward substitution in registers, multiplying
 //            by the stored reciprocal diagonal (as OpenBLAS TRSM does).
-// Row n carries y, so after the last block column it holds z = L^-1 y and y^T K^-1 y = z.z.
+// Row n carries y (row n + 1 a second target), so after the last block column it holds z = L^-1 y and y^T K^-1 y = z.z.
+// Validation RMSE: blocked back substitution (16 x 16 solves in registers + shuffles, columns prefetched a block ahead),
+// then K(Xv, X) alpha with the entries evaluated on the fly or read from the shape table.
 // Failure conventions as in gp_linalg.cuh: pivot <= 0 or +inf -> 1e10, NaN pivot -> NaN metric.
+// Measured structure (profiles/r02_ncu_gp_tiled.txt): barrier bound -- three warps wait while one walks a serial chain.
 #include "common.cuh"
 #include "gp_kernels.cuh"
 
